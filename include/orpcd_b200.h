@@ -1,0 +1,173 @@
+/*
+ * orpcd_b200.h -- C ABI of the B200 (sm_100a) registration hot path.
+ *
+ * The reference (dpolimeni/Multi-scale-pointcloud-registration, package or_pcd)
+ * has no FFI of its own: its plugin API is Python abstract classes
+ * (Optimizer/iOptimizer.py:7-21, Preprocessor/iProcessBlock.py:6-12) whose
+ * concrete classes call Open3D 0.18.0.  Each entry point below replaces one of
+ * those Open3D call sites; the Python classes under
+ * multi-scale-pointcloud-registration_b200/or_pcd_b200/ bind them with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller; the
+ *     library never allocates or frees across this boundary (workspace sizes
+ *     come from the *_workspace_bytes() queries);
+ *   - all work is enqueued on `stream` (a cudaStream_t); calls return after
+ *     enqueueing unless stated otherwise;
+ *   - return value: ORPCD_OK or a negative ORPCD_ERR_* code; no exceptions;
+ *   - point clouds are float64, C-contiguous (N,3) as numpy hands them to the
+ *     reference; symmetric 3x3 matrices are stored as 6 doubles
+ *     (xx, xy, xz, yy, yz, zz); 4x4 transforms are 16 doubles, row-major, in
+ *     Open3D's column convention (x' = R x + t);
+ *   - neighbour ties break towards the lowest index (BASELINE.json north_star).
+ *   - re-entrant per (device, stream); no global mutable state.
+ */
+#ifndef ORPCD_B200_H
+#define ORPCD_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *orpcd_stream_t; /* cudaStream_t */
+
+#define ORPCD_OK 0
+#define ORPCD_ERR_INVALID (-1)   /* bad argument                          */
+#define ORPCD_ERR_WORKSPACE (-2) /* workspace too small / misaligned      */
+#define ORPCD_ERR_CUDA (-3)      /* a CUDA runtime call or launch failed  */
+
+#define ORPCD_MAX_KNN 64
+
+/* Library / build identification. */
+int orpcd_version(void);
+/* Compute capability the kernels were compiled for (100 for sm_100a). */
+int orpcd_compiled_arch(void);
+const char *orpcd_error_string(int code);
+
+/* ------------------------------------------------------------------------
+ * Exact k-nearest neighbours, float64 distances ((dx*dx + dy*dy) + dz*dz,
+ * no FMA contraction), results sorted by (distance, index).
+ * Replaces open3d.geometry.KDTreeFlann.SearchKNN as used inside
+ *   PointCloud.remove_statistical_outlier   (Preprocessor/Outliers/sor.py:69-71)
+ *   PointCloud.estimate_normals             (Optimizer/fastGlobalOptimizer.py:118-127)
+ *   registration_generalized_icp            (Optimizer/generalizedICP.py:59-70)
+ * d_points : [batch][n][3]  (batch stride = points_stride doubles)
+ * d_queries: [batch][m][3]  (batch stride = queries_stride doubles)
+ * d_idx    : [batch][m][k] int32, -1 where fewer than k points exist
+ * d_d2     : [batch][m][k] float64, +inf where fewer than k points exist
+ * 1 <= k <= ORPCD_MAX_KNN.
+ * ---------------------------------------------------------------------- */
+int orpcd_knn_exact(const double *d_points, int n, long long points_stride,
+                    const double *d_queries, int m, long long queries_stride,
+                    int batch, int k, int *d_idx, double *d_d2, orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Statistical outlier removal mask.
+ * Replaces PointCloud.remove_statistical_outlier(nb_neighbors, std_ratio)
+ * (Preprocessor/Outliers/sor.py:69-71).
+ * d_mask  : [n] uint8 (1 = inlier)
+ * d_avg   : [n] float64 mean neighbour distance per point (may be NULL)
+ * d_stats : [4] float64 {cloud_mean, std_dev, threshold, n_inliers}
+ * ---------------------------------------------------------------------- */
+size_t orpcd_sor_workspace_bytes(int n, int nb_neighbors);
+int orpcd_sor_mask(const double *d_points, int n, int nb_neighbors, double std_ratio,
+                   void *d_workspace, size_t workspace_bytes, unsigned char *d_mask,
+                   double *d_avg, double *d_stats, orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Per-point covariance -> normal (closed-form symmetric eigen-solve) ->
+ * GICP covariance R diag(eps,1,1) R^T, for `batch` clouds of n points.
+ * Replaces PointCloud.estimate_normals(KNN(knn) | Hybrid(radius, knn)) and
+ * InitializePointCloudForGeneralizedICP inside registration_generalized_icp
+ * (Optimizer/generalizedICP.py:59-70; fastGlobalOptimizer.py:118-127).
+ * radius <= 0 selects the pure k-NN search.  Any output may be NULL.
+ * d_normals  : [batch][n][3]
+ * d_cov6     : [batch][n][6]  neighbourhood covariance
+ * d_gicp_cov6: [batch][n][6]  (requires gicp_eps > 0)
+ * d_nn_idx   : [batch][n][knn] int32 neighbour lists actually used (-1 padded)
+ * ---------------------------------------------------------------------- */
+size_t orpcd_normals_workspace_bytes(int n, int batch, int knn);
+int orpcd_normals_cov(const double *d_points, int n, long long points_stride, int batch,
+                      int knn, double radius, double gicp_eps, void *d_workspace,
+                      size_t workspace_bytes, double *d_normals, double *d_cov6,
+                      double *d_gicp_cov6, int *d_nn_idx, orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * target * (sx, sy, sz) for a batch of scale candidates
+ * (Aligner/Aligner.py:221-222, `target * new_scale_factors`).
+ * d_scales: [n_scales][3]; d_out: [n_scales][n][3].
+ * ---------------------------------------------------------------------- */
+int orpcd_apply_scale_batch(const double *d_points, int n, const double *d_scales,
+                            int n_scales, double *d_out, orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Batched Generalized-ICP: n_units independent inner registrations
+ * (one per multi-start x scale candidate) advanced together, one launch
+ * sequence per Gauss-Newton iteration for all of them.
+ * Replaces registration_generalized_icp(source, target, max_dist, I,
+ * TransformationEstimationForGeneralizedICP(), ICPConvergenceCriteria(
+ * max_iteration)) at Optimizer/generalizedICP.py:59-70, called once per
+ * start from Aligner/Aligner.py:188-190.
+ *
+ * Unit u registers source set d_unit_src[u] onto target set d_unit_tgt[u].
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    int n_units;
+    int n_src;            /* points per source cloud              */
+    int n_tgt;            /* points per target cloud              */
+    int n_src_sets;
+    int n_tgt_sets;
+    int max_iterations;   /* ICPConvergenceCriteria.max_iteration  */
+    int target_splits;    /* 0 = choose automatically              */
+    int poll_interval;    /* >0: every that many iterations the call waits on
+                             the stream and stops early once every unit is done */
+    int profile;          /* !=0: time every sweep launch with CUDA events on the
+                             stream and synchronise at the end (fills h_profile) */
+    double max_correspondence_distance;
+    double relative_fitness; /* 1e-6 in the reference's call       */
+    double relative_rmse;    /* 1e-6                               */
+} orpcd_gicp_params;
+
+size_t orpcd_gicp_batch_workspace_bytes(const orpcd_gicp_params *p);
+
+/* d_src_points [n_src_sets][n_src][3], d_src_cov6 [n_src_sets][n_src][6],
+ * d_tgt_points [n_tgt_sets][n_tgt][3], d_tgt_cov6 [n_tgt_sets][n_tgt][6],
+ * d_out_T     [n_units][16],
+ * d_out_stats [n_units][4]  {fitness, inlier_rmse, iterations, n_correspondences},
+ * d_out_status[n_units]     0 = ok, 1 = no correspondence (inlier_rmse == 0:
+ *                           the reference raises ValueError, generalizedICP.py:77-81),
+ * d_trace (may be NULL) [n_units][max_iterations+1][2] (fitness, rmse) per Evaluate,
+ * h_profile (HOST, may be NULL) [8]: {kernels launched, ms inside the 1-NN sweep
+ *   kernel*, (query,target) pairs swept*, rounds issued, queries sent to the exact
+ *   work list*, target splits, sweep launches with work*, unit-rounds*};
+ *   entries marked * are filled only when p->profile != 0.                    */
+int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_points,
+                     const double *d_src_cov6, const double *d_tgt_points,
+                     const double *d_tgt_cov6, const int *d_unit_src, const int *d_unit_tgt,
+                     void *d_workspace, size_t workspace_bytes, double *d_out_T,
+                     double *d_out_stats, int *d_out_status, double *d_trace,
+                     double *h_profile, orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Roofline helper: one nearest-neighbour sweep (the dominant kernel of
+ * orpcd_gicp_batch) over `n_units` x n_src queries against n_tgt targets,
+ * exactly as one Gauss-Newton iteration issues it, for timing in isolation.
+ * Uses a workspace prepared by orpcd_gicp_batch on the same parameters.
+ * ---------------------------------------------------------------------- */
+int orpcd_gicp_sweep_only(const orpcd_gicp_params *p, void *d_workspace,
+                          size_t workspace_bytes, orpcd_stream_t stream);
+
+/* FP32 FFMA pipe micro-benchmark (roofline denominator):
+ * launches blocks x 256 threads, each doing iters x 16 dependent-chain FFMAs on
+ * 8 independent accumulators.  FLOPs = blocks*256*iters*16*8*2.  d_sink: [blocks*256]. */
+int orpcd_ffma_burn(int blocks, int iters, float *d_sink, orpcd_stream_t stream);
+/* Same with packed FFMA2 (fma.rn.f32x2): FLOPs = blocks*256*iters*16*8*4. */
+int orpcd_ffma2_burn(int blocks, int iters, float *d_sink, orpcd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORPCD_B200_H */

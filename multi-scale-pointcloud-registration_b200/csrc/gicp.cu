@@ -1,0 +1,860 @@
+// Batched Generalized-ICP for sm_100a: every (multi-start x scale-candidate)
+// inner registration of the Aligner's pattern search advances together, one
+// launch sequence per Gauss-Newton iteration for all of them.
+//
+// Replaces open3d.pipelines.registration.registration_generalized_icp as called
+// from Optimizer/generalizedICP.py:59-70 (once per start, Aligner/Aligner.py:188-190).
+// Algorithm: SURVEY.md Appendix A.4-A.5.
+//
+// Per iteration (all units in each launch):
+//   nn_sweep_kernel   FP32 filter over all (query, target) pairs on the FMA pipe:
+//                     packed FFMA2 (fma.rn.f32x2) on the expanded form
+//                     |p|^2 - 2 q.p, FMNMX3 running minima per 32-target chunk,
+//                     per query (best chunk min, best chunk, second-best chunk min).
+//   nn_resolve_kernel applies the pending rigid update to the stored float64
+//                     source points, proves the best chunk holds the exact
+//                     nearest neighbour (FP32 error bound) and re-ranks that
+//                     chunk in float64 with Open3D's operation order; queries
+//                     whose bound fails go to a work list.
+//   nn_fix_kernel     exact float64 scan, one warp per listed query.
+//   reduce_kernel     Mahalanobis residual/Jacobian per correspondence, warp
+//                     shuffle + block reduction of the 21+6 J^T J / J^T r terms,
+//                     squared error and count; the last block of a unit sums the
+//                     block partials in index order, tests convergence, solves the
+//                     6x6 system (LDLT) and composes the transform.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+// ----------------------------------------------------------------------------
+// configuration
+// ----------------------------------------------------------------------------
+constexpr int NN_THREADS = 128;
+constexpr int NN_Q = 4;                          // queries per thread (two packed pairs)
+constexpr int NN_QPB = NN_THREADS * NN_Q;        // queries per block
+constexpr int NN_CH = 32;                        // targets per chunk (re-rank granularity)
+constexpr int NN_TILE_CH = 32;                   // chunks per shared-memory tile
+constexpr int NN_TILE = NN_CH * NN_TILE_CH;      // 1024 targets = 16 KB per stage
+constexpr int RED_THREADS = 128;
+constexpr int RED_VALS = 29;                     // 21 JTJ + 6 JTr + sum d2 + count
+constexpr int RED_STRIDE = 32;
+constexpr float F32_EPS = 5.9604644775390625e-8f;  // 2^-24, unit roundoff
+
+struct UnitState {
+    double T[16];       // accumulated transform (row-major 4x4, column convention)
+    double U[12];       // pending update [R|t] not yet applied to points / covariances
+    double fitness;     // result of the previous Evaluate
+    double rmse;
+    int iters;
+    int done;
+    int has_update;
+    int n_corr;
+    int src_set;
+    int tgt_set;
+    int status;
+    int pad;
+};
+
+struct TgtMeta {
+    double cx, cy, cz;  // centre subtracted before rounding to float
+    double rmax;        // max |p - c| over the set (slightly inflated)
+};
+
+struct Ctx {
+    int n_units, n_src, n_tgt, nt_pad, n_chunks, splits, chunks_per_split;
+    int max_iter, red_blocks;
+    double r2, rel_fit, rel_rmse;
+    UnitState *state;
+    double *cur_pts;     // [units][n_src][3]
+    double *cur_cov;     // [units][n_src][6]
+    int *corr;           // [units][n_src]
+    double *corr_d2;     // [units][n_src]
+    float *part_m1;      // [units][splits][n_src]
+    int *part_c1;
+    float *part_m2;
+    float4 *tgt4;        // [tgt_sets][nt_pad]  (-2x, -2y, -2z, |p|^2), centred
+    TgtMeta *tgt_meta;   // [tgt_sets]
+    double *red_partial; // [units][red_blocks][RED_STRIDE]
+    unsigned *red_counter;  // [units]
+    int *worklist;       // [units*n_src]
+    int *worklist_count; // [max_iter+2]
+    int *done_count;     // [1]
+    int *round_active;   // [max_iter+2] units still running in each round
+    int ignore_done;     // sweep-only timing mode
+    const double *tgt_pts;   // [tgt_sets][n_tgt][3]
+    const double *tgt_cov;   // [tgt_sets][n_tgt][6]
+    double *out_T, *out_stats, *trace;
+    int *out_status;
+};
+
+// ----------------------------------------------------------------------------
+// small PTX helpers
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack_f2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// a * {b,b} + {c,c}
+__device__ __forceinline__ uint64_t fma2_ss(uint64_t a, float b, float c)
+{
+    uint64_t d;
+    asm("{\n\t.reg .b64 rb, rc;\n\tmov.b64 rb, {%2, %2};\n\tmov.b64 rc, {%3, %3};\n\t"
+        "fma.rn.f32x2 %0, %1, rb, rc;\n\t}"
+        : "=l"(d) : "l"(a), "f"(b), "f"(c));
+    return d;
+}
+// a * {b,b} + c
+__device__ __forceinline__ uint64_t fma2_sv(uint64_t a, float b, uint64_t c)
+{
+    uint64_t d;
+    asm("{\n\t.reg .b64 rb;\n\tmov.b64 rb, {%2, %2};\n\tfma.rn.f32x2 %0, %1, rb, %3;\n\t}"
+        : "=l"(d) : "l"(a), "f"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float min3f(float a, float b, float c)
+{
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Current float64 position of source point i of unit u (pending update applied).
+__device__ __forceinline__ void load_query(const Ctx &c, const UnitState &st, int u, int i, double &x,
+                                           double &y, double &z)
+{
+    const double *p = c.cur_pts + ((size_t)u * c.n_src + i) * 3;
+    x = p[0]; y = p[1]; z = p[2];
+    if (st.has_update) transform_point(st.U, x, y, z);
+}
+
+// ----------------------------------------------------------------------------
+// set-up kernels
+// ----------------------------------------------------------------------------
+__global__ void init_units_kernel(Ctx c, const int *__restrict__ unit_src, const int *__restrict__ unit_tgt,
+                                  const double *__restrict__ src_pts, const double *__restrict__ src_cov)
+{
+    const int u = blockIdx.y;
+    const int ss = unit_src[u];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        UnitState &s = c.state[u];
+        for (int k = 0; k < 16; ++k) s.T[k] = (k % 5 == 0) ? 1.0 : 0.0;
+        for (int k = 0; k < 12; ++k) s.U[k] = (k % 5 == 0) ? 1.0 : 0.0;
+        s.fitness = 0; s.rmse = 0; s.iters = 0; s.done = 0; s.has_update = 0; s.n_corr = 0;
+        s.src_set = ss; s.tgt_set = unit_tgt[u]; s.status = 0; s.pad = 0;
+        c.red_counter[u] = 0;
+        if (u == 0) {
+            *c.done_count = 0;
+            for (int k = 0; k < c.max_iter + 2; ++k) { c.worklist_count[k] = 0; c.round_active[k] = 0; }
+        }
+    }
+    const size_t np = (size_t)c.n_src * 3, nc = (size_t)c.n_src * 6;
+    const double *sp = src_pts + (size_t)ss * np;
+    const double *sc = src_cov + (size_t)ss * nc;
+    double *dp = c.cur_pts + (size_t)u * np;
+    double *dc = c.cur_cov + (size_t)u * nc;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nc; e += (size_t)gridDim.x * blockDim.x) {
+        dc[e] = sc[e];
+        if (e < np) dp[e] = sp[e];
+    }
+}
+
+// one block per target set: bounding-box centre, then centred float4 table.
+__global__ void __launch_bounds__(1024) prep_targets_kernel(Ctx c)
+{
+    __shared__ double red[6][32];
+    __shared__ double ctr[3];
+    __shared__ float rmax_s[32];
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double *pts = c.tgt_pts + (size_t)s * c.n_tgt * 3;
+    double mn[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, mx[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+    for (int i = tid; i < c.n_tgt; i += blockDim.x)
+        for (int k = 0; k < 3; ++k) {
+            const double v = pts[(size_t)i * 3 + k];
+            mn[k] = fmin(mn[k], v);
+            mx[k] = fmax(mx[k], v);
+        }
+    for (int k = 0; k < 3; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    if (lane == 0)
+        for (int k = 0; k < 3; ++k) { red[k][wid] = mn[k]; red[3 + k][wid] = mx[k]; }
+    __syncthreads();
+    if (tid < 3) {
+        double a = CUDART_INF, b = -CUDART_INF;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a = fmin(a, red[tid][w]); b = fmax(b, red[3 + tid][w]); }
+        ctr[tid] = c.n_tgt > 0 ? 0.5 * (a + b) : 0.0;
+    }
+    __syncthreads();
+    const double cx = ctr[0], cy = ctr[1], cz = ctr[2];
+    float4 *out = c.tgt4 + (size_t)s * c.nt_pad;
+    float rm = 0.f;
+    for (int i = tid; i < c.nt_pad; i += blockDim.x) {
+        float4 v;
+        if (i < c.n_tgt) {
+            const float fx = (float)(pts[(size_t)i * 3] - cx);
+            const float fy = (float)(pts[(size_t)i * 3 + 1] - cy);
+            const float fz = (float)(pts[(size_t)i * 3 + 2] - cz);
+            const double w = (double)fx * fx + (double)fy * fy + (double)fz * fz;
+            v = make_float4(-2.f * fx, -2.f * fy, -2.f * fz, (float)w);
+            rm = fmaxf(rm, (float)sqrt(w));
+        } else {
+            v = make_float4(0.f, 0.f, 0.f, 3.0e38f);  // sentinel: never the minimum
+        }
+        out[i] = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+    if (lane == 0) rmax_s[wid] = rm;
+    __syncthreads();
+    if (tid == 0) {
+        float r = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, rmax_s[w]);
+        TgtMeta m;
+        m.cx = cx; m.cy = cy; m.cz = cz;
+        m.rmax = (double)r * (1.0 + 1e-6) + 1e-300;
+        c.tgt_meta[s] = m;
+    }
+}
+
+// ----------------------------------------------------------------------------
+// 1-NN sweep: FP32 filter on the FMA pipe
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c)
+{
+    __shared__ __align__(16) float4 tile[2][NN_TILE];
+    const int u = blockIdx.z, split = blockIdx.y, tid = threadIdx.x;
+    const UnitState &st = c.state[u];
+    if (st.done && !c.ignore_done) return;
+    const TgtMeta tm = c.tgt_meta[st.tgt_set];
+    const float4 *tg = c.tgt4 + (size_t)st.tgt_set * c.nt_pad;
+
+    // this thread's NN_Q queries: i = qbase + k*NN_THREADS + tid
+    const int qbase = blockIdx.x * NN_QPB;
+    float qf[NN_Q][3];
+#pragma unroll
+    for (int k = 0; k < NN_Q; ++k) {
+        const int i = qbase + k * NN_THREADS + tid;
+        double x = tm.cx, y = tm.cy, z = tm.cz;
+        if (i < c.n_src) load_query(c, st, u, i, x, y, z);
+        qf[k][0] = (float)(x - tm.cx);
+        qf[k][1] = (float)(y - tm.cy);
+        qf[k][2] = (float)(z - tm.cz);
+    }
+    uint64_t qx[NN_Q / 2], qy[NN_Q / 2], qz[NN_Q / 2];
+#pragma unroll
+    for (int h = 0; h < NN_Q / 2; ++h) {
+        qx[h] = pack_f2(qf[2 * h][0], qf[2 * h + 1][0]);
+        qy[h] = pack_f2(qf[2 * h][1], qf[2 * h + 1][1]);
+        qz[h] = pack_f2(qf[2 * h][2], qf[2 * h + 1][2]);
+    }
+    float m1[NN_Q], m2[NN_Q];
+    int c1[NN_Q];
+#pragma unroll
+    for (int k = 0; k < NN_Q; ++k) { m1[k] = CUDART_INF_F; m2[k] = CUDART_INF_F; c1[k] = 0; }
+
+    const int cb = split * c.chunks_per_split;
+    const int ce = min(c.n_chunks, cb + c.chunks_per_split);
+    const int n_tiles = (ce - cb + NN_TILE_CH - 1) / NN_TILE_CH;
+
+    auto issue = [&](int t) {
+        if (t < n_tiles) {
+            const int c0 = cb + t * NN_TILE_CH;
+            const int cnt = min(NN_TILE_CH, ce - c0) * NN_CH;
+            const float4 *src = tg + (size_t)c0 * NN_CH;
+            float4 *dst = tile[t & 1];
+            for (int e = tid; e < cnt; e += NN_THREADS) cp_async16(dst + e, src + e);
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    for (int t = 0; t < n_tiles; ++t) {
+        issue(t + 1);
+        cp_async_wait<1>();
+        __syncthreads();
+        const int c0 = cb + t * NN_TILE_CH;
+        const int nch = min(NN_TILE_CH, ce - c0);
+        const float4 *tl = tile[t & 1];
+        for (int ch = 0; ch < nch; ++ch) {
+            const float4 *tc = tl + ch * NN_CH;
+            float mc[NN_Q];
+#pragma unroll
+            for (int k = 0; k < NN_Q; ++k) mc[k] = CUDART_INF_F;
+#pragma unroll
+            for (int j = 0; j < NN_CH; j += 2) {
+                const float4 t0 = tc[j], t1 = tc[j + 1];
+#pragma unroll
+                for (int h = 0; h < NN_Q / 2; ++h) {
+                    uint64_t a0 = fma2_ss(qz[h], t0.z, t0.w);
+                    uint64_t a1 = fma2_ss(qz[h], t1.z, t1.w);
+                    a0 = fma2_sv(qy[h], t0.y, a0);
+                    a1 = fma2_sv(qy[h], t1.y, a1);
+                    a0 = fma2_sv(qx[h], t0.x, a0);
+                    a1 = fma2_sv(qx[h], t1.x, a1);
+                    float a0l, a0h, a1l, a1h;
+                    unpack_f2(a0, a0l, a0h);
+                    unpack_f2(a1, a1l, a1h);
+                    mc[2 * h] = min3f(mc[2 * h], a0l, a1l);
+                    mc[2 * h + 1] = min3f(mc[2 * h + 1], a0h, a1h);
+                }
+            }
+            const int chunk = c0 + ch;
+#pragma unroll
+            for (int k = 0; k < NN_Q; ++k) {
+                m2[k] = fminf(m2[k], fmaxf(m1[k], mc[k]));
+                c1[k] = mc[k] < m1[k] ? chunk : c1[k];
+                m1[k] = fminf(m1[k], mc[k]);
+            }
+        }
+        __syncthreads();
+    }
+    const size_t pbase = ((size_t)u * c.splits + split) * c.n_src;
+#pragma unroll
+    for (int k = 0; k < NN_Q; ++k) {
+        const int i = qbase + k * NN_THREADS + tid;
+        if (i < c.n_src) {
+            c.part_m1[pbase + i] = m1[k];
+            c.part_c1[pbase + i] = c1[k];
+            c.part_m2[pbase + i] = m2[k];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// resolve: merge split partials, certify the best chunk, exact float64 re-rank
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) nn_resolve_kernel(Ctx c, int round)
+{
+    const int u = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const UnitState &st = c.state[u];
+    if (st.done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c.round_active[round], 1);
+    if (i >= c.n_src) return;
+    double x, y, z;
+    load_query(c, st, u, i, x, y, z);
+    if (st.has_update) {
+        double *p = c.cur_pts + ((size_t)u * c.n_src + i) * 3;
+        p[0] = x; p[1] = y; p[2] = z;
+    }
+    const TgtMeta tm = c.tgt_meta[st.tgt_set];
+    const float fx = (float)(x - tm.cx), fy = (float)(y - tm.cy), fz = (float)(z - tm.cz);
+
+    float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
+    int c1 = 0;
+    for (int s = 0; s < c.splits; ++s) {
+        const size_t pi = ((size_t)u * c.splits + s) * c.n_src + i;
+        const float a1 = c.part_m1[pi], a2 = c.part_m2[pi];
+        const int ac = c.part_c1[pi];
+        m2 = fminf(fminf(m2, a2), fmaxf(m1, a1));
+        c1 = a1 < m1 ? ac : c1;
+        m1 = fminf(m1, a1);
+    }
+    // FP32 error bound of the filter (DESIGN.md "1-NN filter bound"):
+    //   |(s + |qf|^2) - D| <= eps32 * (4 rho^2 + 2 d rho),  rho = |qf| + |pf|.
+    const double qn = (double)fx * fx + (double)fy * fy + (double)fz * fz;
+    const double qnorm = sqrt(qn);
+    const double rho_max = qnorm + tm.rmax;
+    const double e_glob = (double)F32_EPS * 6.0 * rho_max * rho_max * 1.001;
+    const double d_ub = sqrt(fmax((double)m1 + qn, 0.0) + e_glob) * (1.0 + 1e-6);
+    const double rho = 2.0 * qnorm + d_ub + 4.0 * (double)F32_EPS * rho_max;
+    const double margin = 2.02 * (double)F32_EPS * (4.0 * rho * rho + 2.0 * d_ub * rho) * 1.001 + 1e-300;
+
+    const size_t oi = (size_t)u * c.n_src + i;
+    if (!((double)m2 > (double)m1 + margin)) {
+        // another chunk may hold the true neighbour: exact scan by a whole warp later
+        const int slot = atomicAdd(&c.worklist_count[round], 1);
+        c.worklist[slot] = (int)oi;
+        return;
+    }
+    const double *tp = c.tgt_pts + (size_t)st.tgt_set * c.n_tgt * 3;
+    const int j0 = c1 * NN_CH, j1 = min(c.n_tgt, j0 + NN_CH);
+    double best = CUDART_INF;
+    int bj = -1;
+    for (int j = j0; j < j1; ++j) {
+        const double d = sqdist3_rn(x, y, z, tp[(size_t)j * 3], tp[(size_t)j * 3 + 1], tp[(size_t)j * 3 + 2]);
+        if (d < best) { best = d; bj = j; }
+    }
+    const bool ok = bj >= 0 && best < c.r2;
+    c.corr[oi] = ok ? bj : -1;
+    c.corr_d2[oi] = ok ? best : 0.0;
+}
+
+// exact float64 scan, one warp per listed query
+__global__ void __launch_bounds__(128) nn_fix_kernel(Ctx c, int round)
+{
+    const int count = c.worklist_count[round];
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int w = gw; w < count; w += nw) {
+        const int item = c.worklist[w];
+        const int u = item / c.n_src;
+        const UnitState &st = c.state[u];
+        const double *p = c.cur_pts + (size_t)item * 3;  // already updated by nn_resolve_kernel
+        const double x = p[0], y = p[1], z = p[2];
+        const double *tp = c.tgt_pts + (size_t)st.tgt_set * c.n_tgt * 3;
+        double best = CUDART_INF;
+        int bj = 0x7fffffff;
+        for (int j = lane; j < c.n_tgt; j += 32) {
+            const double d = sqdist3_rn(x, y, z, tp[(size_t)j * 3], tp[(size_t)j * 3 + 1], tp[(size_t)j * 3 + 2]);
+            if (d < best) { best = d; bj = j; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (od < best || (od == best && oj < bj)) { best = od; bj = oj; }
+        }
+        if (lane == 0) {
+            const bool ok = bj != 0x7fffffff && best < c.r2;
+            c.corr[item] = ok ? bj : -1;
+            c.corr_d2[item] = ok ? best : 0.0;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// dense helpers (float64)
+// ----------------------------------------------------------------------------
+#define JACOBI_ROT(app, aqq, apq, arp, arq, vp, vq)                                        \
+    if (apq != 0.0) {                                                                      \
+        const double theta = (aqq - app) / (2.0 * apq);                                    \
+        const double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0)); \
+        const double cc = 1.0 / sqrt(tt * tt + 1.0), ss = tt * cc;                         \
+        const double npp = app - tt * apq, nqq = aqq + tt * apq;                           \
+        const double nrp = cc * arp - ss * arq, nrq = ss * arp + cc * arq;                 \
+        app = npp; aqq = nqq; apq = 0.0; arp = nrp; arq = nrq;                             \
+        _Pragma("unroll") for (int r = 0; r < 3; ++r) {                                    \
+            const double xx = v[r][vp], yy = v[r][vq];                                     \
+            v[r][vp] = cc * xx - ss * yy;                                                  \
+            v[r][vq] = ss * xx + cc * yy;                                                  \
+        }                                                                                  \
+    }
+
+// W = (M^-1)^(1/2) for symmetric positive definite M via cyclic Jacobi
+// (restates Eigen's M.inverse().sqrt()).
+__device__ __forceinline__ Sym3 inv_sqrt_sym3(const Sym3 &M)
+{
+    double a00 = M.xx, a01 = M.xy, a02 = M.xz, a11 = M.yy, a12 = M.yz, a22 = M.zz;
+    double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = a01 * a01 + a02 * a02 + a12 * a12;
+        const double dg = a00 * a00 + a11 * a11 + a22 * a22;
+        if (off <= 1e-36 * dg) break;  // off-diagonals below 1e-18 |A|: no effect in float64
+        JACOBI_ROT(a00, a11, a01, a02, a12, 0, 1)
+        JACOBI_ROT(a00, a22, a02, a01, a12, 0, 2)
+        JACOBI_ROT(a11, a22, a12, a01, a02, 1, 2)
+    }
+    const double s0 = 1.0 / sqrt(a00), s1 = 1.0 / sqrt(a11), s2 = 1.0 / sqrt(a22);
+    Sym3 W;
+    W.xx = v[0][0] * s0 * v[0][0] + v[0][1] * s1 * v[0][1] + v[0][2] * s2 * v[0][2];
+    W.xy = v[0][0] * s0 * v[1][0] + v[0][1] * s1 * v[1][1] + v[0][2] * s2 * v[1][2];
+    W.xz = v[0][0] * s0 * v[2][0] + v[0][1] * s1 * v[2][1] + v[0][2] * s2 * v[2][2];
+    W.yy = v[1][0] * s0 * v[1][0] + v[1][1] * s1 * v[1][1] + v[1][2] * s2 * v[1][2];
+    W.yz = v[1][0] * s0 * v[2][0] + v[1][1] * s1 * v[2][1] + v[1][2] * s2 * v[2][2];
+    W.zz = v[2][0] * s0 * v[2][0] + v[2][1] * s1 * v[2][1] + v[2][2] * s2 * v[2][2];
+    return W;
+}
+
+// x = A.ldlt().solve(b), 6x6 symmetric, diagonal pivoting (Eigen LDLT restated).
+__device__ void ldlt_solve6(double *A, const double *b, double *x)
+{
+    int perm[6];
+    for (int i = 0; i < 6; ++i) perm[i] = i;
+    for (int k = 0; k < 6; ++k) {
+        int piv = k;
+        double best = fabs(A[k * 6 + k]);
+        for (int i = k + 1; i < 6; ++i)
+            if (fabs(A[i * 6 + i]) > best) { best = fabs(A[i * 6 + i]); piv = i; }
+        if (piv != k) {
+            for (int j = 0; j < 6; ++j) { const double t = A[k * 6 + j]; A[k * 6 + j] = A[piv * 6 + j]; A[piv * 6 + j] = t; }
+            for (int j = 0; j < 6; ++j) { const double t = A[j * 6 + k]; A[j * 6 + k] = A[j * 6 + piv]; A[j * 6 + piv] = t; }
+            const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+        }
+        const double d = A[k * 6 + k];
+        if (d == 0.0) continue;
+        double col[6];
+        for (int i = k + 1; i < 6; ++i) col[i] = A[i * 6 + k];
+        for (int i = k + 1; i < 6; ++i) {
+            const double l = col[i] / d;
+            for (int j = k + 1; j <= i; ++j) A[i * 6 + j] -= l * col[j];
+            A[i * 6 + k] = l;
+        }
+        for (int i = k + 1; i < 6; ++i)
+            for (int j = i + 1; j < 6; ++j) A[i * 6 + j] = A[j * 6 + i];
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) y[i] = b[perm[i]];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < i; ++j) y[i] -= A[i * 6 + j] * y[j];
+    for (int i = 0; i < 6; ++i) y[i] = A[i * 6 + i] != 0.0 ? y[i] / A[i * 6 + i] : 0.0;
+    for (int i = 5; i >= 0; --i)
+        for (int j = i + 1; j < 6; ++j) y[i] -= A[j * 6 + i] * y[j];
+    for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+}
+
+// ----------------------------------------------------------------------------
+// residual / Jacobian reduction + solve
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
+{
+    __shared__ double sm[RED_THREADS / 32][RED_STRIDE];
+    __shared__ double tot[RED_STRIDE];
+    __shared__ int is_last;
+    const int u = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    UnitState &st = c.state[u];
+    if (st.done) return;
+    const int i = blockIdx.x * RED_THREADS + tid;
+    double acc[RED_VALS];
+#pragma unroll
+    for (int k = 0; k < RED_VALS; ++k) acc[k] = 0.0;
+    if (i < c.n_src) {
+        const size_t oi = (size_t)u * c.n_src + i;
+        double *cp = c.cur_cov + oi * 6;
+        Sym3 Cs = load_sym3(cp);
+        if (st.has_update) {
+            Cs = rotate_sym3(st.U, Cs);
+            store_sym3(cp, Cs);
+        }
+        const int j = c.corr[oi];
+        if (j >= 0) {
+            const double *ps = c.cur_pts + oi * 3;  // updated by nn_resolve_kernel
+            const double sx = ps[0], sy = ps[1], sz = ps[2];
+            const size_t tj = (size_t)st.tgt_set * c.n_tgt + j;
+            const double *pt = c.tgt_pts + tj * 3;
+            const Sym3 Ct = load_sym3(c.tgt_cov + tj * 6);
+            const double dx = sx - pt[0], dy = sy - pt[1], dz = sz - pt[2];
+            Sym3 M;
+            M.xx = Ct.xx + Cs.xx; M.xy = Ct.xy + Cs.xy; M.xz = Ct.xz + Cs.xz;
+            M.yy = Ct.yy + Cs.yy; M.yz = Ct.yz + Cs.yz; M.zz = Ct.zz + Cs.zz;
+            const Sym3 W = inv_sqrt_sym3(M);
+            const double Wm[3][3] = {{W.xx, W.xy, W.xz}, {W.xy, W.yy, W.yz}, {W.xz, W.yz, W.zz}};
+            // J = W [ -skew(vs) | I ],  r = W d
+            double J[3][6], rr[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                J[r][0] = Wm[r][1] * (-sz) + Wm[r][2] * sy;
+                J[r][1] = Wm[r][0] * sz + Wm[r][2] * (-sx);
+                J[r][2] = Wm[r][0] * (-sy) + Wm[r][1] * sx;
+                J[r][3] = Wm[r][0]; J[r][4] = Wm[r][1]; J[r][5] = Wm[r][2];
+                rr[r] = Wm[r][0] * dx + Wm[r][1] * dy + Wm[r][2] * dz;
+            }
+            int k = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = a; b < 6; ++b) acc[k++] = J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) acc[21 + a] = J[0][a] * rr[0] + J[1][a] * rr[1] + J[2][a] * rr[2];
+            acc[27] = c.corr_d2[oi];
+            acc[28] = 1.0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RED_VALS; ++k) acc[k] = warp_sum(acc[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < RED_VALS; ++k) sm[wid][k] = acc[k];
+    }
+    __syncthreads();
+    if (tid < RED_VALS) {
+        double s = sm[0][tid];
+#pragma unroll
+        for (int w = 1; w < RED_THREADS / 32; ++w) s += sm[w][tid];
+        c.red_partial[((size_t)u * c.red_blocks + blockIdx.x) * RED_STRIDE + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(&c.red_counter[u], 1u);
+        is_last = (prev == (unsigned)c.red_blocks - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid < RED_VALS) {
+        double s = 0.0;
+        for (int b = 0; b < c.red_blocks; ++b)
+            s += __ldcg(&c.red_partial[((size_t)u * c.red_blocks + b) * RED_STRIDE + tid]);
+        tot[tid] = s;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    c.red_counter[u] = 0;
+    const double n = tot[28];
+    double fitness = 0.0, rmse = 0.0;
+    if (n > 0) { fitness = n / (double)c.n_src; rmse = sqrt(tot[27] / n); }
+    if (c.trace) {
+        double *tr = c.trace + ((size_t)u * (c.max_iter + 1) + round) * 2;
+        tr[0] = fitness; tr[1] = rmse;
+    }
+    const bool converged = round >= 1 && fabs(st.fitness - fitness) < c.rel_fit && fabs(st.rmse - rmse) < c.rel_rmse;
+    st.fitness = fitness;
+    st.rmse = rmse;
+    st.n_corr = (int)n;
+    if (converged || round >= c.max_iter) {
+        st.done = 1;
+        st.has_update = 0;
+        st.status = (rmse == 0.0) ? 1 : 0;
+        for (int k = 0; k < 16; ++k) c.out_T[(size_t)u * 16 + k] = st.T[k];
+        double *os = c.out_stats + (size_t)u * 4;
+        os[0] = fitness; os[1] = rmse; os[2] = (double)st.iters; os[3] = n;
+        c.out_status[u] = st.status;
+        atomicAdd(c.done_count, 1);
+        return;
+    }
+    double Um[12];
+    if (n > 0) {
+        double A[36], nb[6], x[6];
+        int k = 0;
+        for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b) { A[a * 6 + b] = tot[k]; A[b * 6 + a] = tot[k]; ++k; }
+        for (int a = 0; a < 6; ++a) nb[a] = -tot[21 + a];
+        ldlt_solve6(A, nb, x);
+        double sa, ca, sb, cb, sg, cg;
+        sincos(x[0], &sa, &ca);
+        sincos(x[1], &sb, &cb);
+        sincos(x[2], &sg, &cg);
+        Um[0] = cg * cb; Um[1] = cg * sb * sa - sg * ca; Um[2] = cg * sb * ca + sg * sa; Um[3] = x[3];
+        Um[4] = sg * cb; Um[5] = sg * sb * sa + cg * ca; Um[6] = sg * sb * ca - cg * sa; Um[7] = x[4];
+        Um[8] = -sb;     Um[9] = cb * sa;                Um[10] = cb * ca;               Um[11] = x[5];
+    } else {
+        for (int k = 0; k < 12; ++k) Um[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    }
+    // T = U * T
+    double Tn[16];
+    for (int r = 0; r < 3; ++r)
+        for (int cc = 0; cc < 4; ++cc)
+            Tn[r * 4 + cc] = Um[r * 4] * st.T[cc] + Um[r * 4 + 1] * st.T[4 + cc] + Um[r * 4 + 2] * st.T[8 + cc] +
+                             Um[r * 4 + 3] * st.T[12 + cc];
+    Tn[12] = st.T[12]; Tn[13] = st.T[13]; Tn[14] = st.T[14]; Tn[15] = st.T[15];
+    for (int k = 0; k < 16; ++k) st.T[k] = Tn[k];
+    for (int k = 0; k < 12; ++k) st.U[k] = Um[k];
+    st.has_update = 1;
+    st.iters = round + 1;
+}
+
+// ----------------------------------------------------------------------------
+// workspace layout
+// ----------------------------------------------------------------------------
+struct Layout {
+    size_t off_state, off_pts, off_cov, off_corr, off_d2, off_m1, off_c1, off_m2, off_tgt4, off_meta,
+        off_partial, off_counter, off_worklist, off_wcount, off_ract, off_done, total;
+    int nt_pad, n_chunks, splits, chunks_per_split, red_blocks, q_tiles;
+};
+
+bool make_layout(const orpcd_gicp_params *p, Layout &L)
+{
+    if (!p || p->n_units <= 0 || p->n_src <= 0 || p->n_tgt <= 0 || p->n_src_sets <= 0 || p->n_tgt_sets <= 0 ||
+        p->max_iterations < 0 || !(p->max_correspondence_distance > 0) || p->n_units > 65535)
+        return false;
+    if ((long long)p->n_units * p->n_src > 0x7fffffffLL) return false;
+    L.nt_pad = (p->n_tgt + NN_CH - 1) / NN_CH * NN_CH;
+    L.n_chunks = L.nt_pad / NN_CH;
+    L.q_tiles = (p->n_src + NN_QPB - 1) / NN_QPB;
+    int s = p->target_splits;
+    if (s <= 0) {
+        // aim for >= ~16 blocks per SM in flight across the grid, keep >= 8 chunks per split
+        const long long blocks = (long long)p->n_units * L.q_tiles;
+        s = (int)((2368 + blocks - 1) / blocks);
+    }
+    const int s_max = L.n_chunks / 8 > 1 ? L.n_chunks / 8 : 1;
+    if (s > s_max) s = s_max;
+    if (s < 1) s = 1;
+    L.chunks_per_split = (L.n_chunks + s - 1) / s;
+    L.splits = (L.n_chunks + L.chunks_per_split - 1) / L.chunks_per_split;
+    L.red_blocks = (p->n_src + RED_THREADS - 1) / RED_THREADS;
+    const size_t U = p->n_units, ns = p->n_src;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += orpcd_align_up(bytes, 256); return r; };
+    L.off_state = take(U * sizeof(UnitState));
+    L.off_pts = take(U * ns * 3 * sizeof(double));
+    L.off_cov = take(U * ns * 6 * sizeof(double));
+    L.off_corr = take(U * ns * sizeof(int));
+    L.off_d2 = take(U * ns * sizeof(double));
+    L.off_m1 = take(U * L.splits * ns * sizeof(float));
+    L.off_c1 = take(U * L.splits * ns * sizeof(int));
+    L.off_m2 = take(U * L.splits * ns * sizeof(float));
+    L.off_tgt4 = take((size_t)p->n_tgt_sets * L.nt_pad * sizeof(float4));
+    L.off_meta = take((size_t)p->n_tgt_sets * sizeof(TgtMeta));
+    L.off_partial = take(U * L.red_blocks * RED_STRIDE * sizeof(double));
+    L.off_counter = take(U * sizeof(unsigned));
+    L.off_worklist = take(U * ns * sizeof(int));
+    L.off_wcount = take((size_t)(p->max_iterations + 2) * sizeof(int));
+    L.off_ract = take((size_t)(p->max_iterations + 2) * sizeof(int));
+    L.off_done = take(sizeof(int));
+    L.total = o;
+    return true;
+}
+
+void fill_ctx(const orpcd_gicp_params *p, const Layout &L, void *ws, Ctx &c)
+{
+    unsigned char *w = (unsigned char *)ws;
+    c.n_units = p->n_units; c.n_src = p->n_src; c.n_tgt = p->n_tgt;
+    c.nt_pad = L.nt_pad; c.n_chunks = L.n_chunks; c.splits = L.splits; c.chunks_per_split = L.chunks_per_split;
+    c.max_iter = p->max_iterations; c.red_blocks = L.red_blocks;
+    c.r2 = p->max_correspondence_distance * p->max_correspondence_distance;
+    c.rel_fit = p->relative_fitness; c.rel_rmse = p->relative_rmse;
+    c.state = (UnitState *)(w + L.off_state);
+    c.cur_pts = (double *)(w + L.off_pts);
+    c.cur_cov = (double *)(w + L.off_cov);
+    c.corr = (int *)(w + L.off_corr);
+    c.corr_d2 = (double *)(w + L.off_d2);
+    c.part_m1 = (float *)(w + L.off_m1);
+    c.part_c1 = (int *)(w + L.off_c1);
+    c.part_m2 = (float *)(w + L.off_m2);
+    c.tgt4 = (float4 *)(w + L.off_tgt4);
+    c.tgt_meta = (TgtMeta *)(w + L.off_meta);
+    c.red_partial = (double *)(w + L.off_partial);
+    c.red_counter = (unsigned *)(w + L.off_counter);
+    c.worklist = (int *)(w + L.off_worklist);
+    c.worklist_count = (int *)(w + L.off_wcount);
+    c.done_count = (int *)(w + L.off_done);
+    c.round_active = (int *)(w + L.off_ract);
+    c.ignore_done = 0;
+    c.tgt_pts = nullptr; c.tgt_cov = nullptr; c.out_T = nullptr; c.out_stats = nullptr; c.trace = nullptr;
+    c.out_status = nullptr;
+}
+
+}  // namespace
+
+ORPCD_API size_t orpcd_gicp_batch_workspace_bytes(const orpcd_gicp_params *p)
+{
+    Layout L;
+    if (!make_layout(p, L)) return 0;
+    return L.total;
+}
+
+ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_points,
+                               const double *d_src_cov6, const double *d_tgt_points,
+                               const double *d_tgt_cov6, const int *d_unit_src, const int *d_unit_tgt,
+                               void *d_workspace, size_t workspace_bytes, double *d_out_T,
+                               double *d_out_stats, int *d_out_status, double *d_trace, double *h_profile,
+                               orpcd_stream_t stream)
+{
+    Layout L;
+    if (!make_layout(p, L)) return ORPCD_ERR_INVALID;
+    if (!d_src_points || !d_src_cov6 || !d_tgt_points || !d_tgt_cov6 || !d_unit_src || !d_unit_tgt ||
+        !d_out_T || !d_out_stats || !d_out_status)
+        return ORPCD_ERR_INVALID;
+    if (!d_workspace || workspace_bytes < L.total || ((uintptr_t)d_workspace & 255)) return ORPCD_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    Ctx c;
+    fill_ctx(p, L, d_workspace, c);
+    c.tgt_pts = d_tgt_points; c.tgt_cov = d_tgt_cov6;
+    c.out_T = d_out_T; c.out_stats = d_out_stats; c.out_status = d_out_status; c.trace = d_trace;
+    int launches = 0;
+
+    {
+        const int gx = (int)((((size_t)p->n_src * 6) + 255) / 256);
+        dim3 grid(gx > 64 ? 64 : gx, p->n_units);
+        init_units_kernel<<<grid, 256, 0, st>>>(c, d_unit_src, d_unit_tgt, d_src_points, d_src_cov6);
+        ORPCD_CHECK_LAUNCH();
+        prep_targets_kernel<<<p->n_tgt_sets, 1024, 0, st>>>(c);
+        ORPCD_CHECK_LAUNCH();
+        launches += 2;
+    }
+    const dim3 g_sweep(L.q_tiles, L.splits, p->n_units);
+    const dim3 g_res((p->n_src + 127) / 128, p->n_units);
+    const dim3 g_red(L.red_blocks, p->n_units);
+    const int fix_blocks = 148 * 4;
+    // profiling mode: CUDA events around every sweep launch on the caller's stream
+    const bool prof = p->profile != 0 && h_profile != nullptr;
+    const int n_rounds_max = p->max_iterations + 1;
+    cudaEvent_t *ev = nullptr;
+    if (prof) {
+        ev = (cudaEvent_t *)malloc(sizeof(cudaEvent_t) * 2 * n_rounds_max);
+        if (!ev) return ORPCD_ERR_INVALID;
+        for (int k = 0; k < 2 * n_rounds_max; ++k)
+            if (cudaEventCreate(&ev[k]) != cudaSuccess) return ORPCD_ERR_CUDA;
+    }
+    int rounds = 0;
+    for (int round = 0; round <= p->max_iterations; ++round) {
+        if (prof) cudaEventRecord(ev[2 * round], st);
+        nn_sweep_kernel<<<g_sweep, NN_THREADS, 0, st>>>(c);
+        if (prof) cudaEventRecord(ev[2 * round + 1], st);
+        nn_resolve_kernel<<<g_res, 128, 0, st>>>(c, round);
+        nn_fix_kernel<<<fix_blocks, 128, 0, st>>>(c, round);
+        reduce_kernel<<<g_red, RED_THREADS, 0, st>>>(c, round);
+        ORPCD_CHECK_LAUNCH();
+        launches += 4;
+        rounds = round + 1;
+        if (p->poll_interval > 0 && round < p->max_iterations && (round + 1) % p->poll_interval == 0) {
+            int done = 0;
+            if (cudaMemcpyAsync(&done, c.done_count, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                return ORPCD_ERR_CUDA;
+            if (cudaStreamSynchronize(st) != cudaSuccess) return ORPCD_ERR_CUDA;
+            if (done >= p->n_units) break;
+        }
+    }
+    if (h_profile) {
+        for (int k = 0; k < 8; ++k) h_profile[k] = 0.0;
+        h_profile[0] = (double)launches;
+        h_profile[3] = (double)rounds;
+        h_profile[5] = (double)L.splits;
+    }
+    if (prof) {
+        if (cudaStreamSynchronize(st) != cudaSuccess) return ORPCD_ERR_CUDA;
+        double sweep_ms = 0.0;
+        for (int r = 0; r < rounds; ++r) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[2 * r], ev[2 * r + 1]);
+            sweep_ms += ms;
+        }
+        for (int k = 0; k < 2 * n_rounds_max; ++k) cudaEventDestroy(ev[k]);
+        free(ev);
+        int *h = (int *)malloc(sizeof(int) * 2 * (p->max_iterations + 2));
+        if (!h) return ORPCD_ERR_INVALID;
+        cudaMemcpy(h, c.round_active, sizeof(int) * (p->max_iterations + 2), cudaMemcpyDeviceToHost);
+        cudaMemcpy(h + p->max_iterations + 2, c.worklist_count, sizeof(int) * (p->max_iterations + 2),
+                   cudaMemcpyDeviceToHost);
+        double unit_rounds = 0.0, fixed = 0.0;
+        int sweep_launches = 0;
+        for (int r = 0; r < rounds; ++r) {
+            unit_rounds += h[r];
+            fixed += h[p->max_iterations + 2 + r];
+            if (h[r] > 0) ++sweep_launches;
+        }
+        free(h);
+        h_profile[1] = sweep_ms;                                        // total time inside nn_sweep_kernel
+        h_profile[2] = unit_rounds * (double)p->n_src * (double)p->n_tgt;  // (query, target) pairs swept
+        h_profile[4] = fixed;                                           // queries sent to the exact work list
+        h_profile[6] = (double)sweep_launches;                          // sweep launches that had work
+        h_profile[7] = unit_rounds;
+    }
+    return ORPCD_OK;
+}
+
+ORPCD_API int orpcd_gicp_sweep_only(const orpcd_gicp_params *p, void *d_workspace, size_t workspace_bytes,
+                                    orpcd_stream_t stream)
+{
+    Layout L;
+    if (!make_layout(p, L)) return ORPCD_ERR_INVALID;
+    if (!d_workspace || workspace_bytes < L.total || ((uintptr_t)d_workspace & 255)) return ORPCD_ERR_WORKSPACE;
+    Ctx c;
+    fill_ctx(p, L, d_workspace, c);
+    c.ignore_done = 1;
+    const dim3 g_sweep(L.q_tiles, L.splits, p->n_units);
+    nn_sweep_kernel<<<g_sweep, NN_THREADS, 0, (cudaStream_t)stream>>>(c);
+    ORPCD_CHECK_LAUNCH();
+    return ORPCD_OK;
+}

@@ -1,0 +1,104 @@
+"""Generalized-ICP inner block on the B200
+(reference: Optimizer/generalizedICP.py:15-89, which wraps Open3D's
+registration_generalized_icp; algorithm SURVEY.md A.3-A.6)."""
+from typing import NamedTuple, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .. import _lib, ops
+from ..utils.constants import (
+    GICP_COVARIANCE_KNN,
+    GICP_EPSILON,
+    ICP_RELATIVE_FITNESS,
+    ICP_RELATIVE_RMSE,
+    MAX_ITERATIONS,
+    MAXIMUM_CORRESPONDENCE_DISTANCE,
+)
+from ..utils.logger_factory import LoggerFactory
+from .iOptimizer import IOptimizer
+
+_ZERO_LOSS_MSG = (
+    "Optimization failed with loss = 0. Parameters are not well set. "
+    "Probably due to maximum_correspondence_distance set too low."
+)
+
+
+class BatchResult(NamedTuple):
+    transforms: np.ndarray   # (U,4,4) rotation block transposed (row-vector convention), as optimize()
+    rmse: np.ndarray         # (U,)
+    fitness: np.ndarray      # (U,)
+    iterations: np.ndarray   # (U,) int
+    status: np.ndarray       # (U,) 0 ok, 1 = inlier_rmse == 0 (optimize() would raise ValueError)
+    profile: list
+
+
+class GeneralizedICP(IOptimizer):
+    def __init__(
+        self,
+        max_correspondence_distance: float = MAXIMUM_CORRESPONDENCE_DISTANCE,
+        max_iterations: int = MAX_ITERATIONS,
+    ):
+        self._LOG = LoggerFactory.get_logger(log_name=self.__class__.__name__, log_on_file=False)
+        if max_correspondence_distance <= 0:
+            self._LOG.warning(
+                f"max correspondence distance cannot be 0 or less. Provided: {max_correspondence_distance}")
+            max_correspondence_distance = MAXIMUM_CORRESPONDENCE_DISTANCE
+        if max_iterations <= 0:
+            self._LOG.warning(f"max iterations cannot be 0 or less. Provided: {max_iterations}")
+            max_iterations = MAX_ITERATIONS
+        self._max_correspondence_distance = max_correspondence_distance
+        self._max_iterations = max_iterations
+        self._ws = None
+        self.profile = False          # set True to collect sweep timings in BatchResult.profile
+        self.last_profile = None
+
+    # ------------------------------------------------------------------ reference API
+    def optimize(self, source: np.ndarray, target: np.ndarray, **kwargs) -> Tuple[np.ndarray, float]:
+        res = self.optimize_batch(np.asarray(source)[None], np.asarray(target)[None], [0], [0], poll_interval=8)
+        if res.status[0] != 0:
+            self._LOG.error(_ZERO_LOSS_MSG)
+            raise ValueError(_ZERO_LOSS_MSG)
+        return res.transforms[0], float(res.rmse[0])
+
+    # ------------------------------------------------------------------ batched API
+    def optimize_batch(self, sources, targets, unit_src: Sequence[int], unit_tgt: Sequence[int],
+                       poll_interval: int = 0) -> BatchResult:
+        """Run ``len(unit_src)`` independent registrations concurrently.
+
+        sources: (S,Ns,3) host float64 array (or CUDA tensor), the initial source clouds;
+        targets: (C,Nt,3); unit u registers sources[unit_src[u]] onto targets[unit_tgt[u]].
+        Nothing raises for a unit whose final inlier RMSE is 0; it is flagged in ``status``."""
+        t = _lib.torch()
+        d_src = sources if hasattr(sources, "is_cuda") else _lib.to_device(np.asarray(sources))
+        d_tgt = targets if hasattr(targets, "is_cuda") else _lib.to_device(np.asarray(targets))
+        us = t.as_tensor(np.asarray(unit_src, dtype=np.int32)).to("cuda")
+        ut = t.as_tensor(np.asarray(unit_tgt, dtype=np.int32)).to("cuda")
+        d_res = self.optimize_batch_device(d_src, d_tgt, us, ut, poll_interval=poll_interval)
+        T = d_res.T.cpu().numpy()
+        stats = d_res.stats.cpu().numpy()
+        status = d_res.status.cpu().numpy()
+        T[:, :3, :3] = np.transpose(T[:, :3, :3], (0, 2, 1)).copy()   # generalizedICP.py:72-74
+        self.last_profile = d_res.profile
+        return BatchResult(T, stats[:, 1].copy(), stats[:, 0].copy(), stats[:, 2].astype(np.int64), status,
+                           d_res.profile)
+
+    def optimize_batch_device(self, d_src, d_tgt, unit_src, unit_tgt, poll_interval: int = 0, want_trace=False,
+                              src_cov=None, tgt_cov=None):
+        """Device-resident variant: CUDA tensors in, ``ops.GicpBatchResult`` (CUDA tensors) out."""
+        if src_cov is None:
+            src_cov = ops.normals_cov(d_src, knn=GICP_COVARIANCE_KNN, gicp_eps=GICP_EPSILON)["gicp_cov"]
+        if tgt_cov is None:
+            tgt_cov = ops.normals_cov(d_tgt, knn=GICP_COVARIANCE_KNN, gicp_eps=GICP_EPSILON)["gicp_cov"]
+        res = ops.gicp_batch(d_src, src_cov, d_tgt, tgt_cov, unit_src, unit_tgt,
+                             max_correspondence_distance=self._max_correspondence_distance,
+                             max_iterations=self._max_iterations, relative_fitness=ICP_RELATIVE_FITNESS,
+                             relative_rmse=ICP_RELATIVE_RMSE, poll_interval=poll_interval, profile=self.profile,
+                             want_trace=want_trace, ws=self._ws)
+        self._ws = res.workspace
+        return res
+
+    def __repr__(self):
+        return f"""{self.__class__.__name__}
+            (max_correspondence_distance={self._max_correspondence_distance},
+            max_iterations={self._max_iterations})
+        """

@@ -1,0 +1,123 @@
+"""ctypes binding of ``csrc/liborpcd_b200.so`` (C ABI declared in ``include/orpcd_b200.h``).
+
+There is NO CPU fallback: if the CUDA library is missing or no CUDA device is
+present, the B200 blocks raise.  PyTorch is used only to own device memory and
+streams; every kernel on the registration path is in the shared library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "liborpcd_b200.so")
+
+ORPCD_OK = 0
+MAX_KNN = 64
+
+_lib = None
+
+
+class GicpParams(C.Structure):
+    """Mirror of ``orpcd_gicp_params`` (include/orpcd_b200.h)."""
+
+    _fields_ = [
+        ("n_units", C.c_int),
+        ("n_src", C.c_int),
+        ("n_tgt", C.c_int),
+        ("n_src_sets", C.c_int),
+        ("n_tgt_sets", C.c_int),
+        ("max_iterations", C.c_int),
+        ("target_splits", C.c_int),
+        ("poll_interval", C.c_int),
+        ("profile", C.c_int),
+        ("max_correspondence_distance", C.c_double),
+        ("relative_fitness", C.c_double),
+        ("relative_rmse", C.c_double),
+    ]
+
+
+class OrpcdError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library once; fail loudly when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OrpcdError(
+            f"{LIB_PATH} is missing: build it with `make -C multi-scale-pointcloud-registration_b200/csrc` "
+            "(or __graft_entry__.build()).  There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, ip, dp, sz, ll = C.c_void_p, C.c_int, C.c_double, C.c_size_t, C.c_longlong
+    L.orpcd_version.restype = ip
+    L.orpcd_compiled_arch.restype = ip
+    L.orpcd_error_string.restype = C.c_char_p
+    L.orpcd_error_string.argtypes = [ip]
+    L.orpcd_knn_exact.restype = ip
+    L.orpcd_knn_exact.argtypes = [vp, ip, ll, vp, ip, ll, ip, ip, vp, vp, vp]
+    L.orpcd_sor_workspace_bytes.restype = sz
+    L.orpcd_sor_workspace_bytes.argtypes = [ip, ip]
+    L.orpcd_sor_mask.restype = ip
+    L.orpcd_sor_mask.argtypes = [vp, ip, ip, dp, vp, sz, vp, vp, vp, vp]
+    L.orpcd_normals_workspace_bytes.restype = sz
+    L.orpcd_normals_workspace_bytes.argtypes = [ip, ip, ip]
+    L.orpcd_normals_cov.restype = ip
+    L.orpcd_normals_cov.argtypes = [vp, ip, ll, ip, ip, dp, dp, vp, sz, vp, vp, vp, vp, vp]
+    L.orpcd_apply_scale_batch.restype = ip
+    L.orpcd_apply_scale_batch.argtypes = [vp, ip, vp, ip, vp, vp]
+    L.orpcd_gicp_batch_workspace_bytes.restype = sz
+    L.orpcd_gicp_batch_workspace_bytes.argtypes = [C.POINTER(GicpParams)]
+    L.orpcd_gicp_batch.restype = ip
+    L.orpcd_gicp_batch.argtypes = [C.POINTER(GicpParams), vp, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp,
+                                   C.POINTER(C.c_double), vp]
+    L.orpcd_gicp_sweep_only.restype = ip
+    L.orpcd_gicp_sweep_only.argtypes = [C.POINTER(GicpParams), vp, sz, vp]
+    L.orpcd_ffma_burn.restype = ip
+    L.orpcd_ffma_burn.argtypes = [ip, ip, vp, vp]
+    L.orpcd_ffma2_burn.restype = ip
+    L.orpcd_ffma2_burn.argtypes = [ip, ip, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != ORPCD_OK:
+        raise OrpcdError(f"{what} failed: {lib().orpcd_error_string(rc).decode()} ({rc})")
+
+
+_torch = None
+
+
+def torch():
+    """Import torch lazily and insist on a CUDA device (no CPU path exists)."""
+    global _torch
+    if _torch is None:
+        import torch as _t
+
+        if not _t.cuda.is_available():
+            raise OrpcdError("or_pcd_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+        _torch = _t
+    return _torch
+
+
+def stream_ptr() -> int:
+    return int(torch().cuda.current_stream().cuda_stream)
+
+
+def to_device(a: np.ndarray, dtype=np.float64):
+    """Host ndarray -> contiguous CUDA tensor (H2D copy on the current stream)."""
+    t = torch()
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return t.from_numpy(a).to("cuda", non_blocking=False)
+
+
+def workspace(nbytes: int):
+    t = torch()
+    return t.empty(max(int(nbytes), 256), dtype=t.uint8, device="cuda")

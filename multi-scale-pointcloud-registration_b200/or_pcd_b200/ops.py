@@ -1,0 +1,151 @@
+"""Thin tensor-level wrappers over the C ABI (include/orpcd_b200.h).
+
+Inputs/outputs are CUDA ``torch`` tensors (memory ownership and streams only);
+all arithmetic happens in ``csrc/liborpcd_b200.so``.  ``launch_counter`` tallies
+the kernels this process has launched through the library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+from . import _lib
+from ._lib import GicpParams, check
+
+launch_counter = {"kernels": 0}
+
+
+def _t():
+    return _lib.torch()
+
+
+def _f64(x):
+    t = _t()
+    assert x.is_cuda and x.dtype == t.float64 and x.is_contiguous(), "expected contiguous CUDA float64 tensor"
+    return x
+
+
+def knn_exact(points, queries, k: int):
+    """Exact kNN, (idx int32 [B,M,k], d2 float64 [B,M,k]); points [B,N,3] or [N,3]."""
+    t = _t()
+    squeeze = points.dim() == 2
+    if squeeze:
+        points, queries = points[None], queries[None]
+    points, queries = _f64(points), _f64(queries)
+    B, N, _ = points.shape
+    M = queries.shape[1]
+    idx = t.empty((B, M, k), dtype=t.int32, device="cuda")
+    d2 = t.empty((B, M, k), dtype=t.float64, device="cuda")
+    check(_lib.lib().orpcd_knn_exact(points.data_ptr(), N, N * 3, queries.data_ptr(), M, M * 3, B, k,
+                                     idx.data_ptr(), d2.data_ptr(), _lib.stream_ptr()), "orpcd_knn_exact")
+    launch_counter["kernels"] += 1
+    return (idx[0], d2[0]) if squeeze else (idx, d2)
+
+
+def sor_mask(points, nb_neighbors: int, std_ratio: float):
+    """(mask uint8 [N], avg float64 [N], stats float64 [4])."""
+    t = _t()
+    points = _f64(points)
+    N = points.shape[0]
+    L = _lib.lib()
+    ws = _lib.workspace(L.orpcd_sor_workspace_bytes(N, nb_neighbors))
+    mask = t.empty(N, dtype=t.uint8, device="cuda")
+    avg = t.empty(N, dtype=t.float64, device="cuda")
+    stats = t.zeros(4, dtype=t.float64, device="cuda")
+    check(L.orpcd_sor_mask(points.data_ptr(), N, nb_neighbors, float(std_ratio), ws.data_ptr(), ws.numel(),
+                           mask.data_ptr(), avg.data_ptr(), stats.data_ptr(), _lib.stream_ptr()), "orpcd_sor_mask")
+    launch_counter["kernels"] += 4
+    return mask, avg, stats
+
+
+def normals_cov(points, knn: int = 20, radius: float = 0.0, gicp_eps: float = 1e-3, want_normals=False,
+                want_cov=False, want_gicp_cov=True, want_nn=False) -> Dict[str, object]:
+    """Normals / covariances / GICP covariances for clouds [B,N,3] (or [N,3])."""
+    t = _t()
+    squeeze = points.dim() == 2
+    if squeeze:
+        points = points[None]
+    points = _f64(points)
+    B, N, _ = points.shape
+    L = _lib.lib()
+    ws = _lib.workspace(L.orpcd_normals_workspace_bytes(N, B, knn))
+    out = {}
+    nrm = t.empty((B, N, 3), dtype=t.float64, device="cuda") if want_normals else None
+    cov = t.empty((B, N, 6), dtype=t.float64, device="cuda") if want_cov else None
+    gc = t.empty((B, N, 6), dtype=t.float64, device="cuda") if want_gicp_cov else None
+    nn = t.empty((B, N, knn), dtype=t.int32, device="cuda") if want_nn else None
+    p = lambda x: x.data_ptr() if x is not None else None
+    check(L.orpcd_normals_cov(points.data_ptr(), N, N * 3, B, knn, float(radius), float(gicp_eps), ws.data_ptr(),
+                              ws.numel(), p(nrm), p(cov), p(gc), p(nn), _lib.stream_ptr()), "orpcd_normals_cov")
+    launch_counter["kernels"] += 2
+    for k, v in (("normal", nrm), ("cov", cov), ("gicp_cov", gc), ("nn_idx", nn)):
+        if v is not None:
+            out[k] = v[0] if squeeze else v
+    return out
+
+
+def apply_scale_batch(points, scales):
+    """points [N,3] * scales [S,3] -> [S,N,3]."""
+    t = _t()
+    points, scales = _f64(points), _f64(scales)
+    N, S = points.shape[0], scales.shape[0]
+    out = t.empty((S, N, 3), dtype=t.float64, device="cuda")
+    check(_lib.lib().orpcd_apply_scale_batch(points.data_ptr(), N, scales.data_ptr(), S, out.data_ptr(),
+                                             _lib.stream_ptr()), "orpcd_apply_scale_batch")
+    launch_counter["kernels"] += 1
+    return out
+
+
+class GicpBatchResult:
+    __slots__ = ("T", "stats", "status", "trace", "profile", "workspace", "params")
+
+
+def gicp_batch(src_points, src_cov6, tgt_points, tgt_cov6, unit_src, unit_tgt, max_correspondence_distance=0.5,
+               max_iterations=100, relative_fitness=1e-6, relative_rmse=1e-6, target_splits=0, poll_interval=0,
+               profile=False, want_trace=False, ws=None) -> GicpBatchResult:
+    """Batched GICP.  src_* [S,Ns,3]/[S,Ns,6], tgt_* [C,Nt,3]/[C,Nt,6], unit_* int32 [U]."""
+    t = _t()
+    src_points, src_cov6, tgt_points, tgt_cov6 = _f64(src_points), _f64(src_cov6), _f64(tgt_points), _f64(tgt_cov6)
+    S, Ns, _ = src_points.shape
+    Cn, Nt, _ = tgt_points.shape
+    U = unit_src.shape[0]
+    assert unit_src.dtype == t.int32 and unit_tgt.dtype == t.int32 and unit_src.is_cuda and unit_tgt.is_cuda
+    prm = GicpParams(U, Ns, Nt, S, Cn, int(max_iterations), int(target_splits), int(poll_interval), int(bool(profile)),
+                     float(max_correspondence_distance), float(relative_fitness), float(relative_rmse))
+    L = _lib.lib()
+    need = L.orpcd_gicp_batch_workspace_bytes(C.byref(prm))
+    if need == 0:
+        raise _lib.OrpcdError("orpcd_gicp_batch: invalid parameters")
+    if ws is None or ws.numel() < need:
+        ws = _lib.workspace(need)
+    res = GicpBatchResult()
+    res.T = t.empty((U, 4, 4), dtype=t.float64, device="cuda")
+    res.stats = t.empty((U, 4), dtype=t.float64, device="cuda")
+    res.status = t.empty(U, dtype=t.int32, device="cuda")
+    res.trace = t.full((U, max_iterations + 1, 2), float("nan"), dtype=t.float64, device="cuda") if want_trace else None
+    prof = (C.c_double * 8)()
+    check(L.orpcd_gicp_batch(C.byref(prm), src_points.data_ptr(), src_cov6.data_ptr(), tgt_points.data_ptr(),
+                             tgt_cov6.data_ptr(), unit_src.data_ptr(), unit_tgt.data_ptr(), ws.data_ptr(), ws.numel(),
+                             res.T.data_ptr(), res.stats.data_ptr(), res.status.data_ptr(),
+                             res.trace.data_ptr() if want_trace else None, prof, _lib.stream_ptr()),
+          "orpcd_gicp_batch")
+    res.profile = list(prof)
+    res.workspace = ws
+    res.params = prm
+    launch_counter["kernels"] += int(prof[0])
+    return res
+
+
+def gicp_sweep_only(params: GicpParams, ws) -> None:
+    check(_lib.lib().orpcd_gicp_sweep_only(C.byref(params), ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
+          "orpcd_gicp_sweep_only")
+    launch_counter["kernels"] += 1
+
+
+def ffma_burn(blocks: int, iters: int, packed: bool = False):
+    t = _t()
+    sink = t.empty(blocks * 256, dtype=t.float32, device="cuda")
+    fn = _lib.lib().orpcd_ffma2_burn if packed else _lib.lib().orpcd_ffma_burn
+    check(fn(blocks, iters, sink.data_ptr(), _lib.stream_ptr()), "orpcd_ffma_burn")
+    launch_counter["kernels"] += 1
+    return sink

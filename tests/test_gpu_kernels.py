@@ -1,0 +1,178 @@
+"""Parity of the CUDA kernels (through the C ABI) against the CPU oracle on the
+same seeded inputs.  Index / mask work: bit-exact.  Floating point: tolerances
+from BASELINE.json north_star, written beside each assert."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    from or_pcd_b200 import _lib
+
+    return _lib.to_device(a)
+
+
+@pytest.mark.parametrize("k", [1, 20, 64])
+def test_knn_bit_exact_armadillo(oracle, armadillo_pair, k):
+    from or_pcd_b200 import ops
+
+    s, t, _ = armadillo_pair
+    idx, d2 = ops.knn_exact(_dev(t), _dev(s), k)
+    oi, od = oracle.knn(t, s, k)
+    assert np.array_equal(idx.cpu().numpy(), oi)
+    assert np.array_equal(d2.cpu().numpy(), od)          # float64 distances bit-identical
+
+
+def test_knn_ties_duplicates_and_small_clouds(oracle):
+    from or_pcd_b200 import ops
+
+    rng = np.random.default_rng(3)
+    lattice = np.stack(np.meshgrid(np.arange(7.0), np.arange(6.0), np.arange(5.0), indexing="ij"), -1).reshape(-1, 3)
+    dup = np.concatenate([lattice[:50], lattice[:50], rng.standard_normal((13, 3))])
+    for pts in (lattice, dup, rng.standard_normal((5, 3))):
+        for k in (1, 8, 20):
+            idx, d2 = ops.knn_exact(_dev(pts), _dev(pts), k)
+            oi, od = oracle.knn(pts, pts, k, method="brute")
+            assert np.array_equal(idx.cpu().numpy(), oi), (len(pts), k)
+            assert np.array_equal(d2.cpu().numpy(), od)
+
+
+def test_knn_batched(oracle):
+    from or_pcd_b200 import ops
+
+    rng = np.random.default_rng(5)
+    pts = rng.standard_normal((3, 700, 3))
+    qs = rng.standard_normal((3, 333, 3))
+    idx, d2 = ops.knn_exact(_dev(pts), _dev(qs), 7)
+    for b in range(3):
+        oi, od = oracle.knn(pts[b], qs[b], 7)
+        assert np.array_equal(idx[b].cpu().numpy(), oi)
+        assert np.array_equal(d2[b].cpu().numpy(), od)
+
+
+@pytest.mark.parametrize("scan", ["ArmadilloBack_330", "ArmadilloBack_0", "ArmadilloOnHeadMultiple_150"])
+def test_sor_mask_bit_exact(oracle, scan):
+    from or_pcd_b200 import ops
+
+    np.random.seed(1)
+    cloud = oracle.RadiusScaler().process(oracle.load_scan(scan))
+    cloud = cloud[np.random.choice(cloud.shape[0], 5000, replace=False)]
+    mask, avg, stats = ops.sor_mask(_dev(cloud), 64, 2.0)
+    om, oavg, ostats = oracle.sor(cloud, 64, 2.0)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), om)
+    assert np.array_equal(avg.cpu().numpy(), oavg)        # sequential float64 sums: bit-identical
+    st = stats.cpu().numpy()
+    assert st[0] == ostats[0] and st[1] == ostats[1] and st[2] == ostats[2]
+    assert int(st[3]) == int(om.sum())
+
+
+def test_normals_and_gicp_covariances(oracle, armadillo_pair):
+    from or_pcd_b200 import ops
+
+    s, t, _ = armadillo_pair
+    for cloud, radius in ((s, 0.0), (t, 0.0), (s, 0.1)):
+        out = ops.normals_cov(_dev(cloud), knn=20, radius=radius, gicp_eps=1e-3, want_normals=True, want_cov=True,
+                              want_gicp_cov=True, want_nn=True)
+        ref = oracle.normals(cloud, 20, radius, 1e-3)
+        assert np.array_equal(out["nn_idx"].cpu().numpy(), ref["nn_idx"])       # neighbour lists bit-exact
+        cov = out["cov"].cpu().numpy()
+        rc = ref["cov"]
+        ref6 = np.stack([rc[:, 0, 0], rc[:, 0, 1], rc[:, 0, 2], rc[:, 1, 1], rc[:, 1, 2], rc[:, 2, 2]], 1)
+        assert np.array_equal(cov, ref6)                                        # no-FMA float64: bit-exact
+        # normals go through acos/cos (device libm vs glibc): 1e-12 absolute
+        assert np.abs(out["normal"].cpu().numpy() - ref["normal"]).max() < 1e-12
+        g = ref["gicp_cov"]
+        g6 = np.stack([g[:, 0, 0], g[:, 0, 1], g[:, 0, 2], g[:, 1, 1], g[:, 1, 2], g[:, 2, 2]], 1)
+        assert np.abs(out["gicp_cov"].cpu().numpy() - g6).max() < 1e-12
+
+
+def test_apply_scale_batch_bit_exact():
+    from or_pcd_b200 import ops
+
+    rng = np.random.default_rng(0)
+    pts = rng.standard_normal((1000, 3))
+    scales = np.array([[1.0, 1.2, 1.0], [0.8, 1.0, 1.05], [1.0, 1.0, 1.0]])
+    out = ops.apply_scale_batch(_dev(pts), _dev(scales)).cpu().numpy()
+    for i, s in enumerate(scales):
+        assert np.array_equal(out[i], pts * s[None, :])
+
+
+def _rot(a, b, g):
+    rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    rz = np.array([[np.cos(g), -np.sin(g), 0], [np.sin(g), np.cos(g), 0], [0, 0, 1]])
+    return rx @ ry @ rz
+
+
+def _rot_angle(Ra, Rb):
+    c = (np.trace(Ra.T @ Rb) - 1) / 2
+    return np.arccos(np.clip(c, -1, 1))
+
+
+def test_gicp_batch_matches_oracle_traces(oracle, armadillo_pair):
+    """Several starts x two scale candidates in one batch vs the oracle one by one.
+    Tolerances (north_star): rotation 1e-4 rad, translation 1e-5 x bbox diagonal,
+    fitness/rmse 1e-5 relative; iteration counts must agree."""
+    from or_pcd_b200 import _lib, ops
+    from or_pcd_b200.Optimizer import GeneralizedICP
+
+    s, t, _ = armadillo_pair
+    rng = np.random.default_rng(11)
+    starts = []
+    for _ in range(5):
+        a, b, g = rng.uniform(-np.pi / 2, np.pi / 2, 3)
+        starts.append(s @ _rot(a, b, g) + rng.standard_normal(3) * 0.1)
+    starts.append(s.copy())
+    sources = np.stack(starts)
+    targets = np.stack([t, t * np.array([[1.0, 1.2, 1.0]])])
+    unit_src = np.array([0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5], dtype=np.int32)
+    unit_tgt = np.array([0] * 6 + [1] * 6, dtype=np.int32)
+    opt = GeneralizedICP()
+    t_ = _lib.torch()
+    res = opt.optimize_batch_device(_lib.to_device(sources), _lib.to_device(targets),
+                                    t_.as_tensor(unit_src).cuda(), t_.as_tensor(unit_tgt).cuda(), want_trace=True)
+    T = res.T.cpu().numpy()
+    stats = res.stats.cpu().numpy()
+    trace = res.trace.cpu().numpy()
+    diag = np.linalg.norm(t.max(0) - t.min(0))
+    for u in range(len(unit_src)):
+        ref = oracle.gicp(sources[unit_src[u]], targets[unit_tgt[u]], 0.5, 100, want_trace=True)
+        assert int(stats[u, 2]) == ref["iters"], (u, stats[u], ref["iters"])
+        assert int(stats[u, 3]) == ref["n_corr"]
+        assert abs(stats[u, 0] - ref["fitness"]) <= 1e-5 * ref["fitness"]
+        assert abs(stats[u, 1] - ref["rmse"]) <= 1e-5 * ref["rmse"]
+        assert _rot_angle(T[u, :3, :3], ref["T"][:3, :3]) < 1e-4
+        assert np.linalg.norm(T[u, :3, 3] - ref["T"][:3, 3]) < 1e-5 * diag
+        n = ref["iters"] + 1
+        assert np.allclose(trace[u, :n], ref["trace"], rtol=1e-7, atol=1e-12), u
+        assert np.isnan(trace[u, n:]).all()
+
+
+def test_gicp_optimize_plugin_and_error(oracle, armadillo_pair):
+    from or_pcd_b200.Optimizer import GeneralizedICP
+
+    s, t, _ = armadillo_pair
+    T, rmse = GeneralizedICP().optimize(s, t)
+    ref = oracle.GeneralizedICP().optimize(s, t)
+    assert abs(rmse - ref[1]) <= 1e-5 * ref[1]
+    assert _rot_angle(T[:3, :3], ref[0][:3, :3]) < 1e-4
+    # no correspondence within the distance threshold -> inlier_rmse == 0 -> ValueError (generalizedICP.py:77-81)
+    with pytest.raises(ValueError):
+        GeneralizedICP(max_correspondence_distance=1e-3).optimize(s[:200] + 50.0, t[:300])
+    with pytest.raises(ValueError):
+        oracle.GeneralizedICP(max_correspondence_distance=1e-3).optimize(s[:200] + 50.0, t[:300])
+
+
+def test_gicp_small_and_ragged_sizes(oracle):
+    """Sizes that are not multiples of any tile (n_tgt < one chunk, n_src < one block)."""
+    from or_pcd_b200.Optimizer import GeneralizedICP
+
+    rng = np.random.default_rng(2)
+    for ns, nt in ((37, 29), (130, 1025), (513, 64)):
+        tgt = oracle.synthetic_cloud(nt, rng)
+        src = oracle.synthetic_cloud(ns, rng) @ _rot(0.1, -0.05, 0.08) + 0.02
+        T, rmse = GeneralizedICP().optimize(src, tgt)
+        ref_T, ref_rmse = oracle.GeneralizedICP().optimize(src, tgt)
+        assert abs(rmse - ref_rmse) <= 1e-5 * ref_rmse, (ns, nt)
+        assert _rot_angle(T[:3, :3], ref_T[:3, :3]) < 1e-4
