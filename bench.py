@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- GICP candidate evals/s on synthetic 5k-point clouds (BASELINE.json metric).
+
+One STEP = one compass poll round of the Aligner's pattern search recast as a batch:
+6 scale candidates x 30 random starts = 180 independent inner registrations
+(Generalized-ICP to Open3D's stopping rule, max 100 iterations) of a 5000-point source
+onto 5000-point targets, all advanced concurrently on one GPU.  With N GPUs every rank
+runs its own 180 units (30 different starts per candidate: more GPUs = more multi-starts,
+SURVEY.md 8(e)) and a tiny all-gather collects the (rmse, transform) records.
+
+  value  : inner registrations per second, inputs resident in HBM, CUDA-event timed.
+  e2e    : same through the plugin API (GeneralizedICP.optimize_batch) with HOST buffers:
+           H2D of the step's clouds and D2H of its results inside the timed region.
+  roofline: the dominant kernel (nn_sweep_kernel, FP32 FMA pipe bound) -- algorithmic
+           8 FLOP per (query,target) pair over the CUDA-event time spent in that kernel
+           during the timed steps, against the FFMA peak measured in this same run.
+  cpu_baseline: the restated CPU path (oracle/, C + OpenMP, KD-tree) on the host cores.
+
+`--impl reference` times that CPU path alone (Open3D, the reference's arithmetic, is an
+un-vendored dependency that cannot be installed offline).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "multi-scale-pointcloud-registration_b200"))
+
+N_POINTS = 5000
+ATTEMPTS = 30
+SCALES = np.array([[1.2, 1, 1], [0.8, 1, 1], [1, 1.2, 1], [1, 0.8, 1], [1, 1, 1.2], [1, 1, 0.8]], dtype=np.float64)
+WORKLOAD = "synthetic 5k-pt pair, GICP, one compass poll round = 6 scale candidates x 30 starts = 180 inner registrations/step/GPU"
+
+
+# ----------------------------------------------------------------------------- synthetic workload
+def synthetic_cloud(n, rng):
+    """SURVEY.md 8(d) surface sampler."""
+    u = rng.standard_normal((n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    r = 1 + 0.3 * np.sin(3 * u[:, 0]) * np.cos(2 * u[:, 1]) + 0.2 * u[:, 2] ** 3
+    return r[:, None] * u + rng.normal(0, 0.002, (n, 3))
+
+
+def radius_scale(c):
+    c = c - c.mean(0, keepdims=True)
+    return c / np.sqrt((c * c).sum(1)).max()
+
+
+def start_pose(rs, deg=np.pi / 2, std=0.1):
+    a, b, g = rs.uniform(-deg, deg), rs.uniform(-deg, deg), rs.uniform(-deg, deg)
+    rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    rz = np.array([[np.cos(g), -np.sin(g), 0], [np.sin(g), np.cos(g), 0], [0, 0, 1]])
+    return rx @ ry @ rz, rs.standard_normal(3) * std
+
+
+def make_workload(rank, pinned=None):
+    """Same clouds on every rank (seed 1234); the random starts differ per rank."""
+    rng = np.random.default_rng(1234)
+    src = radius_scale(synthetic_cloud(N_POINTS, rng))
+    tgt = radius_scale(synthetic_cloud(N_POINTS, rng) @ start_pose(np.random.RandomState(7), 0.3, 0.05)[0])
+    rs = np.random.RandomState(1000 + rank)
+    n_units = len(SCALES) * ATTEMPTS
+    sources = pinned((n_units, N_POINTS, 3)) if pinned else np.empty((n_units, N_POINTS, 3))
+    for u in range(n_units):
+        r, t = start_pose(rs)
+        sources[u] = src @ r + t
+    targets = pinned((len(SCALES), N_POINTS, 3)) if pinned else np.empty((len(SCALES), N_POINTS, 3))
+    for i, s in enumerate(SCALES):
+        targets[i] = tgt * s[None, :]
+    unit_src = np.arange(n_units, dtype=np.int32)
+    unit_tgt = np.repeat(np.arange(len(SCALES), dtype=np.int32), ATTEMPTS)
+    return src, sources, targets, unit_src, unit_tgt
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """`nvidia-smi -lms 100` streamed for the duration of the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.samples = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is None:
+            return
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 6:
+                self.samples.append(f)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        mhz = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(mhz)}
+
+
+# ----------------------------------------------------------------------------- CPU path
+def cpu_registrations(src_clouds, tgt_clouds, unit_src, unit_tgt, units):
+    """Restated CPU path (oracle, C + OpenMP): `units` inner registrations, wall seconds."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+
+    O.build()
+    t0 = time.perf_counter()
+    iters = 0
+    for u in units:
+        r = O.gicp(src_clouds[unit_src[u]], tgt_clouds[unit_tgt[u]], 0.5, 100)
+        iters += r["iters"]
+    return time.perf_counter() - t0, iters, O.num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.
+    Open3D cannot be installed here, so this is the restated C/OpenMP port (kind "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    _, sources, targets, unit_src, unit_tgt = make_workload(0)
+    per_step = 24          # bounded sample: 24 of the step's 180 registrations (4 per scale candidate)
+    units = [c * ATTEMPTS + k for k in range(per_step // len(SCALES)) for c in range(len(SCALES))]
+    for _ in range(args.warmup):
+        cpu_registrations(sources, targets, unit_src, unit_tgt, units[:6])
+    total_s, cores = 0.0, 1
+    for _ in range(args.steps):
+        s, _, cores = cpu_registrations(sources, targets, unit_src, unit_tgt, units)
+        total_s += s
+    value = per_step * args.steps / total_s
+    line = {"impl": "reference", "metric": "GICP candidate evals/s (5k-pt clouds)", "value": value,
+            "unit": "registrations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "restated CPU path (oracle/, C + OpenMP, KD-tree), not Open3D"},
+            "cpu_baseline": {"value": value, "unit": "registrations/s", "cores": cores, "kind": "port",
+                             "sample": f"{per_step} of the step's 180 registrations per step (4 starts per scale candidate)"},
+            "e2e": {"value": value, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU path
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from or_pcd_b200 import _lib, ops
+    from or_pcd_b200.Optimizer import GeneralizedICP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.lib()
+
+    src, sources, targets, unit_src, unit_tgt = make_workload(rank, pinned=_lib.pinned_empty)
+    n_units = len(unit_src)
+    opt = GeneralizedICP()
+    opt.profile = True
+    d_src, d_tgt = _lib.to_device(sources), _lib.to_device(targets)
+    us, ut = torch.as_tensor(unit_src).cuda(), torch.as_tensor(unit_tgt).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    gather_buf = torch.empty((world, n_units, 20), dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def device_step():
+        """Hot path with inputs resident in HBM: source covariances, target covariances, batched GICP."""
+        sc = opt._rigid_source_covariances(src, d_src)
+        res = opt.optimize_batch_device(d_src, d_tgt, us, ut, src_cov=sc)
+        if world > 1:   # (rmse, fitness, iters, status, T) record per unit, one small all-gather
+            rec = torch.cat([res.stats, res.status.to(torch.float64)[:, None], res.T.reshape(n_units, 16)], 1)[:, :20]
+            dist.all_gather_into_tensor(gather_buf, rec.contiguous())
+        return res
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+
+    # ---- timed: K device-resident steps, L2 flushed between them
+    k0 = ops.launch_counter["kernels"]
+    sweep_ms, pairs, fixed, unit_rounds = 0.0, 0.0, 0.0, 0.0
+    dev_ms = 0.0
+    with ClockSampler(local) as clk:
+        for _ in range(args.steps):
+            flush.fill_(1)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = device_step()
+            e1.record()
+            barrier()
+            dev_ms += e0.elapsed_time(e1)
+            p = res.profile
+            sweep_ms += p[1]; pairs += p[2]; fixed += p[4]; unit_rounds += p[7]
+            sweep_launches = p[6]
+    launches = ops.launch_counter["kernels"] - k0
+    clocks = clk.summary()
+    mean_iters = float(res.stats[:, 2].mean().item())
+
+    # ---- e2e: host buffers in, host results out, through the plugin API
+    opt.profile = False
+    for _ in range(2):
+        opt.optimize_batch(sources, targets, unit_src, unit_tgt, rigid_base=src)
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        barrier()
+        t0 = time.perf_counter()
+        out = opt.optimize_batch(sources, targets, unit_src, unit_tgt, rigid_base=src)
+        torch.cuda.synchronize()
+        e2e_s += time.perf_counter() - t0
+    h2d = sources.nbytes + targets.nbytes + unit_src.nbytes + unit_tgt.nbytes
+    d2h = out.transforms.nbytes + 4 * 8 * n_units + 4 * n_units
+
+    # ---- max over ranks
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        # FFMA peak of this box, this run (roofline denominator)
+        def peak(packed):
+            best = 0.0
+            blocks, iters = 148 * 16, 4096
+            ops.ffma_burn(blocks, 64, packed)
+            torch.cuda.synchronize()
+            for _ in range(5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); ops.ffma_burn(blocks, iters, packed); b.record()
+                torch.cuda.synchronize()
+                best = max(best, blocks * 256.0 * iters * 16 * 8 * (4 if packed else 2) / (a.elapsed_time(b) * 1e-3) / 1e12)
+            return best
+
+        ffma_peak = max(peak(False), peak(True))
+        achieved = 8.0 * pairs / (sweep_ms * 1e-3) / 1e12
+        # CPU baseline on this box's host cores: a bounded sample of the same step
+        cpu_units = [c * ATTEMPTS + k for k in range(2) for c in range(len(SCALES))]
+        cpu_s, _, cores = cpu_registrations(sources, targets, unit_src, unit_tgt, cpu_units)
+        value = world * n_units * args.steps / (dev_ms * 1e-3)
+        line = {
+            "metric": "GICP candidate evals/s (5k-pt clouds)", "value": value, "unit": "registrations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_src": N_POINTS, "n_tgt": N_POINTS, "units_per_gpu": n_units,
+                       "max_iterations": 100, "mean_iterations": mean_iters, "l2": "256 MB flush between timed steps",
+                       "filter_dtype": "f32 (certified) + f64 exact re-rank", "parallelism": f"units x{world}"},
+            "e2e": {"value": world * n_units * args.steps / (e2e_ms * 1e-3), "unit": "registrations/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
+                         "frac": achieved / ffma_peak, "traffic": None,
+                         "kernel": "nn_sweep_kernel", "avg_launch_us": 1e3 * sweep_ms / max(sweep_launches * args.steps, 1),
+                         "share_of_step": sweep_ms / dev_ms,
+                         "note": "8 FLOP per (query,target) pair x pairs swept / CUDA-event time inside the kernel; "
+                                 "peak = FFMA/FFMA2 micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                         "pairs_per_step": pairs / args.steps, "exact_fallback_fraction": fixed / max(unit_rounds * N_POINTS, 1)},
+            "cpu_baseline": {"value": len(cpu_units) / cpu_s, "unit": "registrations/s", "cores": cores, "kind": "port",
+                             "sample": f"{len(cpu_units)} of the step's 180 registrations (2 starts per scale candidate), "
+                                       "restated CPU path (oracle/, C + OpenMP, KD-tree), not Open3D"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

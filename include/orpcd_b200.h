@@ -65,6 +65,28 @@ int orpcd_knn_exact(const double *d_points, int n, long long points_stride,
                     int batch, int k, int *d_idx, double *d_d2, orpcd_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * k-NN of a moved copy of a cloud, re-ranked from the base cloud's lists.
+ * The Aligner registers `attempts` rigid images of one source cloud
+ * (Aligner/Aligner.py:179-185) and Open3D rebuilds the 20-NN graph of each;
+ * here the kc > k nearest neighbours of the BASE cloud (orpcd_knn_exact once)
+ * are re-ranked with exact float64 distances of the moved coordinates.  A
+ * point whose k-th re-ranked distance is not strictly below
+ * d_factor[b] * d_cand_bound[i] (the least a non-candidate can reach) gets an
+ * exact scan, so the output always equals orpcd_knn_exact on the moved cloud.
+ * d_cand_idx  : [n][kc] neighbour lists of the base cloud (self query)
+ * d_cand_bound: [n] base d2 of the last candidate (orpcd_knn_candidate_bound)
+ * d_factor    : [batch] lower bound of moved_d2 / base_d2 (rigid: 1 - 1e-9,
+ *               per-axis scale s: min(s)^2 * (1 - 1e-9))
+ * ---------------------------------------------------------------------- */
+int orpcd_knn_candidate_bound(const int *d_cand_idx, const double *d_cand_d2, int n, int kc,
+                              double *d_bound, orpcd_stream_t stream);
+size_t orpcd_knn_rerank_workspace_bytes(int n, int batch);
+int orpcd_knn_rerank(const int *d_cand_idx, const double *d_cand_bound, int kc,
+                     const double *d_points, int n, long long points_stride, int batch,
+                     const double *d_factor, int k, int *d_idx, double *d_d2, void *d_workspace,
+                     size_t workspace_bytes, orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Statistical outlier removal mask.
  * Replaces PointCloud.remove_statistical_outlier(nb_neighbors, std_ratio)
  * (Preprocessor/Outliers/sor.py:69-71).
@@ -87,13 +109,22 @@ int orpcd_sor_mask(const double *d_points, int n, int nb_neighbors, double std_r
  * d_normals  : [batch][n][3]
  * d_cov6     : [batch][n][6]  neighbourhood covariance
  * d_gicp_cov6: [batch][n][6]  (requires gicp_eps > 0)
+ * d_gicp_axis: [batch][n][3]  unit axis a with d_gicp_cov6 = I - (1-eps) a a^T
  * d_nn_idx   : [batch][n][knn] int32 neighbour lists actually used (-1 padded)
+ * orpcd_normals_cov_from_knn takes neighbour lists computed elsewhere
+ * (orpcd_knn_exact / orpcd_knn_rerank) instead of searching itself.
  * ---------------------------------------------------------------------- */
 size_t orpcd_normals_workspace_bytes(int n, int batch, int knn);
 int orpcd_normals_cov(const double *d_points, int n, long long points_stride, int batch,
                       int knn, double radius, double gicp_eps, void *d_workspace,
                       size_t workspace_bytes, double *d_normals, double *d_cov6,
-                      double *d_gicp_cov6, int *d_nn_idx, orpcd_stream_t stream);
+                      double *d_gicp_cov6, double *d_gicp_axis, int *d_nn_idx,
+                      orpcd_stream_t stream);
+int orpcd_normals_cov_from_knn(const double *d_points, int n, long long points_stride, int batch,
+                               int knn, const int *d_knn_idx, const double *d_knn_d2, double radius,
+                               double gicp_eps, double *d_normals, double *d_cov6,
+                               double *d_gicp_cov6, double *d_gicp_axis, int *d_nn_idx,
+                               orpcd_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * target * (sx, sy, sz) for a batch of scale candidates
@@ -126,15 +157,27 @@ typedef struct {
                              the stream and stops early once every unit is done */
     int profile;          /* !=0: time every sweep launch with CUDA events on the
                              stream and synchronise at the end (fills h_profile) */
+    int cov_mode;         /* 0: d_*_cov hold 3x3 covariances, 6 doubles per point, and
+                                (Cs+Ct)^-1/2 comes from a Jacobi eigen-solve;
+                             1: d_*_cov hold the unit AXIS a of each GICP plane
+                                covariance C = I - (1-eps) a a^T (3 doubles per point,
+                                d_gicp_axis of orpcd_normals_cov) and the whitening
+                                matrix is evaluated in closed form               */
     double max_correspondence_distance;
     double relative_fitness; /* 1e-6 in the reference's call       */
     double relative_rmse;    /* 1e-6                               */
+    double gicp_epsilon;     /* eps of diag(eps,1,1); used by cov_mode 1 (Open3D: 1e-3) */
+    int sweep_q;             /* tuning: queries per thread in the 1-NN sweep (4|8), 0 = auto */
+    int sweep_tj;            /* tuning: targets per inner step (2|4|8), 0 = auto            */
+    int sweep_smem_pad;      /* tuning: unused dynamic smem bytes (caps blocks per SM), 0    */
+    int sweep_mode;          /* tuning: 1 = all packed FFMA2, 2 = FFMA2 + scalar FFMA,
+                                3 = all scalar FFMA, 0 = auto                              */
 } orpcd_gicp_params;
 
 size_t orpcd_gicp_batch_workspace_bytes(const orpcd_gicp_params *p);
 
-/* d_src_points [n_src_sets][n_src][3], d_src_cov6 [n_src_sets][n_src][6],
- * d_tgt_points [n_tgt_sets][n_tgt][3], d_tgt_cov6 [n_tgt_sets][n_tgt][6],
+/* d_src_points [n_src_sets][n_src][3], d_src_cov [n_src_sets][n_src][6 | 3],
+ * d_tgt_points [n_tgt_sets][n_tgt][3], d_tgt_cov [n_tgt_sets][n_tgt][6 | 3]  (see cov_mode),
  * d_out_T     [n_units][16],
  * d_out_stats [n_units][4]  {fitness, inlier_rmse, iterations, n_correspondences},
  * d_out_status[n_units]     0 = ok, 1 = no correspondence (inlier_rmse == 0:
@@ -145,8 +188,8 @@ size_t orpcd_gicp_batch_workspace_bytes(const orpcd_gicp_params *p);
  *   work list*, target splits, sweep launches with work*, unit-rounds*};
  *   entries marked * are filled only when p->profile != 0.                    */
 int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_points,
-                     const double *d_src_cov6, const double *d_tgt_points,
-                     const double *d_tgt_cov6, const int *d_unit_src, const int *d_unit_tgt,
+                     const double *d_src_cov, const double *d_tgt_points,
+                     const double *d_tgt_cov, const int *d_unit_src, const int *d_unit_tgt,
                      void *d_workspace, size_t workspace_bytes, double *d_out_T,
                      double *d_out_stats, int *d_out_status, double *d_trace,
                      double *h_profile, orpcd_stream_t stream);
@@ -166,6 +209,10 @@ int orpcd_gicp_sweep_only(const orpcd_gicp_params *p, void *d_workspace,
 int orpcd_ffma_burn(int blocks, int iters, float *d_sink, orpcd_stream_t stream);
 /* Same with packed FFMA2 (fma.rn.f32x2): FLOPs = blocks*256*iters*16*8*4. */
 int orpcd_ffma2_burn(int blocks, int iters, float *d_sink, orpcd_stream_t stream);
+/* Float64 DFMA: FLOPs = blocks*256*iters*16*8*2.  d_sink: [blocks*256] doubles. */
+int orpcd_dfma_burn(int blocks, int iters, double *d_sink, orpcd_stream_t stream);
+/* Issue-slot probe: FFMA2 chains interleaved with alu_per_fma (0..2) three-input FMNMX per FFMA2. */
+int orpcd_mix_burn(int blocks, int iters, int alu_per_fma, float *d_sink, orpcd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -133,7 +133,7 @@ __device__ void smallest_eigvec(const double *C, double *n)
 
 // C = Rx diag(eps,1,1) Rx^T with Rx the rotation taking e1 onto the normal
 // (identity when the normal is within ~8 degrees of -e1), upper triangle.
-__device__ void gicp_cov_from_normal(const double *nrm, double eps, double *c6)
+__device__ void gicp_cov_from_normal(const double *nrm, double eps, double *c6, double *axis)
 {
     double R[9];
     const double c = nrm[0];
@@ -151,6 +151,8 @@ __device__ void gicp_cov_from_normal(const double *nrm, double eps, double *c6)
         const double f = 1 / (1 + c);
         for (int i = 0; i < 9; ++i) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + sv[i] + sv2[i] * f;
     }
+    if (axis) { axis[0] = R[0]; axis[1] = R[3]; axis[2] = R[6]; }  // R e1
+    if (!c6) return;
     double RD[9];
     for (int i = 0; i < 3; ++i) { RD[i * 3] = R[i * 3] * eps; RD[i * 3 + 1] = R[i * 3 + 1]; RD[i * 3 + 2] = R[i * 3 + 2]; }
     int o = 0;
@@ -164,7 +166,7 @@ normals_cov_kernel(const double *__restrict__ points, int n, long long points_st
                    const int *__restrict__ nn_idx, const double *__restrict__ nn_d2, int knn,
                    double radius2, double gicp_eps, double *__restrict__ normals,
                    double *__restrict__ cov6, double *__restrict__ gicp_cov6,
-                   int *__restrict__ nn_out)
+                   double *__restrict__ gicp_axis, int *__restrict__ nn_out)
 {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,7 +212,9 @@ normals_cov_kernel(const double *__restrict__ points, int n, long long points_st
         double *o = cov6 + row * 6;
         o[0] = C[0]; o[1] = C[1]; o[2] = C[2]; o[3] = C[4]; o[4] = C[5]; o[5] = C[8];
     }
-    if (gicp_cov6) gicp_cov_from_normal(nr, gicp_eps, gicp_cov6 + row * 6);
+    if (gicp_cov6 || gicp_axis)
+        gicp_cov_from_normal(nr, gicp_eps, gicp_cov6 ? gicp_cov6 + row * 6 : nullptr,
+                             gicp_axis ? gicp_axis + row * 3 : nullptr);
 }
 
 __global__ void apply_scale_kernel(const double *__restrict__ pts, int n, const double *__restrict__ scales,
@@ -234,10 +238,11 @@ ORPCD_API size_t orpcd_normals_workspace_bytes(int n, int batch, int knn)
 ORPCD_API int orpcd_normals_cov(const double *d_points, int n, long long points_stride, int batch,
                                 int knn, double radius, double gicp_eps, void *d_workspace,
                                 size_t workspace_bytes, double *d_normals, double *d_cov6,
-                                double *d_gicp_cov6, int *d_nn_idx, orpcd_stream_t stream)
+                                double *d_gicp_cov6, double *d_gicp_axis, int *d_nn_idx,
+                                orpcd_stream_t stream)
 {
     if (!d_points || n <= 0 || batch <= 0 || knn < 1 || knn > ORPCD_MAX_KNN) return ORPCD_ERR_INVALID;
-    if (d_gicp_cov6 && !(gicp_eps > 0)) return ORPCD_ERR_INVALID;
+    if ((d_gicp_cov6 || d_gicp_axis) && !(gicp_eps > 0)) return ORPCD_ERR_INVALID;
     if (!d_workspace || workspace_bytes < orpcd_normals_workspace_bytes(n, batch, knn) ||
         ((uintptr_t)d_workspace & 255))
         return ORPCD_ERR_WORKSPACE;
@@ -250,7 +255,23 @@ ORPCD_API int orpcd_normals_cov(const double *d_points, int n, long long points_
     dim3 grid((n + 127) / 128, batch);
     normals_cov_kernel<<<grid, 128, 0, st>>>(d_points, n, points_stride, idx, d2, knn,
                                              radius > 0 ? radius * radius : 0.0, gicp_eps, d_normals,
-                                             d_cov6, d_gicp_cov6, d_nn_idx);
+                                             d_cov6, d_gicp_cov6, d_gicp_axis, d_nn_idx);
+    ORPCD_CHECK_LAUNCH();
+    return ORPCD_OK;
+}
+
+ORPCD_API int orpcd_normals_cov_from_knn(const double *d_points, int n, long long points_stride, int batch,
+                                         int knn, const int *d_knn_idx, const double *d_knn_d2, double radius,
+                                         double gicp_eps, double *d_normals, double *d_cov6,
+                                         double *d_gicp_cov6, double *d_gicp_axis, int *d_nn_idx,
+                                         orpcd_stream_t stream)
+{
+    if (!d_points || !d_knn_idx || !d_knn_d2 || n <= 0 || batch <= 0 || knn < 1) return ORPCD_ERR_INVALID;
+    if ((d_gicp_cov6 || d_gicp_axis) && !(gicp_eps > 0)) return ORPCD_ERR_INVALID;
+    dim3 grid((n + 127) / 128, batch);
+    normals_cov_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_points, n, points_stride, d_knn_idx, d_knn_d2, knn,
+                                                               radius > 0 ? radius * radius : 0.0, gicp_eps,
+                                                               d_normals, d_cov6, d_gicp_cov6, d_gicp_axis, d_nn_idx);
     ORPCD_CHECK_LAUNCH();
     return ORPCD_OK;
 }

@@ -7,15 +7,19 @@
 // Algorithm: SURVEY.md Appendix A.4-A.5.
 //
 // Per iteration (all units in each launch):
+//   update_kernel     applies the pending rigid update to the stored float64 source
+//                     points and covariances (or covariance axes) and writes the
+//                     centred FP32 copy the sweep reads.
 //   nn_sweep_kernel   FP32 filter over all (query, target) pairs on the FMA pipe:
 //                     packed FFMA2 (fma.rn.f32x2) on the expanded form
 //                     |p|^2 - 2 q.p, FMNMX3 running minima per 32-target chunk,
 //                     per query (best chunk min, best chunk, second-best chunk min).
-//   nn_resolve_kernel applies the pending rigid update to the stored float64
-//                     source points, proves the best chunk holds the exact
-//                     nearest neighbour (FP32 error bound) and re-ranks that
-//                     chunk in float64 with Open3D's operation order; queries
-//                     whose bound fails go to a work list.
+//   nn_resolve_kernel proves with an FP32 error bound that the best chunk holds the
+//                     exact nearest neighbour, then a warp-wide ballot over that
+//                     chunk finds the single target inside the certified margin
+//                     and its float64 distance is taken in Open3D's operation
+//                     order; anything ambiguous at FP32 resolution goes to a work
+//                     list.
 //   nn_fix_kernel     exact float64 scan, one warp per listed query.
 //   reduce_kernel     Mahalanobis residual/Jacobian per correspondence, warp
 //                     shuffle + block reduction of the 21+6 J^T J / J^T r terms,
@@ -32,8 +36,6 @@ namespace {
 // configuration
 // ----------------------------------------------------------------------------
 constexpr int NN_THREADS = 128;
-constexpr int NN_Q = 4;                          // queries per thread (two packed pairs)
-constexpr int NN_QPB = NN_THREADS * NN_Q;        // queries per block
 constexpr int NN_CH = 32;                        // targets per chunk (re-rank granularity)
 constexpr int NN_TILE_CH = 32;                   // chunks per shared-memory tile
 constexpr int NN_TILE = NN_CH * NN_TILE_CH;      // 1024 targets = 16 KB per stage
@@ -64,11 +66,12 @@ struct TgtMeta {
 
 struct Ctx {
     int n_units, n_src, n_tgt, nt_pad, n_chunks, splits, chunks_per_split;
-    int max_iter, red_blocks;
-    double r2, rel_fit, rel_rmse;
+    int max_iter, red_blocks, cov_mode, cov_stride, ignore_done;
+    double r2, rel_fit, rel_rmse, kappa;
     UnitState *state;
     double *cur_pts;     // [units][n_src][3]
-    double *cur_cov;     // [units][n_src][6]
+    double *cur_cov;     // [units][n_src][6] covariances (cov_mode 0) or [..][3] axes (cov_mode 1)
+    float4 *cur_qf;      // [units][n_src] centred FP32 copy of cur_pts (w unused)
     int *corr;           // [units][n_src]
     double *corr_d2;     // [units][n_src]
     float *part_m1;      // [units][splits][n_src]
@@ -82,9 +85,8 @@ struct Ctx {
     int *worklist_count; // [max_iter+2]
     int *done_count;     // [1]
     int *round_active;   // [max_iter+2] units still running in each round
-    int ignore_done;     // sweep-only timing mode
     const double *tgt_pts;   // [tgt_sets][n_tgt][3]
-    const double *tgt_cov;   // [tgt_sets][n_tgt][6]
+    const double *tgt_cov;   // [tgt_sets][n_tgt][cov_stride]
     double *out_T, *out_stats, *trace;
     int *out_status;
 };
@@ -137,15 +139,6 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// Current float64 position of source point i of unit u (pending update applied).
-__device__ __forceinline__ void load_query(const Ctx &c, const UnitState &st, int u, int i, double &x,
-                                           double &y, double &z)
-{
-    const double *p = c.cur_pts + ((size_t)u * c.n_src + i) * 3;
-    x = p[0]; y = p[1]; z = p[2];
-    if (st.has_update) transform_point(st.U, x, y, z);
-}
-
 // ----------------------------------------------------------------------------
 // set-up kernels
 // ----------------------------------------------------------------------------
@@ -166,13 +159,14 @@ __global__ void init_units_kernel(Ctx c, const int *__restrict__ unit_src, const
             for (int k = 0; k < c.max_iter + 2; ++k) { c.worklist_count[k] = 0; c.round_active[k] = 0; }
         }
     }
-    const size_t np = (size_t)c.n_src * 3, nc = (size_t)c.n_src * 6;
+    const size_t np = (size_t)c.n_src * 3, nc = (size_t)c.n_src * c.cov_stride;
     const double *sp = src_pts + (size_t)ss * np;
     const double *sc = src_cov + (size_t)ss * nc;
     double *dp = c.cur_pts + (size_t)u * np;
     double *dc = c.cur_cov + (size_t)u * nc;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nc; e += (size_t)gridDim.x * blockDim.x) {
-        dc[e] = sc[e];
+    const size_t nmax = nc > np ? nc : np;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nmax; e += (size_t)gridDim.x * blockDim.x) {
+        if (e < nc) dc[e] = sc[e];
         if (e < np) dp[e] = sp[e];
     }
 }
@@ -237,40 +231,66 @@ __global__ void __launch_bounds__(1024) prep_targets_kernel(Ctx c)
 }
 
 // ----------------------------------------------------------------------------
-// 1-NN sweep: FP32 filter on the FMA pipe
+// per-round update: p <- U p, C <- R C R^T (or axis <- R axis), centred FP32 copy
+// (PointCloud::Transform of the moving source, Registration.cpp)
 // ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) update_kernel(Ctx c)
+{
+    const int u = blockIdx.y;
+    const UnitState &st = c.state[u];
+    if (st.done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n_src) return;
+    const size_t oi = (size_t)u * c.n_src + i;
+    double *p = c.cur_pts + oi * 3;
+    double x = p[0], y = p[1], z = p[2];
+    if (st.has_update) {
+        transform_point(st.U, x, y, z);
+        p[0] = x; p[1] = y; p[2] = z;
+        if (c.cov_mode == 0) {
+            double *cp = c.cur_cov + oi * 6;
+            store_sym3(cp, rotate_sym3(st.U, load_sym3(cp)));
+        } else {
+            double *ap = c.cur_cov + oi * 3;
+            const double ax = ap[0], ay = ap[1], az = ap[2];
+            ap[0] = st.U[0] * ax + st.U[1] * ay + st.U[2] * az;
+            ap[1] = st.U[4] * ax + st.U[5] * ay + st.U[6] * az;
+            ap[2] = st.U[8] * ax + st.U[9] * ay + st.U[10] * az;
+        }
+    }
+    const TgtMeta tm = c.tgt_meta[st.tgt_set];
+    c.cur_qf[oi] = make_float4((float)(x - tm.cx), (float)(y - tm.cy), (float)(z - tm.cz), 0.f);
+}
+
+// ----------------------------------------------------------------------------
+// 1-NN sweep: FP32 filter on the FMA pipe.  Q queries per thread (Q/2 packed pairs).
+// ----------------------------------------------------------------------------
+template <int Q, int TJ, int MODE>
 __global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c)
 {
     __shared__ __align__(16) float4 tile[2][NN_TILE];
     const int u = blockIdx.z, split = blockIdx.y, tid = threadIdx.x;
     const UnitState &st = c.state[u];
     if (st.done && !c.ignore_done) return;
-    const TgtMeta tm = c.tgt_meta[st.tgt_set];
     const float4 *tg = c.tgt4 + (size_t)st.tgt_set * c.nt_pad;
 
-    // this thread's NN_Q queries: i = qbase + k*NN_THREADS + tid
-    const int qbase = blockIdx.x * NN_QPB;
-    float qf[NN_Q][3];
+    // this thread's Q queries: i = qbase + k*NN_THREADS + tid
+    const int qbase = blockIdx.x * (NN_THREADS * Q);
+    const float4 *qsrc = c.cur_qf + (size_t)u * c.n_src;
+    uint64_t qx[Q / 2], qy[Q / 2], qz[Q / 2];
 #pragma unroll
-    for (int k = 0; k < NN_Q; ++k) {
-        const int i = qbase + k * NN_THREADS + tid;
-        double x = tm.cx, y = tm.cy, z = tm.cz;
-        if (i < c.n_src) load_query(c, st, u, i, x, y, z);
-        qf[k][0] = (float)(x - tm.cx);
-        qf[k][1] = (float)(y - tm.cy);
-        qf[k][2] = (float)(z - tm.cz);
+    for (int h = 0; h < Q / 2; ++h) {
+        const int i0 = qbase + (2 * h) * NN_THREADS + tid, i1 = i0 + NN_THREADS;
+        const float4 a = i0 < c.n_src ? qsrc[i0] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b = i1 < c.n_src ? qsrc[i1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        qx[h] = pack_f2(a.x, b.x);
+        qy[h] = pack_f2(a.y, b.y);
+        qz[h] = pack_f2(a.z, b.z);
     }
-    uint64_t qx[NN_Q / 2], qy[NN_Q / 2], qz[NN_Q / 2];
+    float m1[Q], m2[Q];
+    int c1[Q];
 #pragma unroll
-    for (int h = 0; h < NN_Q / 2; ++h) {
-        qx[h] = pack_f2(qf[2 * h][0], qf[2 * h + 1][0]);
-        qy[h] = pack_f2(qf[2 * h][1], qf[2 * h + 1][1]);
-        qz[h] = pack_f2(qf[2 * h][2], qf[2 * h + 1][2]);
-    }
-    float m1[NN_Q], m2[NN_Q];
-    int c1[NN_Q];
-#pragma unroll
-    for (int k = 0; k < NN_Q; ++k) { m1[k] = CUDART_INF_F; m2[k] = CUDART_INF_F; c1[k] = 0; }
+    for (int k = 0; k < Q; ++k) { m1[k] = CUDART_INF_F; m2[k] = CUDART_INF_F; c1[k] = 0; }
 
     const int cb = split * c.chunks_per_split;
     const int ce = min(c.n_chunks, cb + c.chunks_per_split);
@@ -296,30 +316,76 @@ __global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c)
         const float4 *tl = tile[t & 1];
         for (int ch = 0; ch < nch; ++ch) {
             const float4 *tc = tl + ch * NN_CH;
-            float mc[NN_Q];
+            float mc[Q];
 #pragma unroll
-            for (int k = 0; k < NN_Q; ++k) mc[k] = CUDART_INF_F;
+            for (int k = 0; k < Q; ++k) mc[k] = CUDART_INF_F;
 #pragma unroll
-            for (int j = 0; j < NN_CH; j += 2) {
-                const float4 t0 = tc[j], t1 = tc[j + 1];
+            for (int j = 0; j < NN_CH; j += TJ) {
+                // TJ targets per step: consecutive FFMA2s share the packed query operand so it
+                // is served from the operand-reuse cache (register-bank reads bound the FFMA2
+                // rate otherwise: 2 even + 2 odd registers per cycle pair).
+                float4 t[TJ];
 #pragma unroll
-                for (int h = 0; h < NN_Q / 2; ++h) {
-                    uint64_t a0 = fma2_ss(qz[h], t0.z, t0.w);
-                    uint64_t a1 = fma2_ss(qz[h], t1.z, t1.w);
-                    a0 = fma2_sv(qy[h], t0.y, a0);
-                    a1 = fma2_sv(qy[h], t1.y, a1);
-                    a0 = fma2_sv(qx[h], t0.x, a0);
-                    a1 = fma2_sv(qx[h], t1.x, a1);
-                    float a0l, a0h, a1l, a1h;
-                    unpack_f2(a0, a0l, a0h);
-                    unpack_f2(a1, a1l, a1h);
-                    mc[2 * h] = min3f(mc[2 * h], a0l, a1l);
-                    mc[2 * h + 1] = min3f(mc[2 * h + 1], a0h, a1h);
+                for (int r = 0; r < TJ; ++r) t[r] = tc[j + r];
+#pragma unroll
+                for (int h = 0; h < Q / 2; ++h) {
+                    if (MODE == 0) {
+                        // all three stages packed
+                        uint64_t a[TJ];
+#pragma unroll
+                        for (int r = 0; r < TJ; ++r) a[r] = fma2_ss(qz[h], t[r].z, t[r].w);
+#pragma unroll
+                        for (int r = 0; r < TJ; ++r) a[r] = fma2_sv(qy[h], t[r].y, a[r]);
+#pragma unroll
+                        for (int r = 0; r < TJ; ++r) a[r] = fma2_sv(qx[h], t[r].x, a[r]);
+#pragma unroll
+                        for (int r = 0; r < TJ; r += 2) {
+                            float l0, h0, l1, h1;
+                            unpack_f2(a[r], l0, h0);
+                            unpack_f2(a[r + 1], l1, h1);
+                            mc[2 * h] = min3f(mc[2 * h], l0, l1);
+                            mc[2 * h + 1] = min3f(mc[2 * h + 1], h0, h1);
+                        }
+                    } else {
+                        // stage 1 packed (two broadcast scalars: 2 even + 2 odd register reads, full
+                        // rate); stages 2-3 scalar FFMA (accumulator + query register, target scalar
+                        // from the operand-reuse cache) -- a packed FFMA2 with a register-pair
+                        // accumulator needs 5 register reads and issues every 3 cycles.
+                        float lo[TJ], hi[TJ];
+                        float qyl, qyh, qxl, qxh, qzl, qzh;
+                        unpack_f2(qy[h], qyl, qyh);
+                        unpack_f2(qx[h], qxl, qxh);
+                        unpack_f2(qz[h], qzl, qzh);
+#pragma unroll
+                        for (int r = 0; r < TJ; ++r) {
+                            if (MODE == 1) {
+                                unpack_f2(fma2_ss(qz[h], t[r].z, t[r].w), lo[r], hi[r]);
+                            } else {
+                                lo[r] = __fmaf_rn(qzl, t[r].z, t[r].w);
+                                hi[r] = __fmaf_rn(qzh, t[r].z, t[r].w);
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < TJ; ++r) {
+                            lo[r] = __fmaf_rn(qyl, t[r].y, lo[r]);
+                            hi[r] = __fmaf_rn(qyh, t[r].y, hi[r]);
+                        }
+#pragma unroll
+                        for (int r = 0; r < TJ; ++r) {
+                            lo[r] = __fmaf_rn(qxl, t[r].x, lo[r]);
+                            hi[r] = __fmaf_rn(qxh, t[r].x, hi[r]);
+                        }
+#pragma unroll
+                        for (int r = 0; r < TJ; r += 2) {
+                            mc[2 * h] = min3f(mc[2 * h], lo[r], lo[r + 1]);
+                            mc[2 * h + 1] = min3f(mc[2 * h + 1], hi[r], hi[r + 1]);
+                        }
+                    }
                 }
             }
             const int chunk = c0 + ch;
 #pragma unroll
-            for (int k = 0; k < NN_Q; ++k) {
+            for (int k = 0; k < Q; ++k) {
                 m2[k] = fminf(m2[k], fmaxf(m1[k], mc[k]));
                 c1[k] = mc[k] < m1[k] ? chunk : c1[k];
                 m1[k] = fminf(m1[k], mc[k]);
@@ -329,7 +395,7 @@ __global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c)
     }
     const size_t pbase = ((size_t)u * c.splits + split) * c.n_src;
 #pragma unroll
-    for (int k = 0; k < NN_Q; ++k) {
+    for (int k = 0; k < Q; ++k) {
         const int i = qbase + k * NN_THREADS + tid;
         if (i < c.n_src) {
             c.part_m1[pbase + i] = m1[k];
@@ -340,66 +406,83 @@ __global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c)
 }
 
 // ----------------------------------------------------------------------------
-// resolve: merge split partials, certify the best chunk, exact float64 re-rank
+// resolve: merge split partials, certify the best chunk, pick the exact neighbour
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) nn_resolve_kernel(Ctx c, int round)
 {
     const int u = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const UnitState &st = c.state[u];
-    if (st.done) return;
+    if (st.done) return;  // block-uniform
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&c.round_active[round], 1);
-    if (i >= c.n_src) return;
-    double x, y, z;
-    load_query(c, st, u, i, x, y, z);
-    if (st.has_update) {
-        double *p = c.cur_pts + ((size_t)u * c.n_src + i) * 3;
-        p[0] = x; p[1] = y; p[2] = z;
-    }
+    const bool active = i < c.n_src;
     const TgtMeta tm = c.tgt_meta[st.tgt_set];
-    const float fx = (float)(x - tm.cx), fy = (float)(y - tm.cy), fz = (float)(z - tm.cz);
-
-    float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
+    const size_t oi = (size_t)u * c.n_src + (active ? i : 0);
+    float fx = 0.f, fy = 0.f, fz = 0.f, thr = -CUDART_INF_F;
     int c1 = 0;
-    for (int s = 0; s < c.splits; ++s) {
-        const size_t pi = ((size_t)u * c.splits + s) * c.n_src + i;
-        const float a1 = c.part_m1[pi], a2 = c.part_m2[pi];
-        const int ac = c.part_c1[pi];
-        m2 = fminf(fminf(m2, a2), fmaxf(m1, a1));
-        c1 = a1 < m1 ? ac : c1;
-        m1 = fminf(m1, a1);
+    bool cross = false;
+    if (active) {
+        const float4 qf = c.cur_qf[oi];
+        fx = qf.x; fy = qf.y; fz = qf.z;
+        float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
+        for (int s = 0; s < c.splits; ++s) {
+            const size_t pi = ((size_t)u * c.splits + s) * c.n_src + i;
+            const float a1 = c.part_m1[pi], a2 = c.part_m2[pi];
+            const int ac = c.part_c1[pi];
+            m2 = fminf(fminf(m2, a2), fmaxf(m1, a1));
+            c1 = a1 < m1 ? ac : c1;
+            m1 = fminf(m1, a1);
+        }
+        // FP32 error bound of the filter (DESIGN.md "1-NN filter bound"):
+        //   |(s + |qf|^2) - D| <= eps32 * (4 rho^2 + 2 d rho),  rho = |qf| + |pf|.
+        const double qn = (double)fx * fx + (double)fy * fy + (double)fz * fz;
+        const double qnorm = sqrt(qn);
+        const double rho_max = qnorm + tm.rmax;
+        const double e_glob = (double)F32_EPS * 6.0 * rho_max * rho_max * 1.001;
+        const double d_ub = sqrt(fmax((double)m1 + qn, 0.0) + e_glob) * (1.0 + 1e-6);
+        const double rho = 2.0 * qnorm + d_ub + 4.0 * (double)F32_EPS * rho_max;
+        const double margin = 2.02 * (double)F32_EPS * (4.0 * rho * rho + 2.0 * d_ub * rho) * 1.001 + 1e-300;
+        const double lim = (double)m1 + margin;
+        cross = !((double)m2 > lim);       // another chunk may hold the true neighbour
+        thr = __double2float_ru(lim);
     }
-    // FP32 error bound of the filter (DESIGN.md "1-NN filter bound"):
-    //   |(s + |qf|^2) - D| <= eps32 * (4 rho^2 + 2 d rho),  rho = |qf| + |pf|.
-    const double qn = (double)fx * fx + (double)fy * fy + (double)fz * fz;
-    const double qnorm = sqrt(qn);
-    const double rho_max = qnorm + tm.rmax;
-    const double e_glob = (double)F32_EPS * 6.0 * rho_max * rho_max * 1.001;
-    const double d_ub = sqrt(fmax((double)m1 + qn, 0.0) + e_glob) * (1.0 + 1e-6);
-    const double rho = 2.0 * qnorm + d_ub + 4.0 * (double)F32_EPS * rho_max;
-    const double margin = 2.02 * (double)F32_EPS * (4.0 * rho * rho + 2.0 * d_ub * rho) * 1.001 + 1e-300;
-
-    const size_t oi = (size_t)u * c.n_src + i;
-    if (!((double)m2 > (double)m1 + margin)) {
-        // another chunk may hold the true neighbour: exact scan by a whole warp later
+    // Warp-cooperative pass over each query's best chunk: lane t recomputes the filter
+    // value of target (chunk, t) -- same FMA chain as the sweep, so bit-identical -- and
+    // the ballot counts the targets within the certified margin of the minimum.
+    const float4 *tg = c.tgt4 + (size_t)st.tgt_set * c.nt_pad;
+    int my_cnt = 0, my_first = 0;
+    unsigned rem = __ballot_sync(0xffffffffu, active && !cross);
+    while (rem) {
+        const int l = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const int cc = __shfl_sync(0xffffffffu, c1, l);
+        const float qx = __shfl_sync(0xffffffffu, fx, l);
+        const float qy = __shfl_sync(0xffffffffu, fy, l);
+        const float qz = __shfl_sync(0xffffffffu, fz, l);
+        const float th = __shfl_sync(0xffffffffu, thr, l);
+        const float4 t = tg[(size_t)cc * NN_CH + lane];
+        const float sv = __fmaf_rn(qx, t.x, __fmaf_rn(qy, t.y, __fmaf_rn(qz, t.z, t.w)));
+        const unsigned bal = __ballot_sync(0xffffffffu, sv <= th);
+        if (lane == l) { my_cnt = __popc(bal); my_first = __ffs(bal) - 1; }
+    }
+    if (!active) return;
+    if (cross || my_cnt != 1) {
+        // ambiguous at FP32 resolution: exact float64 scan by a whole warp (nn_fix_kernel)
         const int slot = atomicAdd(&c.worklist_count[round], 1);
         c.worklist[slot] = (int)oi;
         return;
     }
-    const double *tp = c.tgt_pts + (size_t)st.tgt_set * c.n_tgt * 3;
-    const int j0 = c1 * NN_CH, j1 = min(c.n_tgt, j0 + NN_CH);
-    double best = CUDART_INF;
-    int bj = -1;
-    for (int j = j0; j < j1; ++j) {
-        const double d = sqdist3_rn(x, y, z, tp[(size_t)j * 3], tp[(size_t)j * 3 + 1], tp[(size_t)j * 3 + 2]);
-        if (d < best) { best = d; bj = j; }
-    }
-    const bool ok = bj >= 0 && best < c.r2;
-    c.corr[oi] = ok ? bj : -1;
+    const int j = c1 * NN_CH + my_first;
+    const double *p = c.cur_pts + oi * 3;
+    const double *tp = c.tgt_pts + ((size_t)st.tgt_set * c.n_tgt + j) * 3;
+    const double best = sqdist3_rn(p[0], p[1], p[2], tp[0], tp[1], tp[2]);
+    const bool ok = best < c.r2;
+    c.corr[oi] = ok ? j : -1;
     c.corr_d2[oi] = ok ? best : 0.0;
 }
 
-// exact float64 scan, one warp per listed query
+// exact float64 scan, one warp per listed query (4 independent loads in flight per lane)
 __global__ void __launch_bounds__(128) nn_fix_kernel(Ctx c, int round)
 {
     const int count = c.worklist_count[round];
@@ -410,12 +493,24 @@ __global__ void __launch_bounds__(128) nn_fix_kernel(Ctx c, int round)
         const int item = c.worklist[w];
         const int u = item / c.n_src;
         const UnitState &st = c.state[u];
-        const double *p = c.cur_pts + (size_t)item * 3;  // already updated by nn_resolve_kernel
+        const double *p = c.cur_pts + (size_t)item * 3;
         const double x = p[0], y = p[1], z = p[2];
         const double *tp = c.tgt_pts + (size_t)st.tgt_set * c.n_tgt * 3;
         double best = CUDART_INF;
         int bj = 0x7fffffff;
-        for (int j = lane; j < c.n_tgt; j += 32) {
+        int j = lane;
+        for (; j + 96 < c.n_tgt; j += 128) {
+            double d[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double *q = tp + (size_t)(j + 32 * r) * 3;
+                d[r] = sqdist3_rn(x, y, z, q[0], q[1], q[2]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (d[r] < best) { best = d[r]; bj = j + 32 * r; }
+        }
+        for (; j < c.n_tgt; j += 32) {
             const double d = sqdist3_rn(x, y, z, tp[(size_t)j * 3], tp[(size_t)j * 3 + 1], tp[(size_t)j * 3 + 2]);
             if (d < best) { best = d; bj = j; }
         }
@@ -475,6 +570,33 @@ __device__ __forceinline__ Sym3 inv_sqrt_sym3(const Sym3 &M)
     return W;
 }
 
+// Closed form of the same W when both covariances are GICP plane covariances
+//   C = R diag(eps,1,1) R^T = I - kappa a a^T,  kappa = 1 - eps,  a = R e1 (unit).
+// M = 2I - kappa (a a^T + b b^T) has eigenvalues 2, 2 - kappa(1 +- |a.b|) with
+// eigenvectors along a +- sgn(a.b) b, so
+//   W = I/sqrt2 + k+ (a + s b)(a + s b)^T + k- (a - s b)(a - s b)^T,
+//   k+- = kappa / (2 sqrt(l+-) sqrt2 (sqrt(l+-) + sqrt2))      (no cancellation, no 0/0)
+__device__ __forceinline__ Sym3 inv_sqrt_plane_pair(const double *a, const double *b, double kappa)
+{
+    const double dot = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+    const double s = dot >= 0 ? 1.0 : -1.0;
+    const double ac = fmin(fabs(dot), 1.0);
+    const double r2 = 1.4142135623730951;
+    const double lp = sqrt(2.0 - kappa * (1.0 + ac)), lm = sqrt(2.0 - kappa * (1.0 - ac));
+    const double kp = kappa / (2.0 * lp * r2 * (lp + r2)), km = kappa / (2.0 * lm * r2 * (lm + r2));
+    const double px = a[0] + s * b[0], py = a[1] + s * b[1], pz = a[2] + s * b[2];
+    const double mx = a[0] - s * b[0], my = a[1] - s * b[1], mz = a[2] - s * b[2];
+    const double h = 0.70710678118654752;
+    Sym3 W;
+    W.xx = h + kp * px * px + km * mx * mx;
+    W.xy = kp * px * py + km * mx * my;
+    W.xz = kp * px * pz + km * mx * mz;
+    W.yy = h + kp * py * py + km * my * my;
+    W.yz = kp * py * pz + km * my * mz;
+    W.zz = h + kp * pz * pz + km * mz * mz;
+    return W;
+}
+
 // x = A.ldlt().solve(b), 6x6 symmetric, diagonal pivoting (Eigen LDLT restated).
 __device__ void ldlt_solve6(double *A, const double *b, double *x)
 {
@@ -515,6 +637,7 @@ __device__ void ldlt_solve6(double *A, const double *b, double *x)
 // ----------------------------------------------------------------------------
 // residual / Jacobian reduction + solve
 // ----------------------------------------------------------------------------
+template <int COV_MODE>
 __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
 {
     __shared__ double sm[RED_THREADS / 32][RED_STRIDE];
@@ -529,24 +652,24 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
     for (int k = 0; k < RED_VALS; ++k) acc[k] = 0.0;
     if (i < c.n_src) {
         const size_t oi = (size_t)u * c.n_src + i;
-        double *cp = c.cur_cov + oi * 6;
-        Sym3 Cs = load_sym3(cp);
-        if (st.has_update) {
-            Cs = rotate_sym3(st.U, Cs);
-            store_sym3(cp, Cs);
-        }
         const int j = c.corr[oi];
         if (j >= 0) {
-            const double *ps = c.cur_pts + oi * 3;  // updated by nn_resolve_kernel
+            const double *ps = c.cur_pts + oi * 3;
             const double sx = ps[0], sy = ps[1], sz = ps[2];
             const size_t tj = (size_t)st.tgt_set * c.n_tgt + j;
             const double *pt = c.tgt_pts + tj * 3;
-            const Sym3 Ct = load_sym3(c.tgt_cov + tj * 6);
             const double dx = sx - pt[0], dy = sy - pt[1], dz = sz - pt[2];
-            Sym3 M;
-            M.xx = Ct.xx + Cs.xx; M.xy = Ct.xy + Cs.xy; M.xz = Ct.xz + Cs.xz;
-            M.yy = Ct.yy + Cs.yy; M.yz = Ct.yz + Cs.yz; M.zz = Ct.zz + Cs.zz;
-            const Sym3 W = inv_sqrt_sym3(M);
+            Sym3 W;
+            if (COV_MODE == 0) {
+                const Sym3 Cs = load_sym3(c.cur_cov + oi * 6);
+                const Sym3 Ct = load_sym3(c.tgt_cov + tj * 6);
+                Sym3 M;
+                M.xx = Ct.xx + Cs.xx; M.xy = Ct.xy + Cs.xy; M.xz = Ct.xz + Cs.xz;
+                M.yy = Ct.yy + Cs.yy; M.yz = Ct.yz + Cs.yz; M.zz = Ct.zz + Cs.zz;
+                W = inv_sqrt_sym3(M);
+            } else {
+                W = inv_sqrt_plane_pair(c.cur_cov + oi * 3, c.tgt_cov + tj * 3, c.kappa);
+            }
             const double Wm[3][3] = {{W.xx, W.xy, W.xz}, {W.xy, W.yy, W.yz}, {W.xz, W.yz, W.zz}};
             // J = W [ -skew(vs) | I ],  r = W d
             double J[3][6], rr[3];
@@ -657,25 +780,33 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
 // workspace layout
 // ----------------------------------------------------------------------------
 struct Layout {
-    size_t off_state, off_pts, off_cov, off_corr, off_d2, off_m1, off_c1, off_m2, off_tgt4, off_meta,
+    size_t off_state, off_pts, off_cov, off_qf, off_corr, off_d2, off_m1, off_c1, off_m2, off_tgt4, off_meta,
         off_partial, off_counter, off_worklist, off_wcount, off_ract, off_done, total;
-    int nt_pad, n_chunks, splits, chunks_per_split, red_blocks, q_tiles;
+    int nt_pad, n_chunks, splits, chunks_per_split, red_blocks, q_tiles, nn_q, nn_tj, cov_stride, smem_pad, nn_mode;
 };
 
 bool make_layout(const orpcd_gicp_params *p, Layout &L)
 {
     if (!p || p->n_units <= 0 || p->n_src <= 0 || p->n_tgt <= 0 || p->n_src_sets <= 0 || p->n_tgt_sets <= 0 ||
-        p->max_iterations < 0 || !(p->max_correspondence_distance > 0) || p->n_units > 65535)
+        p->max_iterations < 0 || !(p->max_correspondence_distance > 0) || p->n_units > 65535 ||
+        (p->cov_mode != 0 && p->cov_mode != 1))
         return false;
     if ((long long)p->n_units * p->n_src > 0x7fffffffLL) return false;
+    if (p->cov_mode == 1 && !(p->gicp_epsilon > 0 && p->gicp_epsilon < 1)) return false;
+    L.cov_stride = p->cov_mode == 0 ? 6 : 3;
     L.nt_pad = (p->n_tgt + NN_CH - 1) / NN_CH * NN_CH;
     L.n_chunks = L.nt_pad / NN_CH;
-    L.q_tiles = (p->n_src + NN_QPB - 1) / NN_QPB;
+    L.nn_q = (p->sweep_q == 4 || p->sweep_q == 8) ? p->sweep_q : (p->n_src >= 2048 ? 8 : 4);
+    L.nn_mode = (p->sweep_mode >= 1 && p->sweep_mode <= 3) ? p->sweep_mode - 1 : 0;
+    L.smem_pad = p->sweep_smem_pad > 0 && p->sweep_smem_pad <= 190000 ? p->sweep_smem_pad : 0;
+    L.nn_tj = (p->sweep_tj == 2 || p->sweep_tj == 4 || p->sweep_tj == 8) ? p->sweep_tj : 4;
+    L.q_tiles = (p->n_src + NN_THREADS * L.nn_q - 1) / (NN_THREADS * L.nn_q);
     int s = p->target_splits;
     if (s <= 0) {
-        // aim for >= ~16 blocks per SM in flight across the grid, keep >= 8 chunks per split
+        // enough blocks for ~12 waves of 148 SMs x 4 resident blocks, >= 8 chunks per split
         const long long blocks = (long long)p->n_units * L.q_tiles;
-        s = (int)((2368 + blocks - 1) / blocks);
+        s = (int)((7104 + blocks - 1) / blocks);
+        if (s > 8) s = 8;
     }
     const int s_max = L.n_chunks / 8 > 1 ? L.n_chunks / 8 : 1;
     if (s > s_max) s = s_max;
@@ -688,7 +819,8 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     auto take = [&](size_t bytes) { size_t r = o; o += orpcd_align_up(bytes, 256); return r; };
     L.off_state = take(U * sizeof(UnitState));
     L.off_pts = take(U * ns * 3 * sizeof(double));
-    L.off_cov = take(U * ns * 6 * sizeof(double));
+    L.off_cov = take(U * ns * L.cov_stride * sizeof(double));
+    L.off_qf = take(U * ns * sizeof(float4));
     L.off_corr = take(U * ns * sizeof(int));
     L.off_d2 = take(U * ns * sizeof(double));
     L.off_m1 = take(U * L.splits * ns * sizeof(float));
@@ -712,11 +844,14 @@ void fill_ctx(const orpcd_gicp_params *p, const Layout &L, void *ws, Ctx &c)
     c.n_units = p->n_units; c.n_src = p->n_src; c.n_tgt = p->n_tgt;
     c.nt_pad = L.nt_pad; c.n_chunks = L.n_chunks; c.splits = L.splits; c.chunks_per_split = L.chunks_per_split;
     c.max_iter = p->max_iterations; c.red_blocks = L.red_blocks;
+    c.cov_mode = p->cov_mode; c.cov_stride = L.cov_stride; c.ignore_done = 0;
     c.r2 = p->max_correspondence_distance * p->max_correspondence_distance;
     c.rel_fit = p->relative_fitness; c.rel_rmse = p->relative_rmse;
+    c.kappa = p->cov_mode == 1 ? 1.0 - p->gicp_epsilon : 0.0;
     c.state = (UnitState *)(w + L.off_state);
     c.cur_pts = (double *)(w + L.off_pts);
     c.cur_cov = (double *)(w + L.off_cov);
+    c.cur_qf = (float4 *)(w + L.off_qf);
     c.corr = (int *)(w + L.off_corr);
     c.corr_d2 = (double *)(w + L.off_d2);
     c.part_m1 = (float *)(w + L.off_m1);
@@ -730,9 +865,40 @@ void fill_ctx(const orpcd_gicp_params *p, const Layout &L, void *ws, Ctx &c)
     c.worklist_count = (int *)(w + L.off_wcount);
     c.done_count = (int *)(w + L.off_done);
     c.round_active = (int *)(w + L.off_ract);
-    c.ignore_done = 0;
     c.tgt_pts = nullptr; c.tgt_cov = nullptr; c.out_T = nullptr; c.out_stats = nullptr; c.trace = nullptr;
     c.out_status = nullptr;
+}
+
+template <int Q, int TJ, int MODE>
+void launch_sweep_m(const Ctx &c, const dim3 &g, int pad, cudaStream_t st)
+{
+    // `pad` bytes of unused dynamic shared memory cap the resident blocks per SM (tuning)
+    if (pad > 0)
+        cudaFuncSetAttribute(nn_sweep_kernel<Q, TJ, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    nn_sweep_kernel<Q, TJ, MODE><<<g, NN_THREADS, pad, st>>>(c);
+}
+
+template <int Q, int TJ>
+void launch_sweep_t(const Ctx &c, const dim3 &g, int pad, int mode, cudaStream_t st)
+{
+    if (mode == 0) launch_sweep_m<Q, TJ, 0>(c, g, pad, st);
+    else if (mode == 2) launch_sweep_m<Q, TJ, 2>(c, g, pad, st);
+    else launch_sweep_m<Q, TJ, 1>(c, g, pad, st);
+}
+
+void launch_sweep(const Ctx &c, const Layout &L, int n_units, cudaStream_t st)
+{
+    const dim3 g(L.q_tiles, L.splits, n_units);
+    const int pad = L.smem_pad;
+    if (L.nn_q == 8) {
+        if (L.nn_tj == 2) launch_sweep_t<8, 2>(c, g, pad, L.nn_mode, st);
+        else if (L.nn_tj == 8) launch_sweep_t<8, 8>(c, g, pad, L.nn_mode, st);
+        else launch_sweep_t<8, 4>(c, g, pad, L.nn_mode, st);
+    } else {
+        if (L.nn_tj == 2) launch_sweep_t<4, 2>(c, g, pad, L.nn_mode, st);
+        else if (L.nn_tj == 8) launch_sweep_t<4, 8>(c, g, pad, L.nn_mode, st);
+        else launch_sweep_t<4, 4>(c, g, pad, L.nn_mode, st);
+    }
 }
 
 }  // namespace
@@ -745,35 +911,35 @@ ORPCD_API size_t orpcd_gicp_batch_workspace_bytes(const orpcd_gicp_params *p)
 }
 
 ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_points,
-                               const double *d_src_cov6, const double *d_tgt_points,
-                               const double *d_tgt_cov6, const int *d_unit_src, const int *d_unit_tgt,
+                               const double *d_src_cov, const double *d_tgt_points,
+                               const double *d_tgt_cov, const int *d_unit_src, const int *d_unit_tgt,
                                void *d_workspace, size_t workspace_bytes, double *d_out_T,
                                double *d_out_stats, int *d_out_status, double *d_trace, double *h_profile,
                                orpcd_stream_t stream)
 {
     Layout L;
     if (!make_layout(p, L)) return ORPCD_ERR_INVALID;
-    if (!d_src_points || !d_src_cov6 || !d_tgt_points || !d_tgt_cov6 || !d_unit_src || !d_unit_tgt ||
+    if (!d_src_points || !d_src_cov || !d_tgt_points || !d_tgt_cov || !d_unit_src || !d_unit_tgt ||
         !d_out_T || !d_out_stats || !d_out_status)
         return ORPCD_ERR_INVALID;
     if (!d_workspace || workspace_bytes < L.total || ((uintptr_t)d_workspace & 255)) return ORPCD_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     Ctx c;
     fill_ctx(p, L, d_workspace, c);
-    c.tgt_pts = d_tgt_points; c.tgt_cov = d_tgt_cov6;
+    c.tgt_pts = d_tgt_points; c.tgt_cov = d_tgt_cov;
     c.out_T = d_out_T; c.out_stats = d_out_stats; c.out_status = d_out_status; c.trace = d_trace;
     int launches = 0;
 
     {
         const int gx = (int)((((size_t)p->n_src * 6) + 255) / 256);
         dim3 grid(gx > 64 ? 64 : gx, p->n_units);
-        init_units_kernel<<<grid, 256, 0, st>>>(c, d_unit_src, d_unit_tgt, d_src_points, d_src_cov6);
+        init_units_kernel<<<grid, 256, 0, st>>>(c, d_unit_src, d_unit_tgt, d_src_points, d_src_cov);
         ORPCD_CHECK_LAUNCH();
         prep_targets_kernel<<<p->n_tgt_sets, 1024, 0, st>>>(c);
         ORPCD_CHECK_LAUNCH();
         launches += 2;
     }
-    const dim3 g_sweep(L.q_tiles, L.splits, p->n_units);
+    const dim3 g_upd((p->n_src + 255) / 256, p->n_units);
     const dim3 g_res((p->n_src + 127) / 128, p->n_units);
     const dim3 g_red(L.red_blocks, p->n_units);
     const int fix_blocks = 148 * 4;
@@ -789,14 +955,16 @@ ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_p
     }
     int rounds = 0;
     for (int round = 0; round <= p->max_iterations; ++round) {
+        update_kernel<<<g_upd, 256, 0, st>>>(c);
         if (prof) cudaEventRecord(ev[2 * round], st);
-        nn_sweep_kernel<<<g_sweep, NN_THREADS, 0, st>>>(c);
+        launch_sweep(c, L, p->n_units, st);
         if (prof) cudaEventRecord(ev[2 * round + 1], st);
         nn_resolve_kernel<<<g_res, 128, 0, st>>>(c, round);
         nn_fix_kernel<<<fix_blocks, 128, 0, st>>>(c, round);
-        reduce_kernel<<<g_red, RED_THREADS, 0, st>>>(c, round);
+        if (p->cov_mode == 0) reduce_kernel<0><<<g_red, RED_THREADS, 0, st>>>(c, round);
+        else reduce_kernel<1><<<g_red, RED_THREADS, 0, st>>>(c, round);
         ORPCD_CHECK_LAUNCH();
-        launches += 4;
+        launches += 5;
         rounds = round + 1;
         if (p->poll_interval > 0 && round < p->max_iterations && (round + 1) % p->poll_interval == 0) {
             int done = 0;
@@ -853,8 +1021,7 @@ ORPCD_API int orpcd_gicp_sweep_only(const orpcd_gicp_params *p, void *d_workspac
     Ctx c;
     fill_ctx(p, L, d_workspace, c);
     c.ignore_done = 1;
-    const dim3 g_sweep(L.q_tiles, L.splits, p->n_units);
-    nn_sweep_kernel<<<g_sweep, NN_THREADS, 0, (cudaStream_t)stream>>>(c);
+    launch_sweep(c, L, p->n_units, (cudaStream_t)stream);
     ORPCD_CHECK_LAUNCH();
     return ORPCD_OK;
 }

@@ -108,6 +108,17 @@ class Aligner:
             clouds[n] = np.dot(source, r) + t
         return rots, trans, clouds
 
+    def _batch_kwargs(self, source):
+        """Tell optimizers that understand it that every start is a rigid image of ``source``."""
+        import inspect
+
+        try:
+            if "rigid_base" in inspect.signature(self._optimizer.optimize_batch).parameters:
+                return {"rigid_base": source}
+        except (TypeError, ValueError):
+            pass
+        return {}
+
     @staticmethod
     def _compose(rot, trans, current):
         """Start pose followed by the optimizer's result (reference: Aligner.py:196-201)."""
@@ -137,7 +148,8 @@ class Aligner:
             return self._multistart_sequential(source, target)
         rots, trans, clouds = self._draw_starts(source)
         res = self._optimizer.optimize_batch(clouds, np.asarray(target, dtype=np.float64)[None],
-                                             np.arange(self._attempts), np.zeros(self._attempts, dtype=np.int32))
+                                             np.arange(self._attempts), np.zeros(self._attempts, dtype=np.int32),
+                                             **self._batch_kwargs(source))
         self.n_units_evaluated += self._attempts
         return self._best_of_starts(rots, trans, res.transforms, res.rmse, res.status)
 
@@ -177,7 +189,7 @@ class Aligner:
         targets = np.stack([target * (scale + st) for st in steps], axis=0)   # Aligner.py:221-222
         unit_src = np.arange(6 * A, dtype=np.int32)
         unit_tgt = np.repeat(np.arange(6, dtype=np.int32), A)
-        res = self._optimizer.optimize_batch(sources, targets, unit_src, unit_tgt)
+        res = self._optimizer.optimize_batch(sources, targets, unit_src, unit_tgt, **self._batch_kwargs(source))
         self.n_units_evaluated += 6 * A
         return steps, starts, states, res
 

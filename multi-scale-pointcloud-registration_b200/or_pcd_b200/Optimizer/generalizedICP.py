@@ -49,6 +49,11 @@ class GeneralizedICP(IOptimizer):
         self._max_correspondence_distance = max_correspondence_distance
         self._max_iterations = max_iterations
         self._ws = None
+        self._base_key = None         # (shape, digest) of the cached base source cloud
+        self._base_lists = None       # its candidate neighbour lists on the device
+        # closed-form whitening of plane-covariance pairs (C ABI cov_mode 1); False runs the
+        # generic 3x3 covariance path with a Jacobi eigen-solve per correspondence
+        self.analytic_whitening = True
         self.profile = False          # set True to collect sweep timings in BatchResult.profile
         self.last_profile = None
 
@@ -62,18 +67,24 @@ class GeneralizedICP(IOptimizer):
 
     # ------------------------------------------------------------------ batched API
     def optimize_batch(self, sources, targets, unit_src: Sequence[int], unit_tgt: Sequence[int],
-                       poll_interval: int = 0) -> BatchResult:
+                       poll_interval: int = 0, rigid_base: Optional[np.ndarray] = None) -> BatchResult:
         """Run ``len(unit_src)`` independent registrations concurrently.
 
         sources: (S,Ns,3) host float64 array (or CUDA tensor), the initial source clouds;
         targets: (C,Nt,3); unit u registers sources[unit_src[u]] onto targets[unit_tgt[u]].
+        rigid_base: optional (Ns,3) cloud of which every source is a rigid image (the Aligner's
+        random starts): their 20-NN graphs are then re-ranked from the base cloud's neighbour
+        lists instead of searched from scratch -- same result, certified per point.
         Nothing raises for a unit whose final inlier RMSE is 0; it is flagged in ``status``."""
         t = _lib.torch()
         d_src = sources if hasattr(sources, "is_cuda") else _lib.to_device(np.asarray(sources))
         d_tgt = targets if hasattr(targets, "is_cuda") else _lib.to_device(np.asarray(targets))
         us = t.as_tensor(np.asarray(unit_src, dtype=np.int32)).to("cuda")
         ut = t.as_tensor(np.asarray(unit_tgt, dtype=np.int32)).to("cuda")
-        d_res = self.optimize_batch_device(d_src, d_tgt, us, ut, poll_interval=poll_interval)
+        src_cov = None
+        if rigid_base is not None and d_src.shape[1] > self.RERANK_KC:
+            src_cov = self._rigid_source_covariances(rigid_base, d_src)
+        d_res = self.optimize_batch_device(d_src, d_tgt, us, ut, poll_interval=poll_interval, src_cov=src_cov)
         T = d_res.T.cpu().numpy()
         stats = d_res.stats.cpu().numpy()
         status = d_res.status.cpu().numpy()
@@ -82,18 +93,42 @@ class GeneralizedICP(IOptimizer):
         return BatchResult(T, stats[:, 1].copy(), stats[:, 0].copy(), stats[:, 2].astype(np.int64), status,
                            d_res.profile)
 
+    RERANK_KC = 48   # candidates kept per point of the base cloud (k = 20 are needed)
+
+    def _rigid_source_covariances(self, rigid_base: np.ndarray, d_src):
+        """GICP covariances of rigid images of ``rigid_base`` via re-ranked neighbour lists."""
+        import hashlib
+
+        t = _lib.torch()
+        base = np.ascontiguousarray(rigid_base, dtype=np.float64)
+        key = (base.shape, hashlib.blake2b(base.tobytes(), digest_size=16).digest())
+        if key != self._base_key:
+            self._base_lists = ops.knn_candidates(_lib.to_device(base), self.RERANK_KC)
+            self._base_key = key
+        cand, bound = self._base_lists
+        factor = t.full((d_src.shape[0],), 1.0 - 1e-9, dtype=t.float64, device="cuda")
+        idx, d2, n_fixed = ops.knn_rerank(cand, bound, d_src, factor, GICP_COVARIANCE_KNN)
+        self.last_rerank_fixed = n_fixed
+        ax = self.analytic_whitening
+        return ops.normals_cov_from_knn(d_src, idx, d2, gicp_eps=GICP_EPSILON, want_gicp_cov=not ax,
+                                        want_gicp_axis=ax)["gicp_axis" if ax else "gicp_cov"]
+
     def optimize_batch_device(self, d_src, d_tgt, unit_src, unit_tgt, poll_interval: int = 0, want_trace=False,
                               src_cov=None, tgt_cov=None):
         """Device-resident variant: CUDA tensors in, ``ops.GicpBatchResult`` (CUDA tensors) out."""
+        ax = self.analytic_whitening
+        key = "gicp_axis" if ax else "gicp_cov"
         if src_cov is None:
-            src_cov = ops.normals_cov(d_src, knn=GICP_COVARIANCE_KNN, gicp_eps=GICP_EPSILON)["gicp_cov"]
+            src_cov = ops.normals_cov(d_src, knn=GICP_COVARIANCE_KNN, gicp_eps=GICP_EPSILON, want_gicp_cov=not ax,
+                                      want_gicp_axis=ax)[key]
         if tgt_cov is None:
-            tgt_cov = ops.normals_cov(d_tgt, knn=GICP_COVARIANCE_KNN, gicp_eps=GICP_EPSILON)["gicp_cov"]
+            tgt_cov = ops.normals_cov(d_tgt, knn=GICP_COVARIANCE_KNN, gicp_eps=GICP_EPSILON, want_gicp_cov=not ax,
+                                      want_gicp_axis=ax)[key]
         res = ops.gicp_batch(d_src, src_cov, d_tgt, tgt_cov, unit_src, unit_tgt,
                              max_correspondence_distance=self._max_correspondence_distance,
                              max_iterations=self._max_iterations, relative_fitness=ICP_RELATIVE_FITNESS,
                              relative_rmse=ICP_RELATIVE_RMSE, poll_interval=poll_interval, profile=self.profile,
-                             want_trace=want_trace, ws=self._ws)
+                             want_trace=want_trace, ws=self._ws, gicp_epsilon=GICP_EPSILON)
         self._ws = res.workspace
         return res
 

@@ -34,9 +34,15 @@ class GicpParams(C.Structure):
         ("target_splits", C.c_int),
         ("poll_interval", C.c_int),
         ("profile", C.c_int),
+        ("cov_mode", C.c_int),
         ("max_correspondence_distance", C.c_double),
         ("relative_fitness", C.c_double),
         ("relative_rmse", C.c_double),
+        ("gicp_epsilon", C.c_double),
+        ("sweep_q", C.c_int),
+        ("sweep_tj", C.c_int),
+        ("sweep_smem_pad", C.c_int),
+        ("sweep_mode", C.c_int),
     ]
 
 
@@ -62,6 +68,14 @@ def lib():
     L.orpcd_error_string.argtypes = [ip]
     L.orpcd_knn_exact.restype = ip
     L.orpcd_knn_exact.argtypes = [vp, ip, ll, vp, ip, ll, ip, ip, vp, vp, vp]
+    L.orpcd_knn_candidate_bound.restype = ip
+    L.orpcd_knn_candidate_bound.argtypes = [vp, vp, ip, ip, vp, vp]
+    L.orpcd_knn_rerank_workspace_bytes.restype = sz
+    L.orpcd_knn_rerank_workspace_bytes.argtypes = [ip, ip]
+    L.orpcd_knn_rerank.restype = ip
+    L.orpcd_knn_rerank.argtypes = [vp, vp, ip, vp, ip, ll, ip, vp, ip, vp, vp, vp, sz, vp]
+    L.orpcd_normals_cov_from_knn.restype = ip
+    L.orpcd_normals_cov_from_knn.argtypes = [vp, ip, ll, ip, ip, vp, vp, dp, dp, vp, vp, vp, vp, vp, vp]
     L.orpcd_sor_workspace_bytes.restype = sz
     L.orpcd_sor_workspace_bytes.argtypes = [ip, ip]
     L.orpcd_sor_mask.restype = ip
@@ -69,7 +83,7 @@ def lib():
     L.orpcd_normals_workspace_bytes.restype = sz
     L.orpcd_normals_workspace_bytes.argtypes = [ip, ip, ip]
     L.orpcd_normals_cov.restype = ip
-    L.orpcd_normals_cov.argtypes = [vp, ip, ll, ip, ip, dp, dp, vp, sz, vp, vp, vp, vp, vp]
+    L.orpcd_normals_cov.argtypes = [vp, ip, ll, ip, ip, dp, dp, vp, sz, vp, vp, vp, vp, vp, vp]
     L.orpcd_apply_scale_batch.restype = ip
     L.orpcd_apply_scale_batch.argtypes = [vp, ip, vp, ip, vp, vp]
     L.orpcd_gicp_batch_workspace_bytes.restype = sz
@@ -83,6 +97,10 @@ def lib():
     L.orpcd_ffma_burn.argtypes = [ip, ip, vp, vp]
     L.orpcd_ffma2_burn.restype = ip
     L.orpcd_ffma2_burn.argtypes = [ip, ip, vp, vp]
+    L.orpcd_dfma_burn.restype = ip
+    L.orpcd_dfma_burn.argtypes = [ip, ip, vp, vp]
+    L.orpcd_mix_burn.restype = ip
+    L.orpcd_mix_burn.argtypes = [ip, ip, ip, vp, vp]
     _lib = L
     return L
 
@@ -112,10 +130,19 @@ def stream_ptr() -> int:
 
 
 def to_device(a: np.ndarray, dtype=np.float64):
-    """Host ndarray -> contiguous CUDA tensor (H2D copy on the current stream)."""
+    """Host ndarray -> contiguous CUDA tensor (H2D copy on the current stream).  Arrays that
+    live in pinned memory (see ``pinned_empty``) are copied asynchronously."""
     t = torch()
     a = np.ascontiguousarray(a, dtype=dtype)
-    return t.from_numpy(a).to("cuda", non_blocking=False)
+    h = t.from_numpy(a)
+    return h.to("cuda", non_blocking=bool(h.is_pinned()))
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array backed by page-locked host memory (the tensor is kept alive by the array)."""
+    t = torch()
+    td = {np.float64: t.float64, np.float32: t.float32, np.int32: t.int32}[dtype]
+    return t.empty(tuple(shape), dtype=td, pin_memory=True).numpy()   # the array keeps the tensor alive
 
 
 def workspace(nbytes: int):

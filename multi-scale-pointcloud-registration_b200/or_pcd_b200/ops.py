@@ -42,6 +42,61 @@ def knn_exact(points, queries, k: int):
     return (idx[0], d2[0]) if squeeze else (idx, d2)
 
 
+def knn_candidates(base_points, kc: int):
+    """Neighbour lists of a base cloud for later re-ranking: (cand_idx int32 [N,kc], bound float64 [N])."""
+    t = _t()
+    base_points = _f64(base_points)
+    N = base_points.shape[0]
+    idx, d2 = knn_exact(base_points, base_points, kc)
+    bound = t.empty(N, dtype=t.float64, device="cuda")
+    check(_lib.lib().orpcd_knn_candidate_bound(idx.data_ptr(), d2.data_ptr(), N, kc, bound.data_ptr(),
+                                               _lib.stream_ptr()), "orpcd_knn_candidate_bound")
+    launch_counter["kernels"] += 1
+    return idx, bound
+
+
+def knn_rerank(cand_idx, bound, moved_points, factor, k: int):
+    """Exact kNN of moved copies [B,N,3] of the base cloud from its candidate lists.
+    factor: float64 [B] lower bound of moved_d2/base_d2.  Returns (idx [B,N,k], d2 [B,N,k])."""
+    t = _t()
+    moved_points, factor = _f64(moved_points), _f64(factor)
+    B, N, _ = moved_points.shape
+    kc = cand_idx.shape[1]
+    L = _lib.lib()
+    ws = _lib.workspace(L.orpcd_knn_rerank_workspace_bytes(N, B))
+    idx = t.empty((B, N, k), dtype=t.int32, device="cuda")
+    d2 = t.empty((B, N, k), dtype=t.float64, device="cuda")
+    check(L.orpcd_knn_rerank(cand_idx.data_ptr(), bound.data_ptr(), kc, moved_points.data_ptr(), N, N * 3, B,
+                             factor.data_ptr(), k, idx.data_ptr(), d2.data_ptr(), ws.data_ptr(), ws.numel(),
+                             _lib.stream_ptr()), "orpcd_knn_rerank")
+    launch_counter["kernels"] += 2
+    n_fixed = ws[:4].view(t.int32)   # device scalar: points that needed the exact fallback
+    return idx, d2, n_fixed
+
+
+def normals_cov_from_knn(points, nn_idx, nn_d2, radius: float = 0.0, gicp_eps: float = 1e-3, want_normals=False,
+                         want_cov=False, want_gicp_cov=True, want_gicp_axis=False) -> Dict[str, object]:
+    """As normals_cov, from neighbour lists [B,N,k] computed elsewhere."""
+    t = _t()
+    points = _f64(points)
+    B, N, _ = points.shape
+    knn = nn_idx.shape[2]
+    nrm = t.empty((B, N, 3), dtype=t.float64, device="cuda") if want_normals else None
+    cov = t.empty((B, N, 6), dtype=t.float64, device="cuda") if want_cov else None
+    gc = t.empty((B, N, 6), dtype=t.float64, device="cuda") if want_gicp_cov else None
+    ax = t.empty((B, N, 3), dtype=t.float64, device="cuda") if want_gicp_axis else None
+    p = lambda x: x.data_ptr() if x is not None else None
+    check(_lib.lib().orpcd_normals_cov_from_knn(points.data_ptr(), N, N * 3, B, knn, nn_idx.data_ptr(),
+                                                nn_d2.data_ptr(), float(radius), float(gicp_eps), p(nrm), p(cov),
+                                                p(gc), p(ax), None, _lib.stream_ptr()), "orpcd_normals_cov_from_knn")
+    launch_counter["kernels"] += 1
+    out = {}
+    for k_, v in (("normal", nrm), ("cov", cov), ("gicp_cov", gc), ("gicp_axis", ax)):
+        if v is not None:
+            out[k_] = v
+    return out
+
+
 def sor_mask(points, nb_neighbors: int, std_ratio: float):
     """(mask uint8 [N], avg float64 [N], stats float64 [4])."""
     t = _t()
@@ -59,7 +114,7 @@ def sor_mask(points, nb_neighbors: int, std_ratio: float):
 
 
 def normals_cov(points, knn: int = 20, radius: float = 0.0, gicp_eps: float = 1e-3, want_normals=False,
-                want_cov=False, want_gicp_cov=True, want_nn=False) -> Dict[str, object]:
+                want_cov=False, want_gicp_cov=True, want_nn=False, want_gicp_axis=False) -> Dict[str, object]:
     """Normals / covariances / GICP covariances for clouds [B,N,3] (or [N,3])."""
     t = _t()
     squeeze = points.dim() == 2
@@ -74,11 +129,12 @@ def normals_cov(points, knn: int = 20, radius: float = 0.0, gicp_eps: float = 1e
     cov = t.empty((B, N, 6), dtype=t.float64, device="cuda") if want_cov else None
     gc = t.empty((B, N, 6), dtype=t.float64, device="cuda") if want_gicp_cov else None
     nn = t.empty((B, N, knn), dtype=t.int32, device="cuda") if want_nn else None
+    ax = t.empty((B, N, 3), dtype=t.float64, device="cuda") if want_gicp_axis else None
     p = lambda x: x.data_ptr() if x is not None else None
     check(L.orpcd_normals_cov(points.data_ptr(), N, N * 3, B, knn, float(radius), float(gicp_eps), ws.data_ptr(),
-                              ws.numel(), p(nrm), p(cov), p(gc), p(nn), _lib.stream_ptr()), "orpcd_normals_cov")
+                              ws.numel(), p(nrm), p(cov), p(gc), p(ax), p(nn), _lib.stream_ptr()), "orpcd_normals_cov")
     launch_counter["kernels"] += 2
-    for k, v in (("normal", nrm), ("cov", cov), ("gicp_cov", gc), ("nn_idx", nn)):
+    for k, v in (("normal", nrm), ("cov", cov), ("gicp_cov", gc), ("nn_idx", nn), ("gicp_axis", ax)):
         if v is not None:
             out[k] = v[0] if squeeze else v
     return out
@@ -102,16 +158,22 @@ class GicpBatchResult:
 
 def gicp_batch(src_points, src_cov6, tgt_points, tgt_cov6, unit_src, unit_tgt, max_correspondence_distance=0.5,
                max_iterations=100, relative_fitness=1e-6, relative_rmse=1e-6, target_splits=0, poll_interval=0,
-               profile=False, want_trace=False, ws=None) -> GicpBatchResult:
-    """Batched GICP.  src_* [S,Ns,3]/[S,Ns,6], tgt_* [C,Nt,3]/[C,Nt,6], unit_* int32 [U]."""
+               profile=False, want_trace=False, ws=None, gicp_epsilon=1e-3, sweep_q=0, sweep_tj=0, sweep_smem_pad=0, sweep_mode=0) -> GicpBatchResult:
+    """Batched GICP.  src_points [S,Ns,3], tgt_points [C,Nt,3], unit_* int32 [U]; the covariance
+    inputs are either [.,N,6] covariance matrices (generic path) or [.,N,3] plane axes (closed-form
+    whitening, ``cov_mode`` 1 of the C ABI) -- the last dimension selects the mode."""
     t = _t()
     src_points, src_cov6, tgt_points, tgt_cov6 = _f64(src_points), _f64(src_cov6), _f64(tgt_points), _f64(tgt_cov6)
     S, Ns, _ = src_points.shape
     Cn, Nt, _ = tgt_points.shape
     U = unit_src.shape[0]
     assert unit_src.dtype == t.int32 and unit_tgt.dtype == t.int32 and unit_src.is_cuda and unit_tgt.is_cuda
+    assert src_cov6.shape[-1] == tgt_cov6.shape[-1] and src_cov6.shape[-1] in (3, 6)
+    assert src_cov6.shape[:2] == (S, Ns) and tgt_cov6.shape[:2] == (Cn, Nt)
+    cov_mode = 1 if src_cov6.shape[-1] == 3 else 0
     prm = GicpParams(U, Ns, Nt, S, Cn, int(max_iterations), int(target_splits), int(poll_interval), int(bool(profile)),
-                     float(max_correspondence_distance), float(relative_fitness), float(relative_rmse))
+                     cov_mode, float(max_correspondence_distance), float(relative_fitness), float(relative_rmse),
+                     float(gicp_epsilon), int(sweep_q), int(sweep_tj), int(sweep_smem_pad), int(sweep_mode))
     L = _lib.lib()
     need = L.orpcd_gicp_batch_workspace_bytes(C.byref(prm))
     if need == 0:
@@ -147,5 +209,13 @@ def ffma_burn(blocks: int, iters: int, packed: bool = False):
     sink = t.empty(blocks * 256, dtype=t.float32, device="cuda")
     fn = _lib.lib().orpcd_ffma2_burn if packed else _lib.lib().orpcd_ffma_burn
     check(fn(blocks, iters, sink.data_ptr(), _lib.stream_ptr()), "orpcd_ffma_burn")
+    launch_counter["kernels"] += 1
+    return sink
+
+
+def dfma_burn(blocks: int, iters: int):
+    t = _t()
+    sink = t.empty(blocks * 256, dtype=t.float64, device="cuda")
+    check(_lib.lib().orpcd_dfma_burn(blocks, iters, sink.data_ptr(), _lib.stream_ptr()), "orpcd_dfma_burn")
     launch_counter["kernels"] += 1
     return sink

@@ -73,7 +73,7 @@ def test_normals_and_gicp_covariances(oracle, armadillo_pair):
     s, t, _ = armadillo_pair
     for cloud, radius in ((s, 0.0), (t, 0.0), (s, 0.1)):
         out = ops.normals_cov(_dev(cloud), knn=20, radius=radius, gicp_eps=1e-3, want_normals=True, want_cov=True,
-                              want_gicp_cov=True, want_nn=True)
+                              want_gicp_cov=True, want_nn=True, want_gicp_axis=True)
         ref = oracle.normals(cloud, 20, radius, 1e-3)
         assert np.array_equal(out["nn_idx"].cpu().numpy(), ref["nn_idx"])       # neighbour lists bit-exact
         cov = out["cov"].cpu().numpy()
@@ -85,6 +85,10 @@ def test_normals_and_gicp_covariances(oracle, armadillo_pair):
         g = ref["gicp_cov"]
         g6 = np.stack([g[:, 0, 0], g[:, 0, 1], g[:, 0, 2], g[:, 1, 1], g[:, 1, 2], g[:, 2, 2]], 1)
         assert np.abs(out["gicp_cov"].cpu().numpy() - g6).max() < 1e-12
+        # plane axis a: C = I - (1 - eps) a a^T reproduces the covariance (closed-form whitening input)
+        a = out["gicp_axis"].cpu().numpy()
+        Ca = np.eye(3)[None] - (1 - 1e-3) * a[:, :, None] * a[:, None, :]
+        assert np.abs(Ca - g).max() < 1e-12
 
 
 def test_apply_scale_batch_bit_exact():
@@ -110,7 +114,8 @@ def _rot_angle(Ra, Rb):
     return np.arccos(np.clip(c, -1, 1))
 
 
-def test_gicp_batch_matches_oracle_traces(oracle, armadillo_pair):
+@pytest.mark.parametrize("analytic", [True, False])
+def test_gicp_batch_matches_oracle_traces(oracle, armadillo_pair, analytic):
     """Several starts x two scale candidates in one batch vs the oracle one by one.
     Tolerances (north_star): rotation 1e-4 rad, translation 1e-5 x bbox diagonal,
     fitness/rmse 1e-5 relative; iteration counts must agree."""
@@ -129,6 +134,7 @@ def test_gicp_batch_matches_oracle_traces(oracle, armadillo_pair):
     unit_src = np.array([0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5], dtype=np.int32)
     unit_tgt = np.array([0] * 6 + [1] * 6, dtype=np.int32)
     opt = GeneralizedICP()
+    opt.analytic_whitening = analytic
     t_ = _lib.torch()
     res = opt.optimize_batch_device(_lib.to_device(sources), _lib.to_device(targets),
                                     t_.as_tensor(unit_src).cuda(), t_.as_tensor(unit_tgt).cuda(), want_trace=True)
@@ -176,3 +182,42 @@ def test_gicp_small_and_ragged_sizes(oracle):
         ref_T, ref_rmse = oracle.GeneralizedICP().optimize(src, tgt)
         assert abs(rmse - ref_rmse) <= 1e-5 * ref_rmse, (ns, nt)
         assert _rot_angle(T[:3, :3], ref_T[:3, :3]) < 1e-4
+
+
+def test_knn_rerank_equals_exact_knn(oracle, armadillo_pair):
+    """Re-ranked neighbour lists of rigidly moved / scaled copies == brute-force kNN on the copies,
+    including the certified fallback (forced by a factor that certifies nothing)."""
+    from or_pcd_b200 import _lib, ops
+
+    s, t, _ = armadillo_pair
+    rng = np.random.default_rng(4)
+    moved = []
+    for _ in range(3):
+        a, b, g = rng.uniform(-np.pi / 2, np.pi / 2, 3)
+        moved.append(s @ _rot(a, b, g) + rng.standard_normal(3) * 0.1)
+    scale = np.array([1.2, 0.9, 1.0])
+    moved.append(s * scale)
+    moved = np.stack(moved)
+    t_ = _lib.torch()
+    cand, bound = ops.knn_candidates(_dev(s), 48)
+    for factors, expect_all_fixed in (([1 - 1e-9] * 3 + [0.81 * (1 - 1e-9)], False), ([0.0] * 4, True)):
+        idx, d2, n_fixed = ops.knn_rerank(cand, bound, _dev(moved), _dev(np.array(factors)), 20)
+        for b in range(moved.shape[0]):
+            oi, od = oracle.knn(moved[b], moved[b], 20)
+            assert np.array_equal(idx[b].cpu().numpy(), oi), b
+            assert np.array_equal(d2[b].cpu().numpy(), od), b
+        nf = int(n_fixed.cpu().numpy()[0])
+        assert (nf == moved.shape[0] * s.shape[0]) if expect_all_fixed else (nf < 0.05 * s.shape[0] * moved.shape[0])
+
+
+def test_optimize_batch_rigid_base_same_result(oracle, armadillo_pair):
+    from or_pcd_b200.Optimizer import GeneralizedICP
+
+    s, t, _ = armadillo_pair
+    rng = np.random.default_rng(8)
+    srcs = np.stack([s @ _rot(*rng.uniform(-1, 1, 3)) + rng.standard_normal(3) * 0.1 for _ in range(4)])
+    opt = GeneralizedICP()
+    a = opt.optimize_batch(srcs, t[None], [0, 1, 2, 3], [0, 0, 0, 0])
+    b = opt.optimize_batch(srcs, t[None], [0, 1, 2, 3], [0, 0, 0, 0], rigid_base=s)
+    assert np.array_equal(a.transforms, b.transforms) and np.array_equal(a.rmse, b.rmse)
+    assert np.array_equal(a.iterations, b.iterations)

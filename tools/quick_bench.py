@@ -34,10 +34,11 @@ def main():
     d_s, d_t = _lib.to_device(sources), _lib.to_device(targets)
     us = torch.arange(n_units, dtype=torch.int32, device="cuda")
     ut = (torch.arange(n_units, dtype=torch.int32, device="cuda") * 6 // n_units).to(torch.int32)
-    for rep in range(3):
+    for rep in range(int(os.environ.get("REPS", "3"))):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = opt.optimize_batch_device(d_s, d_t, us, ut)
+        sc = opt._rigid_source_covariances(src, d_s) if os.environ.get('RIGID', '1') == '1' else None
+        res = opt.optimize_batch_device(d_s, d_t, us, ut, src_cov=sc)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         p = res.profile
