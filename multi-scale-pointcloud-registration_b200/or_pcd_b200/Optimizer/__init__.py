@@ -1,2 +1,3 @@
-from .iOptimizer import IOptimizer
+from .iOptimizer import BatchResult, IOptimizer
 from .generalizedICP import GeneralizedICP
+from .shardedOptimizer import ShardedOptimizer

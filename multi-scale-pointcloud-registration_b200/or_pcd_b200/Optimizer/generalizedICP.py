@@ -1,7 +1,7 @@
 """Generalized-ICP inner block on the B200
 (reference: Optimizer/generalizedICP.py:15-89, which wraps Open3D's
 registration_generalized_icp; algorithm SURVEY.md A.3-A.6)."""
-from typing import NamedTuple, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -15,21 +15,12 @@ from ..utils.constants import (
     MAXIMUM_CORRESPONDENCE_DISTANCE,
 )
 from ..utils.logger_factory import LoggerFactory
-from .iOptimizer import IOptimizer
+from .iOptimizer import BatchResult, IOptimizer
 
 _ZERO_LOSS_MSG = (
     "Optimization failed with loss = 0. Parameters are not well set. "
     "Probably due to maximum_correspondence_distance set too low."
 )
-
-
-class BatchResult(NamedTuple):
-    transforms: np.ndarray   # (U,4,4) rotation block transposed (row-vector convention), as optimize()
-    rmse: np.ndarray         # (U,)
-    fitness: np.ndarray      # (U,)
-    iterations: np.ndarray   # (U,) int
-    status: np.ndarray       # (U,) 0 ok, 1 = inlier_rmse == 0 (optimize() would raise ValueError)
-    profile: list
 
 
 class GeneralizedICP(IOptimizer):

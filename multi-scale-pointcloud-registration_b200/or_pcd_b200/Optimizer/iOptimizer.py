@@ -5,9 +5,20 @@
 registration of a poll round concurrently; optimizers without it still plug in
 and are driven one call at a time."""
 from abc import ABC, abstractmethod
-from typing import Tuple
+from typing import NamedTuple, Tuple
 
 import numpy as np
+
+
+class BatchResult(NamedTuple):
+    """What ``optimize_batch`` returns: one entry per unit (inner registration)."""
+
+    transforms: np.ndarray   # (U,4,4) rotation block transposed (row-vector convention), as optimize()
+    rmse: np.ndarray         # (U,)
+    fitness: np.ndarray      # (U,)
+    iterations: np.ndarray   # (U,) int
+    status: np.ndarray       # (U,) 0 ok, 1 = optimize() would raise (GICP: inlier_rmse == 0; FGR: no correspondence)
+    profile: list
 
 
 class IOptimizer(ABC):

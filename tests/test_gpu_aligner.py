@@ -1,0 +1,70 @@
+"""End-to-end: Aligner.align() with the B200 GeneralizedICP / SOR blocks on the Armadillo
+pair of BASELINE config 1 against the committed oracle run (tests/golden/golden_v1.npz:
+870 sequential inner registrations of the restated reference).  Tolerances from
+BASELINE.json north_star: chosen scale triple identical; rmse 1e-5 relative; rotation
+1e-4 rad; translation 1e-5 x bbox diagonal; masks bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
+
+
+def _rot_angle(Ra, Rb):
+    return np.arccos(np.clip((np.trace(Ra.T @ Rb) - 1) / 2, -1, 1))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with np.load(GOLDEN) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_preprocessing_blocks_match_golden(golden):
+    from or_pcd_b200.data import load_sample_cloud
+    from or_pcd_b200.Preprocessor import Preprocessor, RandomDownsampler, SOR
+
+    for tag, names in (("back", ("ArmadilloBack_330", "ArmadilloBack_0")),
+                       ("onhead", ("ArmadilloOnHeadMultiple_150", "ArmadilloOnHeadMultiple_240"))):
+        np.random.seed(0)
+        for name in names:
+            blocks = [RandomDownsampler(5000), SOR()]
+            out = Preprocessor(blocks).preprocess(load_sample_cloud(name))
+            assert np.array_equal(np.packbits(blocks[2].last_mask), golden[f"{tag}_{name}_sor_mask"])   # bit-exact
+            assert out.shape[0] == int(golden[f"{tag}_{name}_n_after"])
+            assert np.isclose(blocks[0].scale, golden[f"{tag}_{name}_scale"], rtol=1e-14)
+        assert np.array_equal(np.random.get_state()[1][:8], golden[f"{tag}_rng_after_pre"])
+
+
+def test_align_config1_reproduces_the_oracle_run(golden):
+    from or_pcd_b200.Aligner.Aligner import Aligner
+    from or_pcd_b200.data import load_sample_cloud
+    from or_pcd_b200.Optimizer import GeneralizedICP
+    from or_pcd_b200.Preprocessor import Preprocessor, RandomDownsampler, SOR
+
+    np.random.seed(0)
+    al = Aligner(Preprocessor([RandomDownsampler(5000), SOR()]), Preprocessor([RandomDownsampler(5000), SOR()]),
+                 GeneralizedICP())
+    T, m, scale, errors = al.align(load_sample_cloud("ArmadilloBack_330"), load_sample_cloud("ArmadilloBack_0"),
+                                   refine_registration=False)
+    # decisions: the same candidates, in the same order, with the same verdicts
+    acc = np.array([d["accepted"] for d in al.decision_log])
+    assert np.array_equal(acc, golden["align_back_log_accepted"])
+    assert np.array_equal(np.array([d["scale"].ravel() for d in al.decision_log]), golden["align_back_log_scale"])
+    gm = golden["align_back_log_metric"]
+    lm = np.array([d["metric"] for d in al.decision_log])
+    assert np.abs(lm - gm).max() <= 1e-5 * gm.min()                       # rmse 1e-5 relative
+    assert np.array_equal(scale, golden["align_back_scale"])              # chosen scale triple identical
+    assert abs(m - float(golden["align_back_metric"])) <= 1e-5 * m
+    assert np.allclose(errors, golden["align_back_errors"], rtol=1e-5, atol=0)
+    diag = np.linalg.norm(al.target_pre.max(0) - al.target_pre.min(0))
+    assert _rot_angle(T[:3, :3], golden["align_back_T"][:3, :3]) < 1e-4
+    assert np.linalg.norm(T[:3, 3] - golden["align_back_T"][:3, 3]) < 1e-5 * diag
+    # sequential-equivalent work and RNG position
+    assert al.n_optimize_calls == int(golden["align_back_calls"]) == 870
+    assert np.array_equal(np.random.get_state()[1][:8], golden["align_back_rng_after"])
+    # record how tight the accept margins were (decision parity is only meaningful if they
+    # exceed the run-to-run agreement)
+    print("max |rmse_gpu - rmse_oracle| over the decision log:", np.abs(lm - gm).max())

@@ -1,0 +1,156 @@
+"""Host-side logic of the plugin layer, no GPU needed: the preprocessing blocks that stay
+in numpy, and the Aligner's speculative batch + replay of the reference's sequential
+poll order, accept decisions, RNG consumption and exception behaviour
+(reference: Aligner/Aligner.py:164-317)."""
+import numpy as np
+import pytest
+
+from fakes import FakeBatched, FakeSequential
+
+
+def _cloud(seed, n=600):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((n, 3)) * np.array([1.0, 0.7, 0.4]) + rng.standard_normal(3)
+
+
+def test_radius_scaler_matches_oracle_and_definition(oracle):
+    from or_pcd_b200.Preprocessor import RadiusScaler
+
+    c = _cloud(0, 3000)
+    a, b = RadiusScaler(), oracle.RadiusScaler()
+    out = a.process(c)
+    assert np.array_equal(out, b.process(c))
+    assert np.array_equal(a.mean, b.mean) and a.scale == b.scale and a.mean.shape == (1, 3)
+    assert abs(np.linalg.norm(out, axis=1).max() - 1.0) < 1e-12          # radiusScaler.py:25-30
+    assert np.abs(out.mean(0)).max() < 1e-12
+
+
+def test_random_downsampler_consumes_the_global_stream(oracle):
+    from or_pcd_b200.Preprocessor import RandomDownsampler
+
+    c = _cloud(1, 2000)
+    np.random.seed(5)
+    out = RandomDownsampler(300).process(c)
+    after = np.random.get_state()[1].copy()
+    np.random.seed(5)
+    keep = np.random.choice(2000, 300, replace=False)                     # randomDownsampler.py:35-37
+    assert np.array_equal(out, c[keep])
+    assert np.array_equal(after, np.random.get_state()[1])
+    # non-positive size falls back to the default with a log line, not an exception
+    assert RandomDownsampler(0)._sample_size == 4096
+
+
+def test_preprocessor_inserts_radius_scaler_in_callers_list():
+    from or_pcd_b200.Preprocessor import BaseScaler, Preprocessor, RadiusScaler, RandomDownsampler
+
+    blocks = [RandomDownsampler(100)]
+    p = Preprocessor(blocks)
+    assert isinstance(blocks[0], RadiusScaler) and p.preprocessor_blocks is blocks   # preprocessor.py:19-24
+    blocks2 = [RandomDownsampler(100), RadiusScaler()]
+    Preprocessor(blocks2)
+    assert len(blocks2) == 2 and isinstance(blocks2[1], BaseScaler)
+    np.random.seed(0)
+    assert p.preprocess(_cloud(2)).shape == (100, 3)
+
+
+def _run_pair(oracle, fail_above=np.inf, attempts=5, seed=3):
+    """oracle.Aligner over the sequential fake vs the B200 Aligner over the batched fake."""
+    from or_pcd_b200.Aligner.Aligner import Aligner
+    from or_pcd_b200.Preprocessor import Preprocessor, RandomDownsampler
+
+    src = _cloud(10, 900)
+    tgt = (_cloud(10, 900) * np.array([1.0, 1.31, 0.9]))[::-1].copy()
+    outs = []
+    for kind in ("seq", "batch"):
+        np.random.seed(seed)
+        if kind == "seq":
+            al = oracle.Aligner(oracle.Preprocessor([oracle.RandomDownsampler(400)]),
+                                oracle.Preprocessor([oracle.RandomDownsampler(400)]),
+                                FakeSequential(fail_above), attempts=attempts)
+        else:
+            al = Aligner(Preprocessor([RandomDownsampler(400)]), Preprocessor([RandomDownsampler(400)]),
+                         FakeBatched(fail_above), attempts=attempts)
+        err = None
+        try:
+            res = al.align(src, tgt, refine_registration=False)
+        except ValueError as e:
+            res, err = None, e
+        outs.append((al, res, err, np.random.get_state()[1].copy(), np.random.get_state()[2]))
+    return outs
+
+
+def test_aligner_replays_reference_decisions_and_rng(oracle):
+    (a, ra, ea, sa, pa), (b, rb, eb, sb, pb) = _run_pair(oracle)
+    assert ea is None and eb is None
+    assert len(a.decision_log) == len(b.decision_log) > 7
+    for x, y in zip(a.decision_log, b.decision_log):
+        assert x["accepted"] == y["accepted"] and x["kind"] == y["kind"]
+        assert np.array_equal(x["scale"], y["scale"]) and x["metric"] == y["metric"]
+    assert np.array_equal(ra[0], rb[0]) and ra[1] == rb[1] and np.array_equal(ra[2], rb[2]) and ra[3] == rb[3]
+    assert rb[2].shape == (1, 3)
+    # the global numpy stream is left exactly where the sequential code leaves it
+    assert np.array_equal(sa, sb) and pa == pb
+    # the sequential code ran fewer registrations than the speculative batch evaluated
+    assert b.n_optimize_calls == a._optimizer.calls
+    assert b.n_units_evaluated >= b.n_optimize_calls
+    assert any(d["accepted"] for d in b.decision_log[1:]), "test workload should accept at least one move"
+
+
+def test_aligner_exception_replay(oracle):
+    """A failing unit raises iff the sequential code would have reached it."""
+    # threshold chosen so that only enlarged-z candidates fail
+    probe = _run_pair(oracle)[0][0]
+    z = probe.target_pre.std(0)[2]
+    for fail_above in (z * 1.1, z * 0.5):
+        (a, ra, ea, sa, pa), (b, rb, eb, sb, pb) = _run_pair(oracle, fail_above=fail_above)
+        assert (ea is None) == (eb is None)
+        if ea is None:
+            assert np.array_equal(ra[2], rb[2]) and ra[1] == rb[1]
+            assert np.array_equal(sa, sb) and pa == pb
+        else:
+            assert b.n_optimize_calls == a._optimizer.calls
+
+
+def test_aligner_sequential_plugin_still_works(oracle):
+    """An optimizer with only optimize() (the reference's contract) is driven one call at a time."""
+    from or_pcd_b200.Aligner.Aligner import Aligner
+    from or_pcd_b200.Preprocessor import Preprocessor, RandomDownsampler
+
+    src, tgt = _cloud(4, 500), _cloud(5, 500)
+    np.random.seed(1)
+    ref = oracle.Aligner(oracle.Preprocessor([oracle.RandomDownsampler(200)]),
+                         oracle.Preprocessor([oracle.RandomDownsampler(200)]), FakeSequential(), attempts=3)
+    r0 = ref.align(src, tgt)
+    np.random.seed(1)
+    al = Aligner(Preprocessor([RandomDownsampler(200)]), Preprocessor([RandomDownsampler(200)]), FakeSequential(),
+                 attempts=3)
+    r1 = al.align(src, tgt, refine_registration=False)
+    assert np.array_equal(r0[0], r1[0]) and r0[1] == r1[1] and np.array_equal(r0[2], r1[2]) and r0[3] == r1[3]
+
+
+def test_transfrom_identity(oracle):
+    """Aligner.transfrom (Aligner.py:367-394): with T = I and unit scale factors the call maps
+    the source's normalised frame onto the target's raw frame."""
+    from or_pcd_b200.Aligner.Aligner import Aligner
+    from or_pcd_b200.Preprocessor import Preprocessor, RadiusScaler
+
+    src, tgt = _cloud(6, 300), _cloud(7, 300)
+    ps, pt = Preprocessor([RadiusScaler()]), Preprocessor([RadiusScaler()])
+    al = Aligner(ps, pt, FakeSequential(), attempts=1)
+    ps.preprocess(src); pt.preprocess(tgt)
+    al.transfromation, al.scale_factors = np.eye(4), np.ones((1, 3))
+    out = al.transfrom(src)
+    s, t = ps.preprocessor_blocks[0], pt.preprocessor_blocks[0]
+    assert np.allclose(out, (src - s.mean) / s.scale * t.scale + t.mean, rtol=0, atol=1e-14)
+
+
+def test_aligner_argument_defaults():
+    from or_pcd_b200.Aligner.Aligner import Aligner
+    from or_pcd_b200.Preprocessor import Preprocessor, RadiusScaler
+
+    al = Aligner(Preprocessor([RadiusScaler()]), Preprocessor([RadiusScaler()]), FakeSequential(), attempts=0,
+                 deg=-1, std=0, delta=0, max_iter=0, eps=-2)
+    assert (al._attempts, al._delta, al._eps, al._max_iter, al._std) == (30, 0.2, 0.05, 100, 0.1)   # constants.py:71-77
+    assert "attempts=30" in repr(al)
+    with pytest.raises(NotImplementedError):
+        al.refine_registration(None, None, None)
