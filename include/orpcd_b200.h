@@ -195,6 +195,102 @@ int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_points,
                      double *h_profile, orpcd_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * EvaluateRegistration for a batch of units: source set unit_src[u] moved by
+ * d_T[u] (NULL = identity), nearest target of every source point within
+ * max_correspondence_distance -> fitness, inlier_rmse, correspondence count.
+ * Replaces registration::EvaluateRegistration as used at the end of
+ * registration_fgr_based_on_feature_matching (Optimizer/fastGlobalOptimizer.py:166-174)
+ * and o3d...evaluate_registration.  Uses the same exact 1-NN kernels as
+ * orpcd_gicp_batch (FP32 certified filter + float64 re-rank).  Only the size and
+ * distance fields of `p` are read; workspace as orpcd_gicp_batch_workspace_bytes(p)
+ * with p->cov_mode == 1.
+ * d_out_stats [n_units][4] {fitness, inlier_rmse, 0, n_correspondences};
+ * d_out_status[n_units] 1 = empty correspondence set (the reference raises Warning,
+ * fastGlobalOptimizer.py:181-188); d_out_corr (may be NULL) [n_units][n_src] target
+ * index per source point or -1.
+ * ---------------------------------------------------------------------- */
+int orpcd_evaluate_batch(const orpcd_gicp_params *p, const double *d_src_points,
+                         const double *d_tgt_points, const int *d_unit_src, const int *d_unit_tgt,
+                         const double *d_T, void *d_workspace, size_t workspace_bytes,
+                         double *d_out_stats, int *d_out_status, int *d_out_corr,
+                         orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * FPFH descriptors, 33 float64 per point, point-major [batch][n][33] (the memory
+ * order of Open3D's 33 x N column-major Feature::data_).
+ * Replaces compute_fpfh_feature(cloud, KDTreeSearchParamHybrid(radius, knn))
+ * (Optimizer/fastGlobalOptimizer.py:130-143).  Neighbour lists come from
+ * orpcd_knn_exact / orpcd_knn_rerank (self query, width list_k >= knn, sorted);
+ * radius <= 0 selects the pure k-NN search.  d_spfh is the intermediate SPFH
+ * table (same shape as d_fpfh, also an output).
+ * ---------------------------------------------------------------------- */
+int orpcd_fpfh(const double *d_points, const double *d_normals, int n, long long points_stride,
+               int batch, const int *d_nn_idx, const double *d_nn_d2, int list_k, int knn,
+               double radius, double *d_spfh, double *d_fpfh, orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Nearest neighbour in 33-D feature space (the kd-tree searches of FGR's
+ * InitialMatching, FastGlobalRegistration.cpp; fastGlobalOptimizer.py:166-174).
+ * Features are first packed (orpcd_feature_pack) into TF32 hi/lo operand tiles for
+ * the tcgen05 tensor-core filter; orpcd_feature_match then returns, for pair p and
+ * every row of query set d_pair_q[p], the exact float64 nearest row of database set
+ * d_pair_db[p] (nanoflann summation order, ties -> lowest index).
+ * mode 0: tensor-core filter + certified float64 re-score; mode 1: float64 scan only.
+ * d_packed_* : orpcd_feature_pack_bytes(n) bytes per set, 128-byte aligned
+ * d_set_maxnorm: [n_sets] float, max |f|^2 of each set (written by the pack)
+ * d_nn [n_pairs][n_query] int32; d_nn_d2 (may be NULL) float64;
+ * d_stats (may be NULL) int[1]: rows that needed the exact scan;
+ * d_debug_v (may be NULL) [n_pairs][n_query][ceil(n_db/128)*128] filter values.
+ * ---------------------------------------------------------------------- */
+size_t orpcd_feature_pack_bytes(int n);
+int orpcd_feature_pack(const double *d_features, int n, int n_sets, void *d_packed,
+                       float *d_set_maxnorm, orpcd_stream_t stream);
+size_t orpcd_feature_match_workspace_bytes(int n_query, int n_pairs);
+int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q, int n_query,
+                        const double *d_feat_db, const void *d_packed_db,
+                        const float *d_db_maxnorm, int n_db, const int *d_pair_q,
+                        const int *d_pair_db, int n_pairs, int mode, void *d_workspace,
+                        size_t workspace_bytes, int *d_nn, double *d_nn_d2, int *d_stats,
+                        float *d_debug_v, orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Batched Fast Global Registration after feature matching: per unit
+ * NormalizePointCloud, cross check of the two nearest-neighbour tables,
+ * tuple test (Philox4x32-10 stream keyed per unit), graduated non-convexity
+ * Geman-McClure solve, transform back to the original scale and inversion.
+ * Replaces the body of registration_fgr_based_on_feature_matching
+ * (Optimizer/fastGlobalOptimizer.py:158-174) except the final
+ * EvaluateRegistration (orpcd_evaluate_batch).
+ * d_ij [n_units][n_feat_src]: nearest target feature of every source feature;
+ * d_ji [n_units][n_feat_tgt]: nearest source feature of every target feature;
+ * d_out_T [n_units][16] source -> target, row-major, column convention;
+ * d_out_info [n_units][4] {cross-checked pairs, pairs after the tuple test,
+ *                          tuple trials run, swapped}.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    int n_units;
+    int n_src;             /* points per source cloud                         */
+    int n_tgt;             /* points per target cloud                         */
+    int n_feat_src;        /* rows of the source feature table (= n_src)      */
+    int n_feat_tgt;        /* rows of the target feature table (the reference passes the
+                              SOURCE's features twice: then n_feat_tgt = n_src) */
+    int iteration_number;  /* FastGlobalRegistrationOption.iteration_number   */
+    int decrease_mu;
+    int max_tuple_count;   /* Open3D default 1000                             */
+    int tuple_test;        /* Open3D default true                             */
+    double division_factor;
+    double tuple_scale;
+    double max_correspondence_distance;
+} orpcd_fgr_params;
+
+size_t orpcd_fgr_batch_workspace_bytes(const orpcd_fgr_params *p);
+int orpcd_fgr_batch(const orpcd_fgr_params *p, const double *d_src_points,
+                    const double *d_tgt_points, const int *d_unit_src, const int *d_unit_tgt,
+                    const int *d_ij, const int *d_ji, const unsigned long long *d_tuple_keys,
+                    void *d_workspace, size_t workspace_bytes, double *d_out_T, int *d_out_info,
+                    orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Roofline helper: one nearest-neighbour sweep (the dominant kernel of
  * orpcd_gicp_batch) over `n_units` x n_src queries against n_tgt targets,
  * exactly as one Gauss-Newton iteration issues it, for timing in isolation.

@@ -83,3 +83,100 @@ __device__ __forceinline__ void transform_point(const double *U, double &x, doub
     const double nz = U[8] * x + U[9] * y + U[10] * z + U[11];
     x = nx; y = ny; z = nz;
 }
+
+// ----------------------------------------------------------------------------
+// Deterministic acos / cos (bit-identical twins of det_acos / det_cos in
+// oracle/orpcd_oracle.c; Sun fdlibm's e_acos.c / k_cos.c / k_sin.c algorithms restated
+// with + - * / sqrt and bit masks only, < 1 ulp).  Open3D calls libm here and feeds the
+// results into discontinuous decisions (FastEigen3x3's branches, the source/target role
+// swap of FPFH's pair features); the CUDA math library and glibc differ in the last ulp,
+// and range-grid scans hold structural near-ties, so both sides of the parity tests use
+// this arithmetic.  Requires -fmad=false (no FMA contraction).
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ double det_acos(double x)
+{
+    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17,
+                 pi = 3.14159265358979311600e+00;
+    const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01,
+                 pS2 = 2.01212532134862925881e-01, pS3 = -4.00555345006794114027e-02,
+                 pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05,
+                 qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00,
+                 qS3 = -6.88283971605453293030e-01, qS4 = 7.70381505559019352791e-02;
+    const double ax = fabs(x);
+    if (ax >= 1.0) {
+        if (ax == 1.0) return x > 0 ? 0.0 : pi + 2.0 * pio2_lo;
+        return (x - x) / (x - x);
+    }
+    if (ax < 0.5) {
+        if (ax < 6.938893903907228e-18) return pio2_hi + pio2_lo;   // 2^-57
+        const double z = x * x;
+        const double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const double r = p / q;
+        return pio2_hi - (x - (pio2_lo - x * r));
+    } else if (x < 0) {
+        const double z = (1.0 + x) * 0.5;
+        const double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const double s = sqrt(z);
+        const double r = p / q;
+        const double w = r * s - pio2_lo;
+        return pi - 2.0 * (s + w);
+    } else {
+        const double z = (1.0 - x) * 0.5;
+        const double s = sqrt(z);
+        const double df = __hiloint2double(__double2hiint(s), 0);
+        const double c = (z - df * df) / (s + df);
+        const double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const double r = p / q;
+        const double w = r * s + c;
+        return 2.0 * (df + w);
+    }
+}
+
+__device__ __forceinline__ double det_kcos(double x, double y)
+{
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double ax = fabs(x);
+    if (ax < 7.450580596923828e-09) return 1.0;   // 2^-27
+    const double z = x * x;
+    const double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+    if (ax < 0.3) return 1.0 - (0.5 * z - (z * r - x * y));
+    const double qx = ax > 0.78125 ? 0.28125 : __hiloint2double(__double2hiint(ax) - 0x00200000, 0);
+    const double hz = 0.5 * z - qx;
+    const double a = 1.0 - qx;
+    return a - (hz - (z * r - x * y));
+}
+
+__device__ __forceinline__ double det_ksin(double x, double y)
+{
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double z = x * x;
+    const double v = z * x;
+    const double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+    return x - ((z * (0.5 * y - v * r) - y) - v * S1);
+}
+
+// cos(x) for 0 <= x <= pi
+__device__ __forceinline__ double det_cos(double x)
+{
+    const double pio4 = 7.85398163397448278999e-01, three_pio4 = 2.35619449019234483700e+00;
+    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+    const double pi_hi = 3.14159265358979311600e+00, pi_lo = 1.22464679914735317723e-16;
+    if (x <= pio4) return det_kcos(x, 0.0);
+    if (x < three_pio4) {
+        const double t = x - pio2_hi;
+        const double y = t - pio2_lo;
+        const double yt = (t - y) - pio2_lo;
+        return -det_ksin(y, yt);
+    }
+    const double t = x - pi_hi;
+    const double y = t - pi_lo;
+    const double yt = (t - y) - pi_lo;
+    return -det_kcos(y, yt);
+}

@@ -103,10 +103,10 @@ __device__ void smallest_eigvec(const double *C, double *n)
         const double det = (b00 * c00 - A[1] * c01 + A[2] * c02) / (p * p * p);
         double half_det = det * 0.5;
         half_det = fmin(fmax(half_det, -1.0), 1.0);
-        const double angle = acos(half_det) / 3.0;
+        const double angle = det_acos(half_det) / 3.0;
         const double two_thirds_pi = 2.09439510239319549;
-        const double beta2 = cos(angle) * 2;
-        const double beta0 = cos(angle + two_thirds_pi) * 2;
+        const double beta2 = det_cos(angle) * 2;
+        const double beta0 = det_cos(angle + two_thirds_pi) * 2;
         const double beta1 = -(beta0 + beta2);
         const double ev0 = q + p * beta0, ev1 = q + p * beta1, ev2 = q + p * beta2;
         double e0[3], e1[3], e2[3];

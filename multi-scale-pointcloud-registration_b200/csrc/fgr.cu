@@ -1,0 +1,855 @@
+// Fast Global Registration (Zhou, Park, Koltun) as Open3D 0.18.0 runs it, batched over
+// the Aligner's (multi-start x scale-candidate) units, for sm_100a.
+//
+// Replaces open3d.pipelines.registration.registration_fgr_based_on_feature_matching
+// as called from Optimizer/fastGlobalOptimizer.py:166-174.  Algorithm: SURVEY.md
+// Appendix A.8 (FastGlobalRegistration.cpp: NormalizePointCloud, InitialMatching,
+// AdvancedMatching, OptimizePairwiseRegistration, GetTransformationOriginalScale).
+//
+// Feature matching -- the one dense contraction on this path (N x M x 33) -- runs on the
+// 5th-generation tensor cores:
+//   feat_pack_kernel   float64 features -> two TF32 planes (hi + lo split, K padded 33->40)
+//                      written in global memory as ready-made shared-memory images of
+//                      128-row UMMA operand tiles (K-major, no swizzle) + |f|^2 per row.
+//   feat_match_kernel  one CTA per 128 query rows: operand tiles arrive by TMA bulk copies
+//                      (cp.async.bulk + mbarrier complete_tx, 3 stages), one elected thread
+//                      issues tcgen05.mma kind::tf32 (3 products hi*hi + hi*lo + lo*hi per
+//                      K step: FP32-class accuracy) into two 128x128 FP32 accumulators in
+//                      TMEM, and the four warps read them back with tcgen05.ld to fold
+//                      |d|^2 - 2 q.d into per-row (best 32-column chunk min, chunk id,
+//                      second-best chunk min) while the next tile's MMAs run.
+//   feat_resolve_kernel certifies with an error bound that the best chunk holds the exact
+//                      nearest neighbour and re-scores its 32 candidates in float64 in
+//                      nanoflann's summation order (ties -> lowest index); uncertified rows
+//                      get an exact float64 scan.  Matched indices are therefore exact.
+// The rest (mutual check, tuple test, graduated non-convexity solve) is small float64 work,
+// one block per unit.
+#include "common.cuh"
+
+namespace {
+
+// ----------------------------------------------------------------------------
+// operand tile image
+// ----------------------------------------------------------------------------
+constexpr int FM_DIM = 33;
+constexpr int FM_K = 40;                               // padded to a multiple of the tf32 MMA K (8)
+constexpr int FM_ROWS = 128;                           // UMMA M = N = 128
+constexpr int FM_LBO = FM_ROWS * 16;                   // 2048 B between 16-byte K chunks
+constexpr int FM_SBO = 128;                            // 128 B between 8-row groups
+constexpr int FM_PLANE_BYTES = FM_ROWS * FM_K * 4;     // 20480
+constexpr int FM_NORM_OFF = 2 * FM_PLANE_BYTES;        // hi plane, lo plane, then 128 norms
+constexpr int FM_TILE_BYTES = FM_NORM_OFF + FM_ROWS * 4;   // 41472
+constexpr int FM_STAGES = 3;
+constexpr int FM_SMEM_BYTES = (1 + FM_STAGES) * FM_TILE_BYTES + 128 /*barriers*/ + 128 /*alignment*/;
+constexpr float FM_PAD_NORM = 3.0e38f;
+
+__device__ __forceinline__ int fm_image_offset(int r, int c)
+{
+    return (c >> 2) * FM_LBO + (r >> 3) * FM_SBO + (r & 7) * 16 + (c & 3) * 4;
+}
+
+__device__ __forceinline__ float tf32_rna(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// grid (tiles, sets), 128 threads: thread r packs row r of the tile.
+__global__ void __launch_bounds__(FM_ROWS)
+feat_pack_kernel(const double *__restrict__ feat, int n, int tiles, unsigned char *__restrict__ packed,
+                 float *__restrict__ set_maxnorm)
+{
+    const int set = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
+    const int row = tile * FM_ROWS + r;
+    unsigned char *img = packed + ((size_t)set * tiles + tile) * FM_TILE_BYTES;
+    float norm = FM_PAD_NORM;
+    double nd = 0.0;
+    const double *f = feat + ((size_t)set * n + (row < n ? row : 0)) * FM_DIM;
+    for (int c = 0; c < FM_K; ++c) {
+        float hi = 0.f, lo = 0.f;
+        if (row < n && c < FM_DIM) {
+            const double v = f[c];
+            nd += v * v;
+            const float x = (float)v;
+            hi = tf32_rna(x);
+            lo = tf32_rna(x - hi);
+        }
+        const int o = fm_image_offset(r, c);
+        *reinterpret_cast<float *>(img + o) = hi;
+        *reinterpret_cast<float *>(img + FM_PLANE_BYTES + o) = lo;
+    }
+    if (row < n) {
+        norm = __double2float_rn(nd);
+        atomicMax(reinterpret_cast<int *>(set_maxnorm + set), __float_as_int(norm));   // norms are >= 0
+    }
+    *reinterpret_cast<float *>(img + FM_NORM_OFF + r * 4) = norm;
+}
+
+// ----------------------------------------------------------------------------
+// PTX wrappers: mbarrier, TMA bulk copy, tcgen05
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA engine, 1-D bulk copy global -> shared, completion counted on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, no swizzle, canonical ((8,n),2):((16 B, SBO), LBO)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(FM_LBO >> 4) << 16;
+    d |= (uint64_t)(FM_SBO >> 4) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = 128
+constexpr uint32_t FM_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(FM_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------
+// tensor-core filter: per query row (best chunk min, chunk id, second-best chunk min) of
+//   v(row, col) = |d_col|^2 - 2 q_row . d_col          (= dist^2 - |q_row|^2)
+// grid (query tiles, pairs); 128 threads; thread t owns query row t of the tile.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(FM_ROWS, 1)
+feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const unsigned char *__restrict__ packed_db,
+                  int db_tiles, const int *__restrict__ pair_q, const int *__restrict__ pair_db, int nq,
+                  float *__restrict__ out_m1, int *__restrict__ out_c1, float *__restrict__ out_m2,
+                  float *__restrict__ dbg_v)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    unsigned char *sA = smem;
+    unsigned char *sB = smem + FM_TILE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (1 + FM_STAGES) * FM_TILE_BYTES);
+    // bars[0]: A landed; bars[1..3]: B stage landed; bars[4..5]: accumulator complete; bars[6] low word: TMEM base
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int pair = blockIdx.y, qt = blockIdx.x;
+    const unsigned char *gA = packed_q + ((size_t)pair_q[pair] * q_tiles + qt) * FM_TILE_BYTES;
+    const unsigned char *gB = packed_db + (size_t)pair_db[pair] * db_tiles * FM_TILE_BYTES;
+    const uint32_t bar_a = smem_u32(bars), bar_full0 = smem_u32(bars + 1), bar_mma0 = smem_u32(bars + 4);
+
+    if (tid == 0) {
+        mbar_init(bar_a, 1);
+        for (int s = 0; s < FM_STAGES; ++s) mbar_init(bar_full0 + 8 * s, 1);
+        mbar_init(bar_mma0, 1);
+        mbar_init(bar_mma0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {   // 256 TMEM columns: two 128 x 128 FP32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (tid == 0) {
+        mbar_expect_tx(bar_a, FM_TILE_BYTES);
+        tma_bulk_g2s(smem_u32(sA), gA, FM_TILE_BYTES, bar_a);
+        for (int s = 0; s < FM_STAGES && s < db_tiles; ++s) {
+            mbar_expect_tx(bar_full0 + 8 * s, FM_TILE_BYTES);
+            tma_bulk_g2s(smem_u32(sB + (size_t)s * FM_TILE_BYTES), gB + (size_t)s * FM_TILE_BYTES, FM_TILE_BYTES,
+                         bar_full0 + 8 * s);
+        }
+    }
+
+    float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
+    int c1 = 0;
+    const int row = qt * FM_ROWS + tid;
+
+    // iteration t: thread 0 issues the MMAs of tile t, then everyone runs the epilogue of tile t-1
+    for (int t = 0; t <= db_tiles; ++t) {
+        if (t < db_tiles && tid == 0) {
+            if (t == 0) mbar_wait(bar_a, 0);
+            const int s = t % FM_STAGES;
+            mbar_wait(bar_full0 + 8 * s, (t / FM_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + FM_PLANE_BYTES;
+            const uint32_t b_hi = smem_u32(sB + (size_t)s * FM_TILE_BYTES), b_lo = b_hi + FM_PLANE_BYTES;
+            const uint32_t acc = tmem_base + (uint32_t)(t & 1) * FM_ROWS;
+#pragma unroll
+            for (int k = 0; k < FM_K / 8; ++k) {
+                const uint32_t ko = (uint32_t)k * 2 * FM_LBO;   // two 16-byte K chunks per MMA (K = 8 tf32)
+                umma_tf32(acc, umma_desc(a_hi + ko), umma_desc(b_hi + ko), k > 0);
+                umma_tf32(acc, umma_desc(a_hi + ko), umma_desc(b_lo + ko), 1);
+                umma_tf32(acc, umma_desc(a_lo + ko), umma_desc(b_hi + ko), 1);
+            }
+            umma_commit(bar_mma0 + 8 * (t & 1));   // implies tcgen05.fence::before_thread_sync
+        }
+        __syncwarp();   // warp 0 must be converged again for the .sync.aligned TMEM loads below
+        if (t >= 1) {
+            const int e = t - 1, s = e % FM_STAGES;
+            mbar_wait(bar_full0 + 8 * s, (e / FM_STAGES) & 1);   // tile e's norms (TMA-written) visible to this thread
+            mbar_wait(bar_mma0 + 8 * (e & 1), (e >> 1) & 1);
+            tc_fence_after();
+            const float *dn = reinterpret_cast<const float *>(sB + (size_t)s * FM_TILE_BYTES + FM_NORM_OFF);
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(e & 1) * FM_ROWS;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(taddr + ch * 32, v);
+                float mc = CUDART_INF_F;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float val = __fmaf_rn(-2.f, __uint_as_float(v[j]), dn[ch * 32 + j]);
+                    mc = fminf(mc, val);
+                    if (dbg_v && row < nq)
+                        dbg_v[((size_t)pair * nq + row) * ((size_t)db_tiles * FM_ROWS) + (size_t)e * FM_ROWS + ch * 32 + j] = val;
+                }
+                const int chunk = e * 4 + ch;
+                m2 = fminf(m2, fmaxf(m1, mc));
+                c1 = mc < m1 ? chunk : c1;
+                m1 = fminf(m1, mc);
+            }
+            tc_fence_before();
+            __syncthreads();   // accumulator e&1 and stage s are free again
+            if (tid == 0 && e + FM_STAGES < db_tiles) {
+                const int nt = e + FM_STAGES;
+                mbar_expect_tx(bar_full0 + 8 * s, FM_TILE_BYTES);
+                tma_bulk_g2s(smem_u32(sB + (size_t)s * FM_TILE_BYTES), gB + (size_t)nt * FM_TILE_BYTES, FM_TILE_BYTES,
+                             bar_full0 + 8 * s);
+            }
+        }
+    }
+    if (row < nq) {
+        const size_t o = (size_t)pair * nq + row;
+        out_m1[o] = m1;
+        out_c1[o] = c1;
+        out_m2[o] = m2;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+}
+
+// nanoflann L2_Adaptor::evalMetric for dim 33: groups of four summed left to right, then the tail.
+__device__ __forceinline__ double sqdist33(const double *__restrict__ a, const double *__restrict__ b)
+{
+    double result = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        const double d0 = a[i] - b[i], d1 = a[i + 1] - b[i + 1], d2 = a[i + 2] - b[i + 2], d3 = a[i + 3] - b[i + 3];
+        result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    const double d0 = a[32] - b[32];
+    result += d0 * d0;
+    return result;
+}
+
+// One warp per query row: certify the best chunk, exact float64 re-score (or exact scan).
+// stats[0] += rows that needed the exact scan.
+__global__ void __launch_bounds__(128)
+feat_resolve_kernel(const double *__restrict__ feat_q, int nq, const double *__restrict__ feat_db, int ndb,
+                    const int *__restrict__ pair_q, const int *__restrict__ pair_db,
+                    const float *__restrict__ db_maxnorm, const float *__restrict__ in_m1,
+                    const int *__restrict__ in_c1, const float *__restrict__ in_m2, int force_exact,
+                    int *__restrict__ out_nn, double *__restrict__ out_d2, int *__restrict__ stats)
+{
+    const int pair = blockIdx.y, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= nq) return;
+    const double *q = feat_q + ((size_t)pair_q[pair] * nq + row) * FM_DIM;
+    const double *db = feat_db + (size_t)pair_db[pair] * ndb * FM_DIM;
+    double qv[FM_DIM];
+    double qn = 0.0;
+#pragma unroll
+    for (int k = 0; k < FM_DIM; ++k) { qv[k] = q[k]; qn += qv[k] * qv[k]; }
+    const size_t o = (size_t)pair * nq + row;
+    const float m1 = in_m1[o], m2 = in_m2[o];
+    const int c1 = in_c1[o];
+    // filter error bound (DESIGN.md "feature filter bound"): |v - (d^2 - |q|^2)| <= 2^-15 |q| Dmax + 2^-23 Dmax^2
+    const double dmax = sqrt((double)db_maxnorm[pair_db[pair]]);
+    const double E = 2.0 * (ldexp(sqrt(qn) * dmax, -15) + ldexp(dmax * dmax, -23));
+    const bool certified = !force_exact && (double)m2 > (double)m1 + E;
+    double best = CUDART_INF;
+    int bj = 0x7fffffff;
+    if (certified) {
+        const int j = c1 * 32 + lane;
+        if (j < ndb) { best = sqdist33(qv, db + (size_t)j * FM_DIM); bj = j; }
+    } else {
+        for (int j = lane; j < ndb; j += 32) {
+            const double d = sqdist33(qv, db + (size_t)j * FM_DIM);
+            if (d < best) { best = d; bj = j; }
+        }
+        if (lane == 0 && stats) atomicAdd(stats, 1);
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best, s);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, s);
+        if (od < best || (od == best && oj < bj)) { best = od; bj = oj; }
+    }
+    if (lane == 0) {
+        out_nn[o] = bj == 0x7fffffff ? -1 : bj;
+        if (out_d2) out_d2[o] = best;
+    }
+}
+
+// ----------------------------------------------------------------------------
+// per-unit float64 stages (one block per unit)
+// ----------------------------------------------------------------------------
+constexpr int FG_THREADS = 256;
+
+struct FgrUnit {
+    double mean_s[3], mean_t[3];
+    double scale;        // scale_global
+    int n_init, n_pairs, trials, swapped;
+};
+
+struct FgrCtx {
+    int n_units, n_src, n_tgt, n_feat_src, n_feat_tgt, cap;
+    int iteration_number, decrease_mu, max_tuple, tuple_test;
+    double division_factor, tuple_scale, max_corr_dist;
+    const double *src_pts, *tgt_pts;
+    const int *unit_src, *unit_tgt;
+    const int *ij, *ji;                 // [U][n_feat_src], [U][n_feat_tgt]
+    const unsigned long long *keys;     // [U]
+    FgrUnit *unit;
+    int2 *corres_init, *corres;         // [U][cap]
+    double *qcur;                       // [U][cap][3]
+    double *out_T;
+    int *out_info;
+};
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < FG_THREADS / 32; ++w) s += sh[w];
+    return s;
+}
+__device__ __forceinline__ double block_max(double v, double *sh)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < FG_THREADS / 32; ++w) s = fmax(s, sh[w]);
+    return s;
+}
+// exclusive block scan of 0/1 flags; returns this thread's offset, total in `total`
+__device__ __forceinline__ int block_scan_flag(int flag, int *sh, int &total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int within = __popc(bal & ((1u << lane) - 1u));
+    __syncthreads();
+    if (lane == 0) sh[wid] = __popc(bal);
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int w = 0; w < FG_THREADS / 32; ++w) {
+        if (w < wid) base += sh[w];
+        tot += sh[w];
+    }
+    total = tot;
+    return base + within;
+}
+
+// NormalizePointCloud (means, global scale) + InitialMatching's cross check, per unit.
+__global__ void __launch_bounds__(FG_THREADS) fgr_prepare_kernel(FgrCtx c)
+{
+    __shared__ double shd[FG_THREADS / 32];
+    __shared__ int shi[FG_THREADS / 32];
+    __shared__ int s_cnt;
+    const int u = blockIdx.x, tid = threadIdx.x;
+    const double *sp = c.src_pts + (size_t)c.unit_src[u] * c.n_src * 3;
+    const double *tp = c.tgt_pts + (size_t)c.unit_tgt[u] * c.n_tgt * 3;
+    double mean[2][3];
+    for (int w = 0; w < 2; ++w) {
+        const double *p = w == 0 ? sp : tp;
+        const int n = w == 0 ? c.n_src : c.n_tgt;
+        for (int k = 0; k < 3; ++k) {
+            double a = 0.0;
+            for (int i = tid; i < n; i += FG_THREADS) a += p[(size_t)i * 3 + k];
+            mean[w][k] = block_sum(a, shd) / (double)n;
+        }
+    }
+    double mx = 0.0;
+    for (int w = 0; w < 2; ++w) {
+        const double *p = w == 0 ? sp : tp;
+        const int n = w == 0 ? c.n_src : c.n_tgt;
+        for (int i = tid; i < n; i += FG_THREADS) {
+            const double x = p[(size_t)i * 3] - mean[w][0], y = p[(size_t)i * 3 + 1] - mean[w][1],
+                         z = p[(size_t)i * 3 + 2] - mean[w][2];
+            mx = fmax(mx, sqrt(x * x + y * y + z * z));
+        }
+    }
+    const double scale = block_max(mx, shd);
+    // cross check in ascending source-feature index (std::map order)
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    const int *ij = c.ij + (size_t)u * c.n_feat_src;
+    const int *ji = c.ji + (size_t)u * c.n_feat_tgt;
+    int2 *out = c.corres_init + (size_t)u * c.cap;
+    for (int base = 0; base < c.n_feat_src; base += FG_THREADS) {
+        const int i = base + tid;
+        int flag = 0, j = -1;
+        if (i < c.n_feat_src) {
+            j = ij[i];
+            flag = j >= 0 && j < c.n_feat_tgt && ji[j] == i && i < c.n_src && j < c.n_tgt;
+        }
+        int total;
+        const int off = block_scan_flag(flag, shi, total);
+        const int cnt0 = s_cnt;
+        if (flag) out[cnt0 + off] = make_int2(i, j);
+        __syncthreads();
+        if (tid == 0) s_cnt = cnt0 + total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        FgrUnit &fu = c.unit[u];
+        for (int k = 0; k < 3; ++k) { fu.mean_s[k] = mean[0][k]; fu.mean_t[k] = mean[1][k]; }
+        fu.scale = scale;
+        fu.n_init = s_cnt;
+        fu.n_pairs = 0; fu.trials = 0;
+        fu.swapped = c.n_tgt > c.n_src ? 1 : 0;
+    }
+}
+
+// Philox4x32-10, counter (t, 0, 0, 0): the project's documented tuple-test stream
+__device__ __forceinline__ void philox4x32_10(unsigned long long counter, unsigned long long key, uint32_t out[4])
+{
+    uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32), c2 = 0u, c3 = 0u;
+    uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        if (r > 0) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ void norm_point(const double *p, int i, const double *mean, double scale, double o[3])
+{
+    o[0] = (p[(size_t)i * 3] - mean[0]) / scale;
+    o[1] = (p[(size_t)i * 3 + 1] - mean[1]) / scale;
+    o[2] = (p[(size_t)i * 3 + 2] - mean[2]) / scale;
+}
+__device__ __forceinline__ double dist3(const double a[3], const double b[3])
+{
+    const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
+    return sqrt(x * x + y * y + z * z);
+}
+
+// AdvancedMatching's tuple test: trials are independent given the counter-based stream, so a block
+// evaluates 256 at a time and keeps the accepted ones in trial order (= the sequential semantics).
+__global__ void __launch_bounds__(FG_THREADS) fgr_tuple_kernel(FgrCtx c)
+{
+    __shared__ int shi[FG_THREADS / 32];
+    __shared__ int s_cnt;
+    const int u = blockIdx.x, tid = threadIdx.x;
+    FgrUnit &fu = c.unit[u];
+    const int ncorr = fu.n_init;
+    const int2 *in = c.corres_init + (size_t)u * c.cap;
+    int2 *out = c.corres + (size_t)u * c.cap;
+    if (!c.tuple_test) {
+        for (int i = tid; i < ncorr; i += FG_THREADS) out[i] = in[i];
+        if (tid == 0) { fu.n_pairs = ncorr; fu.trials = 0; }
+        return;
+    }
+    const double *sp = c.src_pts + (size_t)c.unit_src[u] * c.n_src * 3;
+    const double *tp = c.tgt_pts + (size_t)c.unit_tgt[u] * c.n_tgt * 3;
+    const double ms[3] = {fu.mean_s[0], fu.mean_s[1], fu.mean_s[2]};
+    const double mt[3] = {fu.mean_t[0], fu.mean_t[1], fu.mean_t[2]};
+    const double scale = fu.scale, ts = c.tuple_scale;
+    const bool swapped = fu.swapped != 0;
+    const unsigned long long key = c.keys[u];
+    const long long n_trials = (long long)ncorr * 100;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    long long done = 0;
+    for (long long base = 0; base < n_trials; base += FG_THREADS) {
+        const long long t = base + tid;
+        int flag = 0;
+        int2 pr[3];
+        if (t < n_trials) {
+            uint32_t r[4];
+            philox4x32_10((unsigned long long)t, key, r);
+            double a[3][3], b[3][3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int idx = (int)(((unsigned long long)r[k] * (unsigned long long)ncorr) >> 32);
+                pr[k] = in[idx];
+                norm_point(sp, pr[k].x, ms, scale, a[k]);
+                norm_point(tp, pr[k].y, mt, scale, b[k]);
+            }
+            // fi = the larger cloud: li on the source unless the target is larger (swap)
+            double li0, li1, li2, lj0, lj1, lj2;
+            if (!swapped) {
+                li0 = dist3(a[0], a[1]); li1 = dist3(a[1], a[2]); li2 = dist3(a[2], a[0]);
+                lj0 = dist3(b[0], b[1]); lj1 = dist3(b[1], b[2]); lj2 = dist3(b[2], b[0]);
+            } else {
+                li0 = dist3(b[0], b[1]); li1 = dist3(b[1], b[2]); li2 = dist3(b[2], b[0]);
+                lj0 = dist3(a[0], a[1]); lj1 = dist3(a[1], a[2]); lj2 = dist3(a[2], a[0]);
+            }
+            flag = (li0 * ts < lj0) && (lj0 < li0 / ts) && (li1 * ts < lj1) && (lj1 < li1 / ts) &&
+                   (li2 * ts < lj2) && (lj2 < li2 / ts);
+        }
+        int total;
+        const int off = block_scan_flag(flag, shi, total);
+        const int cnt0 = s_cnt;
+        if (flag && cnt0 + off < c.max_tuple) {
+            int2 *o = out + (size_t)(cnt0 + off) * 3;
+            o[0] = pr[0]; o[1] = pr[1]; o[2] = pr[2];
+        }
+        // trials the sequential loop would have run: up to and including the one that fills the quota
+        __syncthreads();
+        if (cnt0 + total >= c.max_tuple) {
+            // position of the accepting trial that reaches max_tuple
+            if (flag && cnt0 + off == c.max_tuple - 1) fu.trials = (int)(t + 1);
+            if (tid == 0) s_cnt = c.max_tuple;
+            __syncthreads();
+            done = -1;
+            break;
+        }
+        if (tid == 0) s_cnt = cnt0 + total;
+        __syncthreads();
+        done = base + FG_THREADS < n_trials ? base + FG_THREADS : n_trials;
+    }
+    if (tid == 0) {
+        fu.n_pairs = s_cnt * 3;
+        if (done >= 0) fu.trials = (int)done;
+    }
+}
+
+// x = A.ldlt().solve(b), 6x6 symmetric (possibly negative definite), diagonal pivoting.
+__device__ void fgr_ldlt_solve6(double *A, const double *b, double *x)
+{
+    int perm[6];
+    for (int i = 0; i < 6; ++i) perm[i] = i;
+    for (int k = 0; k < 6; ++k) {
+        int piv = k;
+        double best = fabs(A[k * 6 + k]);
+        for (int i = k + 1; i < 6; ++i)
+            if (fabs(A[i * 6 + i]) > best) { best = fabs(A[i * 6 + i]); piv = i; }
+        if (piv != k) {
+            for (int j = 0; j < 6; ++j) { const double t = A[k * 6 + j]; A[k * 6 + j] = A[piv * 6 + j]; A[piv * 6 + j] = t; }
+            for (int j = 0; j < 6; ++j) { const double t = A[j * 6 + k]; A[j * 6 + k] = A[j * 6 + piv]; A[j * 6 + piv] = t; }
+            const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+        }
+        const double d = A[k * 6 + k];
+        if (d == 0.0) continue;
+        double col[6];
+        for (int i = k + 1; i < 6; ++i) col[i] = A[i * 6 + k];
+        for (int i = k + 1; i < 6; ++i) {
+            const double l = col[i] / d;
+            for (int j = k + 1; j <= i; ++j) A[i * 6 + j] -= l * col[j];
+            A[i * 6 + k] = l;
+        }
+        for (int i = k + 1; i < 6; ++i)
+            for (int j = i + 1; j < 6; ++j) A[i * 6 + j] = A[j * 6 + i];
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) y[i] = b[perm[i]];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < i; ++j) y[i] -= A[i * 6 + j] * y[j];
+    for (int i = 0; i < 6; ++i) y[i] = A[i * 6 + i] != 0.0 ? y[i] / A[i * 6 + i] : 0.0;
+    for (int i = 5; i >= 0; --i)
+        for (int j = i + 1; j < 6; ++j) y[i] -= A[j * 6 + i] * y[j];
+    for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+}
+
+// OptimizePairwiseRegistration (graduated non-convexity, Geman-McClure weights) and
+// GetTransformationOriginalScale(...).inverse(), one block per unit.
+__global__ void __launch_bounds__(FG_THREADS) fgr_gnc_kernel(FgrCtx c)
+{
+    __shared__ double sh_part[FG_THREADS / 32][28];
+    __shared__ double sh_delta[12];
+    const int u = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const FgrUnit fu = c.unit[u];
+    const int ncorr = fu.n_pairs;
+    const int2 *cor = c.corres + (size_t)u * c.cap;
+    double *qc = c.qcur + (size_t)u * c.cap * 3;
+    const double *sp = c.src_pts + (size_t)c.unit_src[u] * c.n_src * 3;
+    const double *tp = c.tgt_pts + (size_t)c.unit_tgt[u] * c.n_tgt * 3;
+    double trans[16];
+    for (int k = 0; k < 16; ++k) trans[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    if (ncorr >= 10) {
+        for (int i = tid; i < ncorr; i += FG_THREADS) {
+            double q[3];
+            norm_point(tp, cor[i].y, fu.mean_t, fu.scale, q);
+            qc[(size_t)i * 3] = q[0]; qc[(size_t)i * 3 + 1] = q[1]; qc[(size_t)i * 3 + 2] = q[2];
+        }
+        double par = 1.0;   // scale_start (use_absolute_scale = false)
+        for (int itr = 0; itr < c.iteration_number; ++itr) {
+            double acc[27];
+#pragma unroll
+            for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+            for (int i = tid; i < ncorr; i += FG_THREADS) {
+                double p[3];
+                norm_point(sp, cor[i].x, fu.mean_s, fu.scale, p);
+                const double qx = qc[(size_t)i * 3], qy = qc[(size_t)i * 3 + 1], qz = qc[(size_t)i * 3 + 2];
+                const double rx = p[0] - qx, ry = p[1] - qy, rz = p[2] - qz;
+                const double temp = par / ((rx * rx + ry * ry + rz * rz) + par);
+                const double s = temp * temp;
+                const double J[3][6] = {{0.0, -qz, qy, -1.0, 0.0, 0.0}, {qz, 0.0, -qx, 0.0, -1.0, 0.0}, {-qy, qx, 0.0, 0.0, 0.0, -1.0}};
+                const double rr[3] = {rx, ry, rz};
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    int k = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                        for (int b = a; b < 6; ++b) acc[k++] += J[r][a] * J[r][b] * s;
+                    }
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) acc[21 + a] += J[r][a] * rr[r] * s;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 27; ++k) acc[k] = warp_sum(acc[k]);
+            __syncthreads();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 27; ++k) sh_part[wid][k] = acc[k];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double tot[27];
+                for (int k = 0; k < 27; ++k) {
+                    double s = 0.0;
+                    for (int w = 0; w < FG_THREADS / 32; ++w) s += sh_part[w][k];
+                    tot[k] = s;
+                }
+                double A[36], x[6];
+                int k = 0;
+                for (int a = 0; a < 6; ++a)
+                    for (int b = a; b < 6; ++b) { A[a * 6 + b] = -tot[k]; A[b * 6 + a] = -tot[k]; ++k; }
+                fgr_ldlt_solve6(A, tot + 21, x);
+                double sa, ca, sb, cb, sg, cg;
+                sincos(x[0], &sa, &ca);
+                sincos(x[1], &sb, &cb);
+                sincos(x[2], &sg, &cg);
+                sh_delta[0] = cg * cb; sh_delta[1] = cg * sb * sa - sg * ca; sh_delta[2] = cg * sb * ca + sg * sa; sh_delta[3] = x[3];
+                sh_delta[4] = sg * cb; sh_delta[5] = sg * sb * sa + cg * ca; sh_delta[6] = sg * sb * ca - cg * sa; sh_delta[7] = x[4];
+                sh_delta[8] = -sb;     sh_delta[9] = cb * sa;                sh_delta[10] = cb * ca;               sh_delta[11] = x[5];
+            }
+            __syncthreads();
+            double D[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) D[k] = sh_delta[k];
+            // trans = delta * trans  (every thread keeps its own copy; only thread 0's is used)
+            double Tn[12];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+                    Tn[r * 4 + cc] = D[r * 4] * trans[cc] + D[r * 4 + 1] * trans[4 + cc] + D[r * 4 + 2] * trans[8 + cc] +
+                                     D[r * 4 + 3] * trans[12 + cc];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) trans[k] = Tn[k];
+            for (int i = tid; i < ncorr; i += FG_THREADS) {
+                double x = qc[(size_t)i * 3], y = qc[(size_t)i * 3 + 1], z = qc[(size_t)i * 3 + 2];
+                transform_point(D, x, y, z);
+                qc[(size_t)i * 3] = x; qc[(size_t)i * 3 + 1] = y; qc[(size_t)i * 3 + 2] = z;
+            }
+            if (c.decrease_mu && itr % 4 == 0 && par > c.max_corr_dist) par /= c.division_factor;
+        }
+    }
+    if (tid != 0) return;
+    // t' = -R mean_t + t * scale + mean_s ; result = [R | t']^-1 = [R^T | -R^T t']
+    double tt[3];
+    for (int r = 0; r < 3; ++r)
+        tt[r] = -(trans[r * 4] * fu.mean_t[0] + trans[r * 4 + 1] * fu.mean_t[1] + trans[r * 4 + 2] * fu.mean_t[2]) +
+                trans[r * 4 + 3] * fu.scale + fu.mean_s[r];
+    double *T = c.out_T + (size_t)u * 16;
+    for (int r = 0; r < 3; ++r) {
+        for (int cc = 0; cc < 3; ++cc) T[r * 4 + cc] = trans[cc * 4 + r];
+        T[r * 4 + 3] = -(trans[0 * 4 + r] * tt[0] + trans[1 * 4 + r] * tt[1] + trans[2 * 4 + r] * tt[2]);
+    }
+    T[12] = T[13] = T[14] = 0.0; T[15] = 1.0;
+    int *info = c.out_info + (size_t)u * 4;
+    info[0] = fu.n_init; info[1] = fu.n_pairs; info[2] = fu.trials; info[3] = fu.swapped;
+}
+
+struct FgrLayout {
+    size_t off_unit, off_init, off_cor, off_q, total;
+    int cap;
+};
+
+bool fgr_layout(const orpcd_fgr_params *p, FgrLayout &L)
+{
+    if (!p || p->n_units <= 0 || p->n_src <= 0 || p->n_tgt <= 0 || p->n_feat_src <= 0 || p->n_feat_tgt <= 0 ||
+        p->iteration_number < 0 || p->max_tuple_count <= 0 || !(p->tuple_scale > 0) || !(p->division_factor > 0))
+        return false;
+    const long long tup = 3LL * p->max_tuple_count;
+    const long long cap = tup > p->n_feat_src ? tup : p->n_feat_src;
+    if (cap > 0x3fffffff) return false;
+    L.cap = (int)cap;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += orpcd_align_up(bytes, 256); return r; };
+    const size_t U = p->n_units;
+    L.off_unit = take(U * sizeof(FgrUnit));
+    L.off_init = take(U * L.cap * sizeof(int2));
+    L.off_cor = take(U * L.cap * sizeof(int2));
+    L.off_q = take(U * L.cap * 3 * sizeof(double));
+    L.total = o;
+    return true;
+}
+
+}  // namespace
+
+ORPCD_API size_t orpcd_feature_pack_bytes(int n)
+{
+    if (n <= 0) return 0;
+    return (size_t)((n + FM_ROWS - 1) / FM_ROWS) * FM_TILE_BYTES;
+}
+
+ORPCD_API int orpcd_feature_pack(const double *d_features, int n, int n_sets, void *d_packed, float *d_set_maxnorm,
+                                 orpcd_stream_t stream)
+{
+    if (!d_features || !d_packed || !d_set_maxnorm || n <= 0 || n_sets <= 0) return ORPCD_ERR_INVALID;
+    if ((uintptr_t)d_packed & 127) return ORPCD_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(d_set_maxnorm, 0, sizeof(float) * n_sets, st) != cudaSuccess) return ORPCD_ERR_CUDA;
+    const int tiles = (n + FM_ROWS - 1) / FM_ROWS;
+    feat_pack_kernel<<<dim3(tiles, n_sets), FM_ROWS, 0, st>>>(d_features, n, tiles, (unsigned char *)d_packed,
+                                                             d_set_maxnorm);
+    ORPCD_CHECK_LAUNCH();
+    return ORPCD_OK;
+}
+
+ORPCD_API size_t orpcd_feature_match_workspace_bytes(int n_query, int n_pairs)
+{
+    if (n_query <= 0 || n_pairs <= 0) return 0;
+    return 3 * orpcd_align_up((size_t)n_query * n_pairs * 4, 256);
+}
+
+ORPCD_API int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q, int n_query,
+                                  const double *d_feat_db, const void *d_packed_db, const float *d_db_maxnorm,
+                                  int n_db, const int *d_pair_q, const int *d_pair_db, int n_pairs, int mode,
+                                  void *d_workspace, size_t workspace_bytes, int *d_nn, double *d_nn_d2,
+                                  int *d_stats, float *d_debug_v, orpcd_stream_t stream)
+{
+    if (!d_feat_q || !d_packed_q || !d_feat_db || !d_packed_db || !d_db_maxnorm || !d_pair_q || !d_pair_db || !d_nn)
+        return ORPCD_ERR_INVALID;
+    if (n_query <= 0 || n_db <= 0 || n_pairs <= 0 || n_pairs > 65535 || mode < 0 || mode > 1) return ORPCD_ERR_INVALID;
+    if (!d_workspace || workspace_bytes < orpcd_feature_match_workspace_bytes(n_query, n_pairs) ||
+        ((uintptr_t)d_workspace & 255))
+        return ORPCD_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t slice = orpcd_align_up((size_t)n_query * n_pairs * 4, 256);
+    float *m1 = (float *)d_workspace;
+    int *c1 = (int *)((unsigned char *)d_workspace + slice);
+    float *m2 = (float *)((unsigned char *)d_workspace + 2 * slice);
+    const int q_tiles = (n_query + FM_ROWS - 1) / FM_ROWS, db_tiles = (n_db + FM_ROWS - 1) / FM_ROWS;
+    if (mode == 0) {
+        if (cudaFuncSetAttribute(feat_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FM_SMEM_BYTES) !=
+            cudaSuccess)
+            return ORPCD_ERR_CUDA;
+        feat_match_kernel<<<dim3(q_tiles, n_pairs), FM_ROWS, FM_SMEM_BYTES, st>>>(
+            (const unsigned char *)d_packed_q, q_tiles, (const unsigned char *)d_packed_db, db_tiles, d_pair_q,
+            d_pair_db, n_query, m1, c1, m2, d_debug_v);
+        ORPCD_CHECK_LAUNCH();
+    }
+    if (d_stats && cudaMemsetAsync(d_stats, 0, sizeof(int), st) != cudaSuccess) return ORPCD_ERR_CUDA;
+    feat_resolve_kernel<<<dim3((n_query + 3) / 4, n_pairs), 128, 0, st>>>(d_feat_q, n_query, d_feat_db, n_db, d_pair_q,
+                                                                          d_pair_db, d_db_maxnorm, m1, c1, m2,
+                                                                          mode == 1, d_nn, d_nn_d2, d_stats);
+    ORPCD_CHECK_LAUNCH();
+    return ORPCD_OK;
+}
+
+ORPCD_API size_t orpcd_fgr_batch_workspace_bytes(const orpcd_fgr_params *p)
+{
+    FgrLayout L;
+    if (!fgr_layout(p, L)) return 0;
+    return L.total;
+}
+
+ORPCD_API int orpcd_fgr_batch(const orpcd_fgr_params *p, const double *d_src_points, const double *d_tgt_points,
+                              const int *d_unit_src, const int *d_unit_tgt, const int *d_ij, const int *d_ji,
+                              const unsigned long long *d_tuple_keys, void *d_workspace, size_t workspace_bytes,
+                              double *d_out_T, int *d_out_info, orpcd_stream_t stream)
+{
+    FgrLayout L;
+    if (!fgr_layout(p, L)) return ORPCD_ERR_INVALID;
+    if (!d_src_points || !d_tgt_points || !d_unit_src || !d_unit_tgt || !d_ij || !d_ji || !d_tuple_keys || !d_out_T ||
+        !d_out_info)
+        return ORPCD_ERR_INVALID;
+    if (!d_workspace || workspace_bytes < L.total || ((uintptr_t)d_workspace & 255)) return ORPCD_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char *w = (unsigned char *)d_workspace;
+    FgrCtx c;
+    c.n_units = p->n_units; c.n_src = p->n_src; c.n_tgt = p->n_tgt;
+    c.n_feat_src = p->n_feat_src; c.n_feat_tgt = p->n_feat_tgt; c.cap = L.cap;
+    c.iteration_number = p->iteration_number; c.decrease_mu = p->decrease_mu;
+    c.max_tuple = p->max_tuple_count; c.tuple_test = p->tuple_test;
+    c.division_factor = p->division_factor; c.tuple_scale = p->tuple_scale; c.max_corr_dist = p->max_correspondence_distance;
+    c.src_pts = d_src_points; c.tgt_pts = d_tgt_points; c.unit_src = d_unit_src; c.unit_tgt = d_unit_tgt;
+    c.ij = d_ij; c.ji = d_ji; c.keys = d_tuple_keys;
+    c.unit = (FgrUnit *)(w + L.off_unit);
+    c.corres_init = (int2 *)(w + L.off_init);
+    c.corres = (int2 *)(w + L.off_cor);
+    c.qcur = (double *)(w + L.off_q);
+    c.out_T = d_out_T; c.out_info = d_out_info;
+    fgr_prepare_kernel<<<p->n_units, FG_THREADS, 0, st>>>(c);
+    fgr_tuple_kernel<<<p->n_units, FG_THREADS, 0, st>>>(c);
+    fgr_gnc_kernel<<<p->n_units, FG_THREADS, 0, st>>>(c);
+    ORPCD_CHECK_LAUNCH();
+    return ORPCD_OK;
+}

@@ -1,0 +1,165 @@
+// FPFH descriptors (Rusu et al.) as Open3D 0.18.0 computes them, float64.
+//
+// Replaces open3d.pipelines.registration.compute_fpfh_feature(cloud,
+// KDTreeSearchParamHybrid(radius, max_nn)) as called from
+// Optimizer/fastGlobalOptimizer.py:130-143.  Algorithm: SURVEY.md Appendix A.7
+// (Feature.cpp: ComputePairFeatures, ComputeSPFHFeature, ComputeFPFHFeature).
+//
+// Both passes run over neighbour lists computed elsewhere (orpcd_knn_exact /
+// orpcd_knn_rerank: exact float64, sorted by (distance, index)); the Hybrid search is
+// the k-NN list truncated at d2 < radius^2.  One thread per point; every sum is taken in
+// neighbour order like the CPU code; the one discontinuous libm call (the acos comparison that
+// picks the pair's source point) uses the deterministic det_acos shared with the oracle, so the
+// only remaining difference is the device atan2 within an ulp of a histogram-bin edge.
+#include "common.cuh"
+
+namespace {
+
+constexpr int FP_THREADS = 128;
+constexpr int FP_DIM = 33;
+
+__device__ __forceinline__ int hist_bin(double x)
+{
+    int h = (int)floor(x);
+    if (h < 0) h = 0;
+    if (h >= 11) h = 10;
+    return h;
+}
+
+// ComputePairFeatures(p1, n1, p2, n2): f0 = atan2 angle, f1, f2; returns false for the zero vector.
+__device__ __forceinline__ bool pair_features(const double *p1, const double *n1, const double *p2,
+                                              const double *n2, double &f0, double &f1, double &f2)
+{
+    double dx = p2[0] - p1[0], dy = p2[1] - p1[1], dz = p2[2] - p1[2];
+    f0 = f1 = f2 = 0.0;
+    const double len = sqrt(dx * dx + dy * dy + dz * dz);
+    if (len == 0.0) return false;
+    double ax = n1[0], ay = n1[1], az = n1[2], bx = n2[0], by = n2[1], bz = n2[2];
+    const double angle1 = (ax * dx + ay * dy + az * dz) / len;
+    const double angle2 = (bx * dx + by * dy + bz * dz) / len;
+    double g2;
+    if (det_acos(fabs(angle1)) > det_acos(fabs(angle2))) {
+        ax = n2[0]; ay = n2[1]; az = n2[2];
+        bx = n1[0]; by = n1[1]; bz = n1[2];
+        dx *= -1.0; dy *= -1.0; dz *= -1.0;
+        g2 = -angle2;
+    } else {
+        g2 = angle1;
+    }
+    // v = dp x a
+    double vx = dy * az - dz * ay, vy = dz * ax - dx * az, vz = dx * ay - dy * ax;
+    const double vn = sqrt(vx * vx + vy * vy + vz * vz);
+    if (vn == 0.0) return false;
+    vx /= vn; vy /= vn; vz /= vn;
+    // w = a x v
+    const double wx = ay * vz - az * vy, wy = az * vx - ax * vz, wz = ax * vy - ay * vx;
+    f2 = g2;
+    f1 = vx * bx + vy * by + vz * bz;
+    f0 = atan2(wx * bx + wy * by + wz * bz, ax * bx + ay * by + az * bz);
+    return true;
+}
+
+// SPFH: 3 x 11-bin histograms of the pair features to the neighbours (self excluded).
+__global__ void __launch_bounds__(FP_THREADS)
+spfh_kernel(const double *__restrict__ points, const double *__restrict__ normals, int n, long long stride,
+            const int *__restrict__ nn_idx, const double *__restrict__ nn_d2, int list_k, int knn, double radius2,
+            double *__restrict__ spfh)
+{
+    __shared__ double hist[FP_DIM][FP_THREADS];   // bin-major: conflict free
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int i = blockIdx.x * FP_THREADS + tid;
+    if (i >= n) return;
+    const double PI = 3.14159265358979323846;
+    const double *pts = points + (size_t)b * stride;
+    const double *nrm = normals + (size_t)b * stride;
+    const size_t row = (size_t)b * n + i;
+    const int *idx = nn_idx + row * list_k;
+    const double *d2 = nn_d2 + row * list_k;
+#pragma unroll
+    for (int j = 0; j < FP_DIM; ++j) hist[j][tid] = 0.0;
+    int cnt = 0;
+    for (; cnt < knn; ++cnt) {
+        if (idx[cnt] < 0) break;
+        if (radius2 > 0 && !(d2[cnt] < radius2)) break;
+    }
+    if (cnt > 1) {
+        const double incr = 100.0 / (double)(cnt - 1);
+        const double *p1 = pts + (size_t)i * 3, *n1 = nrm + (size_t)i * 3;
+        for (int k = 1; k < cnt; ++k) {
+            const int id = idx[k];
+            double f0, f1, f2;
+            pair_features(p1, n1, pts + (size_t)id * 3, nrm + (size_t)id * 3, f0, f1, f2);
+            hist[hist_bin(11 * (f0 + PI) / (2.0 * PI))][tid] += incr;
+            hist[11 + hist_bin(11 * (f1 + 1.0) * 0.5)][tid] += incr;
+            hist[22 + hist_bin(11 * (f2 + 1.0) * 0.5)][tid] += incr;
+        }
+    }
+    double *o = spfh + row * FP_DIM;
+#pragma unroll
+    for (int j = 0; j < FP_DIM; ++j) o[j] = hist[j][tid];
+}
+
+// FPFH: own SPFH + the 1/d2-weighted, per-histogram renormalised SPFH of the neighbours.
+__global__ void __launch_bounds__(FP_THREADS)
+fpfh_kernel(int n, const int *__restrict__ nn_idx, const double *__restrict__ nn_d2, int list_k, int knn,
+            double radius2, const double *__restrict__ spfh, double *__restrict__ fpfh)
+{
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * FP_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const size_t row = (size_t)b * n + i;
+    const int *idx = nn_idx + row * list_k;
+    const double *d2 = nn_d2 + row * list_k;
+    const double *sp = spfh + (size_t)b * n * FP_DIM;
+    double acc[FP_DIM];
+#pragma unroll
+    for (int j = 0; j < FP_DIM; ++j) acc[j] = 0.0;
+    int cnt = 0;
+    for (; cnt < knn; ++cnt) {
+        if (idx[cnt] < 0) break;
+        if (radius2 > 0 && !(d2[cnt] < radius2)) break;
+    }
+    double *o = fpfh + row * FP_DIM;
+    if (cnt > 1) {
+        double sum[3] = {0.0, 0.0, 0.0};
+        for (int k = 1; k < cnt; ++k) {
+            const double dist = d2[k];
+            if (dist == 0.0) continue;
+            const double *s = sp + (size_t)idx[k] * FP_DIM;
+#pragma unroll
+            for (int j = 0; j < FP_DIM; ++j) {
+                const double val = s[j] / dist;
+                sum[j / 11] += val;
+                acc[j] += val;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (sum[j] != 0.0) sum[j] = 100.0 / sum[j];
+        const double *self = sp + (size_t)i * FP_DIM;
+#pragma unroll
+        for (int j = 0; j < FP_DIM; ++j) o[j] = acc[j] * sum[j / 11] + self[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < FP_DIM; ++j) o[j] = 0.0;
+    }
+}
+
+}  // namespace
+
+ORPCD_API int orpcd_fpfh(const double *d_points, const double *d_normals, int n, long long points_stride,
+                         int batch, const int *d_nn_idx, const double *d_nn_d2, int list_k, int knn, double radius,
+                         double *d_spfh, double *d_fpfh, orpcd_stream_t stream)
+{
+    if (!d_points || !d_normals || !d_nn_idx || !d_nn_d2 || !d_spfh || !d_fpfh) return ORPCD_ERR_INVALID;
+    if (n <= 0 || batch <= 0 || knn < 1 || list_k < knn) return ORPCD_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid((n + FP_THREADS - 1) / FP_THREADS, batch);
+    const double r2 = radius > 0 ? radius * radius : 0.0;
+    spfh_kernel<<<grid, FP_THREADS, 0, st>>>(d_points, d_normals, n, points_stride, d_nn_idx, d_nn_d2, list_k, knn, r2,
+                                             d_spfh);
+    ORPCD_CHECK_LAUNCH();
+    fpfh_kernel<<<grid, FP_THREADS, 0, st>>>(n, d_nn_idx, d_nn_d2, list_k, knn, r2, d_spfh, d_fpfh);
+    ORPCD_CHECK_LAUNCH();
+    return ORPCD_OK;
+}

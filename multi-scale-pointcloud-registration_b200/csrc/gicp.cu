@@ -143,15 +143,16 @@ __device__ __forceinline__ void cp_async_wait()
 // set-up kernels
 // ----------------------------------------------------------------------------
 __global__ void init_units_kernel(Ctx c, const int *__restrict__ unit_src, const int *__restrict__ unit_tgt,
-                                  const double *__restrict__ src_pts, const double *__restrict__ src_cov)
+                                  const double *__restrict__ src_pts, const double *__restrict__ src_cov,
+                                  const double *__restrict__ init_T)
 {
     const int u = blockIdx.y;
     const int ss = unit_src[u];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         UnitState &s = c.state[u];
-        for (int k = 0; k < 16; ++k) s.T[k] = (k % 5 == 0) ? 1.0 : 0.0;
-        for (int k = 0; k < 12; ++k) s.U[k] = (k % 5 == 0) ? 1.0 : 0.0;
-        s.fitness = 0; s.rmse = 0; s.iters = 0; s.done = 0; s.has_update = 0; s.n_corr = 0;
+        for (int k = 0; k < 16; ++k) s.T[k] = init_T ? init_T[(size_t)u * 16 + k] : ((k % 5 == 0) ? 1.0 : 0.0);
+        for (int k = 0; k < 12; ++k) s.U[k] = s.T[k];
+        s.fitness = 0; s.rmse = 0; s.iters = 0; s.done = 0; s.has_update = init_T ? 1 : 0; s.n_corr = 0;
         s.src_set = ss; s.tgt_set = unit_tgt[u]; s.status = 0; s.pad = 0;
         c.red_counter[u] = 0;
         if (u == 0) {
@@ -159,7 +160,7 @@ __global__ void init_units_kernel(Ctx c, const int *__restrict__ unit_src, const
             for (int k = 0; k < c.max_iter + 2; ++k) { c.worklist_count[k] = 0; c.round_active[k] = 0; }
         }
     }
-    const size_t np = (size_t)c.n_src * 3, nc = (size_t)c.n_src * c.cov_stride;
+    const size_t np = (size_t)c.n_src * 3, nc = src_cov ? (size_t)c.n_src * c.cov_stride : 0;
     const double *sp = src_pts + (size_t)ss * np;
     const double *sc = src_cov + (size_t)ss * nc;
     double *dp = c.cur_pts + (size_t)u * np;
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(256) update_kernel(Ctx c)
         if (c.cov_mode == 0) {
             double *cp = c.cur_cov + oi * 6;
             store_sym3(cp, rotate_sym3(st.U, load_sym3(cp)));
-        } else {
+        } else if (c.cov_mode == 1) {
             double *ap = c.cur_cov + oi * 3;
             const double ax = ap[0], ay = ap[1], az = ap[2];
             ap[0] = st.U[0] * ax + st.U[1] * ay + st.U[2] * az;
@@ -660,6 +661,11 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
             const double *pt = c.tgt_pts + tj * 3;
             const double dx = sx - pt[0], dy = sy - pt[1], dz = sz - pt[2];
             Sym3 W;
+            if (COV_MODE == 2) {
+                // EvaluateRegistration only: squared error and count
+                acc[27] = c.corr_d2[oi];
+                acc[28] = 1.0;
+            } else {
             if (COV_MODE == 0) {
                 const Sym3 Cs = load_sym3(c.cur_cov + oi * 6);
                 const Sym3 Ct = load_sym3(c.tgt_cov + tj * 6);
@@ -690,6 +696,7 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
             for (int a = 0; a < 6; ++a) acc[21 + a] = J[0][a] * rr[0] + J[1][a] * rr[1] + J[2][a] * rr[2];
             acc[27] = c.corr_d2[oi];
             acc[28] = 1.0;
+            }
         }
     }
 #pragma unroll
@@ -933,7 +940,7 @@ ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_p
     {
         const int gx = (int)((((size_t)p->n_src * 6) + 255) / 256);
         dim3 grid(gx > 64 ? 64 : gx, p->n_units);
-        init_units_kernel<<<grid, 256, 0, st>>>(c, d_unit_src, d_unit_tgt, d_src_points, d_src_cov);
+        init_units_kernel<<<grid, 256, 0, st>>>(c, d_unit_src, d_unit_tgt, d_src_points, d_src_cov, nullptr);
         ORPCD_CHECK_LAUNCH();
         prep_targets_kernel<<<p->n_tgt_sets, 1024, 0, st>>>(c);
         ORPCD_CHECK_LAUNCH();
@@ -1009,6 +1016,46 @@ ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_p
         h_profile[6] = (double)sweep_launches;                          // sweep launches that had work
         h_profile[7] = unit_rounds;
     }
+    return ORPCD_OK;
+}
+
+ORPCD_API int orpcd_evaluate_batch(const orpcd_gicp_params *p_in, const double *d_src_points,
+                                   const double *d_tgt_points, const int *d_unit_src, const int *d_unit_tgt,
+                                   const double *d_T, void *d_workspace, size_t workspace_bytes,
+                                   double *d_out_stats, int *d_out_status, int *d_out_corr, orpcd_stream_t stream)
+{
+    if (!p_in) return ORPCD_ERR_INVALID;
+    orpcd_gicp_params q = *p_in;
+    q.cov_mode = 1;
+    if (!(q.gicp_epsilon > 0 && q.gicp_epsilon < 1)) q.gicp_epsilon = 1e-3;
+    Layout L;
+    if (!make_layout(&q, L)) return ORPCD_ERR_INVALID;
+    if (!d_src_points || !d_tgt_points || !d_unit_src || !d_unit_tgt || !d_out_stats || !d_out_status)
+        return ORPCD_ERR_INVALID;
+    if (!d_workspace || workspace_bytes < L.total || ((uintptr_t)d_workspace & 255)) return ORPCD_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    Ctx c;
+    fill_ctx(&q, L, d_workspace, c);
+    c.cov_mode = 2;       // no covariances: Evaluate only
+    c.max_iter = 0;       // round 0 is the evaluation; the unit is done right after it
+    c.tgt_pts = d_tgt_points; c.tgt_cov = nullptr;
+    // out_T is required by the reduction's epilogue: park it in the (unused) covariance slice
+    c.out_T = c.cur_cov; c.out_stats = d_out_stats; c.out_status = d_out_status; c.trace = nullptr;
+    if ((size_t)q.n_units * 16 > (size_t)q.n_units * q.n_src * 3) return ORPCD_ERR_INVALID;
+    const int gx = (int)((((size_t)q.n_src * 3) + 255) / 256);
+    init_units_kernel<<<dim3(gx > 64 ? 64 : gx, q.n_units), 256, 0, st>>>(c, d_unit_src, d_unit_tgt, d_src_points,
+                                                                          nullptr, d_T);
+    prep_targets_kernel<<<q.n_tgt_sets, 1024, 0, st>>>(c);
+    update_kernel<<<dim3((q.n_src + 255) / 256, q.n_units), 256, 0, st>>>(c);
+    launch_sweep(c, L, q.n_units, st);
+    nn_resolve_kernel<<<dim3((q.n_src + 127) / 128, q.n_units), 128, 0, st>>>(c, 0);
+    nn_fix_kernel<<<148 * 4, 128, 0, st>>>(c, 0);
+    reduce_kernel<2><<<dim3(L.red_blocks, q.n_units), RED_THREADS, 0, st>>>(c, 0);
+    ORPCD_CHECK_LAUNCH();
+    if (d_out_corr &&
+        cudaMemcpyAsync(d_out_corr, c.corr, sizeof(int) * (size_t)q.n_units * q.n_src, cudaMemcpyDeviceToDevice, st) !=
+            cudaSuccess)
+        return ORPCD_ERR_CUDA;
     return ORPCD_OK;
 }
 

@@ -134,6 +134,10 @@ class Aligner:
         for n in range(len(rots)):
             self.n_optimize_calls += 1
             if status[n] != 0:
+                # what optimize() would have raised for this start (GICP: ValueError, FGR: Warning)
+                raise_failure = getattr(self._optimizer, "raise_failure", None)
+                if raise_failure is not None:
+                    raise_failure()
                 self._LOG.error(_ZERO_LOSS_MSG)
                 raise ValueError(_ZERO_LOSS_MSG)
             if metrics[n] < metric:

@@ -1,3 +1,4 @@
 from .iOptimizer import BatchResult, IOptimizer
 from .generalizedICP import GeneralizedICP
+from .fastGlobalOptimizer import FastGlobalOptimizer
 from .shardedOptimizer import ShardedOptimizer

@@ -52,9 +52,13 @@ class GeneralizedICP(IOptimizer):
     def optimize(self, source: np.ndarray, target: np.ndarray, **kwargs) -> Tuple[np.ndarray, float]:
         res = self.optimize_batch(np.asarray(source)[None], np.asarray(target)[None], [0], [0], poll_interval=8)
         if res.status[0] != 0:
-            self._LOG.error(_ZERO_LOSS_MSG)
-            raise ValueError(_ZERO_LOSS_MSG)
+            self.raise_failure()
         return res.transforms[0], float(res.rmse[0])
+
+    def raise_failure(self):
+        """inlier_rmse == 0 (generalizedICP.py:77-81)."""
+        self._LOG.error(_ZERO_LOSS_MSG)
+        raise ValueError(_ZERO_LOSS_MSG)
 
     # ------------------------------------------------------------------ batched API
     def optimize_batch(self, sources, targets, unit_src: Sequence[int], unit_tgt: Sequence[int],

@@ -115,5 +115,11 @@ class ShardedOptimizer(IOptimizer):
         dist.all_gather_into_tensor(out, mine_t, group=self._group)
         return unpack_records(out.cpu().numpy().reshape(world, n_slots, RECORD_F64), n_units, world)
 
+    def raise_failure(self):
+        raise_failure = getattr(self._inner, "raise_failure", None)
+        if raise_failure is not None:
+            raise_failure()
+        raise ValueError("inner registration failed")
+
     def __repr__(self):
         return f"{self.__class__.__name__}({self._inner!r})"

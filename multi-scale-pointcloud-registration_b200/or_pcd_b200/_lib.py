@@ -46,6 +46,25 @@ class GicpParams(C.Structure):
     ]
 
 
+class FgrParams(C.Structure):
+    """Mirror of ``orpcd_fgr_params`` (include/orpcd_b200.h)."""
+
+    _fields_ = [
+        ("n_units", C.c_int),
+        ("n_src", C.c_int),
+        ("n_tgt", C.c_int),
+        ("n_feat_src", C.c_int),
+        ("n_feat_tgt", C.c_int),
+        ("iteration_number", C.c_int),
+        ("decrease_mu", C.c_int),
+        ("max_tuple_count", C.c_int),
+        ("tuple_test", C.c_int),
+        ("division_factor", C.c_double),
+        ("tuple_scale", C.c_double),
+        ("max_correspondence_distance", C.c_double),
+    ]
+
+
 class OrpcdError(RuntimeError):
     pass
 
@@ -93,6 +112,22 @@ def lib():
                                    C.POINTER(C.c_double), vp]
     L.orpcd_gicp_sweep_only.restype = ip
     L.orpcd_gicp_sweep_only.argtypes = [C.POINTER(GicpParams), vp, sz, vp]
+    L.orpcd_evaluate_batch.restype = ip
+    L.orpcd_evaluate_batch.argtypes = [C.POINTER(GicpParams), vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp]
+    L.orpcd_fpfh.restype = ip
+    L.orpcd_fpfh.argtypes = [vp, vp, ip, ll, ip, vp, vp, ip, ip, dp, vp, vp, vp]
+    L.orpcd_feature_pack_bytes.restype = sz
+    L.orpcd_feature_pack_bytes.argtypes = [ip]
+    L.orpcd_feature_pack.restype = ip
+    L.orpcd_feature_pack.argtypes = [vp, ip, ip, vp, vp, vp]
+    L.orpcd_feature_match_workspace_bytes.restype = sz
+    L.orpcd_feature_match_workspace_bytes.argtypes = [ip, ip]
+    L.orpcd_feature_match.restype = ip
+    L.orpcd_feature_match.argtypes = [vp, vp, ip, vp, vp, vp, ip, vp, vp, ip, ip, vp, sz, vp, vp, vp, vp, vp]
+    L.orpcd_fgr_batch_workspace_bytes.restype = sz
+    L.orpcd_fgr_batch_workspace_bytes.argtypes = [C.POINTER(FgrParams)]
+    L.orpcd_fgr_batch.restype = ip
+    L.orpcd_fgr_batch.argtypes = [C.POINTER(FgrParams), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp]
     L.orpcd_ffma_burn.restype = ip
     L.orpcd_ffma_burn.argtypes = [ip, ip, vp, vp]
     L.orpcd_ffma2_burn.restype = ip

@@ -10,7 +10,7 @@ import ctypes as C
 from typing import Dict, Optional
 
 from . import _lib
-from ._lib import GicpParams, check
+from ._lib import FgrParams, GicpParams, check
 
 launch_counter = {"kernels": 0}
 
@@ -196,6 +196,125 @@ def gicp_batch(src_points, src_cov6, tgt_points, tgt_cov6, unit_src, unit_tgt, m
     res.params = prm
     launch_counter["kernels"] += int(prof[0])
     return res
+
+
+def evaluate_batch(src_points, tgt_points, unit_src, unit_tgt, transforms=None, max_correspondence_distance=0.5,
+                   want_corr=False, ws=None):
+    """EvaluateRegistration per unit: (stats [U,4] = fitness, rmse, 0, n_corr; status [U]; corr [U,Ns] | None; ws)."""
+    t = _t()
+    src_points, tgt_points = _f64(src_points), _f64(tgt_points)
+    S, Ns, _ = src_points.shape
+    Cn, Nt, _ = tgt_points.shape
+    U = unit_src.shape[0]
+    prm = GicpParams(U, Ns, Nt, S, Cn, 0, 0, 0, 0, 1, float(max_correspondence_distance), 1e-6, 1e-6, 1e-3, 0, 0, 0, 0)
+    L = _lib.lib()
+    need = L.orpcd_gicp_batch_workspace_bytes(C.byref(prm))
+    if need == 0:
+        raise _lib.OrpcdError("orpcd_evaluate_batch: invalid parameters")
+    if ws is None or ws.numel() < need:
+        ws = _lib.workspace(need)
+    stats = t.empty((U, 4), dtype=t.float64, device="cuda")
+    status = t.empty(U, dtype=t.int32, device="cuda")
+    corr = t.empty((U, Ns), dtype=t.int32, device="cuda") if want_corr else None
+    if transforms is not None:
+        transforms = _f64(transforms)
+        assert transforms.shape == (U, 4, 4)
+    check(L.orpcd_evaluate_batch(C.byref(prm), src_points.data_ptr(), tgt_points.data_ptr(), unit_src.data_ptr(),
+                                 unit_tgt.data_ptr(), transforms.data_ptr() if transforms is not None else None,
+                                 ws.data_ptr(), ws.numel(), stats.data_ptr(), status.data_ptr(),
+                                 corr.data_ptr() if want_corr else None, _lib.stream_ptr()), "orpcd_evaluate_batch")
+    launch_counter["kernels"] += 7
+    return stats, status, corr, ws
+
+
+def fpfh(points, normals, nn_idx, nn_d2, knn: int, radius: float, want_spfh=False):
+    """FPFH descriptors [B,N,33] float64 from neighbour lists [B,N,list_k] (self query, sorted)."""
+    t = _t()
+    points, normals, nn_d2 = _f64(points), _f64(normals), _f64(nn_d2)
+    B, N, _ = points.shape
+    assert nn_idx.dtype == t.int32 and nn_idx.is_contiguous() and nn_idx.shape[:2] == (B, N)
+    list_k = nn_idx.shape[2]
+    spfh = t.empty((B, N, 33), dtype=t.float64, device="cuda")
+    out = t.empty((B, N, 33), dtype=t.float64, device="cuda")
+    check(_lib.lib().orpcd_fpfh(points.data_ptr(), normals.data_ptr(), N, N * 3, B, nn_idx.data_ptr(),
+                                nn_d2.data_ptr(), list_k, int(knn), float(radius), spfh.data_ptr(), out.data_ptr(),
+                                _lib.stream_ptr()), "orpcd_fpfh")
+    launch_counter["kernels"] += 2
+    return (out, spfh) if want_spfh else out
+
+
+class PackedFeatures:
+    """Feature sets [S,N,33] float64 plus their TF32 hi/lo operand-tile images for the tcgen05 filter."""
+    __slots__ = ("features", "packed", "maxnorm", "n", "n_sets")
+
+
+def feature_pack(features) -> PackedFeatures:
+    t = _t()
+    features = _f64(features)
+    S, N, D = features.shape
+    assert D == 33
+    L = _lib.lib()
+    pf = PackedFeatures()
+    pf.features, pf.n, pf.n_sets = features, N, S
+    pf.packed = t.empty(L.orpcd_feature_pack_bytes(N) * S, dtype=t.uint8, device="cuda")
+    pf.maxnorm = t.empty(S, dtype=t.float32, device="cuda")
+    check(L.orpcd_feature_pack(features.data_ptr(), N, S, pf.packed.data_ptr(), pf.maxnorm.data_ptr(),
+                               _lib.stream_ptr()), "orpcd_feature_pack")
+    launch_counter["kernels"] += 1
+    return pf
+
+
+def feature_match(query: PackedFeatures, db: PackedFeatures, pair_q, pair_db, mode: int = 0, want_d2=False,
+                  want_debug=False):
+    """For pair p: nearest row of db set pair_db[p] for every row of query set pair_q[p].
+    Returns (nn int32 [P,Nq], d2 | None, n_exact_scans (device int32[1]), debug | None)."""
+    t = _t()
+    P = pair_q.shape[0]
+    assert pair_q.dtype == t.int32 and pair_db.dtype == t.int32 and pair_q.is_cuda and pair_db.is_cuda
+    L = _lib.lib()
+    ws = _lib.workspace(L.orpcd_feature_match_workspace_bytes(query.n, P))
+    nn = t.empty((P, query.n), dtype=t.int32, device="cuda")
+    d2 = t.empty((P, query.n), dtype=t.float64, device="cuda") if want_d2 else None
+    stats = t.zeros(1, dtype=t.int32, device="cuda")
+    dbg = None
+    if want_debug:
+        dbg = t.full((P, query.n, (db.n + 127) // 128 * 128), float("nan"), dtype=t.float32, device="cuda")
+    check(L.orpcd_feature_match(query.features.data_ptr(), query.packed.data_ptr(), query.n, db.features.data_ptr(),
+                                db.packed.data_ptr(), db.maxnorm.data_ptr(), db.n, pair_q.data_ptr(),
+                                pair_db.data_ptr(), P, int(mode), ws.data_ptr(), ws.numel(), nn.data_ptr(),
+                                d2.data_ptr() if want_d2 else None, stats.data_ptr(),
+                                dbg.data_ptr() if want_debug else None, _lib.stream_ptr()), "orpcd_feature_match")
+    launch_counter["kernels"] += 2 if mode == 0 else 1
+    return nn, d2, stats, dbg
+
+
+def fgr_batch(src_points, tgt_points, unit_src, unit_tgt, ij, ji, keys, division_factor=1.4, tuple_scale=0.9,
+              max_correspondence_distance=0.5, iteration_number=100, decrease_mu=True, max_tuple_count=1000,
+              tuple_test=True):
+    """Cross check + tuple test + GNC solve per unit.  Returns (T [U,4,4] source->target, info int32 [U,4])."""
+    t = _t()
+    src_points, tgt_points = _f64(src_points), _f64(tgt_points)
+    U = unit_src.shape[0]
+    Ns, Nt = src_points.shape[1], tgt_points.shape[1]
+    assert ij.dtype == t.int32 and ji.dtype == t.int32 and ij.shape[0] == U and ji.shape[0] == U
+    assert ij.is_contiguous() and ji.is_contiguous()
+    assert keys.dtype == t.int64 and keys.shape[0] == U and keys.is_cuda
+    prm = FgrParams(U, Ns, Nt, ij.shape[1], ji.shape[1], int(iteration_number), int(bool(decrease_mu)),
+                    int(max_tuple_count), int(bool(tuple_test)), float(division_factor), float(tuple_scale),
+                    float(max_correspondence_distance))
+    L = _lib.lib()
+    need = L.orpcd_fgr_batch_workspace_bytes(C.byref(prm))
+    if need == 0:
+        raise _lib.OrpcdError("orpcd_fgr_batch: invalid parameters")
+    ws = _lib.workspace(need)
+    T = t.empty((U, 4, 4), dtype=t.float64, device="cuda")
+    info = t.empty((U, 4), dtype=t.int32, device="cuda")
+    check(L.orpcd_fgr_batch(C.byref(prm), src_points.data_ptr(), tgt_points.data_ptr(), unit_src.data_ptr(),
+                            unit_tgt.data_ptr(), ij.data_ptr(), ji.data_ptr(),
+                            keys.data_ptr(), ws.data_ptr(), ws.numel(), T.data_ptr(), info.data_ptr(),
+                            _lib.stream_ptr()), "orpcd_fgr_batch")
+    launch_counter["kernels"] += 3
+    return T, info
 
 
 def gicp_sweep_only(params: GicpParams, ws) -> None:

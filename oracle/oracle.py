@@ -164,6 +164,66 @@ def gicp(source, target, max_dist=0.5, max_iter=100, eps=1e-3, src_cov=None, tgt
     return out
 
 
+def fpfh(points, normals_, knn_k: int = 20, radius: float = 0.1, want_spfh=False):
+    """compute_fpfh_feature(cloud, Hybrid(radius, knn)) (A.7; fastGlobalOptimizer.py:130-143).
+    Returns (n,33) float64 (Open3D's 33xN column-major data_ has the same memory order)."""
+    points = _f64(points, 3); normals_ = _f64(normals_, 3)
+    n = points.shape[0]
+    out = np.empty((n, 33)); sp = np.empty((n, 33)) if want_spfh else None
+    rc = lib().oracle_fpfh(_d(points), _d(normals_), C.c_int(n), C.c_int(knn_k), C.c_double(radius), _d(out),
+                           _d(sp) if want_spfh else None)
+    assert rc == 0
+    return (out, sp) if want_spfh else out
+
+
+def philox(counter: int, key: int):
+    out = (C.c_uint32 * 4)()
+    lib().oracle_philox(C.c_uint64(counter), C.c_uint64(key), out)
+    return list(out)
+
+
+_M64 = (1 << 64) - 1
+
+
+def tuple_key(seed: int, source: np.ndarray, target: np.ndarray) -> int:
+    """Key of the tuple-test random stream of one registration.  The reference never seeds
+    Open3D's generator; this project derives the key from the call's own
+    inputs (sizes and the bit patterns of the first/last point of each cloud), so the
+    sequential reference control flow and a batched evaluation draw identical streams
+    without any shared call counter."""
+    h = (int(seed) * 0x9E3779B97F4A7C15 + 0x243F6A8885A308D3) & _M64
+    words = [source.shape[0], target.shape[0]]
+    for c in (source[0], source[-1], target[0], target[-1]):
+        words.extend(int(v) for v in np.ascontiguousarray(c, dtype=np.float64).view(np.uint64))
+    for w in words:
+        h = ((h ^ (w & _M64)) * 0xBF58476D1CE4E5B9) & _M64
+        h ^= h >> 31
+    return h
+
+
+def fgr(source, target, feat_s, feat_t, division_factor=1.4, tuple_scale=0.9, max_corr_dist=0.5,
+        iteration_number=100, decrease_mu=True, max_tuple_count=1000, tuple_test=True, key=0, want_corres=False):
+    """registration_fgr_based_on_feature_matching (A.8; fastGlobalOptimizer.py:158-174).
+    Returns dict(T source->target (column convention), fitness, rmse, n_corr, n_initial, n_pairs, trials, swapped)."""
+    source = _f64(source, 3); target = _f64(target, 3)
+    feat_s = _f64(feat_s, 33); feat_t = _f64(feat_t, 33)
+    T = np.empty(16); fit = C.c_double(); rmse = C.c_double(); nc = C.c_int()
+    info = np.zeros(4, dtype=np.int32)
+    cor = np.full((3 * max(max_tuple_count, 1) if tuple_test else max(feat_s.shape[0], 1), 2), -1, dtype=np.int32)
+    rc = lib().oracle_fgr(_d(source), C.c_int(source.shape[0]), _d(target), C.c_int(target.shape[0]),
+                          _d(feat_s), C.c_int(feat_s.shape[0]), _d(feat_t), C.c_int(feat_t.shape[0]),
+                          C.c_double(division_factor), C.c_double(tuple_scale), C.c_double(max_corr_dist),
+                          C.c_int(iteration_number), C.c_int(int(bool(decrease_mu))), C.c_int(max_tuple_count),
+                          C.c_int(int(bool(tuple_test))), C.c_uint64(key), _d(T), C.byref(fit), C.byref(rmse),
+                          C.byref(nc), _i(info), _i(cor))
+    assert rc == 0
+    out = dict(T=T.reshape(4, 4), fitness=fit.value, rmse=rmse.value, n_corr=nc.value, n_initial=int(info[0]),
+               n_pairs=int(info[1]), trials=int(info[2]), swapped=bool(info[3]))
+    if want_corres:
+        out["corres"] = cor[: info[1]].copy()
+    return out
+
+
 # --------------------------------------------------------------------------
 # The reference's Python layer, restated over the primitives above
 # --------------------------------------------------------------------------
@@ -245,6 +305,54 @@ class GeneralizedICP:
         roto[:3, :3] = roto[:3, :3].T
         if r["rmse"] == 0:
             raise ValueError("Optimization failed with loss = 0. Parameters are not well set.")
+        return roto, r["rmse"]
+
+
+class FastGlobalOptimizer:
+    """Optimizer/fastGlobalOptimizer.py:23-190 restated.  ``feature_mode``:
+    "reference_compat" reproduces the reference literally -- BOTH feature sets are the FPFH of the
+    source cloud (fastGlobalOptimizer.py:137-138 passes source_copy twice; SURVEY.md B.4);
+    "fixed" computes the target's features from the target."""
+
+    def __init__(self, division_factor=1.4, tuple_scale=0.9, maximum_correspondence_distance=0.5,
+                 iteration_number=100, decrease_mu=True, normal_estimate_radius=0.1, normal_estimate_knn=20,
+                 fpfh_radius=0.1, fpfh_knn=20, feature_mode="reference_compat", tuple_seed=0):
+        self._division_factor = division_factor if division_factor > 0 else 1.4
+        self._tuple_scale = tuple_scale if tuple_scale > 0 else 0.9
+        self._maximum_correspondence_distance = (maximum_correspondence_distance
+                                                 if maximum_correspondence_distance > 0 else 0.5)
+        self._iteration_number = iteration_number if iteration_number > 0 else 100
+        self._decrease_mu = decrease_mu
+        self._normal_estimate_radius = normal_estimate_radius if normal_estimate_radius > 0 else 0.1
+        self._normal_estimate_knn = normal_estimate_knn if normal_estimate_knn > 0 else 20
+        self._fpfh_radius = fpfh_radius if fpfh_radius > 0 else 0.1
+        self._fpfh_knn = fpfh_knn if fpfh_knn > 0 else 20
+        self.feature_mode = feature_mode
+        self.tuple_seed = tuple_seed
+        self.calls = 0
+
+    def get_fpfh_features(self, source, target):
+        """fastGlobalOptimizer.py:109-144."""
+        ns = normals(source, self._normal_estimate_knn, self._normal_estimate_radius)["normal"]
+        fs = fpfh(source, ns, self._fpfh_knn, self._fpfh_radius)
+        if self.feature_mode == "reference_compat":
+            return fs, fs
+        nt = normals(target, self._normal_estimate_knn, self._normal_estimate_radius)["normal"]
+        return fs, fpfh(target, nt, self._fpfh_knn, self._fpfh_radius)
+
+    def optimize(self, source, target, **kwargs):
+        """fastGlobalOptimizer.py:146-190."""
+        source = _f64(source, 3); target = _f64(target, 3)
+        fs, ft = self.get_fpfh_features(source, target)
+        r = fgr(source, target, fs, ft, self._division_factor, self._tuple_scale,
+                self._maximum_correspondence_distance, self._iteration_number, self._decrease_mu,
+                key=tuple_key(self.tuple_seed, source, target))
+        self.calls += 1
+        self.last = r
+        roto = np.copy(r["T"])
+        roto[:3, :3] = roto[:3, :3].T
+        if r["n_corr"] == 0:
+            raise Warning("Optimization failed with no correspondences. Parameters are not well set.")
         return roto, r["rmse"]
 
 

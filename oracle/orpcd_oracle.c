@@ -333,6 +333,120 @@ ORACLE_API int oracle_sor(const double *pts, int n, int nb_neighbors, double std
 }
 
 /* ------------------------------------------------------------------------ */
+/* Deterministic acos / cos                                                  */
+/* ------------------------------------------------------------------------ */
+/* Open3D calls libm's acos / cos inside FastEigen3x3 and acos inside FPFH's
+ * ComputePairFeatures, where the results feed DISCONTINUOUS decisions (which
+ * eigenvector branch, which point of a pair is the "source").  libm results
+ * are not specified bit for bit (glibc and the CUDA math library differ in the
+ * last ulp), and range-grid scans contain structural near-ties (neighbouring
+ * points with the same neighbour set have normals equal to ~1e-16), so the two
+ * sides of a parity test would take different branches on a few points in
+ * 5000.  The oracle and the CUDA path therefore share these implementations,
+ * which use only + - * / sqrt and bit masks (Sun fdlibm's e_acos.c / k_cos.c /
+ * k_sin.c algorithms restated, < 1 ulp), compiled without FMA contraction on
+ * both sides: bit-identical results.                                        */
+static inline double dbl_clear_low(double x)
+{
+    uint64_t u; memcpy(&u, &x, 8); u &= 0xFFFFFFFF00000000ull; memcpy(&x, &u, 8); return x;
+}
+static inline uint32_t dbl_high(double x) { uint64_t u; memcpy(&u, &x, 8); return (uint32_t)(u >> 32); }
+static inline double dbl_from_high(uint32_t hi) { uint64_t u = (uint64_t)hi << 32; double x; memcpy(&x, &u, 8); return x; }
+
+static double det_acos(double x)
+{
+    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17,
+                 pi = 3.14159265358979311600e+00;
+    const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01,
+                 pS2 = 2.01212532134862925881e-01, pS3 = -4.00555345006794114027e-02,
+                 pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05,
+                 qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00,
+                 qS3 = -6.88283971605453293030e-01, qS4 = 7.70381505559019352791e-02;
+    const double ax = fabs(x);
+    if (ax >= 1.0) {
+        if (ax == 1.0) return x > 0 ? 0.0 : pi + 2.0 * pio2_lo;
+        return (x - x) / (x - x);
+    }
+    if (ax < 0.5) {
+        if (ax < 6.938893903907228e-18) return pio2_hi + pio2_lo;   /* 2^-57 */
+        const double z = x * x;
+        const double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const double r = p / q;
+        return pio2_hi - (x - (pio2_lo - x * r));
+    } else if (x < 0) {
+        const double z = (1.0 + x) * 0.5;
+        const double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const double s = sqrt(z);
+        const double r = p / q;
+        const double w = r * s - pio2_lo;
+        return pi - 2.0 * (s + w);
+    } else {
+        const double z = (1.0 - x) * 0.5;
+        const double s = sqrt(z);
+        const double df = dbl_clear_low(s);
+        const double c = (z - df * df) / (s + df);
+        const double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const double r = p / q;
+        const double w = r * s + c;
+        return 2.0 * (df + w);
+    }
+}
+
+/* cos on |x| <= pi/4 (+ tail y) */
+static double det_kcos(double x, double y)
+{
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double ax = fabs(x);
+    if (ax < 7.450580596923828e-09) return 1.0;   /* 2^-27 */
+    const double z = x * x;
+    const double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+    if (ax < 0.3) return 1.0 - (0.5 * z - (z * r - x * y));
+    const double qx = ax > 0.78125 ? 0.28125 : dbl_from_high(dbl_high(ax) - 0x00200000u);
+    const double hz = 0.5 * z - qx;
+    const double a = 1.0 - qx;
+    return a - (hz - (z * r - x * y));
+}
+
+/* sin on |x| <= pi/4 (+ tail y) */
+static double det_ksin(double x, double y)
+{
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double z = x * x;
+    const double v = z * x;
+    const double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+    return x - ((z * (0.5 * y - v * r) - y) - v * S1);
+}
+
+/* cos(x) for 0 <= x <= pi (the only range FastEigen3x3 needs) */
+static double det_cos(double x)
+{
+    const double pio4 = 7.85398163397448278999e-01, three_pio4 = 2.35619449019234483700e+00;
+    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+    const double pi_hi = 3.14159265358979311600e+00, pi_lo = 1.22464679914735317723e-16;
+    if (x <= pio4) return det_kcos(x, 0.0);
+    if (x < three_pio4) {
+        const double t = x - pio2_hi;                 /* exact (Sterbenz) */
+        const double y = t - pio2_lo;
+        const double yt = (t - y) - pio2_lo;
+        return -det_ksin(y, yt);
+    }
+    const double t = x - pi_hi;                       /* exact (Sterbenz) */
+    const double y = t - pi_lo;
+    const double yt = (t - y) - pi_lo;
+    return -det_kcos(y, yt);
+}
+
+ORACLE_API double oracle_det_acos(double x) { return det_acos(x); }
+ORACLE_API double oracle_det_cos(double x) { return det_cos(x); }
+
+/* ------------------------------------------------------------------------ */
 /* Covariance + FastEigen3x3 normal (EstimateNormals.cpp)     */
 /* ------------------------------------------------------------------------ */
 
@@ -447,10 +561,10 @@ static void smallest_eigvec(const double C[9], double n[3])
         double det = (b00 * c00 - A[1] * c01 + A[2] * c02) / (p * p * p);
         double half_det = det * 0.5;
         half_det = fmin(fmax(half_det, -1.0), 1.0);
-        double angle = acos(half_det) / 3.0;
+        double angle = det_acos(half_det) / 3.0;
         const double two_thirds_pi = 2.09439510239319549;
-        double beta2 = cos(angle) * 2;
-        double beta0 = cos(angle + two_thirds_pi) * 2;
+        double beta2 = det_cos(angle) * 2;
+        double beta0 = det_cos(angle + two_thirds_pi) * 2;
         double beta1 = -(beta0 + beta2);
         double ev0 = q + p * beta0, ev1 = q + p * beta1, ev2 = q + p * beta2;
         double e0[3], e1[3], e2[3];
@@ -837,6 +951,301 @@ ORACLE_API int oracle_gicp(const double *source, int ns, const double *target, i
     *fitness_out = fit; *rmse_out = rmse; *iters_out = it;
     if (n_corr_out) *n_corr_out = nc;
     free(src); free(scov); free(tcov); free(corr); free(cd); free(work); kd_free(tt);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* K4: ComputeFPFHFeature (Feature.cpp;                       */
+/*     fastGlobalOptimizer.py:130-143)                                       */
+/* ------------------------------------------------------------------------ */
+
+/* ComputePairFeatures(p1, n1, p2, n2) -> (f0 atan2 angle, f1, f2, f3 distance) */
+static void pair_features(const double *p1, const double *n1, const double *p2, const double *n2, double f[4])
+{
+    double dp[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+    f[0] = f[1] = f[2] = f[3] = 0.0;
+    const double len = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]);
+    if (len == 0.0) return;
+    double a[3] = {n1[0], n1[1], n1[2]}, b[3] = {n2[0], n2[1], n2[2]};
+    const double angle1 = dot3(a, dp) / len;
+    const double angle2 = dot3(b, dp) / len;
+    double f2;
+    if (det_acos(fabs(angle1)) > det_acos(fabs(angle2))) {
+        a[0] = n2[0]; a[1] = n2[1]; a[2] = n2[2];
+        b[0] = n1[0]; b[1] = n1[1]; b[2] = n1[2];
+        dp[0] *= -1.0; dp[1] *= -1.0; dp[2] *= -1.0;
+        f2 = -angle2;
+    } else {
+        f2 = angle1;
+    }
+    double v[3], w[3];
+    cross3(dp, a, v);
+    const double vn = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (vn == 0.0) return;
+    v[0] /= vn; v[1] /= vn; v[2] /= vn;
+    cross3(a, v, w);
+    f[3] = len;
+    f[2] = f2;
+    f[1] = dot3(v, b);
+    f[0] = atan2(dot3(w, b), dot3(a, b));
+}
+
+static inline int hist_bin(double x)
+{
+    int h = (int)floor(x);
+    if (h < 0) h = 0;
+    if (h >= 11) h = 10;
+    return h;
+}
+
+/* features: n x 33 (point-major; Open3D's 33 x N column-major Feature::data_ has the same
+ * memory order).  radius <= 0 => KDTreeSearchParamKNN(knn), else Hybrid(radius, knn).
+ * spfh_out (optional) n x 33.                                                          */
+ORACLE_API int oracle_fpfh(const double *pts, const double *normals, int n, int knn, double radius,
+                           double *fpfh_out, double *spfh_out)
+{
+    const double PI = 3.14159265358979323846;
+    KDTree *t = kd_build(pts, n, 3);
+    const double r2 = radius * radius;
+    double *spfh = (double *)calloc((size_t)n * 33, sizeof(double));
+    int *nn_idx = (int *)malloc((size_t)n * knn * sizeof(int));
+    double *nn_d2 = (double *)malloc((size_t)n * knn * sizeof(double));
+    int *nn_cnt = (int *)malloc((size_t)n * sizeof(int));
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < n; ++i) {
+        int *idx = nn_idx + (size_t)i * knn;
+        double *d2 = nn_d2 + (size_t)i * knn;
+        int c = kd_knn(t, pts + (size_t)i * 3, knn, idx, d2);
+        if (radius > 0) { int cc = 0; while (cc < c && d2[cc] < r2) ++cc; c = cc; }
+        nn_cnt[i] = c;
+        if (c > 1) {
+            double *h = spfh + (size_t)i * 33;
+            const double incr = 100.0 / (double)(c - 1);
+            for (int k = 1; k < c; ++k) {
+                double f[4];
+                pair_features(pts + (size_t)i * 3, normals + (size_t)i * 3, pts + (size_t)idx[k] * 3,
+                              normals + (size_t)idx[k] * 3, f);
+                h[hist_bin(11 * (f[0] + PI) / (2.0 * PI))] += incr;
+                h[11 + hist_bin(11 * (f[1] + 1.0) * 0.5)] += incr;
+                h[22 + hist_bin(11 * (f[2] + 1.0) * 0.5)] += incr;
+            }
+        }
+    }
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < n; ++i) {
+        double *o = fpfh_out + (size_t)i * 33;
+        for (int j = 0; j < 33; ++j) o[j] = 0.0;
+        const int c = nn_cnt[i];
+        if (c > 1) {
+            const int *idx = nn_idx + (size_t)i * knn;
+            const double *d2 = nn_d2 + (size_t)i * knn;
+            double sum[3] = {0.0, 0.0, 0.0};
+            for (int k = 1; k < c; ++k) {
+                const double dist = d2[k];
+                if (dist == 0.0) continue;
+                const double *sp = spfh + (size_t)idx[k] * 33;
+                for (int j = 0; j < 33; ++j) {
+                    const double val = sp[j] / dist;
+                    sum[j / 11] += val;
+                    o[j] += val;
+                }
+            }
+            for (int j = 0; j < 3; ++j) if (sum[j] != 0.0) sum[j] = 100.0 / sum[j];
+            const double *self = spfh + (size_t)i * 33;
+            for (int j = 0; j < 33; ++j) { o[j] *= sum[j / 11]; o[j] += self[j]; }
+        }
+    }
+    if (spfh_out) memcpy(spfh_out, spfh, (size_t)n * 33 * sizeof(double));
+    free(spfh); free(nn_idx); free(nn_d2); free(nn_cnt); kd_free(t);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* K5: FastGlobalRegistrationBasedOnFeatureMatching                          */
+/*     (FastGlobalRegistration.cpp;                           */
+/*      fastGlobalOptimizer.py:158-174)                                      */
+/* ------------------------------------------------------------------------ */
+
+/* Philox4x32-10 (Salmon et al. 2011).  The reference leaves Open3D's std::mt19937 unseeded
+ * (SURVEY.md B.5), so the tuple test has no reproducible stream to match; this project
+ * fixes one: trial t of a registration keyed `key` draws
+ *   (r0, r1, r2) = philox(counter = (t, 0, 0, 0), key)[0..2],  rand_k = (r_k * ncorr) >> 32. */
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
+{
+    for (int r = 0; r < 10; ++r) {
+        if (r > 0) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+}
+
+ORACLE_API void oracle_philox(uint64_t counter, uint64_t key, uint32_t *out4)
+{
+    uint32_t c[4] = {(uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u};
+    philox4x32_10(c, (uint32_t)key, (uint32_t)(key >> 32));
+    memcpy(out4, c, sizeof(c));
+}
+
+static inline double norm3(const double *a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
+static inline double dist3(const double *a, const double *b)
+{
+    const double d[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+    return norm3(d);
+}
+
+/* source (ns x 3), target (nt x 3); feat_s (nfs x 33), feat_t (nft x 33): the feature
+ * sets handed to Open3D (in the reference both are the SOURCE's features, so nft == ns;
+ * matched pairs whose target index is >= nt -- an out-of-bounds read in Open3D -- are
+ * dropped).
+ * T_out: source -> target, row-major 4x4, column convention.
+ * info_out (optional) int[4]: {#cross-checked pairs, #pairs after the tuple test,
+ *                              #tuple trials run, swapped}.
+ * corres_out (optional): up to 3*max_tuple_count (src, tgt) pairs after the tuple test. */
+ORACLE_API int oracle_fgr(const double *source, int ns, const double *target, int nt,
+                          const double *feat_s, int nfs, const double *feat_t, int nft,
+                          double division_factor, double tuple_scale, double max_corr_dist,
+                          int iteration_number, int decrease_mu, int max_tuple_count, int tuple_test,
+                          uint64_t tuple_key, double *T_out, double *fitness_out, double *rmse_out,
+                          int *n_corr_out, int *info_out, int *corres_out)
+{
+    /* ---- NormalizePointCloud (use_absolute_scale = false) */
+    double *pc[2];
+    int np[2] = {ns, nt};
+    double mean[2][3];
+    double scale = 0.0;
+    pc[0] = (double *)malloc((size_t)(ns > 0 ? ns : 1) * 3 * sizeof(double));
+    pc[1] = (double *)malloc((size_t)(nt > 0 ? nt : 1) * 3 * sizeof(double));
+    memcpy(pc[0], source, (size_t)ns * 3 * sizeof(double));
+    memcpy(pc[1], target, (size_t)nt * 3 * sizeof(double));
+    for (int i = 0; i < 2; ++i) {
+        double m[3] = {0, 0, 0};
+        for (int ii = 0; ii < np[i]; ++ii) { m[0] += pc[i][ii * 3]; m[1] += pc[i][ii * 3 + 1]; m[2] += pc[i][ii * 3 + 2]; }
+        m[0] /= np[i]; m[1] /= np[i]; m[2] /= np[i];
+        memcpy(mean[i], m, sizeof(m));
+        for (int ii = 0; ii < np[i]; ++ii) { pc[i][ii * 3] -= m[0]; pc[i][ii * 3 + 1] -= m[1]; pc[i][ii * 3 + 2] -= m[2]; }
+        for (int ii = 0; ii < np[i]; ++ii) { const double t = norm3(pc[i] + (size_t)ii * 3); if (t > scale) scale = t; }
+    }
+    const double scale_global = scale, scale_start = 1.0;
+    for (int i = 0; i < 2; ++i)
+        for (int e = 0; e < np[i] * 3; ++e) pc[i][e] /= scale_global;
+
+    /* ---- InitialMatching: nearest source feature of every target feature, and back; cross check */
+    int *ji = (int *)malloc((size_t)(nft > 0 ? nft : 1) * sizeof(int));
+    int *ij = (int *)malloc((size_t)(nfs > 0 ? nfs : 1) * sizeof(int));
+    double *dtmp = (double *)malloc((size_t)((nfs > nft ? nfs : nft) + 1) * sizeof(double));
+    oracle_knn(feat_s, nfs, 33, feat_t, nft, 1, 0, ji, dtmp);
+    oracle_knn(feat_t, nft, 33, feat_s, nfs, 1, 0, ij, dtmp);
+    int (*corres)[2] = (int (*)[2])malloc((size_t)(nfs > 0 ? nfs : 1) * sizeof(int[2]));
+    int ncorr = 0;
+    for (int i = 0; i < nfs; ++i) {          /* std::map order = ascending i */
+        const int j = ij[i];
+        if (j < 0 || ji[j] != i) continue;
+        if (i >= ns || j >= nt) continue;    /* out-of-range in Open3D (UB); dropped here */
+        corres[ncorr][0] = i; corres[ncorr][1] = j; ++ncorr;
+    }
+    const int n_initial = ncorr;
+
+    /* ---- AdvancedMatching: swap so that `fi` is the larger cloud, tuple test, swap back */
+    int fi = 0, fj = 1, swapped = 0;
+    if (np[fj] > np[fi]) {
+        fi = 1; fj = 0; swapped = 1;
+        for (int c = 0; c < ncorr; ++c) { const int t = corres[c][0]; corres[c][0] = corres[c][1]; corres[c][1] = t; }
+    }
+    int trials_run = 0;
+    if (tuple_test) {
+        int (*tup)[2] = (int (*)[2])malloc((size_t)(3 * (max_tuple_count > 0 ? max_tuple_count : 1)) * sizeof(int[2]));
+        int cnt = 0;
+        const long long number_of_trial = (long long)ncorr * 100;
+        for (long long t = 0; t < number_of_trial && cnt < max_tuple_count; ++t) {
+            uint32_t r[4] = {(uint32_t)t, (uint32_t)((uint64_t)t >> 32), 0u, 0u};
+            philox4x32_10(r, (uint32_t)tuple_key, (uint32_t)(tuple_key >> 32));
+            const int r0 = (int)(((uint64_t)r[0] * (uint64_t)ncorr) >> 32);
+            const int r1 = (int)(((uint64_t)r[1] * (uint64_t)ncorr) >> 32);
+            const int r2 = (int)(((uint64_t)r[2] * (uint64_t)ncorr) >> 32);
+            const int idi0 = corres[r0][0], idj0 = corres[r0][1];
+            const int idi1 = corres[r1][0], idj1 = corres[r1][1];
+            const int idi2 = corres[r2][0], idj2 = corres[r2][1];
+            const double *pi0 = pc[fi] + (size_t)idi0 * 3, *pi1 = pc[fi] + (size_t)idi1 * 3, *pi2 = pc[fi] + (size_t)idi2 * 3;
+            const double *pj0 = pc[fj] + (size_t)idj0 * 3, *pj1 = pc[fj] + (size_t)idj1 * 3, *pj2 = pc[fj] + (size_t)idj2 * 3;
+            const double li0 = dist3(pi0, pi1), li1 = dist3(pi1, pi2), li2 = dist3(pi2, pi0);
+            const double lj0 = dist3(pj0, pj1), lj1 = dist3(pj1, pj2), lj2 = dist3(pj2, pj0);
+            ++trials_run;
+            if ((li0 * tuple_scale < lj0) && (lj0 < li0 / tuple_scale) && (li1 * tuple_scale < lj1) &&
+                (lj1 < li1 / tuple_scale) && (li2 * tuple_scale < lj2) && (lj2 < li2 / tuple_scale)) {
+                tup[cnt * 3][0] = idi0; tup[cnt * 3][1] = idj0;
+                tup[cnt * 3 + 1][0] = idi1; tup[cnt * 3 + 1][1] = idj1;
+                tup[cnt * 3 + 2][0] = idi2; tup[cnt * 3 + 2][1] = idj2;
+                ++cnt;
+            }
+        }
+        free(corres);
+        corres = tup;
+        ncorr = cnt * 3;
+    }
+    if (swapped)
+        for (int c = 0; c < ncorr; ++c) { const int t = corres[c][0]; corres[c][0] = corres[c][1]; corres[c][1] = t; }
+
+    /* ---- OptimizePairwiseRegistration: graduated non-convexity, Geman-McClure weights */
+    double trans[16];
+    for (int k = 0; k < 16; ++k) trans[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    if (ncorr >= 10) {
+        double par = scale_start;
+        double *q = (double *)malloc((size_t)nt * 3 * sizeof(double));   /* moving copy of cloud 1 */
+        memcpy(q, pc[1], (size_t)nt * 3 * sizeof(double));
+        for (int itr = 0; itr < iteration_number; ++itr) {
+            double JTJ[36], JTr[6];
+            for (int k = 0; k < 36; ++k) JTJ[k] = 0.0;
+            for (int k = 0; k < 6; ++k) JTr[k] = 0.0;
+            for (int c = 0; c < ncorr; ++c) {
+                const double *pp = pc[0] + (size_t)corres[c][0] * 3;
+                const double *qq = q + (size_t)corres[c][1] * 3;
+                const double rpq[3] = {pp[0] - qq[0], pp[1] - qq[1], pp[2] - qq[2]};
+                const double temp = par / (dot3(rpq, rpq) + par);
+                const double s = temp * temp;
+                const double J[3][6] = {{0, -qq[2], qq[1], -1, 0, 0},
+                                        {qq[2], 0, -qq[0], 0, -1, 0},
+                                        {-qq[1], qq[0], 0, 0, 0, -1}};
+                for (int r = 0; r < 3; ++r) {
+                    for (int a = 0; a < 6; ++a) {
+                        for (int b = 0; b < 6; ++b) JTJ[a * 6 + b] += J[r][a] * J[r][b] * s;
+                        JTr[a] += J[r][a] * rpq[r] * s;
+                    }
+                }
+            }
+            double A[36], x[6], delta[16];
+            for (int k = 0; k < 36; ++k) A[k] = -JTJ[k];
+            ldlt_solve6(A, JTr, x);
+            vec6_to_mat4(x, delta);
+            mat4_mul(delta, trans, trans);
+            transform_cloud(q, NULL, nt, delta);
+            if (decrease_mu && itr % 4 == 0 && par > max_corr_dist) par /= division_factor;
+        }
+        free(q);
+    }
+
+    /* ---- GetTransformationOriginalScale, then its inverse (source -> target) */
+    double tt[3];
+    for (int r = 0; r < 3; ++r)
+        tt[r] = -(trans[r * 4] * mean[1][0] + trans[r * 4 + 1] * mean[1][1] + trans[r * 4 + 2] * mean[1][2]) +
+                trans[r * 4 + 3] * scale_global + mean[0][r];
+    double T[16];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) T[r * 4 + c] = trans[c * 4 + r];          /* R^T */
+        T[r * 4 + 3] = -(trans[0 * 4 + r] * tt[0] + trans[1 * 4 + r] * tt[1] + trans[2 * 4 + r] * tt[2]);
+    }
+    T[12] = T[13] = T[14] = 0.0; T[15] = 1.0;
+    memcpy(T_out, T, sizeof(T));
+
+    /* ---- EvaluateRegistration(source_orig, target_orig, max_corr_dist, T) */
+    oracle_evaluate(source, ns, target, nt, max_corr_dist, T, fitness_out, rmse_out, n_corr_out, NULL);
+    if (info_out) { info_out[0] = n_initial; info_out[1] = ncorr; info_out[2] = trials_run; info_out[3] = swapped; }
+    if (corres_out) memcpy(corres_out, corres, (size_t)ncorr * sizeof(int[2]));
+    free(corres); free(ji); free(ij); free(dtmp); free(pc[0]); free(pc[1]);
     return 0;
 }
 

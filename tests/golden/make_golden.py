@@ -99,6 +99,16 @@ def main():
         nn = O.normals(s, 20, 0.0, 1e-3)
         out[f"{tag}_src_nn20_head"] = nn["nn_idx"][:64]
         out[f"{tag}_src_normals_head"] = nn["normal"][:64]
+        # ---- oracle FGR (config 2): FPFH of the source, one registration per feature mode
+        fs = O.fpfh(s, O.normals(s, 20, 0.1)["normal"], 20, 0.1)
+        out[f"{tag}_src_fpfh_head"] = fs[:64]
+        out[f"{tag}_src_fpfh_colsum"] = fs.sum(0)
+        for mode in ("reference_compat", "fixed"):
+            fo = O.FastGlobalOptimizer(feature_mode=mode)
+            T, rm = fo.optimize(s, t)
+            out[f"{tag}_fgr_{mode}_T"] = T
+            out[f"{tag}_fgr_{mode}_stats"] = np.array([fo.last["fitness"], rm, fo.last["n_corr"], fo.last["n_initial"],
+                                                        fo.last["n_pairs"], fo.last["trials"]])
 
     # ---- full align() decision log of config 1 (README pipeline, GICP, attempts=30, seed 0)
     np.random.seed(0)

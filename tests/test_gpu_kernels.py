@@ -80,8 +80,8 @@ def test_normals_and_gicp_covariances(oracle, armadillo_pair):
         rc = ref["cov"]
         ref6 = np.stack([rc[:, 0, 0], rc[:, 0, 1], rc[:, 0, 2], rc[:, 1, 1], rc[:, 1, 2], rc[:, 2, 2]], 1)
         assert np.array_equal(cov, ref6)                                        # no-FMA float64: bit-exact
-        # normals go through acos/cos (device libm vs glibc): 1e-12 absolute
-        assert np.abs(out["normal"].cpu().numpy() - ref["normal"]).max() < 1e-12
+        # FastEigen3x3's acos / cos are the deterministic det_acos / det_cos on both sides: bit-exact
+        assert np.array_equal(out["normal"].cpu().numpy(), ref["normal"])
         g = ref["gicp_cov"]
         g6 = np.stack([g[:, 0, 0], g[:, 0, 1], g[:, 0, 2], g[:, 1, 1], g[:, 1, 2], g[:, 2, 2]], 1)
         assert np.abs(out["gicp_cov"].cpu().numpy() - g6).max() < 1e-12
