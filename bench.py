@@ -128,6 +128,8 @@ def cpu_registrations(src_clouds, tgt_clouds, unit_src, unit_tgt, units):
     import oracle as O
 
     O.build()
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    O.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     t0 = time.perf_counter()
     iters = 0
     for u in units:
@@ -267,9 +269,15 @@ def run_b200(args):
 
         ffma_peak = max(peak(False), peak(True))
         achieved = 8.0 * pairs / (sweep_ms * 1e-3) / 1e12
-        # CPU baseline on this box's host cores: a bounded sample of the same step
+        # CPU baseline on this box's host cores: a bounded sample of the same step (N = 1 only)
         cpu_units = [c * ATTEMPTS + k for k in range(2) for c in range(len(SCALES))]
-        cpu_s, _, cores = cpu_registrations(sources, targets, unit_src, unit_tgt, cpu_units)
+        if world == 1:
+            cpu_s, _, cores = cpu_registrations(sources, targets, unit_src, unit_tgt, cpu_units)
+            cpu_baseline = {"value": len(cpu_units) / cpu_s, "unit": "registrations/s", "cores": cores, "kind": "port",
+                            "sample": f"{len(cpu_units)} of the step's 180 registrations (2 starts per scale candidate), "
+                                      "restated CPU path (oracle/, C + OpenMP, KD-tree), not Open3D"}
+        else:
+            cpu_baseline = None
         value = world * n_units * args.steps / (dev_ms * 1e-3)
         line = {
             "metric": "GICP candidate evals/s (5k-pt clouds)", "value": value, "unit": "registrations/s",
@@ -289,10 +297,9 @@ def run_b200(args):
                          "note": "8 FLOP per (query,target) pair x pairs swept / CUDA-event time inside the kernel; "
                                  "peak = FFMA/FFMA2 micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
                          "pairs_per_step": pairs / args.steps, "exact_fallback_fraction": fixed / max(unit_rounds * N_POINTS, 1)},
-            "cpu_baseline": {"value": len(cpu_units) / cpu_s, "unit": "registrations/s", "cores": cores, "kind": "port",
-                             "sample": f"{len(cpu_units)} of the step's 180 registrations (2 starts per scale candidate), "
-                                       "restated CPU path (oracle/, C + OpenMP, KD-tree), not Open3D"},
         }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
