@@ -11,9 +11,10 @@ SURVEY.md 8(e)) and a tiny all-gather collects the (rmse, transform) records.
   value  : inner registrations per second, inputs resident in HBM, CUDA-event timed.
   e2e    : same through the plugin API (GeneralizedICP.optimize_batch) with HOST buffers:
            H2D of the step's clouds and D2H of its results inside the timed region.
-  roofline: the dominant kernel (nn_sweep_kernel, FP32 FMA pipe bound) -- algorithmic
-           8 FLOP per (query,target) pair over the CUDA-event time spent in that kernel
-           during the timed steps, against the FFMA peak measured in this same run.
+  roofline: the dominant kernel (nn_sweep_cull_kernel, FP32 FMA pipe bound) -- 8 FLOP per
+           (query,target) pair the kernel actually evaluated (chunks it culls are not counted;
+           the brute-force equivalent is reported beside it) over the CUDA-event time spent
+           in that kernel during the timed steps, against the FFMA peak measured in this run.
   cpu_baseline: the restated CPU path (oracle/, C + OpenMP, KD-tree) on the host cores.
 
 `--impl reference` times that CPU path alone (Open3D, the reference's arithmetic, is an
@@ -212,7 +213,7 @@ def run_b200(args):
 
     # ---- timed: K device-resident steps, L2 flushed between them
     k0 = ops.launch_counter["kernels"]
-    sweep_ms, pairs, fixed, unit_rounds = 0.0, 0.0, 0.0, 0.0
+    sweep_ms, pairs, fixed, unit_rounds = 0.0, 0.0, 0.0, 0.0   # pairs = (query,target) pairs evaluated by the sweep
     dev_ms = 0.0
     with ClockSampler(local) as clk:
         for _ in range(args.steps):
@@ -285,18 +286,23 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_src": N_POINTS, "n_tgt": N_POINTS, "units_per_gpu": n_units,
                        "max_iterations": 100, "mean_iterations": mean_iters, "l2": "256 MB flush between timed steps",
-                       "filter_dtype": "f32 (certified) + f64 exact re-rank", "parallelism": f"units x{world}"},
+                       "filter_dtype": "f32 (certified, chunk-culled) + f64 exact re-rank", "parallelism": f"units x{world}"},
             "e2e": {"value": world * n_units * args.steps / (e2e_ms * 1e-3), "unit": "registrations/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
                          "frac": achieved / ffma_peak, "traffic": None,
-                         "kernel": "nn_sweep_kernel", "avg_launch_us": 1e3 * sweep_ms / max(sweep_launches * args.steps, 1),
+                         "kernel": "nn_sweep_cull_kernel", "avg_launch_us": 1e3 * sweep_ms / max(sweep_launches * args.steps, 1),
                          "share_of_step": sweep_ms / dev_ms,
-                         "note": "8 FLOP per (query,target) pair x pairs swept / CUDA-event time inside the kernel; "
-                                 "peak = FFMA/FFMA2 micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
-                         "pairs_per_step": pairs / args.steps, "exact_fallback_fraction": fixed / max(unit_rounds * N_POINTS, 1)},
+                         "note": "8 FLOP per (query,target) pair x pairs the kernel evaluated / CUDA-event time inside the "
+                                 "kernel; peak = FFMA/FFMA2 micro-benchmark measured in this run (MEASURED_PEAKS.json has "
+                                 "no FP32 figure); brute force would evaluate pairs_brute_force_per_step",
+                         "pairs_per_step": pairs / args.steps,
+                         "pairs_brute_force_per_step": unit_rounds * N_POINTS * N_POINTS / args.steps,
+                         "culled_fraction": 1.0 - pairs / max(unit_rounds * N_POINTS * N_POINTS, 1),
+                         "brute_force_equivalent_tflops": 8.0 * unit_rounds * N_POINTS * N_POINTS / (sweep_ms * 1e-3) / 1e12,
+                         "exact_fallback_fraction": fixed / max(unit_rounds * N_POINTS, 1)},
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline

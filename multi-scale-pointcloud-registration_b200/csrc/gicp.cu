@@ -26,6 +26,7 @@
 //                     squared error and count; the last block of a unit sums the
 //                     block partials in index order, tests convergence, solves the
 //                     6x6 system (LDLT) and composes the transform.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -85,6 +86,13 @@ struct Ctx {
     int *worklist_count; // [max_iter+2]
     int *done_count;     // [1]
     int *round_active;   // [max_iter+2] units still running in each round
+    unsigned long long *visit_count;  // [max_iter+2] (query, target) pairs the sweep evaluated per round
+    int *sperm;          // [src_sets][n_src]  spatially sorted position -> original source index
+    int *tperm;          // [tgt_sets][nt_pad] spatially sorted position -> original target index (-1 = padding)
+    float4 *chunk_sph;   // [tgt_sets][n_chunks] bounding sphere (centre, radius) of each 32-target chunk, centred coords
+    unsigned long long *sortbuf;  // Morton keys being sorted
+    double *bbox;        // [max(src_sets, tgt_sets)][6]
+    float dcap;          // max correspondence distance (inflated): nothing farther is ever needed
     const double *tgt_pts;   // [tgt_sets][n_tgt][3]
     const double *tgt_cov;   // [tgt_sets][n_tgt][cov_stride]
     double *out_T, *out_stats, *trace;
@@ -140,6 +148,162 @@ __device__ __forceinline__ void cp_async_wait()
 }
 
 // ----------------------------------------------------------------------------
+// spatial (Morton) ordering of every source and target set: consecutive indices are then
+// close in space, which is what lets a warp of the sweep skip whole 32-target chunks
+// ----------------------------------------------------------------------------
+constexpr int SORT_TILE = 1024;
+
+__global__ void __launch_bounds__(256) bbox_kernel(const double *__restrict__ pts, int n, double *__restrict__ bbox)
+{
+    __shared__ double red[6][8];
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double *p = pts + (size_t)s * n * 3;
+    double mn[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, mx[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+    for (int i = tid; i < n; i += 256)
+        for (int k = 0; k < 3; ++k) {
+            const double v = p[(size_t)i * 3 + k];
+            mn[k] = fmin(mn[k], v);
+            mx[k] = fmax(mx[k], v);
+        }
+    for (int k = 0; k < 3; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    if (lane == 0)
+        for (int k = 0; k < 3; ++k) { red[k][wid] = mn[k]; red[3 + k][wid] = mx[k]; }
+    __syncthreads();
+    if (tid < 3) {
+        double a = CUDART_INF, b = -CUDART_INF;
+        for (int w = 0; w < 8; ++w) { a = fmin(a, red[tid][w]); b = fmax(b, red[3 + tid][w]); }
+        bbox[(size_t)s * 6 + tid] = a;
+        bbox[(size_t)s * 6 + 3 + tid] = b;
+    }
+}
+
+__device__ __forceinline__ unsigned part1by2(unsigned x)
+{
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+
+// key = (30-bit Morton code << 32) | index; padding entries sort last.  grid (pad2/256, sets)
+__global__ void __launch_bounds__(256) morton_kernel(const double *__restrict__ pts, int n, int pad2,
+                                                    const double *__restrict__ bbox, unsigned long long *__restrict__ keys)
+{
+    const int s = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= pad2) return;
+    unsigned long long key = ~0ull;
+    if (i < n) {
+        const double *b = bbox + (size_t)s * 6;
+        const double ext = fmax(fmax(b[3] - b[0], b[4] - b[1]), b[5] - b[2]);
+        const double inv = ext > 0 ? 1024.0 / ext : 0.0;
+        const double *p = pts + ((size_t)s * n + i) * 3;
+        unsigned q[3];
+        for (int k = 0; k < 3; ++k) {
+            const int v = (int)((p[k] - b[k]) * inv);
+            q[k] = (unsigned)(v < 0 ? 0 : (v > 1023 ? 1023 : v));
+        }
+        // Hilbert index (Skilling, "Programming the Hilbert curve", 2004: axes -> transpose), 10 bits per
+        // axis: unlike the Z-order it has no long jumps, so runs of consecutive points stay compact
+        {
+            const unsigned M = 1u << 9;
+            for (unsigned Qb = M; Qb > 1; Qb >>= 1) {
+                const unsigned P = Qb - 1;
+                for (int k = 0; k < 3; ++k) {
+                    if (q[k] & Qb) q[0] ^= P;
+                    else { const unsigned t = (q[0] ^ q[k]) & P; q[0] ^= t; q[k] ^= t; }
+                }
+            }
+            for (int k = 1; k < 3; ++k) q[k] ^= q[k - 1];
+            unsigned t = 0;
+            for (unsigned Qb = M; Qb > 1; Qb >>= 1)
+                if (q[2] & Qb) t ^= Qb - 1;
+            for (int k = 0; k < 3; ++k) q[k] ^= t;
+        }
+        // interleave the transposed form: bit b of axis k -> bit 3*b + (2 - k)
+        const unsigned code = (part1by2(q[0]) << 2) | (part1by2(q[1]) << 1) | part1by2(q[2]);
+        key = ((unsigned long long)code << 32) | (unsigned)i;
+    }
+    keys[(size_t)s * pad2 + i] = key;
+}
+
+// bitonic network on 64-bit keys: FULL sorts each 1024-element tile, otherwise the last ten
+// steps (j = 512..1) of merge phase k run in shared memory.  grid (pad2/1024, sets), 512 threads
+template <bool FULL>
+__global__ void __launch_bounds__(512) bitonic_local_kernel(unsigned long long *__restrict__ keys, int pad2, int k_phase)
+{
+    __shared__ unsigned long long sh[SORT_TILE];
+    unsigned long long *base = keys + (size_t)blockIdx.y * pad2 + (size_t)blockIdx.x * SORT_TILE;
+    const int t = threadIdx.x;
+    sh[t] = base[t];
+    sh[t + 512] = base[t + 512];
+    __syncthreads();
+    for (int k = FULL ? 2 : k_phase; k <= (FULL ? SORT_TILE : k_phase); k <<= 1) {
+        for (int j = (FULL ? k : SORT_TILE) >> 1; j > 0; j >>= 1) {
+            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            const int l = i | j;
+            const bool up = (((blockIdx.x * SORT_TILE + i) & k) == 0);
+            const unsigned long long a = sh[i], b = sh[l];
+            if ((a > b) == up) { sh[i] = b; sh[l] = a; }
+            __syncthreads();
+        }
+    }
+    base[t] = sh[t];
+    base[t + 512] = sh[t + 512];
+}
+
+// one global compare-exchange step (j >= 1024).  grid (pad2/512, sets), 256 threads
+__global__ void __launch_bounds__(256) bitonic_global_kernel(unsigned long long *__restrict__ keys, int pad2, int j, int k)
+{
+    unsigned long long *base = keys + (size_t)blockIdx.y * pad2;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= pad2 / 2) return;
+    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    const int l = i | j;
+    const bool up = ((i & k) == 0);
+    const unsigned long long a = base[i], b = base[l];
+    if ((a > b) == up) { base[i] = b; base[l] = a; }
+}
+
+// grid (ceil(out_n/256), sets): perm[pos] = original index at sorted position pos (-1 for padding)
+__global__ void __launch_bounds__(256) perm_kernel(const unsigned long long *__restrict__ keys, int n, int pad2,
+                                                  int out_n, int *__restrict__ perm)
+{
+    const int s = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= out_n) return;
+    perm[(size_t)s * out_n + i] = i < n ? (int)(unsigned)(keys[(size_t)s * pad2 + i] & 0xffffffffull) : -1;
+}
+
+int sort_pad(int n)
+{
+    int p = SORT_TILE;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// perm [sets][out_n] <- Morton order of pts [sets][n][3]
+int spatial_perm(const double *pts, int n, int sets, int out_n, double *bbox, unsigned long long *keys, int *perm,
+                 cudaStream_t st)
+{
+    const int pad2 = sort_pad(n);
+    bbox_kernel<<<sets, 256, 0, st>>>(pts, n, bbox);
+    morton_kernel<<<dim3(pad2 / 256, sets), 256, 0, st>>>(pts, n, pad2, bbox, keys);
+    bitonic_local_kernel<true><<<dim3(pad2 / SORT_TILE, sets), 512, 0, st>>>(keys, pad2, 0);
+    for (int k = 2 * SORT_TILE; k <= pad2; k <<= 1) {
+        for (int j = k >> 1; j >= SORT_TILE; j >>= 1)
+            bitonic_global_kernel<<<dim3((pad2 / 2 + 255) / 256, sets), 256, 0, st>>>(keys, pad2, j, k);
+        bitonic_local_kernel<false><<<dim3(pad2 / SORT_TILE, sets), 512, 0, st>>>(keys, pad2, k);
+    }
+    perm_kernel<<<dim3((out_n + 255) / 256, sets), 256, 0, st>>>(keys, n, pad2, out_n, perm);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ----------------------------------------------------------------------------
 // set-up kernels
 // ----------------------------------------------------------------------------
 __global__ void init_units_kernel(Ctx c, const int *__restrict__ unit_src, const int *__restrict__ unit_tgt,
@@ -157,18 +321,19 @@ __global__ void init_units_kernel(Ctx c, const int *__restrict__ unit_src, const
         c.red_counter[u] = 0;
         if (u == 0) {
             *c.done_count = 0;
-            for (int k = 0; k < c.max_iter + 2; ++k) { c.worklist_count[k] = 0; c.round_active[k] = 0; }
+            for (int k = 0; k < c.max_iter + 2; ++k) { c.worklist_count[k] = 0; c.round_active[k] = 0; c.visit_count[k] = 0ull; }
         }
     }
-    const size_t np = (size_t)c.n_src * 3, nc = src_cov ? (size_t)c.n_src * c.cov_stride : 0;
-    const double *sp = src_pts + (size_t)ss * np;
-    const double *sc = src_cov + (size_t)ss * nc;
-    double *dp = c.cur_pts + (size_t)u * np;
-    double *dc = c.cur_cov + (size_t)u * nc;
-    const size_t nmax = nc > np ? nc : np;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nmax; e += (size_t)gridDim.x * blockDim.x) {
-        if (e < nc) dc[e] = sc[e];
-        if (e < np) dp[e] = sp[e];
+    const int cs = src_cov ? c.cov_stride : 0;
+    const double *sp = src_pts + (size_t)ss * c.n_src * 3;
+    const double *sc = src_cov + (size_t)ss * c.n_src * cs;
+    const int *perm = c.sperm + (size_t)ss * c.n_src;
+    double *dp = c.cur_pts + (size_t)u * c.n_src * 3;
+    double *dc = c.cur_cov + (size_t)u * c.n_src * cs;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < c.n_src; p += gridDim.x * blockDim.x) {
+        const int i = perm[p];   // unit-local arrays live in spatially sorted order
+        for (int k = 0; k < 3; ++k) dp[(size_t)p * 3 + k] = sp[(size_t)i * 3 + k];
+        for (int k = 0; k < cs; ++k) dc[(size_t)p * cs + k] = sc[(size_t)i * cs + k];
     }
 }
 
@@ -203,10 +368,12 @@ __global__ void __launch_bounds__(1024) prep_targets_kernel(Ctx c)
     __syncthreads();
     const double cx = ctr[0], cy = ctr[1], cz = ctr[2];
     float4 *out = c.tgt4 + (size_t)s * c.nt_pad;
+    const int *perm = c.tperm + (size_t)s * c.nt_pad;
     float rm = 0.f;
-    for (int i = tid; i < c.nt_pad; i += blockDim.x) {
+    for (int pos = tid; pos < c.nt_pad; pos += blockDim.x) {
         float4 v;
-        if (i < c.n_tgt) {
+        const int i = perm[pos];   // table in spatially sorted order
+        if (i >= 0) {
             const float fx = (float)(pts[(size_t)i * 3] - cx);
             const float fy = (float)(pts[(size_t)i * 3 + 1] - cy);
             const float fz = (float)(pts[(size_t)i * 3 + 2] - cz);
@@ -216,11 +383,11 @@ __global__ void __launch_bounds__(1024) prep_targets_kernel(Ctx c)
         } else {
             v = make_float4(0.f, 0.f, 0.f, 3.0e38f);  // sentinel: never the minimum
         }
-        out[i] = v;
+        out[pos] = v;
     }
     for (int o = 16; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o));
     if (lane == 0) rmax_s[wid] = rm;
-    __syncthreads();
+    __syncthreads();   // also orders the table writes before the sphere pass below
     if (tid == 0) {
         float r = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, rmax_s[w]);
@@ -229,13 +396,31 @@ __global__ void __launch_bounds__(1024) prep_targets_kernel(Ctx c)
         m.rmax = (double)r * (1.0 + 1e-6) + 1e-300;
         c.tgt_meta[s] = m;
     }
+    // bounding sphere of every 32-target chunk (centred FP32 coordinates, radius rounded up)
+    float4 *sph = c.chunk_sph + (size_t)s * c.n_chunks;
+    for (int ch = wid; ch < c.n_chunks; ch += (int)(blockDim.x >> 5)) {
+        const float4 t = out[(size_t)ch * NN_CH + lane];
+        const bool valid = t.w < 1.0e38f;
+        const float x = -0.5f * t.x, y = -0.5f * t.y, z = -0.5f * t.z;
+        float lo[3] = {valid ? x : CUDART_INF_F, valid ? y : CUDART_INF_F, valid ? z : CUDART_INF_F};
+        float hi[3] = {valid ? x : -CUDART_INF_F, valid ? y : -CUDART_INF_F, valid ? z : -CUDART_INF_F};
+        for (int k = 0; k < 3; ++k)
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+                hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+            }
+        const float mx = 0.5f * (lo[0] + hi[0]), my = 0.5f * (lo[1] + hi[1]), mz = 0.5f * (lo[2] + hi[2]);
+        float r = valid ? sqrtf((x - mx) * (x - mx) + (y - my) * (y - my) + (z - mz) * (z - mz)) : 0.f;
+        for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+        if (lane == 0) sph[ch] = make_float4(mx, my, mz, r * (1.f + 1e-5f) + 1e-30f);
+    }
 }
 
 // ----------------------------------------------------------------------------
 // per-round update: p <- U p, C <- R C R^T (or axis <- R axis), centred FP32 copy
 // (PointCloud::Transform of the moving source, Registration.cpp)
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) update_kernel(Ctx c)
+__global__ void __launch_bounds__(256) update_kernel(Ctx c, int round)
 {
     const int u = blockIdx.y;
     const UnitState &st = c.state[u];
@@ -260,14 +445,26 @@ __global__ void __launch_bounds__(256) update_kernel(Ctx c)
         }
     }
     const TgtMeta tm = c.tgt_meta[st.tgt_set];
-    c.cur_qf[oi] = make_float4((float)(x - tm.cx), (float)(y - tm.cy), (float)(z - tm.cz), 0.f);
+    // upper bound of this point's nearest-neighbour distance that matters: the distance to the
+    // target it was matched to in the previous round, never more than the correspondence cut-off
+    float dub = c.dcap;
+    if (round >= 1) {
+        const int j = c.corr[oi];
+        if (j >= 0) {
+            const double *tp = c.tgt_pts + ((size_t)st.tgt_set * c.n_tgt + j) * 3;
+            const double dx = x - tp[0], dy = y - tp[1], dz = z - tp[2];
+            const float d = __double2float_ru(sqrt(dx * dx + dy * dy + dz * dz)) * (1.f + 1e-6f);
+            dub = fminf(dub, d);
+        }
+    }
+    c.cur_qf[oi] = make_float4((float)(x - tm.cx), (float)(y - tm.cy), (float)(z - tm.cz), dub);
 }
 
 // ----------------------------------------------------------------------------
 // 1-NN sweep: FP32 filter on the FMA pipe.  Q queries per thread (Q/2 packed pairs).
 // ----------------------------------------------------------------------------
 template <int Q, int TJ, int MODE>
-__global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c)
+__global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c, int round)
 {
     __shared__ __align__(16) float4 tile[2][NN_TILE];
     const int u = blockIdx.z, split = blockIdx.y, tid = threadIdx.x;
@@ -404,6 +601,172 @@ __global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c)
             c.part_m2[pbase + i] = m2[k];
         }
     }
+    if (tid == 0 && !c.ignore_done) {
+        const int nq = min(NN_THREADS * Q, c.n_src - qbase);
+        atomicAdd(c.visit_count + round, (unsigned long long)(ce - cb) * NN_CH * nq);
+    }
+}
+
+// ----------------------------------------------------------------------------
+// 1-NN sweep with chunk culling.  Same FP32 filter arithmetic as nn_sweep_kernel, but every
+// warp owns 32*Q spatially consecutive queries (a compact patch), reads the target chunks it
+// needs straight through L1 (broadcast float4 loads) and skips every 32-target chunk whose
+// bounding sphere lies farther from the patch than any of its queries can still be matched:
+//   dist(patch centre, chunk centre) - r_chunk  >  r_patch + max_q d_ub(q)
+// where d_ub(q) is the distance to q's previous correspondence (capped at the correspondence
+// cut-off).  Skipped chunks provably hold no nearest neighbour, so the (best chunk, second
+// best) certificate over the visited chunks is still a certificate over all targets.
+// ----------------------------------------------------------------------------
+constexpr int CULL_WARPS = 2;      // warps per block; warps are independent workers
+constexpr int CULL_RING = 4;       // chunk buffers per warp (512 B each), filled by cp.async
+constexpr int CULL_LIST = 1024;    // visit-list capacity per pass (chunk ids)
+
+template <int Q>
+__global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, int round)
+{
+    constexpr int TJ = 4;
+    __shared__ __align__(16) float4 ring[CULL_WARPS][CULL_RING][NN_CH];
+    __shared__ unsigned short vlist[CULL_WARPS][CULL_LIST];
+    const int u = blockIdx.z, split = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const UnitState &st = c.state[u];
+    if (st.done && !c.ignore_done) return;
+    const int wbase = (blockIdx.x * CULL_WARPS + warp) * (32 * Q);
+    if (wbase >= c.n_src) return;
+    const float4 *tg = c.tgt4 + (size_t)st.tgt_set * c.nt_pad;
+    const float4 *sph = c.chunk_sph + (size_t)st.tgt_set * c.n_chunks;
+    const float4 *qsrc = c.cur_qf + (size_t)u * c.n_src;
+
+    uint64_t qx[Q / 2], qy[Q / 2], qz[Q / 2];
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    float D = 0.f, rw = 0.f, pcx, pcy, pcz;
+    {
+        float4 qv[Q];
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+            const int i = min(wbase + k * 32 + lane, c.n_src - 1);   // tail lanes repeat the last query
+            qv[k] = qsrc[i];
+            lo[0] = fminf(lo[0], qv[k].x); hi[0] = fmaxf(hi[0], qv[k].x);
+            lo[1] = fminf(lo[1], qv[k].y); hi[1] = fmaxf(hi[1], qv[k].y);
+            lo[2] = fminf(lo[2], qv[k].z); hi[2] = fmaxf(hi[2], qv[k].z);
+            D = fmaxf(D, qv[k].w);
+        }
+#pragma unroll
+        for (int h = 0; h < Q / 2; ++h) {
+            qx[h] = pack_f2(qv[2 * h].x, qv[2 * h + 1].x);
+            qy[h] = pack_f2(qv[2 * h].y, qv[2 * h + 1].y);
+            qz[h] = pack_f2(qv[2 * h].z, qv[2 * h + 1].z);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+                hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+            }
+        for (int o = 16; o > 0; o >>= 1) D = fmaxf(D, __shfl_xor_sync(0xffffffffu, D, o));
+        pcx = 0.5f * (lo[0] + hi[0]); pcy = 0.5f * (lo[1] + hi[1]); pcz = 0.5f * (lo[2] + hi[2]);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+            const float dx = qv[k].x - pcx, dy = qv[k].y - pcy, dz = qv[k].z - pcz;
+            rw = fmaxf(rw, sqrtf(dx * dx + dy * dy + dz * dz));
+        }
+        for (int o = 16; o > 0; o >>= 1) rw = fmaxf(rw, __shfl_xor_sync(0xffffffffu, rw, o));
+    }
+    // FP32 slack: every quantity below carries a few ulps of the coordinate magnitude
+    const float mag = fabsf(pcx) + fabsf(pcy) + fabsf(pcz) + rw + (float)c.tgt_meta[st.tgt_set].rmax;
+    const float reach = (rw + D) * (1.f + 4e-6f) + 8e-6f * mag;
+
+    float m1[Q], m2[Q];
+    int c1[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) { m1[k] = CUDART_INF_F; m2[k] = CUDART_INF_F; c1[k] = 0; }
+
+    const int cb = split * c.chunks_per_split;
+    const int ce = min(c.n_chunks, cb + c.chunks_per_split);
+    int visited = 0;
+    unsigned short *vl = vlist[warp];
+    for (int pass = cb; pass < ce; pass += CULL_LIST) {
+        // 1) visit list of this pass: lane-parallel sphere tests, order-preserving compaction
+        const int pe = min(ce, pass + CULL_LIST);
+        int nv = 0;
+        for (int base = pass; base < pe; base += 32) {
+            const int chunk = base + lane;
+            bool need = false;
+            if (chunk < pe) {
+                const float4 sp = __ldg(sph + chunk);
+                const float sx = sp.x - pcx, sy = sp.y - pcy, sz = sp.z - pcz;
+                need = !(sqrtf(sx * sx + sy * sy + sz * sz) - sp.w > reach);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, need);
+            if (need) vl[nv + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(chunk - pass);
+            nv += __popc(bal);
+        }
+        __syncwarp();
+        visited += nv;
+        // 2) stream the listed chunks through the warp's ring (one 16-byte cp.async per lane per chunk)
+        auto issue = [&](int k) {
+            if (k < nv) cp_async16(&ring[warp][k % CULL_RING][lane], tg + (size_t)(pass + vl[k]) * NN_CH + lane);
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int k = 0; k < CULL_RING - 1; ++k) issue(k);
+        for (int k = 0; k < nv; ++k) {
+            issue(k + CULL_RING - 1);
+            cp_async_wait<CULL_RING - 1>();
+            __syncwarp();
+            const float4 *tc = ring[warp][k % CULL_RING];
+            float mc[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) mc[q] = CUDART_INF_F;
+#pragma unroll
+            for (int j = 0; j < NN_CH; j += TJ) {
+                float4 t[TJ];
+#pragma unroll
+                for (int r = 0; r < TJ; ++r) t[r] = tc[j + r];
+#pragma unroll
+                for (int h = 0; h < Q / 2; ++h) {
+                    uint64_t a[TJ];
+#pragma unroll
+                    for (int r = 0; r < TJ; ++r) a[r] = fma2_ss(qz[h], t[r].z, t[r].w);
+#pragma unroll
+                    for (int r = 0; r < TJ; ++r) a[r] = fma2_sv(qy[h], t[r].y, a[r]);
+#pragma unroll
+                    for (int r = 0; r < TJ; ++r) a[r] = fma2_sv(qx[h], t[r].x, a[r]);
+#pragma unroll
+                    for (int r = 0; r < TJ; r += 2) {
+                        float l0, h0, l1, h1;
+                        unpack_f2(a[r], l0, h0);
+                        unpack_f2(a[r + 1], l1, h1);
+                        mc[2 * h] = min3f(mc[2 * h], l0, l1);
+                        mc[2 * h + 1] = min3f(mc[2 * h + 1], h0, h1);
+                    }
+                }
+            }
+            const int chunk = pass + vl[k];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                m2[q] = fminf(m2[q], fmaxf(m1[q], mc[q]));
+                c1[q] = mc[q] < m1[q] ? chunk : c1[q];
+                m1[q] = fminf(m1[q], mc[q]);
+            }
+            __syncwarp();   // everyone is done with this slot before it is refilled
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+    }
+    const size_t pbase = ((size_t)u * c.splits + split) * c.n_src;
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+        const int i = wbase + k * 32 + lane;
+        if (i < c.n_src) {
+            c.part_m1[pbase + i] = m1[k];
+            c.part_c1[pbase + i] = c1[k];
+            c.part_m2[pbase + i] = m2[k];
+        }
+    }
+    if (lane == 0 && !c.ignore_done) {
+        const int nq = min(32 * Q, c.n_src - wbase);
+        atomicAdd(c.visit_count + round, (unsigned long long)visited * NN_CH * nq);
+    }
 }
 
 // ----------------------------------------------------------------------------
@@ -422,7 +785,7 @@ __global__ void __launch_bounds__(128) nn_resolve_kernel(Ctx c, int round)
     const size_t oi = (size_t)u * c.n_src + (active ? i : 0);
     float fx = 0.f, fy = 0.f, fz = 0.f, thr = -CUDART_INF_F;
     int c1 = 0;
-    bool cross = false;
+    bool cross = false, none = false;
     if (active) {
         const float4 qf = c.cur_qf[oi];
         fx = qf.x; fy = qf.y; fz = qf.z;
@@ -447,6 +810,8 @@ __global__ void __launch_bounds__(128) nn_resolve_kernel(Ctx c, int round)
         const double lim = (double)m1 + margin;
         cross = !((double)m2 > lim);       // another chunk may hold the true neighbour
         thr = __double2float_ru(lim);
+        none = !(m1 < CUDART_INF_F);       // the sweep visited no chunk: nothing within the cut-off
+        if (none) cross = true;            // (keeps this query out of the ballot pass)
     }
     // Warp-cooperative pass over each query's best chunk: lane t recomputes the filter
     // value of target (chunk, t) -- same FMA chain as the sweep, so bit-identical -- and
@@ -468,13 +833,18 @@ __global__ void __launch_bounds__(128) nn_resolve_kernel(Ctx c, int round)
         if (lane == l) { my_cnt = __popc(bal); my_first = __ffs(bal) - 1; }
     }
     if (!active) return;
+    if (none) {
+        c.corr[oi] = -1;
+        c.corr_d2[oi] = 0.0;
+        return;
+    }
     if (cross || my_cnt != 1) {
         // ambiguous at FP32 resolution: exact float64 scan by a whole warp (nn_fix_kernel)
         const int slot = atomicAdd(&c.worklist_count[round], 1);
         c.worklist[slot] = (int)oi;
         return;
     }
-    const int j = c1 * NN_CH + my_first;
+    const int j = c.tperm[(size_t)st.tgt_set * c.nt_pad + c1 * NN_CH + my_first];   // sorted position -> index
     const double *p = c.cur_pts + oi * 3;
     const double *tp = c.tgt_pts + ((size_t)st.tgt_set * c.n_tgt + j) * 3;
     const double best = sqdist3_rn(p[0], p[1], p[2], tp[0], tp[1], tp[2]);
@@ -783,13 +1153,24 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
     st.iters = round + 1;
 }
 
+// correspondences of unit u in the caller's source order (the unit arrays are spatially sorted)
+__global__ void __launch_bounds__(256) unpermute_corr_kernel(Ctx c, int *__restrict__ out)
+{
+    const int u = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= c.n_src) return;
+    const int i = c.sperm[(size_t)c.state[u].src_set * c.n_src + p];
+    out[(size_t)u * c.n_src + i] = c.corr[(size_t)u * c.n_src + p];
+}
+
 // ----------------------------------------------------------------------------
 // workspace layout
 // ----------------------------------------------------------------------------
 struct Layout {
     size_t off_state, off_pts, off_cov, off_qf, off_corr, off_d2, off_m1, off_c1, off_m2, off_tgt4, off_meta,
-        off_partial, off_counter, off_worklist, off_wcount, off_ract, off_done, total;
+        off_partial, off_counter, off_worklist, off_wcount, off_ract, off_done, off_visit, off_sperm, off_tperm,
+        off_sph, off_sort, off_bbox, total;
     int nt_pad, n_chunks, splits, chunks_per_split, red_blocks, q_tiles, nn_q, nn_tj, cov_stride, smem_pad, nn_mode;
+    int cull;
 };
 
 bool make_layout(const orpcd_gicp_params *p, Layout &L)
@@ -804,15 +1185,19 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     L.nt_pad = (p->n_tgt + NN_CH - 1) / NN_CH * NN_CH;
     L.n_chunks = L.nt_pad / NN_CH;
     L.nn_q = (p->sweep_q == 4 || p->sweep_q == 8) ? p->sweep_q : (p->n_src >= 2048 ? 8 : 4);
-    L.nn_mode = (p->sweep_mode >= 1 && p->sweep_mode <= 3) ? p->sweep_mode - 1 : 0;
     L.smem_pad = p->sweep_smem_pad > 0 && p->sweep_smem_pad <= 190000 ? p->sweep_smem_pad : 0;
     L.nn_tj = (p->sweep_tj == 2 || p->sweep_tj == 4 || p->sweep_tj == 8) ? p->sweep_tj : 4;
+    L.nn_mode = (p->sweep_mode >= 1 && p->sweep_mode <= 3) ? p->sweep_mode - 1 : 0;
+    L.cull = !(p->sweep_mode >= 1 && p->sweep_mode <= 3);   // 0 (auto): culled sweep; 1..3: dense variants
+    if (L.cull && !(p->sweep_q == 4 || p->sweep_q == 8)) L.nn_q = 4;   // smaller patches cull better
     L.q_tiles = (p->n_src + NN_THREADS * L.nn_q - 1) / (NN_THREADS * L.nn_q);
     int s = p->target_splits;
     if (s <= 0) {
-        // enough blocks for ~12 waves of 148 SMs x 4 resident blocks, >= 8 chunks per split
+        // dense sweep: enough blocks for ~12 waves of 148 SMs x 4 resident blocks, >= 8 chunks per split;
+        // culled sweep: each warp already skips most chunks, 2 waves are enough
         const long long blocks = (long long)p->n_units * L.q_tiles;
-        s = (int)((7104 + blocks - 1) / blocks);
+        const long long want = L.cull ? 1480 : 7104;
+        s = (int)((want + blocks - 1) / blocks);
         if (s > 8) s = 8;
     }
     const int s_max = L.n_chunks / 8 > 1 ? L.n_chunks / 8 : 1;
@@ -841,6 +1226,13 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     L.off_wcount = take((size_t)(p->max_iterations + 2) * sizeof(int));
     L.off_ract = take((size_t)(p->max_iterations + 2) * sizeof(int));
     L.off_done = take(sizeof(int));
+    L.off_visit = take((size_t)(p->max_iterations + 2) * sizeof(unsigned long long));
+    L.off_sperm = take((size_t)p->n_src_sets * ns * sizeof(int));
+    L.off_tperm = take((size_t)p->n_tgt_sets * L.nt_pad * sizeof(int));
+    L.off_sph = take((size_t)p->n_tgt_sets * L.n_chunks * sizeof(float4));
+    const size_t sort_s = (size_t)p->n_src_sets * sort_pad(p->n_src), sort_t = (size_t)p->n_tgt_sets * sort_pad(p->n_tgt);
+    L.off_sort = take((sort_s > sort_t ? sort_s : sort_t) * sizeof(unsigned long long));
+    L.off_bbox = take((size_t)(p->n_src_sets > p->n_tgt_sets ? p->n_src_sets : p->n_tgt_sets) * 6 * sizeof(double));
     L.total = o;
     return true;
 }
@@ -872,40 +1264,79 @@ void fill_ctx(const orpcd_gicp_params *p, const Layout &L, void *ws, Ctx &c)
     c.worklist_count = (int *)(w + L.off_wcount);
     c.done_count = (int *)(w + L.off_done);
     c.round_active = (int *)(w + L.off_ract);
+    c.visit_count = (unsigned long long *)(w + L.off_visit);
+    c.sperm = (int *)(w + L.off_sperm);
+    c.tperm = (int *)(w + L.off_tperm);
+    c.chunk_sph = (float4 *)(w + L.off_sph);
+    c.sortbuf = (unsigned long long *)(w + L.off_sort);
+    c.bbox = (double *)(w + L.off_bbox);
+    c.dcap = (float)(p->max_correspondence_distance * (1.0 + 1e-5)) * (1.f + 1e-6f) + 1e-30f;
     c.tgt_pts = nullptr; c.tgt_cov = nullptr; c.out_T = nullptr; c.out_stats = nullptr; c.trace = nullptr;
     c.out_status = nullptr;
 }
 
 template <int Q, int TJ, int MODE>
-void launch_sweep_m(const Ctx &c, const dim3 &g, int pad, cudaStream_t st)
+void launch_sweep_m(const Ctx &c, const dim3 &g, int pad, int round, cudaStream_t st)
 {
     // `pad` bytes of unused dynamic shared memory cap the resident blocks per SM (tuning)
     if (pad > 0)
         cudaFuncSetAttribute(nn_sweep_kernel<Q, TJ, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-    nn_sweep_kernel<Q, TJ, MODE><<<g, NN_THREADS, pad, st>>>(c);
+    nn_sweep_kernel<Q, TJ, MODE><<<g, NN_THREADS, pad, st>>>(c, round);
 }
 
 template <int Q, int TJ>
-void launch_sweep_t(const Ctx &c, const dim3 &g, int pad, int mode, cudaStream_t st)
+void launch_sweep_t(const Ctx &c, const dim3 &g, int pad, int mode, int round, cudaStream_t st)
 {
-    if (mode == 0) launch_sweep_m<Q, TJ, 0>(c, g, pad, st);
-    else if (mode == 2) launch_sweep_m<Q, TJ, 2>(c, g, pad, st);
-    else launch_sweep_m<Q, TJ, 1>(c, g, pad, st);
+    if (mode == 0) launch_sweep_m<Q, TJ, 0>(c, g, pad, round, st);
+    else if (mode == 2) launch_sweep_m<Q, TJ, 2>(c, g, pad, round, st);
+    else launch_sweep_m<Q, TJ, 1>(c, g, pad, round, st);
 }
 
-void launch_sweep(const Ctx &c, const Layout &L, int n_units, cudaStream_t st)
+void launch_sweep(const Ctx &c, const Layout &L, int n_units, int round, cudaStream_t st)
 {
     const dim3 g(L.q_tiles, L.splits, n_units);
     const int pad = L.smem_pad;
-    if (L.nn_q == 8) {
-        if (L.nn_tj == 2) launch_sweep_t<8, 2>(c, g, pad, L.nn_mode, st);
-        else if (L.nn_tj == 8) launch_sweep_t<8, 8>(c, g, pad, L.nn_mode, st);
-        else launch_sweep_t<8, 4>(c, g, pad, L.nn_mode, st);
-    } else {
-        if (L.nn_tj == 2) launch_sweep_t<4, 2>(c, g, pad, L.nn_mode, st);
-        else if (L.nn_tj == 8) launch_sweep_t<4, 8>(c, g, pad, L.nn_mode, st);
-        else launch_sweep_t<4, 4>(c, g, pad, L.nn_mode, st);
+    if (L.cull) {
+        const dim3 gc((c.n_src + CULL_WARPS * 32 * L.nn_q - 1) / (CULL_WARPS * 32 * L.nn_q), L.splits, n_units);
+        if (L.nn_q == 8) nn_sweep_cull_kernel<8><<<gc, CULL_WARPS * 32, 0, st>>>(c, round);
+        else nn_sweep_cull_kernel<4><<<gc, CULL_WARPS * 32, 0, st>>>(c, round);
+        return;
     }
+    if (L.nn_q == 8) {
+        if (L.nn_tj == 2) launch_sweep_t<8, 2>(c, g, pad, L.nn_mode, round, st);
+        else if (L.nn_tj == 8) launch_sweep_t<8, 8>(c, g, pad, L.nn_mode, round, st);
+        else launch_sweep_t<8, 4>(c, g, pad, L.nn_mode, round, st);
+    } else {
+        if (L.nn_tj == 2) launch_sweep_t<4, 2>(c, g, pad, L.nn_mode, round, st);
+        else if (L.nn_tj == 8) launch_sweep_t<4, 8>(c, g, pad, L.nn_mode, round, st);
+        else launch_sweep_t<4, 4>(c, g, pad, L.nn_mode, round, st);
+    }
+}
+
+// Morton permutations of all source and target sets, the sorted FP32 target tables and the unit state
+int prepare_batch(const Ctx &c, const Layout &L, const orpcd_gicp_params *p, const double *d_src_points,
+                  const double *d_src_cov, const int *d_unit_src, const int *d_unit_tgt, const double *d_init_T,
+                  cudaStream_t st, int *launches)
+{
+    if (spatial_perm(d_src_points, p->n_src, p->n_src_sets, p->n_src, c.bbox, c.sortbuf, c.sperm, st) != 0) return -1;
+    if (spatial_perm(c.tgt_pts, p->n_tgt, p->n_tgt_sets, L.nt_pad, c.bbox, c.sortbuf, c.tperm, st) != 0) return -1;
+    const int gx = (p->n_src + 255) / 256;
+    init_units_kernel<<<dim3(gx > 64 ? 64 : gx, p->n_units), 256, 0, st>>>(c, d_unit_src, d_unit_tgt, d_src_points,
+                                                                          d_src_cov, d_init_T);
+    prep_targets_kernel<<<p->n_tgt_sets, 1024, 0, st>>>(c);
+    if (launches) {
+        int per_sort = 0;
+        for (int n : {p->n_src, p->n_tgt}) {
+            const int pad2 = sort_pad(n);
+            per_sort += 4;   // bbox, morton, local sort, perm
+            for (int k = 2 * SORT_TILE; k <= pad2; k <<= 1) {
+                for (int j = k >> 1; j >= SORT_TILE; j >>= 1) ++per_sort;
+                ++per_sort;
+            }
+        }
+        *launches += per_sort + 2;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace
@@ -937,15 +1368,8 @@ ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_p
     c.out_T = d_out_T; c.out_stats = d_out_stats; c.out_status = d_out_status; c.trace = d_trace;
     int launches = 0;
 
-    {
-        const int gx = (int)((((size_t)p->n_src * 6) + 255) / 256);
-        dim3 grid(gx > 64 ? 64 : gx, p->n_units);
-        init_units_kernel<<<grid, 256, 0, st>>>(c, d_unit_src, d_unit_tgt, d_src_points, d_src_cov, nullptr);
-        ORPCD_CHECK_LAUNCH();
-        prep_targets_kernel<<<p->n_tgt_sets, 1024, 0, st>>>(c);
-        ORPCD_CHECK_LAUNCH();
-        launches += 2;
-    }
+    if (prepare_batch(c, L, p, d_src_points, d_src_cov, d_unit_src, d_unit_tgt, nullptr, st, &launches) != 0)
+        return ORPCD_ERR_CUDA;
     const dim3 g_upd((p->n_src + 255) / 256, p->n_units);
     const dim3 g_res((p->n_src + 127) / 128, p->n_units);
     const dim3 g_red(L.red_blocks, p->n_units);
@@ -962,9 +1386,9 @@ ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_p
     }
     int rounds = 0;
     for (int round = 0; round <= p->max_iterations; ++round) {
-        update_kernel<<<g_upd, 256, 0, st>>>(c);
+        update_kernel<<<g_upd, 256, 0, st>>>(c, round);
         if (prof) cudaEventRecord(ev[2 * round], st);
-        launch_sweep(c, L, p->n_units, st);
+        launch_sweep(c, L, p->n_units, round, st);
         if (prof) cudaEventRecord(ev[2 * round + 1], st);
         nn_resolve_kernel<<<g_res, 128, 0, st>>>(c, round);
         nn_fix_kernel<<<fix_blocks, 128, 0, st>>>(c, round);
@@ -990,9 +1414,12 @@ ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_p
     if (prof) {
         if (cudaStreamSynchronize(st) != cudaSuccess) return ORPCD_ERR_CUDA;
         double sweep_ms = 0.0;
+        float *round_ms = (float *)malloc(sizeof(float) * n_rounds_max);
+        if (!round_ms) return ORPCD_ERR_INVALID;
         for (int r = 0; r < rounds; ++r) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ev[2 * r], ev[2 * r + 1]);
+            round_ms[r] = ms;
             sweep_ms += ms;
         }
         for (int k = 0; k < 2 * n_rounds_max; ++k) cudaEventDestroy(ev[k]);
@@ -1009,12 +1436,25 @@ ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_p
             fixed += h[p->max_iterations + 2 + r];
             if (h[r] > 0) ++sweep_launches;
         }
+        unsigned long long *hv = (unsigned long long *)malloc(sizeof(unsigned long long) * (p->max_iterations + 2));
+        if (!hv) return ORPCD_ERR_INVALID;
+        cudaMemcpy(hv, c.visit_count, sizeof(unsigned long long) * (p->max_iterations + 2), cudaMemcpyDeviceToHost);
+        double visited = 0.0;
+        for (int r = 0; r < rounds; ++r) visited += (double)hv[r];
+        if (getenv("ORPCD_DEBUG_ROUNDS")) {
+            for (int r = 0; r < rounds; ++r)
+                fprintf(stderr, "round %3d active %4d visited %.3f sweep_us %.1f worklist %d\n", r, h[r],
+                        h[r] > 0 ? (double)hv[r] / ((double)h[r] * p->n_src * p->n_tgt) : 0.0, round_ms[r] * 1e3,
+                        h[p->max_iterations + 2 + r]);
+        }
+        free(hv);
         free(h);
-        h_profile[1] = sweep_ms;                                        // total time inside nn_sweep_kernel
-        h_profile[2] = unit_rounds * (double)p->n_src * (double)p->n_tgt;  // (query, target) pairs swept
+        free(round_ms);
+        h_profile[1] = sweep_ms;                                        // total time inside the sweep kernel
+        h_profile[2] = visited;                                         // (query, target) pairs the sweep evaluated
         h_profile[4] = fixed;                                           // queries sent to the exact work list
         h_profile[6] = (double)sweep_launches;                          // sweep launches that had work
-        h_profile[7] = unit_rounds;
+        h_profile[7] = unit_rounds;                                     // brute force would be unit_rounds*n_src*n_tgt pairs
     }
     return ORPCD_OK;
 }
@@ -1042,20 +1482,16 @@ ORPCD_API int orpcd_evaluate_batch(const orpcd_gicp_params *p_in, const double *
     // out_T is required by the reduction's epilogue: park it in the (unused) covariance slice
     c.out_T = c.cur_cov; c.out_stats = d_out_stats; c.out_status = d_out_status; c.trace = nullptr;
     if ((size_t)q.n_units * 16 > (size_t)q.n_units * q.n_src * 3) return ORPCD_ERR_INVALID;
-    const int gx = (int)((((size_t)q.n_src * 3) + 255) / 256);
-    init_units_kernel<<<dim3(gx > 64 ? 64 : gx, q.n_units), 256, 0, st>>>(c, d_unit_src, d_unit_tgt, d_src_points,
-                                                                          nullptr, d_T);
-    prep_targets_kernel<<<q.n_tgt_sets, 1024, 0, st>>>(c);
-    update_kernel<<<dim3((q.n_src + 255) / 256, q.n_units), 256, 0, st>>>(c);
-    launch_sweep(c, L, q.n_units, st);
+    if (prepare_batch(c, L, &q, d_src_points, nullptr, d_unit_src, d_unit_tgt, d_T, st, nullptr) != 0)
+        return ORPCD_ERR_CUDA;
+    update_kernel<<<dim3((q.n_src + 255) / 256, q.n_units), 256, 0, st>>>(c, 0);
+    launch_sweep(c, L, q.n_units, 0, st);
     nn_resolve_kernel<<<dim3((q.n_src + 127) / 128, q.n_units), 128, 0, st>>>(c, 0);
     nn_fix_kernel<<<148 * 4, 128, 0, st>>>(c, 0);
     reduce_kernel<2><<<dim3(L.red_blocks, q.n_units), RED_THREADS, 0, st>>>(c, 0);
+    if (d_out_corr)   // back to the caller's source order
+        unpermute_corr_kernel<<<dim3((q.n_src + 255) / 256, q.n_units), 256, 0, st>>>(c, d_out_corr);
     ORPCD_CHECK_LAUNCH();
-    if (d_out_corr &&
-        cudaMemcpyAsync(d_out_corr, c.corr, sizeof(int) * (size_t)q.n_units * q.n_src, cudaMemcpyDeviceToDevice, st) !=
-            cudaSuccess)
-        return ORPCD_ERR_CUDA;
     return ORPCD_OK;
 }
 
@@ -1068,7 +1504,7 @@ ORPCD_API int orpcd_gicp_sweep_only(const orpcd_gicp_params *p, void *d_workspac
     Ctx c;
     fill_ctx(p, L, d_workspace, c);
     c.ignore_done = 1;
-    launch_sweep(c, L, p->n_units, (cudaStream_t)stream);
+    launch_sweep(c, L, p->n_units, 0, (cudaStream_t)stream);
     ORPCD_CHECK_LAUNCH();
     return ORPCD_OK;
 }

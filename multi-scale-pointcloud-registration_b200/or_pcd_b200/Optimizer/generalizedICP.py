@@ -46,6 +46,9 @@ class GeneralizedICP(IOptimizer):
         # generic 3x3 covariance path with a Jacobi eigen-solve per correspondence
         self.analytic_whitening = True
         self.profile = False          # set True to collect sweep timings in BatchResult.profile
+        self.sweep_mode = 0           # tuning: 0 = chunk-culled 1-NN sweep, 1..3 = dense sweep variants
+        self.sweep_q = 0              # tuning: queries per thread (4 | 8), 0 = auto
+        self.target_splits = 0        # tuning: target splits per sweep, 0 = auto
         self.last_profile = None
 
     # ------------------------------------------------------------------ reference API
@@ -123,7 +126,8 @@ class GeneralizedICP(IOptimizer):
                              max_correspondence_distance=self._max_correspondence_distance,
                              max_iterations=self._max_iterations, relative_fitness=ICP_RELATIVE_FITNESS,
                              relative_rmse=ICP_RELATIVE_RMSE, poll_interval=poll_interval, profile=self.profile,
-                             want_trace=want_trace, ws=self._ws, gicp_epsilon=GICP_EPSILON)
+                             want_trace=want_trace, ws=self._ws, gicp_epsilon=GICP_EPSILON,
+                             sweep_mode=self.sweep_mode, sweep_q=self.sweep_q, target_splits=self.target_splits)
         self._ws = res.workspace
         return res
 

@@ -31,6 +31,9 @@ def main():
     targets = np.stack([tgt * s for s in scales])
     opt = GeneralizedICP()
     opt.profile = True
+    opt.sweep_mode = int(os.environ.get("SWEEP_MODE", "0"))
+    opt.sweep_q = int(os.environ.get("SWEEP_Q", "0"))
+    opt.target_splits = int(os.environ.get("SPLITS", "0"))
     d_s, d_t = _lib.to_device(sources), _lib.to_device(targets)
     us = torch.arange(n_units, dtype=torch.int32, device="cuda")
     ut = (torch.arange(n_units, dtype=torch.int32, device="cuda") * 6 // n_units).to(torch.int32)
@@ -44,7 +47,8 @@ def main():
         p = res.profile
         st = res.stats.cpu().numpy()
         print(json.dumps(dict(rep=rep, units=n_units, wall_s=dt, evals_per_s=n_units / dt, launches=p[0],
-                              sweep_ms=p[1], pairs=p[2], sweep_tflops_alg=8 * p[2] / max(p[1], 1e-9) / 1e9,
+                              sweep_ms=p[1], pairs_visited=p[2], pairs_brute=p[7] * 5000.0 * 5000.0,
+                              visited_fraction=p[2] / max(p[7] * 25e6, 1), sweep_tflops_executed=8 * p[2] / max(p[1], 1e-9) / 1e9,
                               fixed=p[4], splits=p[5], unit_rounds=p[7], mean_iters=float(st[:, 2].mean()),
                               rmse_min=float(st[:, 1].min()))))
 
