@@ -43,6 +43,7 @@ constexpr int NN_TILE = NN_CH * NN_TILE_CH;      // 1024 targets = 16 KB per sta
 constexpr int RED_THREADS = 128;
 constexpr int RED_VALS = 29;                     // 21 JTJ + 6 JTr + sum d2 + count
 constexpr int RED_STRIDE = 32;
+constexpr int RED_PER_THREAD = 4;                // correspondences accumulated per thread before the shuffles
 constexpr float F32_EPS = 5.9604644775390625e-8f;  // 2^-24, unit roundoff
 
 struct UnitState {
@@ -639,12 +640,14 @@ __global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, i
     uint64_t qx[Q / 2], qy[Q / 2], qz[Q / 2];
     float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     float D = 0.f, rw = 0.f, pcx, pcy, pcz;
+    float dq[Q];
     {
         float4 qv[Q];
 #pragma unroll
         for (int k = 0; k < Q; ++k) {
             const int i = min(wbase + k * 32 + lane, c.n_src - 1);   // tail lanes repeat the last query
             qv[k] = qsrc[i];
+            dq[k] = qv[k].w;
             lo[0] = fminf(lo[0], qv[k].x); hi[0] = fmaxf(hi[0], qv[k].x);
             lo[1] = fminf(lo[1], qv[k].y); hi[1] = fmaxf(hi[1], qv[k].y);
             lo[2] = fminf(lo[2], qv[k].z); hi[2] = fmaxf(hi[2], qv[k].z);
@@ -674,6 +677,8 @@ __global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, i
     // FP32 slack: every quantity below carries a few ulps of the coordinate magnitude
     const float mag = fabsf(pcx) + fabsf(pcy) + fabsf(pcz) + rw + (float)c.tgt_meta[st.tgt_set].rmax;
     const float reach = (rw + D) * (1.f + 4e-6f) + 8e-6f * mag;
+#pragma unroll
+    for (int k = 0; k < Q; ++k) dq[k] = dq[k] * (1.f + 4e-6f) + 8e-6f * mag;   // per-query reach, inflated
 
     float m1[Q], m2[Q];
     int c1[Q];
@@ -685,20 +690,43 @@ __global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, i
     int visited = 0;
     unsigned short *vl = vlist[warp];
     for (int pass = cb; pass < ce; pass += CULL_LIST) {
-        // 1) visit list of this pass: lane-parallel sphere tests, order-preserving compaction
+        // 1) visit list of this pass.  Coarse test, lane-parallel over chunks: chunk sphere against the
+        //    patch sphere inflated by the largest d_ub.  Survivors get the exact test: a chunk is needed
+        //    iff SOME query q of the patch has it within reach, dist(q, chunk centre) <= d_ub(q) + r_chunk.
         const int pe = min(ce, pass + CULL_LIST);
         int nv = 0;
         for (int base = pass; base < pe; base += 32) {
             const int chunk = base + lane;
             bool need = false;
+            float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
             if (chunk < pe) {
-                const float4 sp = __ldg(sph + chunk);
+                sp = __ldg(sph + chunk);
                 const float sx = sp.x - pcx, sy = sp.y - pcy, sz = sp.z - pcz;
                 need = !(sqrtf(sx * sx + sy * sy + sz * sz) - sp.w > reach);
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, need);
-            if (need) vl[nv + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(chunk - pass);
-            nv += __popc(bal);
+            unsigned bal = __ballot_sync(0xffffffffu, need);
+            while (bal) {
+                const int l = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const float sx = __shfl_sync(0xffffffffu, sp.x, l), sy = __shfl_sync(0xffffffffu, sp.y, l);
+                const float sz = __shfl_sync(0xffffffffu, sp.z, l), sr = __shfl_sync(0xffffffffu, sp.w, l);
+                bool mine = false;
+#pragma unroll
+                for (int h = 0; h < Q / 2; ++h) {
+                    float x0, x1, y0, y1, z0, z1;
+                    unpack_f2(qx[h], x0, x1);
+                    unpack_f2(qy[h], y0, y1);
+                    unpack_f2(qz[h], z0, z1);
+                    const float ax = x0 - sx, ay = y0 - sy, az = z0 - sz, bx = x1 - sx, by = y1 - sy, bz = z1 - sz;
+                    const float ta = dq[2 * h] + sr, tb = dq[2 * h + 1] + sr;
+                    mine |= (ax * ax + ay * ay + az * az) <= ta * ta * (1.f + 1e-6f);
+                    mine |= (bx * bx + by * by + bz * bz) <= tb * tb * (1.f + 1e-6f);
+                }
+                if (__any_sync(0xffffffffu, mine)) {
+                    if (lane == 0) vl[nv] = (unsigned short)(base + l - pass);
+                    ++nv;
+                }
+            }
         }
         __syncwarp();
         visited += nv;
@@ -842,6 +870,7 @@ __global__ void __launch_bounds__(128) nn_resolve_kernel(Ctx c, int round)
         // ambiguous at FP32 resolution: exact float64 scan by a whole warp (nn_fix_kernel)
         const int slot = atomicAdd(&c.worklist_count[round], 1);
         c.worklist[slot] = (int)oi;
+        c.corr[oi] = c1;   // best chunk of the filter: where nn_fix_kernel starts its exact search
         return;
     }
     const int j = c.tperm[(size_t)st.tgt_set * c.nt_pad + c1 * NN_CH + my_first];   // sorted position -> index
@@ -853,7 +882,10 @@ __global__ void __launch_bounds__(128) nn_resolve_kernel(Ctx c, int round)
     c.corr_d2[oi] = ok ? best : 0.0;
 }
 
-// exact float64 scan, one warp per listed query (4 independent loads in flight per lane)
+// Exact float64 search, one warp per listed query.  The best chunk of the FP32 filter is scored first;
+// every other 32-target chunk is scored only if its bounding sphere comes within that distance of the
+// query (strict test with FP32 slack, so equal-distance candidates are never skipped), lane-parallel
+// over chunks for the test and over the 32 targets for the scoring.  Ties -> lowest original index.
 __global__ void __launch_bounds__(128) nn_fix_kernel(Ctx c, int round)
 {
     const int count = c.worklist_count[round];
@@ -867,23 +899,38 @@ __global__ void __launch_bounds__(128) nn_fix_kernel(Ctx c, int round)
         const double *p = c.cur_pts + (size_t)item * 3;
         const double x = p[0], y = p[1], z = p[2];
         const double *tp = c.tgt_pts + (size_t)st.tgt_set * c.n_tgt * 3;
+        const int *perm = c.tperm + (size_t)st.tgt_set * c.nt_pad;
+        const float4 *sph = c.chunk_sph + (size_t)st.tgt_set * c.n_chunks;
+        const float4 qf = c.cur_qf[item];
+        const int c1 = c.corr[item];   // nn_resolve_kernel parked the filter's best chunk here
         double best = CUDART_INF;
         int bj = 0x7fffffff;
-        int j = lane;
-        for (; j + 96 < c.n_tgt; j += 128) {
-            double d[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const double *q = tp + (size_t)(j + 32 * r) * 3;
-                d[r] = sqdist3_rn(x, y, z, q[0], q[1], q[2]);
+        auto score = [&](int chunk) {
+            const int j = perm[(size_t)chunk * NN_CH + lane];
+            if (j >= 0) {
+                const double d = sqdist3_rn(x, y, z, tp[(size_t)j * 3], tp[(size_t)j * 3 + 1], tp[(size_t)j * 3 + 2]);
+                if (d < best || (d == best && j < bj)) { best = d; bj = j; }
             }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if (d[r] < best) { best = d[r]; bj = j + 32 * r; }
-        }
-        for (; j < c.n_tgt; j += 32) {
-            const double d = sqdist3_rn(x, y, z, tp[(size_t)j * 3], tp[(size_t)j * 3 + 1], tp[(size_t)j * 3 + 2]);
-            if (d < best) { best = d; bj = j; }
+        };
+        score(c1);
+        double wb = best;
+        for (int o = 16; o > 0; o >>= 1) wb = fmin(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+        const float mag = fabsf(qf.x) + fabsf(qf.y) + fabsf(qf.z) + (float)c.tgt_meta[st.tgt_set].rmax;
+        const float thr = __double2float_ru(sqrt(wb)) * (1.f + 4e-6f) + 8e-6f * mag;   // inf if chunk c1 was empty
+        for (int base = 0; base < c.n_chunks; base += 32) {
+            const int chunk = base + lane;
+            bool need = false;
+            if (chunk < c.n_chunks && chunk != c1) {
+                const float4 sp = sph[chunk];
+                const float sx = sp.x - qf.x, sy = sp.y - qf.y, sz = sp.z - qf.z;
+                need = !(sqrtf(sx * sx + sy * sy + sz * sz) - sp.w > thr);
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, need);
+            while (bal) {
+                const int l = __ffs(bal) - 1;
+                bal &= bal - 1;
+                score(base + l);
+            }
         }
         for (int o = 16; o > 0; o >>= 1) {
             const double od = __shfl_xor_sync(0xffffffffu, best, o);
@@ -1017,11 +1064,15 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
     const int u = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     UnitState &st = c.state[u];
     if (st.done) return;
-    const int i = blockIdx.x * RED_THREADS + tid;
     double acc[RED_VALS];
 #pragma unroll
     for (int k = 0; k < RED_VALS; ++k) acc[k] = 0.0;
-    if (i < c.n_src) {
+    // RED_PER_THREAD correspondences per thread (block-strided, so loads stay coalesced): the 29-value
+    // warp-shuffle reduction -- the SHFL pipe is what bounds this kernel -- is paid once per four points
+#pragma unroll 1
+    for (int rep = 0; rep < RED_PER_THREAD; ++rep) {
+        const int i = (blockIdx.x * RED_PER_THREAD + rep) * RED_THREADS + tid;
+        if (i >= c.n_src) break;
         const size_t oi = (size_t)u * c.n_src + i;
         const int j = c.corr[oi];
         if (j >= 0) {
@@ -1033,8 +1084,8 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
             Sym3 W;
             if (COV_MODE == 2) {
                 // EvaluateRegistration only: squared error and count
-                acc[27] = c.corr_d2[oi];
-                acc[28] = 1.0;
+                acc[27] += c.corr_d2[oi];
+                acc[28] += 1.0;
             } else {
             if (COV_MODE == 0) {
                 const Sym3 Cs = load_sym3(c.cur_cov + oi * 6);
@@ -1061,11 +1112,11 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
 #pragma unroll
             for (int a = 0; a < 6; ++a)
 #pragma unroll
-                for (int b = a; b < 6; ++b) acc[k++] = J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b];
+                for (int b = a; b < 6; ++b) acc[k++] += J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b];
 #pragma unroll
-            for (int a = 0; a < 6; ++a) acc[21 + a] = J[0][a] * rr[0] + J[1][a] * rr[1] + J[2][a] * rr[2];
-            acc[27] = c.corr_d2[oi];
-            acc[28] = 1.0;
+            for (int a = 0; a < 6; ++a) acc[21 + a] += J[0][a] * rr[0] + J[1][a] * rr[1] + J[2][a] * rr[2];
+            acc[27] += c.corr_d2[oi];
+            acc[28] += 1.0;
             }
         }
     }
@@ -1205,7 +1256,7 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     if (s < 1) s = 1;
     L.chunks_per_split = (L.n_chunks + s - 1) / s;
     L.splits = (L.n_chunks + L.chunks_per_split - 1) / L.chunks_per_split;
-    L.red_blocks = (p->n_src + RED_THREADS - 1) / RED_THREADS;
+    L.red_blocks = (p->n_src + RED_THREADS * RED_PER_THREAD - 1) / (RED_THREADS * RED_PER_THREAD);
     const size_t U = p->n_units, ns = p->n_src;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += orpcd_align_up(bytes, 256); return r; };
