@@ -68,3 +68,71 @@ def test_align_config1_reproduces_the_oracle_run(golden):
     # record how tight the accept margins were (decision parity is only meaningful if they
     # exceed the run-to-run agreement)
     print("max |rmse_gpu - rmse_oracle| over the decision log:", np.abs(lm - gm).max())
+
+
+def _golden(name):
+    with np.load(os.path.join(os.path.dirname(GOLDEN), name)) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _check_against_run(al, T, m, scale, errors, g, calls):
+    acc = np.array([d["accepted"] for d in al.decision_log])
+    assert np.array_equal(acc, g["log_accepted"])
+    assert np.array_equal(np.array([d["scale"].ravel() for d in al.decision_log]), g["log_scale"])
+    lm = np.array([d["metric"] for d in al.decision_log])
+    assert np.abs(lm - g["log_metric"]).max() <= 1e-5 * g["log_metric"].min()      # rmse 1e-5 relative
+    assert np.array_equal(scale, g["scale"])                                      # chosen scale triple identical
+    assert abs(m - float(g["metric"])) <= 1e-5 * m
+    assert np.allclose(errors, g["errors"], rtol=1e-5, atol=0)
+    diag = np.linalg.norm(al.target_pre.max(0) - al.target_pre.min(0))
+    assert _rot_angle(T[:3, :3], g["T"][:3, :3]) < 1e-4
+    assert np.linalg.norm(T[:3, 3] - g["T"][:3, 3]) < 1e-5 * diag
+    assert al.n_optimize_calls == int(g["calls"]) == calls
+    assert np.array_equal(np.random.get_state()[1][:8], g["rng_after"])
+
+
+def test_align_config3_onhead_64_starts():
+    """BASELINE config 3: OnHead pair, attempts=64 (2496 sequential-equivalent registrations)."""
+    from or_pcd_b200.Aligner.Aligner import Aligner
+    from or_pcd_b200.data import load_sample_cloud
+    from or_pcd_b200.Optimizer import GeneralizedICP
+    from or_pcd_b200.Preprocessor import Preprocessor, RandomDownsampler, SOR
+
+    np.random.seed(0)
+    al = Aligner(Preprocessor([RandomDownsampler(5000), SOR()]), Preprocessor([RandomDownsampler(5000), SOR()]),
+                 GeneralizedICP(), attempts=64)
+    T, m, scale, errors = al.align(load_sample_cloud("ArmadilloOnHeadMultiple_150"),
+                                   load_sample_cloud("ArmadilloOnHeadMultiple_240"), refine_registration=False)
+    _check_against_run(al, T, m, scale, errors, _golden("golden_onhead64.npz"), 2496)
+
+
+def test_align_config2_fgr_reference_compat():
+    """BASELINE config 2: Back pair, FastGlobalOptimizer in the reference's literal feature mode."""
+    from or_pcd_b200.Aligner.Aligner import Aligner
+    from or_pcd_b200.data import load_sample_cloud
+    from or_pcd_b200.Optimizer import FastGlobalOptimizer
+    from or_pcd_b200.Preprocessor import Preprocessor, RandomDownsampler, SOR
+
+    np.random.seed(0)
+    al = Aligner(Preprocessor([RandomDownsampler(5000), SOR()]), Preprocessor([RandomDownsampler(5000), SOR()]),
+                 FastGlobalOptimizer(feature_mode="reference_compat"))
+    T, m, scale, errors = al.align(load_sample_cloud("ArmadilloBack_330"), load_sample_cloud("ArmadilloBack_0"),
+                                   refine_registration=False)
+    g = _golden("golden_fgr_back.npz")
+    _check_against_run(al, T, m, scale, errors, g, int(g["calls"]))
+
+
+def test_fgr_single_calls_match_golden(golden, armadillo_pair):
+    from or_pcd_b200.Optimizer import FastGlobalOptimizer
+
+    s, t, _ = armadillo_pair
+    for mode in ("reference_compat", "fixed"):
+        opt = FastGlobalOptimizer(feature_mode=mode)
+        T, rmse = opt.optimize(s, t)
+        gs = golden[f"back_fgr_{mode}_stats"]          # fitness, rmse, n_corr, n_initial, n_pairs, trials
+        assert opt.last_info[0, 0] == int(gs[3]) and opt.last_info[0, 1] == int(gs[4]) and opt.last_info[0, 2] == int(gs[5])
+        assert abs(rmse - gs[1]) <= 1e-5 * gs[1]
+        assert _rot_angle(T[:3, :3], golden[f"back_fgr_{mode}_T"][:3, :3]) < 1e-4
+    fs, _ = FastGlobalOptimizer().get_fpfh_features(s, t)
+    assert np.allclose(fs[:64], golden["back_src_fpfh_head"], rtol=0, atol=1e-9)
+    assert np.allclose(fs.sum(0), golden["back_src_fpfh_colsum"], rtol=1e-12)

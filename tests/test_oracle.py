@@ -187,3 +187,69 @@ def test_gicp_frozen_results(oracle, golden):
         rr = oracle.gicp(np.dot(s, rot) + tr, t, 0.5, 100)
         assert np.array_equal(rr["T"], golden["back_gicp_starts_T"][k])
         assert np.array_equal([rr["fitness"], rr["rmse"], rr["iters"], rr["n_corr"]], golden["back_gicp_starts_stats"][k])
+
+
+# ------------------------------------------------------------------ FPFH / FGR restatement
+def test_philox_known_answer(oracle):
+    """Philox4x32-10 test vector of Salmon et al. (Random123 kat_vectors): counter 0, key 0."""
+    assert oracle.philox(0, 0) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert oracle.philox(1, 0) != oracle.philox(0, 0)
+
+
+def test_det_acos_cos_within_one_ulp_of_libm(oracle):
+    import ctypes as C
+
+    L = oracle.lib()
+    L.oracle_det_acos.restype = C.c_double; L.oracle_det_acos.argtypes = [C.c_double]
+    L.oracle_det_cos.restype = C.c_double; L.oracle_det_cos.argtypes = [C.c_double]
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-1, 1, 20000), [1.0, -1.0, 0.0, 0.5, -0.5], 1 - 10 ** rng.uniform(-16, 0, 2000)])
+    a = np.array([L.oracle_det_acos(float(x)) for x in xs])
+    assert (np.abs(a - np.arccos(xs)) <= np.spacing(np.arccos(xs)) + 1e-300).all()
+    ys = np.concatenate([rng.uniform(0, np.pi, 20000), [0.0, np.pi, np.pi / 4, 3 * np.pi / 4, np.pi / 2]])
+    c = np.array([L.oracle_det_cos(float(y)) for y in ys])
+    assert np.abs(c - np.cos(ys)).max() <= 1.2e-16
+
+
+def test_fpfh_structure(oracle):
+    rng = np.random.default_rng(6)
+    pts = oracle.RadiusScaler().process(oracle.synthetic_cloud(1500, rng))
+    nrm = oracle.normals(pts, 20, 0.1)["normal"]
+    f, sp = oracle.fpfh(pts, nrm, 20, 0.1, want_spfh=True)
+    assert f.shape == (1500, 33) and (f >= 0).all() and (sp >= 0).all()
+    has = sp.sum(1) > 0
+    assert np.allclose(sp[has].reshape(-1, 3, 11).sum(2), 100.0)           # three histograms of 100 % each
+    assert np.allclose(f[has].reshape(-1, 3, 11).sum(2), 200.0, atol=1e-9)  # weighted neighbours (100) + own SPFH (100)
+    # translating the points (same normals) leaves the descriptor unchanged.  With re-estimated normals
+    # it does not: on a near-spherical patch a chord makes EQUAL angles with the normals at its two
+    # ends, so ComputePairFeatures' "which end is the source" test is a structural near-tie that a
+    # 1e-11 change of a normal flips (f2 changes sign) -- the reason oracle and CUDA share det_acos.
+    p2 = pts + np.array([0.3, -0.2, 0.1])
+    assert np.abs(f - oracle.fpfh(p2, nrm, 20, 0.1)).max() < 1e-9
+
+
+def test_fgr_recovers_a_known_rigid_motion(oracle):
+    rng = np.random.default_rng(8)
+    src = oracle.RadiusScaler().process(oracle.synthetic_cloud(1200, rng))
+    a = 0.5
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    t = np.array([0.05, 0.02, -0.04])
+    tgt = (src @ R.T + t)[rng.permutation(1200)]
+    T, rmse = oracle.FastGlobalOptimizer(feature_mode="fixed").optimize(src, tgt)
+    assert np.allclose(T[:3, :3], R.T, atol=1e-6) and np.allclose(T[:3, 3], t, atol=1e-6) and rmse < 1e-6
+    # the reference's literal mode pairs point i with target index i: meaningless on a shuffled target
+    T2, rmse2 = oracle.FastGlobalOptimizer(feature_mode="reference_compat").optimize(src, tgt)
+    assert rmse2 > 10 * rmse
+
+
+def test_fgr_frozen_results(oracle, golden):
+    pre = _preprocess(oracle, "back")
+    s, t = (np.ascontiguousarray(p[1][p[2]]) for p in pre)
+    fs = oracle.fpfh(s, oracle.normals(s, 20, 0.1)["normal"], 20, 0.1)
+    assert np.array_equal(fs[:64], golden["back_src_fpfh_head"])
+    for mode in ("reference_compat", "fixed"):
+        fo = oracle.FastGlobalOptimizer(feature_mode=mode)
+        T, rm = fo.optimize(s, t)
+        assert np.array_equal(T, golden[f"back_fgr_{mode}_T"])
+        assert np.array_equal([fo.last["fitness"], rm, fo.last["n_corr"], fo.last["n_initial"], fo.last["n_pairs"],
+                               fo.last["trials"]], golden[f"back_fgr_{mode}_stats"])
