@@ -618,11 +618,11 @@ __global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c, int round)
 // cut-off).  Skipped chunks provably hold no nearest neighbour, so the (best chunk, second
 // best) certificate over the visited chunks is still a certificate over all targets.
 // ----------------------------------------------------------------------------
-constexpr int CULL_WARPS = 2;      // warps per block; warps are independent workers
+// warps per block (template parameter W): warps are independent workers, 2 by default
 constexpr int CULL_RING = 4;       // chunk buffers per warp (512 B each), filled by cp.async
 constexpr int CULL_LIST = 1024;    // visit-list capacity per pass (chunk ids)
 
-template <int Q>
+template <int Q, int CULL_WARPS>
 __global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, int round)
 {
     constexpr int TJ = 4;
@@ -1348,9 +1348,17 @@ void launch_sweep(const Ctx &c, const Layout &L, int n_units, int round, cudaStr
     const dim3 g(L.q_tiles, L.splits, n_units);
     const int pad = L.smem_pad;
     if (L.cull) {
-        const dim3 gc((c.n_src + CULL_WARPS * 32 * L.nn_q - 1) / (CULL_WARPS * 32 * L.nn_q), L.splits, n_units);
-        if (L.nn_q == 8) nn_sweep_cull_kernel<8><<<gc, CULL_WARPS * 32, 0, st>>>(c, round);
-        else nn_sweep_cull_kernel<4><<<gc, CULL_WARPS * 32, 0, st>>>(c, round);
+        const int W = L.nn_tj == 2 ? 1 : (L.nn_tj == 8 ? 4 : 2);   // tuning: sweep_tj selects warps per block here
+        const dim3 gc((c.n_src + W * 32 * L.nn_q - 1) / (W * 32 * L.nn_q), L.splits, n_units);
+        if (L.nn_q == 8) {
+            if (W == 1) nn_sweep_cull_kernel<8, 1><<<gc, 32, 0, st>>>(c, round);
+            else if (W == 4) nn_sweep_cull_kernel<8, 4><<<gc, 128, 0, st>>>(c, round);
+            else nn_sweep_cull_kernel<8, 2><<<gc, 64, 0, st>>>(c, round);
+        } else {
+            if (W == 1) nn_sweep_cull_kernel<4, 1><<<gc, 32, 0, st>>>(c, round);
+            else if (W == 4) nn_sweep_cull_kernel<4, 4><<<gc, 128, 0, st>>>(c, round);
+            else nn_sweep_cull_kernel<4, 2><<<gc, 64, 0, st>>>(c, round);
+        }
         return;
     }
     if (L.nn_q == 8) {

@@ -49,6 +49,7 @@ class GeneralizedICP(IOptimizer):
         self.sweep_mode = 0           # tuning: 0 = chunk-culled 1-NN sweep, 1..3 = dense sweep variants
         self.sweep_q = 0              # tuning: queries per thread (4 | 8), 0 = auto
         self.target_splits = 0        # tuning: target splits per sweep, 0 = auto
+        self.sweep_tj = 0             # tuning: dense sweep targets per step; culled sweep warps per block (2->1, 4->2, 8->4)
         self.last_profile = None
 
     # ------------------------------------------------------------------ reference API
@@ -127,7 +128,8 @@ class GeneralizedICP(IOptimizer):
                              max_iterations=self._max_iterations, relative_fitness=ICP_RELATIVE_FITNESS,
                              relative_rmse=ICP_RELATIVE_RMSE, poll_interval=poll_interval, profile=self.profile,
                              want_trace=want_trace, ws=self._ws, gicp_epsilon=GICP_EPSILON,
-                             sweep_mode=self.sweep_mode, sweep_q=self.sweep_q, target_splits=self.target_splits)
+                             sweep_mode=self.sweep_mode, sweep_q=self.sweep_q, target_splits=self.target_splits,
+                             sweep_tj=self.sweep_tj)
         self._ws = res.workspace
         return res
 
