@@ -195,6 +195,25 @@ int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_points,
                      double *h_profile, orpcd_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Batched point-to-point / point-to-plane ICP with Open3D's loop and stopping
+ * rule (|d fitness| < relative_fitness and |d rmse| < relative_rmse, or
+ * max_iterations).  Replaces registration_icp(source, target, threshold, init,
+ * TransformationEstimationPointToPoint() | PointToPlane(), ICPConvergenceCriteria(
+ * max_iteration)) at Aligner/Aligner.py:353-360 (Aligner.refine_registration).
+ * point_to_plane == 0: Umeyama/Kabsch step from the correspondences;
+ * point_to_plane != 0: Gauss-Newton step on (vs - vt).nt with d_tgt_normals
+ *                      [n_tgt_sets][n_tgt][3] (Open3D raises without target normals).
+ * d_init_T (may be NULL) [n_units][16] initial transforms, Open3D column convention.
+ * Only the size, distance and convergence fields of `p` are read; workspace as
+ * orpcd_gicp_batch_workspace_bytes(p) with p->cov_mode == 1.  Outputs as orpcd_gicp_batch.
+ * ---------------------------------------------------------------------- */
+int orpcd_icp_batch(const orpcd_gicp_params *p, int point_to_plane, const double *d_src_points,
+                    const double *d_tgt_points, const double *d_tgt_normals, const int *d_unit_src,
+                    const int *d_unit_tgt, const double *d_init_T, void *d_workspace,
+                    size_t workspace_bytes, double *d_out_T, double *d_out_stats, int *d_out_status,
+                    orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * EvaluateRegistration for a batch of units: source set unit_src[u] moved by
  * d_T[u] (NULL = identity), nearest target of every source point within
  * max_correspondence_distance -> fitness, inlier_rmse, correspondence count.
@@ -289,6 +308,31 @@ int orpcd_fgr_batch(const orpcd_fgr_params *p, const double *d_src_points,
                     const int *d_ij, const int *d_ji, const unsigned long long *d_tuple_keys,
                     void *d_workspace, size_t workspace_bytes, double *d_out_T, int *d_out_info,
                     orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Farthest point sampling (PointNet++), float64, bit-exact with the reference's
+ * numpy/scipy loop (Preprocessor/Downsamplers/farthestDownsampler.py:33-54):
+ * d_out_indices[0] = first_index (the reference draws it with np.random.randint),
+ * then sample_size-1 steps of dist = min(dist, |p - cloud|), next = first argmax.
+ * d_dist_workspace: [n] float64, needed when n > 16384 (may be NULL otherwise).
+ * ---------------------------------------------------------------------- */
+int orpcd_farthest_point_sample(const double *d_points, int n, int first_index, int sample_size,
+                                double *d_dist_workspace, int *d_out_indices, orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Voxel-grid down-sampling: one output point per occupied voxel, the average of
+ * the voxel's points taken in index order.  Replaces PointCloud.voxel_down_sample
+ * (Preprocessor/Downsamplers/voxelDownsampler.py:83,95).  Open3D emits the voxels
+ * in std::unordered_map order (unspecified); here they come in lexicographic
+ * (ix, iy, iz) order of the voxel index, so parity is as a set / after sorting.
+ * d_out_points [n][3] (first *d_out_count rows valid), d_out_first_index (may be
+ * NULL) [n] lowest point index of each voxel, d_out_count int32[1]: number of
+ * voxels, or -1 when the grid is too fine for a 64-bit (cell, index) word.
+ * ---------------------------------------------------------------------- */
+size_t orpcd_voxel_downsample_workspace_bytes(int n);
+int orpcd_voxel_downsample(const double *d_points, int n, double voxel_size, void *d_workspace,
+                           size_t workspace_bytes, double *d_out_points, int *d_out_first_index,
+                           int *d_out_count, orpcd_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Roofline helper: one nearest-neighbour sweep (the dominant kernel of

@@ -30,6 +30,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "sort.cuh"
 
 namespace {
 
@@ -146,162 +147,6 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait()
 {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// ----------------------------------------------------------------------------
-// spatial (Morton) ordering of every source and target set: consecutive indices are then
-// close in space, which is what lets a warp of the sweep skip whole 32-target chunks
-// ----------------------------------------------------------------------------
-constexpr int SORT_TILE = 1024;
-
-__global__ void __launch_bounds__(256) bbox_kernel(const double *__restrict__ pts, int n, double *__restrict__ bbox)
-{
-    __shared__ double red[6][8];
-    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const double *p = pts + (size_t)s * n * 3;
-    double mn[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, mx[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
-    for (int i = tid; i < n; i += 256)
-        for (int k = 0; k < 3; ++k) {
-            const double v = p[(size_t)i * 3 + k];
-            mn[k] = fmin(mn[k], v);
-            mx[k] = fmax(mx[k], v);
-        }
-    for (int k = 0; k < 3; ++k)
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-            mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-        }
-    if (lane == 0)
-        for (int k = 0; k < 3; ++k) { red[k][wid] = mn[k]; red[3 + k][wid] = mx[k]; }
-    __syncthreads();
-    if (tid < 3) {
-        double a = CUDART_INF, b = -CUDART_INF;
-        for (int w = 0; w < 8; ++w) { a = fmin(a, red[tid][w]); b = fmax(b, red[3 + tid][w]); }
-        bbox[(size_t)s * 6 + tid] = a;
-        bbox[(size_t)s * 6 + 3 + tid] = b;
-    }
-}
-
-__device__ __forceinline__ unsigned part1by2(unsigned x)
-{
-    x &= 0x3ffu;
-    x = (x | (x << 16)) & 0x030000ffu;
-    x = (x | (x << 8)) & 0x0300f00fu;
-    x = (x | (x << 4)) & 0x030c30c3u;
-    x = (x | (x << 2)) & 0x09249249u;
-    return x;
-}
-
-// key = (30-bit Morton code << 32) | index; padding entries sort last.  grid (pad2/256, sets)
-__global__ void __launch_bounds__(256) morton_kernel(const double *__restrict__ pts, int n, int pad2,
-                                                    const double *__restrict__ bbox, unsigned long long *__restrict__ keys)
-{
-    const int s = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= pad2) return;
-    unsigned long long key = ~0ull;
-    if (i < n) {
-        const double *b = bbox + (size_t)s * 6;
-        const double ext = fmax(fmax(b[3] - b[0], b[4] - b[1]), b[5] - b[2]);
-        const double inv = ext > 0 ? 1024.0 / ext : 0.0;
-        const double *p = pts + ((size_t)s * n + i) * 3;
-        unsigned q[3];
-        for (int k = 0; k < 3; ++k) {
-            const int v = (int)((p[k] - b[k]) * inv);
-            q[k] = (unsigned)(v < 0 ? 0 : (v > 1023 ? 1023 : v));
-        }
-        // Hilbert index (Skilling, "Programming the Hilbert curve", 2004: axes -> transpose), 10 bits per
-        // axis: unlike the Z-order it has no long jumps, so runs of consecutive points stay compact
-        {
-            const unsigned M = 1u << 9;
-            for (unsigned Qb = M; Qb > 1; Qb >>= 1) {
-                const unsigned P = Qb - 1;
-                for (int k = 0; k < 3; ++k) {
-                    if (q[k] & Qb) q[0] ^= P;
-                    else { const unsigned t = (q[0] ^ q[k]) & P; q[0] ^= t; q[k] ^= t; }
-                }
-            }
-            for (int k = 1; k < 3; ++k) q[k] ^= q[k - 1];
-            unsigned t = 0;
-            for (unsigned Qb = M; Qb > 1; Qb >>= 1)
-                if (q[2] & Qb) t ^= Qb - 1;
-            for (int k = 0; k < 3; ++k) q[k] ^= t;
-        }
-        // interleave the transposed form: bit b of axis k -> bit 3*b + (2 - k)
-        const unsigned code = (part1by2(q[0]) << 2) | (part1by2(q[1]) << 1) | part1by2(q[2]);
-        key = ((unsigned long long)code << 32) | (unsigned)i;
-    }
-    keys[(size_t)s * pad2 + i] = key;
-}
-
-// bitonic network on 64-bit keys: FULL sorts each 1024-element tile, otherwise the last ten
-// steps (j = 512..1) of merge phase k run in shared memory.  grid (pad2/1024, sets), 512 threads
-template <bool FULL>
-__global__ void __launch_bounds__(512) bitonic_local_kernel(unsigned long long *__restrict__ keys, int pad2, int k_phase)
-{
-    __shared__ unsigned long long sh[SORT_TILE];
-    unsigned long long *base = keys + (size_t)blockIdx.y * pad2 + (size_t)blockIdx.x * SORT_TILE;
-    const int t = threadIdx.x;
-    sh[t] = base[t];
-    sh[t + 512] = base[t + 512];
-    __syncthreads();
-    for (int k = FULL ? 2 : k_phase; k <= (FULL ? SORT_TILE : k_phase); k <<= 1) {
-        for (int j = (FULL ? k : SORT_TILE) >> 1; j > 0; j >>= 1) {
-            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-            const int l = i | j;
-            const bool up = (((blockIdx.x * SORT_TILE + i) & k) == 0);
-            const unsigned long long a = sh[i], b = sh[l];
-            if ((a > b) == up) { sh[i] = b; sh[l] = a; }
-            __syncthreads();
-        }
-    }
-    base[t] = sh[t];
-    base[t + 512] = sh[t + 512];
-}
-
-// one global compare-exchange step (j >= 1024).  grid (pad2/512, sets), 256 threads
-__global__ void __launch_bounds__(256) bitonic_global_kernel(unsigned long long *__restrict__ keys, int pad2, int j, int k)
-{
-    unsigned long long *base = keys + (size_t)blockIdx.y * pad2;
-    const int t = blockIdx.x * 256 + threadIdx.x;
-    if (t >= pad2 / 2) return;
-    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-    const int l = i | j;
-    const bool up = ((i & k) == 0);
-    const unsigned long long a = base[i], b = base[l];
-    if ((a > b) == up) { base[i] = b; base[l] = a; }
-}
-
-// grid (ceil(out_n/256), sets): perm[pos] = original index at sorted position pos (-1 for padding)
-__global__ void __launch_bounds__(256) perm_kernel(const unsigned long long *__restrict__ keys, int n, int pad2,
-                                                  int out_n, int *__restrict__ perm)
-{
-    const int s = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= out_n) return;
-    perm[(size_t)s * out_n + i] = i < n ? (int)(unsigned)(keys[(size_t)s * pad2 + i] & 0xffffffffull) : -1;
-}
-
-int sort_pad(int n)
-{
-    int p = SORT_TILE;
-    while (p < n) p <<= 1;
-    return p;
-}
-
-// perm [sets][out_n] <- Morton order of pts [sets][n][3]
-int spatial_perm(const double *pts, int n, int sets, int out_n, double *bbox, unsigned long long *keys, int *perm,
-                 cudaStream_t st)
-{
-    const int pad2 = sort_pad(n);
-    bbox_kernel<<<sets, 256, 0, st>>>(pts, n, bbox);
-    morton_kernel<<<dim3(pad2 / 256, sets), 256, 0, st>>>(pts, n, pad2, bbox, keys);
-    bitonic_local_kernel<true><<<dim3(pad2 / SORT_TILE, sets), 512, 0, st>>>(keys, pad2, 0);
-    for (int k = 2 * SORT_TILE; k <= pad2; k <<= 1) {
-        for (int j = k >> 1; j >= SORT_TILE; j >>= 1)
-            bitonic_global_kernel<<<dim3((pad2 / 2 + 255) / 256, sets), 256, 0, st>>>(keys, pad2, j, k);
-        bitonic_local_kernel<false><<<dim3(pad2 / SORT_TILE, sets), 512, 0, st>>>(keys, pad2, k);
-    }
-    perm_kernel<<<dim3((out_n + 255) / 256, sets), 256, 0, st>>>(keys, n, pad2, out_n, perm);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // ----------------------------------------------------------------------------
@@ -1052,6 +897,64 @@ __device__ void ldlt_solve6(double *A, const double *b, double *x)
     for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
 }
 
+// Eigen::umeyama(src, dst, with_scaling = false) from the one-pass sums
+//   tot[0..2] = sum s, tot[3..5] = sum t, tot[6..14] = sum t s^T (row-major), n correspondences:
+// sigma = sum t s^T / n - mt ms^T; right singular vectors from the Jacobi eigen-decomposition of
+// sigma^T sigma; optimal proper rotation R = [u1 u2 u1xu2][v1 v2 v1xv2]^T; translation mt - R ms.
+// (TransformationEstimationPointToPoint::ComputeTransformation, Aligner/Aligner.py:353-360.)
+__device__ void umeyama_from_sums(const double *tot, double n, double *Um)
+{
+    for (int k = 0; k < 12; ++k) Um[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    if (!(n > 0)) return;
+    const double ms[3] = {tot[0] / n, tot[1] / n, tot[2] / n}, mt[3] = {tot[3] / n, tot[4] / n, tot[5] / n};
+    double S[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int cc = 0; cc < 3; ++cc) S[r][cc] = tot[6 + r * 3 + cc] / n - mt[r] * ms[cc];
+    double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
+    for (int k = 0; k < 3; ++k) {
+        a00 += S[k][0] * S[k][0]; a01 += S[k][0] * S[k][1]; a02 += S[k][0] * S[k][2];
+        a11 += S[k][1] * S[k][1]; a12 += S[k][1] * S[k][2]; a22 += S[k][2] * S[k][2];
+    }
+    double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        const double off = a01 * a01 + a02 * a02 + a12 * a12;
+        if (off == 0.0) break;
+        JACOBI_ROT(a00, a11, a01, a02, a12, 0, 1)
+        JACOBI_ROT(a00, a22, a02, a01, a12, 0, 2)
+        JACOBI_ROT(a11, a22, a12, a01, a02, 1, 2)
+    }
+    const double w[3] = {a00, a11, a22};
+    int o0 = 0, o1 = 1, o2 = 2;
+    if (w[o1] > w[o0]) { const int t = o0; o0 = o1; o1 = t; }
+    if (w[o2] > w[o0]) { const int t = o0; o0 = o2; o2 = t; }
+    if (w[o2] > w[o1]) { const int t = o1; o1 = o2; o2 = t; }
+    const double v1[3] = {v[0][o0], v[1][o0], v[2][o0]}, v2[3] = {v[0][o1], v[1][o1], v[2][o1]};
+    const double v3[3] = {v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]};
+    double u1[3], u2[3];
+    for (int r = 0; r < 3; ++r) {
+        u1[r] = S[r][0] * v1[0] + S[r][1] * v1[1] + S[r][2] * v1[2];
+        u2[r] = S[r][0] * v2[0] + S[r][1] * v2[1] + S[r][2] * v2[2];
+    }
+    const double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    if (!(n1 > 0)) return;
+    for (int r = 0; r < 3; ++r) u1[r] /= n1;
+    const double d12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+    for (int r = 0; r < 3; ++r) u2[r] -= d12 * u1[r];
+    double n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+    if (!(n2 > 1e-300)) {
+        double e[3] = {0, 0, 0};
+        e[fabs(u1[0]) <= fabs(u1[1]) ? (fabs(u1[0]) <= fabs(u1[2]) ? 0 : 2) : (fabs(u1[1]) <= fabs(u1[2]) ? 1 : 2)] = 1.0;
+        u2[0] = u1[1] * e[2] - u1[2] * e[1]; u2[1] = u1[2] * e[0] - u1[0] * e[2]; u2[2] = u1[0] * e[1] - u1[1] * e[0];
+        n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+    }
+    for (int r = 0; r < 3; ++r) u2[r] /= n2;
+    const double u3[3] = {u1[1] * u2[2] - u1[2] * u2[1], u1[2] * u2[0] - u1[0] * u2[2], u1[0] * u2[1] - u1[1] * u2[0]};
+    for (int r = 0; r < 3; ++r) {
+        for (int cc = 0; cc < 3; ++cc) Um[r * 4 + cc] = u1[r] * v1[cc] + u2[r] * v2[cc] + u3[r] * v3[cc];
+        Um[r * 4 + 3] = mt[r] - (Um[r * 4] * ms[0] + Um[r * 4 + 1] * ms[1] + Um[r * 4 + 2] * ms[2]);
+    }
+}
+
 // ----------------------------------------------------------------------------
 // residual / Jacobian reduction + solve
 // ----------------------------------------------------------------------------
@@ -1084,6 +987,31 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
             Sym3 W;
             if (COV_MODE == 2) {
                 // EvaluateRegistration only: squared error and count
+                acc[27] += c.corr_d2[oi];
+                acc[28] += 1.0;
+            } else if (COV_MODE == 3) {
+                // point-to-point (Umeyama): sums of s, t and t s^T
+                const double tx = pt[0], ty = pt[1], tz = pt[2];
+                acc[0] += sx; acc[1] += sy; acc[2] += sz;
+                acc[3] += tx; acc[4] += ty; acc[5] += tz;
+                acc[6] += tx * sx; acc[7] += tx * sy; acc[8] += tx * sz;
+                acc[9] += ty * sx; acc[10] += ty * sy; acc[11] += ty * sz;
+                acc[12] += tz * sx; acc[13] += tz * sy; acc[14] += tz * sz;
+                acc[27] += c.corr_d2[oi];
+                acc[28] += 1.0;
+            } else if (COV_MODE == 4) {
+                // point-to-plane: r = (vs - vt).nt, J = [vs x nt, nt]
+                const double *nt = c.tgt_cov + tj * 3;
+                const double nx = nt[0], ny = nt[1], nz = nt[2];
+                const double r = dx * nx + dy * ny + dz * nz;
+                const double J[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
+                int k = 0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int b = a; b < 6; ++b) acc[k++] += J[a] * J[b];
+#pragma unroll
+                for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
                 acc[27] += c.corr_d2[oi];
                 acc[28] += 1.0;
             } else {
@@ -1174,7 +1102,9 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
         return;
     }
     double Um[12];
-    if (n > 0) {
+    if (COV_MODE == 3) {
+        umeyama_from_sums(tot, n, Um);
+    } else if (n > 0) {
         double A[36], nb[6], x[6];
         int k = 0;
         for (int a = 0; a < 6; ++a)
@@ -1407,27 +1337,32 @@ ORPCD_API size_t orpcd_gicp_batch_workspace_bytes(const orpcd_gicp_params *p)
     return L.total;
 }
 
-ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_points,
-                               const double *d_src_cov, const double *d_tgt_points,
-                               const double *d_tgt_cov, const int *d_unit_src, const int *d_unit_tgt,
-                               void *d_workspace, size_t workspace_bytes, double *d_out_T,
-                               double *d_out_stats, int *d_out_status, double *d_trace, double *h_profile,
-                               orpcd_stream_t stream)
+namespace {
+
+// est_mode: 0 / 1 = Generalized-ICP (covariances / plane axes), 3 = point-to-point, 4 = point-to-plane
+// (d_tgt_cov = target normals).  d_init_T: optional initial transforms [n_units][16].
+int run_registration(const orpcd_gicp_params *p, int est_mode, const double *d_src_points,
+                     const double *d_src_cov, const double *d_tgt_points, const double *d_tgt_cov,
+                     const int *d_unit_src, const int *d_unit_tgt, const double *d_init_T, void *d_workspace,
+                     size_t workspace_bytes, double *d_out_T, double *d_out_stats, int *d_out_status,
+                     double *d_trace, double *h_profile, orpcd_stream_t stream)
 {
     Layout L;
     if (!make_layout(p, L)) return ORPCD_ERR_INVALID;
-    if (!d_src_points || !d_src_cov || !d_tgt_points || !d_tgt_cov || !d_unit_src || !d_unit_tgt ||
-        !d_out_T || !d_out_stats || !d_out_status)
+    if (!d_src_points || !d_tgt_points || !d_unit_src || !d_unit_tgt || !d_out_T || !d_out_stats || !d_out_status)
         return ORPCD_ERR_INVALID;
+    if ((est_mode <= 1 && (!d_src_cov || !d_tgt_cov)) || (est_mode == 4 && !d_tgt_cov)) return ORPCD_ERR_INVALID;
     if (!d_workspace || workspace_bytes < L.total || ((uintptr_t)d_workspace & 255)) return ORPCD_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     Ctx c;
     fill_ctx(p, L, d_workspace, c);
     c.tgt_pts = d_tgt_points; c.tgt_cov = d_tgt_cov;
     c.out_T = d_out_T; c.out_stats = d_out_stats; c.out_status = d_out_status; c.trace = d_trace;
+    c.cov_mode = est_mode;
     int launches = 0;
 
-    if (prepare_batch(c, L, p, d_src_points, d_src_cov, d_unit_src, d_unit_tgt, nullptr, st, &launches) != 0)
+    if (prepare_batch(c, L, p, d_src_points, est_mode <= 1 ? d_src_cov : nullptr, d_unit_src, d_unit_tgt, d_init_T, st,
+                      &launches) != 0)
         return ORPCD_ERR_CUDA;
     const dim3 g_upd((p->n_src + 255) / 256, p->n_units);
     const dim3 g_res((p->n_src + 127) / 128, p->n_units);
@@ -1451,8 +1386,10 @@ ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_p
         if (prof) cudaEventRecord(ev[2 * round + 1], st);
         nn_resolve_kernel<<<g_res, 128, 0, st>>>(c, round);
         nn_fix_kernel<<<fix_blocks, 128, 0, st>>>(c, round);
-        if (p->cov_mode == 0) reduce_kernel<0><<<g_red, RED_THREADS, 0, st>>>(c, round);
-        else reduce_kernel<1><<<g_red, RED_THREADS, 0, st>>>(c, round);
+        if (est_mode == 0) reduce_kernel<0><<<g_red, RED_THREADS, 0, st>>>(c, round);
+        else if (est_mode == 1) reduce_kernel<1><<<g_red, RED_THREADS, 0, st>>>(c, round);
+        else if (est_mode == 3) reduce_kernel<3><<<g_red, RED_THREADS, 0, st>>>(c, round);
+        else reduce_kernel<4><<<g_red, RED_THREADS, 0, st>>>(c, round);
         ORPCD_CHECK_LAUNCH();
         launches += 5;
         rounds = round + 1;
@@ -1516,6 +1453,37 @@ ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_p
         h_profile[7] = unit_rounds;                                     // brute force would be unit_rounds*n_src*n_tgt pairs
     }
     return ORPCD_OK;
+}
+
+}  // namespace
+
+ORPCD_API int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_points,
+                               const double *d_src_cov, const double *d_tgt_points,
+                               const double *d_tgt_cov, const int *d_unit_src, const int *d_unit_tgt,
+                               void *d_workspace, size_t workspace_bytes, double *d_out_T,
+                               double *d_out_stats, int *d_out_status, double *d_trace, double *h_profile,
+                               orpcd_stream_t stream)
+{
+    if (!p || (p->cov_mode != 0 && p->cov_mode != 1)) return ORPCD_ERR_INVALID;
+    return run_registration(p, p->cov_mode, d_src_points, d_src_cov, d_tgt_points, d_tgt_cov, d_unit_src, d_unit_tgt,
+                            nullptr, d_workspace, workspace_bytes, d_out_T, d_out_stats, d_out_status, d_trace,
+                            h_profile, stream);
+}
+
+ORPCD_API int orpcd_icp_batch(const orpcd_gicp_params *p_in, int point_to_plane, const double *d_src_points,
+                              const double *d_tgt_points, const double *d_tgt_normals, const int *d_unit_src,
+                              const int *d_unit_tgt, const double *d_init_T, void *d_workspace,
+                              size_t workspace_bytes, double *d_out_T, double *d_out_stats, int *d_out_status,
+                              orpcd_stream_t stream)
+{
+    if (!p_in || (point_to_plane && !d_tgt_normals)) return ORPCD_ERR_INVALID;
+    orpcd_gicp_params q = *p_in;
+    q.cov_mode = 1;                      // workspace layout of the plane-axis path (3 doubles per point)
+    if (!(q.gicp_epsilon > 0 && q.gicp_epsilon < 1)) q.gicp_epsilon = 1e-3;
+    q.profile = 0;
+    return run_registration(&q, point_to_plane ? 4 : 3, d_src_points, nullptr, d_tgt_points, d_tgt_normals, d_unit_src,
+                            d_unit_tgt, d_init_T, d_workspace, workspace_bytes, d_out_T, d_out_stats, d_out_status,
+                            nullptr, nullptr, stream);
 }
 
 ORPCD_API int orpcd_evaluate_batch(const orpcd_gicp_params *p_in, const double *d_src_points,

@@ -271,13 +271,34 @@ class Aligner:
         return optimal_transformation, optimal_metric, optimal_scale_factors, errors
 
     def refine_registration(self, source, target, initial_transform, max_iteration: int = REFINER_MAX_ITER,
-                            distance_threshold: float = REFINER_DISTANCE_THRESHOLD, icp_type: str = "PointToPoint"):
-        """ICP polish (reference: Aligner.py:319-364).  Not on the measured hot path
-        (the reference's default call is itself defective,
-        SURVEY.md B.7); call ``align(..., refine_registration=False)``."""
-        raise NotImplementedError(
-            "refine_registration (Open3D point-to-point/point-to-plane ICP) is not part of the B200 hot path yet; "
-            "use align(..., refine_registration=False)")
+                            distance_threshold: float = REFINER_DISTANCE_THRESHOLD, icp_type: str = "PointToPoint",
+                            target_normals: Optional[np.ndarray] = None):
+        """ICP polish on the GPU (reference: Aligner.py:319-364, Open3D registration_icp).
+
+        Mirrors the reference literally: ``initial_transform`` is handed over as Open3D's ``init``
+        (column convention -- the reference passes its row-convention matrix here, SURVEY.md B.7, and
+        so does ``align``), and the returned matrix is Open3D's ``result.transformation`` untouched.
+        ``icp_type="PointToPlane"`` needs target normals; the reference never supplies them and Open3D
+        raises, so without ``target_normals`` (an extension of this port: (M,3) array) the same
+        RuntimeError is raised here."""
+        from .. import _lib, ops
+
+        if icp_type not in ("PointToPoint", "PointToPlane"):
+            raise TypeError("icp_type must be 'PointToPoint' or 'PointToPlane'")
+        if icp_type == "PointToPlane" and target_normals is None:
+            raise RuntimeError("[Open3D Error] TransformationEstimationPointToPlane and "
+                               "TransformationEstimationColoredICP require pre-computed normal vectors for target "
+                               "PointCloud.")
+        t = _lib.torch()
+        d_src = _lib.to_device(np.asarray(source, dtype=np.float64)[None])
+        d_tgt = _lib.to_device(np.asarray(target, dtype=np.float64)[None])
+        zero = t.zeros(1, dtype=t.int32, device="cuda")
+        init = _lib.to_device(np.asarray(initial_transform, dtype=np.float64).reshape(1, 4, 4))
+        normals = None
+        if icp_type == "PointToPlane":
+            normals = _lib.to_device(np.asarray(target_normals, dtype=np.float64)[None])
+        T, stats, _ = ops.icp_batch(d_src, d_tgt, zero, zero, init, normals, distance_threshold, max_iteration)
+        return T[0].cpu().numpy(), float(stats[0, 1].item())
 
     def transfrom(self, source: np.ndarray) -> np.ndarray:
         """Apply the found registration to a raw cloud (reference: Aligner.py:367-394)."""

@@ -112,6 +112,14 @@ def lib():
                                    C.POINTER(C.c_double), vp]
     L.orpcd_gicp_sweep_only.restype = ip
     L.orpcd_gicp_sweep_only.argtypes = [C.POINTER(GicpParams), vp, sz, vp]
+    L.orpcd_farthest_point_sample.restype = ip
+    L.orpcd_farthest_point_sample.argtypes = [vp, ip, ip, ip, vp, vp, vp]
+    L.orpcd_voxel_downsample_workspace_bytes.restype = sz
+    L.orpcd_voxel_downsample_workspace_bytes.argtypes = [ip]
+    L.orpcd_voxel_downsample.restype = ip
+    L.orpcd_voxel_downsample.argtypes = [vp, ip, dp, vp, sz, vp, vp, vp, vp]
+    L.orpcd_icp_batch.restype = ip
+    L.orpcd_icp_batch.argtypes = [C.POINTER(GicpParams), ip, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp]
     L.orpcd_evaluate_batch.restype = ip
     L.orpcd_evaluate_batch.argtypes = [C.POINTER(GicpParams), vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp]
     L.orpcd_fpfh.restype = ip

@@ -198,6 +198,77 @@ def gicp_batch(src_points, src_cov6, tgt_points, tgt_cov6, unit_src, unit_tgt, m
     return res
 
 
+def farthest_point_sample(points, first_index: int, sample_size: int):
+    """Indices (int32 [sample_size]) of the farthest-point sample of points [N,3] starting at first_index."""
+    t = _t()
+    points = _f64(points)
+    N = points.shape[0]
+    out = t.empty(sample_size, dtype=t.int32, device="cuda")
+    ws = t.empty(N, dtype=t.float64, device="cuda") if N > 16384 else None
+    check(_lib.lib().orpcd_farthest_point_sample(points.data_ptr(), N, int(first_index), int(sample_size),
+                                                 ws.data_ptr() if ws is not None else None, out.data_ptr(),
+                                                 _lib.stream_ptr()), "orpcd_farthest_point_sample")
+    launch_counter["kernels"] += 1
+    return out
+
+
+def voxel_downsample(points, voxel_size: float, ws=None):
+    """(voxel averages [n_voxels,3] in lexicographic voxel order, first point index of each voxel, workspace)."""
+    t = _t()
+    points = _f64(points)
+    N = points.shape[0]
+    L = _lib.lib()
+    need = L.orpcd_voxel_downsample_workspace_bytes(N)
+    if ws is None or ws.numel() < need:
+        ws = _lib.workspace(need)
+    out = t.empty((N, 3), dtype=t.float64, device="cuda")
+    first = t.empty(N, dtype=t.int32, device="cuda")
+    count = t.zeros(1, dtype=t.int32, device="cuda")
+    check(L.orpcd_voxel_downsample(points.data_ptr(), N, float(voxel_size), ws.data_ptr(), ws.numel(), out.data_ptr(),
+                                   first.data_ptr(), count.data_ptr(), _lib.stream_ptr()), "orpcd_voxel_downsample")
+    launch_counter["kernels"] += 8
+    n = int(count.item())
+    if n < 0:
+        raise _lib.OrpcdError("voxel_size is too small.")    # Open3D: "[VoxelDownSample] voxel_size is too small."
+    return out[:n], first[:n], ws
+
+
+def icp_batch(src_points, tgt_points, unit_src, unit_tgt, init_transforms=None, tgt_normals=None,
+              max_correspondence_distance=0.5, max_iterations=200, relative_fitness=1e-6, relative_rmse=1e-6,
+              poll_interval=8):
+    """Point-to-point (tgt_normals None) or point-to-plane ICP per unit.
+    Returns (T [U,4,4] column convention, stats [U,4] = fitness, rmse, iterations, n_corr, status [U])."""
+    t = _t()
+    src_points, tgt_points = _f64(src_points), _f64(tgt_points)
+    S, Ns, _ = src_points.shape
+    Cn, Nt, _ = tgt_points.shape
+    U = unit_src.shape[0]
+    prm = GicpParams(U, Ns, Nt, S, Cn, int(max_iterations), 0, int(poll_interval), 0, 1,
+                     float(max_correspondence_distance), float(relative_fitness), float(relative_rmse), 1e-3, 0, 0, 0, 0)
+    L = _lib.lib()
+    need = L.orpcd_gicp_batch_workspace_bytes(C.byref(prm))
+    if need == 0:
+        raise _lib.OrpcdError("orpcd_icp_batch: invalid parameters")
+    ws = _lib.workspace(need)
+    T = t.empty((U, 4, 4), dtype=t.float64, device="cuda")
+    stats = t.empty((U, 4), dtype=t.float64, device="cuda")
+    status = t.empty(U, dtype=t.int32, device="cuda")
+    if init_transforms is not None:
+        init_transforms = _f64(init_transforms)
+        assert init_transforms.shape == (U, 4, 4)
+    if tgt_normals is not None:
+        tgt_normals = _f64(tgt_normals)
+        assert tgt_normals.shape == tgt_points.shape
+    check(L.orpcd_icp_batch(C.byref(prm), 1 if tgt_normals is not None else 0, src_points.data_ptr(),
+                            tgt_points.data_ptr(), tgt_normals.data_ptr() if tgt_normals is not None else None,
+                            unit_src.data_ptr(), unit_tgt.data_ptr(),
+                            init_transforms.data_ptr() if init_transforms is not None else None, ws.data_ptr(),
+                            ws.numel(), T.data_ptr(), stats.data_ptr(), status.data_ptr(), _lib.stream_ptr()),
+          "orpcd_icp_batch")
+    launch_counter["kernels"] += 5 * (int(max_iterations) + 1)
+    return T, stats, status
+
+
 def evaluate_batch(src_points, tgt_points, unit_src, unit_tgt, transforms=None, max_correspondence_distance=0.5,
                    want_corr=False, ws=None):
     """EvaluateRegistration per unit: (stats [U,4] = fitness, rmse, 0, n_corr; status [U]; corr [U,Ns] | None; ws)."""

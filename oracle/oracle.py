@@ -164,6 +164,24 @@ def gicp(source, target, max_dist=0.5, max_iter=100, eps=1e-3, src_cov=None, tgt
     return out
 
 
+def icp(source, target, max_dist=0.5, max_iter=200, init_T=None, mode="PointToPoint", target_normals=None):
+    """registration_icp (A.4 loop with TransformationEstimationPointToPoint / PointToPlane;
+    Aligner/Aligner.py:353-360).  init_T / returned T: Open3D column convention."""
+    source = _f64(source, 3); target = _f64(target, 3)
+    T = np.empty(16); fit = C.c_double(); rmse = C.c_double(); iters = C.c_int(); nc = C.c_int()
+    it = _f64(init_T).reshape(16).copy() if init_T is not None else None
+    tn = _f64(target_normals, 3) if target_normals is not None else None
+    m = {"PointToPoint": 0, "PointToPlane": 1}[mode]
+    rc = lib().oracle_icp(_d(source), C.c_int(source.shape[0]), _d(target), C.c_int(target.shape[0]),
+                          C.c_double(max_dist), C.c_int(max_iter), _d(it) if it is not None else None, C.c_int(m),
+                          _d(tn) if tn is not None else None, _d(T), C.byref(fit), C.byref(rmse), C.byref(iters),
+                          C.byref(nc))
+    if rc != 0:
+        raise RuntimeError("TransformationEstimationPointToPlane and TransformationEstimationColoredICP "
+                           "require pre-computed normal vectors for target PointCloud.")
+    return dict(T=T.reshape(4, 4), fitness=fit.value, rmse=rmse.value, iters=iters.value, n_corr=nc.value)
+
+
 def fpfh(points, normals_, knn_k: int = 20, radius: float = 0.1, want_spfh=False):
     """compute_fpfh_feature(cloud, Hybrid(radius, knn)) (A.7; fastGlobalOptimizer.py:130-143).
     Returns (n,33) float64 (Open3D's 33xN column-major data_ has the same memory order)."""
@@ -306,6 +324,85 @@ class GeneralizedICP:
         if r["rmse"] == 0:
             raise ValueError("Optimization failed with loss = 0. Parameters are not well set.")
         return roto, r["rmse"]
+
+
+def fps(points, first: int, k: int):
+    """Farthest point sampling indices (farthestDownsampler.py:33-54 with the first index given)."""
+    points = _f64(points, 3)
+    out = np.empty(k, dtype=np.int32)
+    rc = lib().oracle_fps(_d(points), C.c_int(points.shape[0]), C.c_int(int(first)), C.c_int(int(k)), _i(out))
+    assert rc == 0
+    return out
+
+
+def voxel_downsample(points, voxel_size: float):
+    """PointCloud.voxel_down_sample (voxelDownsampler.py:83,95), voxels in lexicographic index order.
+    Returns (points (m,3), first point index of each voxel (m,))."""
+    points = _f64(points, 3)
+    out = np.empty_like(points); first = np.empty(points.shape[0], dtype=np.int32)
+    lib().oracle_voxel_downsample.restype = C.c_int
+    m = lib().oracle_voxel_downsample(_d(points), C.c_int(points.shape[0]), C.c_double(voxel_size), _d(out), _i(first))
+    assert m >= 0
+    return out[:m].copy(), first[:m].copy()
+
+
+class FarthestDownsampler:
+    """Preprocessor/Downsamplers/farthestDownsampler.py:10-57."""
+
+    is_scaler = False
+
+    def __init__(self, sample_size=4096):
+        self._sample_size = sample_size if sample_size > 0 else 4096
+
+    def process(self, cloud):
+        first = np.random.randint(low=0, high=cloud.shape[0])
+        self.last_indices = fps(cloud, first, self._sample_size).astype(np.int64)
+        return cloud[self.last_indices]
+
+
+class VoxelDownsampler:
+    """Preprocessor/Downsamplers/voxelDownsampler.py:14-136 (compass search on the voxel size)."""
+
+    is_scaler = False
+
+    def __init__(self, target_points, base_voxel_size=0.01, min_voxel_size=0.0001, delta=0.01, eps=0.0005):
+        if target_points <= 0:
+            raise ValueError(f"target points cannot be 0 or less. Provided: {target_points}")
+        self._target_points = target_points
+        self._min_voxel_size = min_voxel_size if min_voxel_size > 0 else 0.0001
+        self._base_voxel_size = base_voxel_size if base_voxel_size > 0 else 0.01
+        self._delta = delta if delta > 0 else 0.01
+        self._eps = eps if eps > 0 else 0.0005
+        self.probes = []
+
+    def _ds(self, cloud, size):
+        pts, _ = voxel_downsample(cloud, size)
+        self.probes.append((size, pts.shape[0]))
+        return pts
+
+    def compass_step(self, delta, cloud, current):
+        new = current + delta
+        if new <= self._min_voxel_size:
+            new = self._min_voxel_size
+        ds = self._ds(cloud, new)
+        return ds, new, np.abs(self._target_points - ds.shape[0])
+
+    def process(self, cloud):
+        cur = self._base_voxel_size
+        best = self._ds(cloud, cur)
+        metric = np.abs(self._target_points - best.shape[0])
+        while self._delta >= self._eps:
+            ds, new, m = self.compass_step(self._delta, cloud, cur)
+            if m < metric:
+                cur, metric, best = new, m, ds
+                continue
+            ds, new, m = self.compass_step(-self._delta, cloud, cur)
+            if m < metric:
+                cur, metric, best = new, m, ds
+                continue
+            self._delta = self._delta / 2
+        self.voxel_size = cur
+        return best
 
 
 class FastGlobalOptimizer:

@@ -480,6 +480,7 @@ static inline double dot3(const double a[3], const double b[3])
 {
     return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
 }
+static inline double norm3(const double *a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
 
 /* eigenvector of the symmetric A (row-major 3x3) for eigenvalue ev: the
  * largest of the three row cross products of A - ev*I, normalised.         */
@@ -955,6 +956,143 @@ ORACLE_API int oracle_gicp(const double *source, int ns, const double *target, i
 }
 
 /* ------------------------------------------------------------------------ */
+/* K6: registration_icp, point-to-point / point-to-plane                     */
+/*     (Registration.cpp RegistrationICP, TransformationEstimation.cpp;      */
+/*      Aligner/Aligner.py:319-364)                                          */
+/* ------------------------------------------------------------------------ */
+
+/* Eigen::umeyama(src, dst, with_scaling = false) over the correspondences, restated: means,
+ * demeaned cross-covariance sigma = 1/n sum (t - mt)(s - ms)^T, optimal proper rotation from the
+ * two leading singular pairs, R = [u1 u2 u1xu2] [v1 v2 v1xv2]^T (equals U diag(1,1,det(U)det(V)) V^T
+ * of the full SVD), translation mt - R ms.                                            */
+static void umeyama_step(const double *src, const double *tgt, const int *corr, int ns, double U[16])
+{
+    double ms[3] = {0, 0, 0}, mt[3] = {0, 0, 0};
+    int n = 0;
+    for (int i = 0; i < ns; ++i) {
+        const int j = corr[i];
+        if (j < 0) continue;
+        for (int k = 0; k < 3; ++k) { ms[k] += src[(size_t)i * 3 + k]; mt[k] += tgt[(size_t)j * 3 + k]; }
+        ++n;
+    }
+    for (int k = 0; k < 16; ++k) U[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    if (n == 0) return;
+    for (int k = 0; k < 3; ++k) { ms[k] /= n; mt[k] /= n; }
+    double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < ns; ++i) {
+        const int j = corr[i];
+        if (j < 0) continue;
+        double a[3], b[3];
+        for (int k = 0; k < 3; ++k) { a[k] = tgt[(size_t)j * 3 + k] - mt[k]; b[k] = src[(size_t)i * 3 + k] - ms[k]; }
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) S[r * 3 + c] += a[r] * b[c];
+    }
+    for (int k = 0; k < 9; ++k) S[k] /= n;
+    /* eigen-decomposition of S^T S: right singular vectors */
+    double B[9], w[3], V[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) B[r * 3 + c] = S[0 * 3 + r] * S[0 * 3 + c] + S[1 * 3 + r] * S[1 * 3 + c] + S[2 * 3 + r] * S[2 * 3 + c];
+    jacobi3(B, w, V);
+    int o[3] = {0, 1, 2};   /* order by decreasing eigenvalue */
+    for (int a = 0; a < 2; ++a)
+        for (int b = a + 1; b < 3; ++b)
+            if (w[o[b]] > w[o[a]]) { int t = o[a]; o[a] = o[b]; o[b] = t; }
+    double v1[3] = {V[0 * 3 + o[0]], V[1 * 3 + o[0]], V[2 * 3 + o[0]]};
+    double v2[3] = {V[0 * 3 + o[1]], V[1 * 3 + o[1]], V[2 * 3 + o[1]]};
+    double v3[3]; cross3(v1, v2, v3);
+    double u1[3], u2[3], u3[3];
+    for (int r = 0; r < 3; ++r) { u1[r] = S[r * 3] * v1[0] + S[r * 3 + 1] * v1[1] + S[r * 3 + 2] * v1[2];
+                                  u2[r] = S[r * 3] * v2[0] + S[r * 3 + 1] * v2[1] + S[r * 3 + 2] * v2[2]; }
+    double n1 = norm3(u1);
+    if (!(n1 > 0)) return;                 /* sigma = 0: no information, identity */
+    for (int r = 0; r < 3; ++r) u1[r] /= n1;
+    double d12 = dot3(u1, u2);
+    for (int r = 0; r < 3; ++r) u2[r] -= d12 * u1[r];
+    double n2 = norm3(u2);
+    if (!(n2 > 1e-300)) {                  /* rank 1: any unit vector orthogonal to u1 */
+        double e[3] = {0, 0, 0};
+        e[fabs(u1[0]) <= fabs(u1[1]) ? (fabs(u1[0]) <= fabs(u1[2]) ? 0 : 2) : (fabs(u1[1]) <= fabs(u1[2]) ? 1 : 2)] = 1.0;
+        cross3(u1, e, u2); n2 = norm3(u2);
+    }
+    for (int r = 0; r < 3; ++r) u2[r] /= n2;
+    cross3(u1, u2, u3);
+    double R[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) R[r * 3 + c] = u1[r] * v1[c] + u2[r] * v2[c] + u3[r] * v3[c];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) U[r * 4 + c] = R[r * 3 + c];
+        U[r * 4 + 3] = mt[r] - (R[r * 3] * ms[0] + R[r * 3 + 1] * ms[1] + R[r * 3 + 2] * ms[2]);
+    }
+}
+
+/* TransformationEstimationPointToPlane::ComputeTransformation: r = (vs - vt).nt, J = [vs x nt, nt]. */
+static void point_to_plane_step(const double *src, const double *tgt, const double *tn, const int *corr, int ns, double U[16])
+{
+    double JTJ[36], JTr[6];
+    for (int k = 0; k < 36; ++k) JTJ[k] = 0;
+    for (int k = 0; k < 6; ++k) JTr[k] = 0;
+    int n = 0;
+    for (int i = 0; i < ns; ++i) {
+        const int j = corr[i];
+        if (j < 0) continue;
+        const double *vs = src + (size_t)i * 3, *vt = tgt + (size_t)j * 3, *nt = tn + (size_t)j * 3;
+        const double d[3] = {vs[0] - vt[0], vs[1] - vt[1], vs[2] - vt[2]};
+        const double r = dot3(d, nt);
+        double J[6];
+        cross3(vs, nt, J);
+        J[3] = nt[0]; J[4] = nt[1]; J[5] = nt[2];
+        for (int a = 0; a < 6; ++a) {
+            for (int b = 0; b < 6; ++b) JTJ[a * 6 + b] += J[a] * J[b];
+            JTr[a] += J[a] * r;
+        }
+        ++n;
+    }
+    for (int k = 0; k < 16; ++k) U[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    if (n == 0) return;
+    double nb[6], x[6];
+    for (int a = 0; a < 6; ++a) nb[a] = -JTr[a];
+    ldlt_solve6(JTJ, nb, x);
+    vec6_to_mat4(x, U);
+}
+
+/* registration_icp(source, target, max_dist, init, estimation, ICPConvergenceCriteria(max_iteration)).
+ * mode 0 = TransformationEstimationPointToPoint, 1 = PointToPlane (tgt_normals required).
+ * init_T: row-major 4x4 in Open3D's column convention, or NULL for identity.            */
+ORACLE_API int oracle_icp(const double *source, int ns, const double *target, int nt, double max_dist,
+                          int max_iter, const double *init_T, int mode, const double *tgt_normals,
+                          double *T_out, double *fitness_out, double *rmse_out, int *iters_out, int *n_corr_out)
+{
+    if (mode == 1 && !tgt_normals) return -1;
+    double *src = (double *)malloc((size_t)ns * 3 * sizeof(double));
+    memcpy(src, source, (size_t)ns * 3 * sizeof(double));
+    double T[16];
+    for (int k = 0; k < 16; ++k) T[k] = init_T ? init_T[k] : ((k % 5 == 0) ? 1.0 : 0.0);
+    if (init_T) transform_cloud(src, NULL, ns, T);
+    KDTree *tt = kd_build(target, nt, 3);
+    int *corr = (int *)malloc(ns * sizeof(int));
+    double *cd = (double *)malloc(ns * sizeof(double));
+    double fit, rmse; int nc;
+    evaluate_corr(src, ns, tt, max_dist, corr, cd, &fit, &rmse, &nc);
+    int it = 0;
+    for (int i = 0; i < max_iter; ++i) {
+        double U[16];
+        if (mode == 0) umeyama_step(src, target, corr, ns, U);
+        else point_to_plane_step(src, target, tgt_normals, corr, ns, U);
+        mat4_mul(U, T, T);
+        transform_cloud(src, NULL, ns, U);
+        const double ofit = fit, ormse = rmse;
+        evaluate_corr(src, ns, tt, max_dist, corr, cd, &fit, &rmse, &nc);
+        it = i + 1;
+        if (fabs(ofit - fit) < 1e-6 && fabs(ormse - rmse) < 1e-6) break;
+    }
+    memcpy(T_out, T, sizeof(T));
+    *fitness_out = fit; *rmse_out = rmse; *iters_out = it;
+    if (n_corr_out) *n_corr_out = nc;
+    free(src); free(corr); free(cd); kd_free(tt);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
 /* K4: ComputeFPFHFeature (Feature.cpp;                       */
 /*     fastGlobalOptimizer.py:130-143)                                       */
 /* ------------------------------------------------------------------------ */
@@ -1091,7 +1229,6 @@ ORACLE_API void oracle_philox(uint64_t counter, uint64_t key, uint32_t *out4)
     memcpy(out4, c, sizeof(c));
 }
 
-static inline double norm3(const double *a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
 static inline double dist3(const double *a, const double *b)
 {
     const double d[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
@@ -1247,6 +1384,81 @@ ORACLE_API int oracle_fgr(const double *source, int ns, const double *target, in
     if (corres_out) memcpy(corres_out, corres, (size_t)ncorr * sizeof(int[2]));
     free(corres); free(ji); free(ij); free(dtmp); free(pc[0]); free(pc[1]);
     return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Down-samplers                                   */
+/* ------------------------------------------------------------------------ */
+
+/* Preprocessor/Downsamplers/farthestDownsampler.py:33-54: distances start at 1e6; per step
+ * dist = min(dist, cdist(point, cloud)) (scipy euclidean: sqrt of the coordinate-order sum of
+ * squares), next = np.argmax(dist) (first maximum).  out_idx[0] = first.                    */
+ORACLE_API int oracle_fps(const double *pts, int n, int first, int k, int *out_idx)
+{
+    if (n <= 0 || k <= 0 || first < 0 || first >= n) return -1;
+    double *dist = (double *)malloc((size_t)n * sizeof(double));
+    for (int i = 0; i < n; ++i) dist[i] = 1e6;
+    int cur = first;
+    out_idx[0] = cur;
+    for (int s = 0; s + 1 < k; ++s) {
+        const double *p = pts + (size_t)cur * 3;
+        int best = 0;
+        double bv = -1.0;
+        for (int i = 0; i < n; ++i) {
+            const double d = sqrt(sqdist(pts + (size_t)i * 3, p, 3));
+            if (d < dist[i]) dist[i] = d;
+            if (dist[i] > bv) { bv = dist[i]; best = i; }
+        }
+        cur = best;
+        out_idx[s + 1] = cur;
+    }
+    free(dist);
+    return 0;
+}
+
+typedef struct { long long c[3]; int idx; } VoxelRec;
+static int voxel_cmp(const void *a, const void *b)
+{
+    const VoxelRec *x = (const VoxelRec *)a, *y = (const VoxelRec *)b;
+    for (int k = 0; k < 3; ++k) if (x->c[k] != y->c[k]) return x->c[k] < y->c[k] ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+/* PointCloud::VoxelDownSample(voxel_size) (voxelDownsampler.py:83,95): voxel index
+ * floor((p - (min_bound - voxel_size/2)) / voxel_size), per-voxel average with the points added in
+ * index order.  Output in lexicographic voxel-index order (Open3D: unordered_map order).
+ * Returns the number of voxels; out (n x 3) holds that many points.                         */
+ORACLE_API int oracle_voxel_downsample(const double *pts, int n, double voxel_size, double *out, int *first_idx)
+{
+    if (n <= 0 || !(voxel_size > 0)) return -1;
+    double mn[3] = {INFINITY, INFINITY, INFINITY};
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) if (pts[(size_t)i * 3 + k] < mn[k]) mn[k] = pts[(size_t)i * 3 + k];
+    double vmin[3];
+    for (int k = 0; k < 3; ++k) vmin[k] = mn[k] - voxel_size * 0.5;
+    VoxelRec *rec = (VoxelRec *)malloc((size_t)n * sizeof(VoxelRec));
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) rec[i].c[k] = (long long)floor((pts[(size_t)i * 3 + k] - vmin[k]) / voxel_size);
+        rec[i].idx = i;
+    }
+    qsort(rec, n, sizeof(VoxelRec), voxel_cmp);
+    int m = 0;
+    for (int i = 0; i < n;) {
+        int j = i;
+        double s[3] = {0, 0, 0};
+        while (j < n && rec[j].c[0] == rec[i].c[0] && rec[j].c[1] == rec[i].c[1] && rec[j].c[2] == rec[i].c[2]) {
+            const double *p = pts + (size_t)rec[j].idx * 3;
+            s[0] += p[0]; s[1] += p[1]; s[2] += p[2];
+            ++j;
+        }
+        const double cnt = (double)(j - i);
+        out[(size_t)m * 3] = s[0] / cnt; out[(size_t)m * 3 + 1] = s[1] / cnt; out[(size_t)m * 3 + 2] = s[2] / cnt;
+        if (first_idx) first_idx[m] = rec[i].idx;
+        ++m;
+        i = j;
+    }
+    free(rec);
+    return m;
 }
 
 ORACLE_API int oracle_num_threads(void)

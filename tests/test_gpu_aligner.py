@@ -136,3 +136,36 @@ def test_fgr_single_calls_match_golden(golden, armadillo_pair):
     fs, _ = FastGlobalOptimizer().get_fpfh_features(s, t)
     assert np.allclose(fs[:64], golden["back_src_fpfh_head"], rtol=0, atol=1e-9)
     assert np.allclose(fs.sum(0), golden["back_src_fpfh_colsum"], rtol=1e-12)
+
+
+def test_refine_registration_icp(oracle, armadillo_pair):
+    """Aligner.refine_registration: point-to-point and point-to-plane ICP against
+    the oracle's restatement of Open3D registration_icp, literal conventions of the reference."""
+    from or_pcd_b200.Aligner.Aligner import Aligner
+    from or_pcd_b200.Optimizer import GeneralizedICP
+    from or_pcd_b200.Preprocessor import Preprocessor, RadiusScaler
+
+    s, t, _ = armadillo_pair
+    al = Aligner(Preprocessor([RadiusScaler()]), Preprocessor([RadiusScaler()]), GeneralizedICP())
+    a = 0.3
+    init = np.eye(4)
+    init[:3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    init[:3, 3] = [0.02, -0.01, 0.03]
+    diag = np.linalg.norm(t.max(0) - t.min(0))
+    for init_T in (np.eye(4), init):
+        T, rmse = al.refine_registration(s, t, init_T, icp_type="PointToPoint")
+        ref = oracle.icp(s, t, 0.5, 200, init_T, "PointToPoint")
+        assert abs(rmse - ref["rmse"]) <= 1e-5 * ref["rmse"]                       # north_star tolerances
+        assert _rot_angle(T[:3, :3], ref["T"][:3, :3]) < 1e-4
+        assert np.linalg.norm(T[:3, 3] - ref["T"][:3, 3]) < 1e-5 * diag
+        tn = oracle.normals(t, 20, 0.0)["normal"]
+        T, rmse = al.refine_registration(s, t, init_T, icp_type="PointToPlane", target_normals=tn)
+        ref = oracle.icp(s, t, 0.5, 200, init_T, "PointToPlane", tn)
+        assert abs(rmse - ref["rmse"]) <= 1e-5 * ref["rmse"]
+        assert _rot_angle(T[:3, :3], ref["T"][:3, :3]) < 1e-4
+        assert np.linalg.norm(T[:3, 3] - ref["T"][:3, 3]) < 1e-5 * diag
+    # the reference's default call (PointToPlane, no target normals) raises inside Open3D
+    with pytest.raises(RuntimeError):
+        al.refine_registration(s, t, np.eye(4), icp_type="PointToPlane")
+    with pytest.raises(RuntimeError):
+        oracle.icp(s, t, mode="PointToPlane")

@@ -152,5 +152,6 @@ def test_aligner_argument_defaults():
                  deg=-1, std=0, delta=0, max_iter=0, eps=-2)
     assert (al._attempts, al._delta, al._eps, al._max_iter, al._std) == (30, 0.2, 0.05, 100, 0.1)   # constants.py:71-77
     assert "attempts=30" in repr(al)
-    with pytest.raises(NotImplementedError):
-        al.refine_registration(None, None, None)
+    # the reference's default refinement (PointToPlane without target normals) raises inside Open3D
+    with pytest.raises(RuntimeError):
+        al.refine_registration(np.zeros((4, 3)), np.zeros((4, 3)), np.eye(4), icp_type="PointToPlane")

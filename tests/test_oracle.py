@@ -254,3 +254,54 @@ def test_fgr_frozen_results(oracle, golden):
         assert np.array_equal(T, golden[f"back_fgr_{mode}_T"])
         assert np.array_equal([fo.last["fitness"], rm, fo.last["n_corr"], fo.last["n_initial"], fo.last["n_pairs"],
                                fo.last["trials"]], golden[f"back_fgr_{mode}_stats"])
+
+
+def test_icp_against_numpy_kabsch_and_known_motion(oracle):
+    """registration_icp restatement: one point-to-point step equals numpy's SVD Kabsch solution on the
+    same correspondences; both estimators recover a known rigid motion."""
+    rng = np.random.default_rng(0)
+    src = oracle.RadiusScaler().process(oracle.synthetic_cloud(2000, rng))
+    a = 0.2
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    t = np.array([0.03, -0.02, 0.01])
+    tgt = src @ R.T + t
+    _, j = cKDTree(tgt).query(src)
+    ms, mt = src.mean(0), tgt[j].mean(0)
+    U, _, Vt = np.linalg.svd((tgt[j] - mt).T @ (src - ms) / len(src))
+    Rk = U @ np.diag([1, 1, np.sign(np.linalg.det(U) * np.linalg.det(Vt))]) @ Vt
+    one = oracle.icp(src, tgt, 0.5, 1)
+    assert np.allclose(one["T"][:3, :3], Rk, atol=1e-13) and np.allclose(one["T"][:3, 3], mt - Rk @ ms, atol=1e-13)
+    r = oracle.icp(src, tgt, 0.5, 200)
+    assert np.allclose(r["T"][:3, :3], R, atol=1e-10) and np.allclose(r["T"][:3, 3], t, atol=1e-10) and r["iters"] < 200
+    tn = oracle.normals(tgt, 20, 0.0)["normal"]
+    r = oracle.icp(src, tgt, 0.5, 200, mode="PointToPlane", target_normals=tn)
+    assert np.allclose(r["T"][:3, :3], R, atol=1e-10) and np.allclose(r["T"][:3, 3], t, atol=1e-10)
+    # initial transform: starting at the answer converges immediately
+    T0 = np.eye(4); T0[:3, :3] = R; T0[:3, 3] = t
+    r = oracle.icp(src, tgt, 0.5, 200, init_T=T0)
+    assert r["iters"] <= 2 and r["rmse"] < 1e-12
+    with pytest.raises(RuntimeError):
+        oracle.icp(src, tgt, mode="PointToPlane")
+
+
+def test_downsampler_fixtures(oracle):
+    """FPS indices in the fixture come from the reference's own FarthestDownsampler class
+    (tests/golden/make_golden_downsamplers.py); the oracle must reproduce them, and its voxel grid must
+    agree with a numpy restatement."""
+    with np.load(os.path.join(os.path.dirname(GOLDEN), "golden_downsamplers.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    cloud = oracle.RadiusScaler().process(oracle.load_scan("ArmadilloBack_30"))
+    np.random.seed(4)
+    blk = oracle.FarthestDownsampler(700)
+    blk.process(cloud)
+    assert np.array_equal(blk.last_indices, g["fps_ArmadilloBack_30_indices"])
+    pts, first = oracle.voxel_downsample(cloud, 0.05)
+    vmin = cloud.min(0) - 0.025
+    u, inv = np.unique(np.floor((cloud - vmin) / 0.05).astype(np.int64), axis=0, return_inverse=True)
+    inv = inv.ravel()
+    avg = np.stack([np.bincount(inv, cloud[:, k]) / np.bincount(inv) for k in range(3)], 1)
+    assert len(pts) == len(u) and np.allclose(pts, avg, rtol=0, atol=1e-15)
+    assert np.array_equal(first, [np.flatnonzero(inv == v)[0] for v in range(len(u))])
+    v = oracle.VoxelDownsampler(2000)
+    out = v.process(cloud)
+    assert np.array_equal(np.array(v.probes), g["voxel_ArmadilloBack_30_probes"]) and out.shape[0] == int(g["voxel_ArmadilloBack_30_count"])
