@@ -30,6 +30,16 @@ def load_sample_cloud(cloud_name: str) -> np.ndarray:
         return z[cloud_name].astype(np.float64)
 
 
+def load_cloud(path: str) -> np.ndarray:
+    """(N,3) float64 cloud from a file, the two on-disk formats of the reference's driver
+    (main.py:55-71): ``.npz`` archives with a ``points`` array (first three columns), anything else
+    is read as PLY (``o3d.io.read_point_cloud`` in the reference)."""
+    if path.lower().endswith(".npz"):
+        with np.load(path, allow_pickle=True) as z:
+            return np.ascontiguousarray(np.array(z["points"])[:, :3], dtype=np.float64)
+    return read_ply_vertices(path)
+
+
 def read_ply_vertices(path: str) -> np.ndarray:
     """x,y,z of the ``vertex`` element of an ascii / binary_little_endian / binary_big_endian
     PLY file as (N,3) float64.  Elements before ``vertex`` must be fixed-size."""

@@ -2,6 +2,8 @@
 in numpy, and the Aligner's speculative batch + replay of the reference's sequential
 poll order, accept decisions, RNG consumption and exception behaviour
 (reference: Aligner/Aligner.py:164-317)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -155,3 +157,31 @@ def test_aligner_argument_defaults():
     # the reference's default refinement (PointToPlane without target normals) raises inside Open3D
     with pytest.raises(RuntimeError):
         al.refine_registration(np.zeros((4, 3)), np.zeros((4, 3)), np.eye(4), icp_type="PointToPlane")
+
+
+def test_cloud_io_ply_and_npz(tmp_path):
+    """On-disk formats either side of the path: big/little-endian binary and ascii
+    PLY vertices (float32 widened to float64 like Open3D's reader) and the driver's .npz layout."""
+    from or_pcd_b200.data import load_cloud, load_sample_cloud, read_ply_vertices, sample_cloud_names
+
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal((57, 3)).astype(np.float32)
+    for fmt, order in (("binary_big_endian", ">"), ("binary_little_endian", "<")):
+        hdr = (f"ply\nformat {fmt} 1.0\nobj_info test\nelement vertex 57\nproperty float x\nproperty float y\n"
+               "property float z\nelement range_grid 2\nproperty list uchar int vertex_indices\nend_header\n")
+        path = tmp_path / f"{fmt}.ply"
+        path.write_bytes(hdr.encode() + v.astype(order + "f4").tobytes() + b"\x01\x00\x00\x00\x05\x00")
+        out = read_ply_vertices(str(path))
+        assert out.dtype == np.float64 and np.array_equal(out, v.astype(np.float64))
+    path = tmp_path / "ascii.ply"
+    path.write_text("ply\nformat ascii 1.0\nelement vertex 3\nproperty float z\nproperty float x\nproperty float y\n"
+                    "end_header\n3 1 2\n6 4 5\n9 7 8\n")
+    assert np.array_equal(load_cloud(str(path)), [[1, 2, 3], [4, 5, 6], [7, 8, 9]])
+    np.savez(tmp_path / "c.npz", points=np.hstack([v, np.ones((57, 2), np.float32)]))
+    assert np.array_equal(load_cloud(str(tmp_path / "c.npz")), v.astype(np.float64))
+    assert "ArmadilloBack_330" in sample_cloud_names() and load_sample_cloud("ArmadilloBack_330").shape == (29116, 3)
+    ref = "/root/reference/data/ArmadilloBack_330.ply"
+    if os.path.exists(ref):      # authoring container only: the bundled scans equal the reference's PLY files
+        assert np.array_equal(read_ply_vertices(ref), load_sample_cloud("ArmadilloBack_330"))
+    with pytest.raises(FileNotFoundError):
+        load_sample_cloud("nope")
