@@ -254,21 +254,28 @@ int orpcd_fpfh(const double *d_points, const double *d_normals, int n, long long
  * the tcgen05 tensor-core filter; orpcd_feature_match then returns, for pair p and
  * every row of query set d_pair_q[p], the exact float64 nearest row of database set
  * d_pair_db[p] (nanoflann summation order, ties -> lowest index).
- * mode 0: tensor-core filter + certified float64 re-score; mode 1: float64 scan only.
+ * mode 0: tensor-core filter (the three smallest 32-row chunk minima + the fourth as a bound)
+ * + certified float64 re-score; mode 1: float64 scan only.
+ * Distances are translation invariant, so the filter runs on features centred on
+ * d_center[33] (NULL = no centring; e.g. the mean feature of one set from
+ * orpcd_feature_center): smaller norms give a tighter certificate.  The same vector
+ * must be given to the pack of both sides and to the match.  Exact distances are
+ * always taken on the original values.
  * d_packed_* : orpcd_feature_pack_bytes(n) bytes per set, 128-byte aligned
  * d_set_maxnorm: [n_sets] float, max |f|^2 of each set (written by the pack)
  * d_nn [n_pairs][n_query] int32; d_nn_d2 (may be NULL) float64;
- * d_stats (may be NULL) int[1]: rows that needed the exact scan;
+ * d_stats (may be NULL) int[2]: rows that needed the exact scan, chunks re-scored;
  * d_debug_v (may be NULL) [n_pairs][n_query][ceil(n_db/128)*128] filter values.
  * ---------------------------------------------------------------------- */
 size_t orpcd_feature_pack_bytes(int n);
-int orpcd_feature_pack(const double *d_features, int n, int n_sets, void *d_packed,
-                       float *d_set_maxnorm, orpcd_stream_t stream);
+int orpcd_feature_center(const double *d_features, int n, double *d_center, orpcd_stream_t stream);
+int orpcd_feature_pack(const double *d_features, int n, int n_sets, const double *d_center,
+                       void *d_packed, float *d_set_maxnorm, orpcd_stream_t stream);
 size_t orpcd_feature_match_workspace_bytes(int n_query, int n_pairs);
 int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q, int n_query,
                         const double *d_feat_db, const void *d_packed_db,
-                        const float *d_db_maxnorm, int n_db, const int *d_pair_q,
-                        const int *d_pair_db, int n_pairs, int mode, void *d_workspace,
+                        const float *d_db_maxnorm, int n_db, const double *d_center,
+                        const int *d_pair_q, const int *d_pair_db, int n_pairs, int mode, void *d_workspace,
                         size_t workspace_bytes, int *d_nn, double *d_nn_d2, int *d_stats,
                         float *d_debug_v, orpcd_stream_t stream);
 

@@ -40,6 +40,11 @@ constexpr int FM_PLANE_BYTES = FM_ROWS * FM_K * 4;     // 20480
 constexpr int FM_NORM_OFF = 2 * FM_PLANE_BYTES;        // hi plane, lo plane, then 128 norms
 constexpr int FM_TILE_BYTES = FM_NORM_OFF + FM_ROWS * 4;   // 41472
 constexpr int FM_STAGES = 3;
+// After the operand tiles of a set comes a feature-major float64 copy for the exact re-score, one block of
+// [33][32] doubles per 32-row chunk, so that 32 lanes scoring the 32 rows of a chunk read 256 contiguous bytes
+// per feature.
+constexpr int FM_CHUNK_F64_BYTES = 33 * 32 * 8;         // 8448
+constexpr int FM_SET_BYTES_PER_TILE = FM_TILE_BYTES + 4 * FM_CHUNK_F64_BYTES;   // 75264
 constexpr int FM_SMEM_BYTES = (1 + FM_STAGES) * FM_TILE_BYTES + 128 /*barriers*/ + 128 /*alignment*/;
 constexpr float FM_PAD_NORM = 3.0e38f;
 
@@ -57,24 +62,30 @@ __device__ __forceinline__ float tf32_rna(float x)
 
 // grid (tiles, sets), 128 threads: thread r packs row r of the tile.
 __global__ void __launch_bounds__(FM_ROWS)
-feat_pack_kernel(const double *__restrict__ feat, int n, int tiles, unsigned char *__restrict__ packed,
-                 float *__restrict__ set_maxnorm)
+feat_pack_kernel(const double *__restrict__ feat, int n, int tiles, const double *__restrict__ center,
+                 unsigned char *__restrict__ packed, float *__restrict__ set_maxnorm)
 {
     const int set = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
     const int row = tile * FM_ROWS + r;
-    unsigned char *img = packed + ((size_t)set * tiles + tile) * FM_TILE_BYTES;
+    unsigned char *set_base = packed + (size_t)set * tiles * FM_SET_BYTES_PER_TILE;
+    unsigned char *img = set_base + (size_t)tile * FM_TILE_BYTES;
+    double *tr = reinterpret_cast<double *>(set_base + (size_t)tiles * FM_TILE_BYTES +
+                                            (size_t)(tile * 4 + (r >> 5)) * FM_CHUNK_F64_BYTES) + (r & 31);
     float norm = FM_PAD_NORM;
     double nd = 0.0;
     const double *f = feat + ((size_t)set * n + (row < n ? row : 0)) * FM_DIM;
     for (int c = 0; c < FM_K; ++c) {
         float hi = 0.f, lo = 0.f;
         if (row < n && c < FM_DIM) {
-            const double v = f[c];
+            // distances are translation invariant: the filter works on features centred on `center`
+            // (smaller norms -> a tighter error bound); the exact re-score uses the original values
+            const double v = center ? f[c] - center[c] : f[c];
             nd += v * v;
             const float x = (float)v;
             hi = tf32_rna(x);
             lo = tf32_rna(x - hi);
         }
+        if (c < FM_DIM) tr[c * 32] = row < n ? f[c] : 0.0;
         const int o = fm_image_offset(r, c);
         *reinterpret_cast<float *>(img + o) = hi;
         *reinterpret_cast<float *>(img + FM_PLANE_BYTES + o) = lo;
@@ -84,6 +95,22 @@ feat_pack_kernel(const double *__restrict__ feat, int n, int tiles, unsigned cha
         atomicMax(reinterpret_cast<int *>(set_maxnorm + set), __float_as_int(norm));   // norms are >= 0
     }
     *reinterpret_cast<float *>(img + FM_NORM_OFF + r * 4) = norm;
+}
+
+// mean feature of one set (fixed summation order): 33 x 31 threads, thread (k, part) sums rows part, part+31, ...
+__global__ void __launch_bounds__(1023) feat_center_kernel(const double *__restrict__ feat, int n, double *__restrict__ center)
+{
+    __shared__ double part[31][FM_DIM];
+    const int k = threadIdx.x % FM_DIM, p = threadIdx.x / FM_DIM;
+    double s = 0.0;
+    for (int r = p; r < n; r += 31) s += feat[(size_t)r * FM_DIM + k];
+    part[p][k] = s;
+    __syncthreads();
+    if (p == 0) {
+        double t = 0.0;
+        for (int q = 0; q < 31; ++q) t += part[q][k];
+        center[k] = t / (double)n;
+    }
 }
 
 // ----------------------------------------------------------------------------
@@ -173,8 +200,7 @@ template <bool DEBUG>
 __global__ void __launch_bounds__(FM_ROWS, 1)
 feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const unsigned char *__restrict__ packed_db,
                   int db_tiles, const int *__restrict__ pair_q, const int *__restrict__ pair_db, int nq,
-                  float *__restrict__ out_m1, int *__restrict__ out_c1, float *__restrict__ out_m2,
-                  float *__restrict__ dbg_v)
+                  float *__restrict__ out_m, int *__restrict__ out_c, size_t out_stride, float *__restrict__ dbg_v)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -185,8 +211,8 @@ feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int pair = blockIdx.y, qt = blockIdx.x;
-    const unsigned char *gA = packed_q + ((size_t)pair_q[pair] * q_tiles + qt) * FM_TILE_BYTES;
-    const unsigned char *gB = packed_db + (size_t)pair_db[pair] * db_tiles * FM_TILE_BYTES;
+    const unsigned char *gA = packed_q + (size_t)pair_q[pair] * q_tiles * FM_SET_BYTES_PER_TILE + (size_t)qt * FM_TILE_BYTES;
+    const unsigned char *gB = packed_db + (size_t)pair_db[pair] * db_tiles * FM_SET_BYTES_PER_TILE;
     const uint32_t bar_a = smem_u32(bars), bar_full0 = smem_u32(bars + 1), bar_mma0 = smem_u32(bars + 4);
 
     if (tid == 0) {
@@ -215,8 +241,9 @@ feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const
         }
     }
 
-    float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
-    int c1 = 0;
+    // the FM_TOP smallest chunk minima (ascending, with chunk ids) and the next one as the bound for the rest
+    float m1 = CUDART_INF_F, m2 = CUDART_INF_F, m3 = CUDART_INF_F, m4 = CUDART_INF_F;
+    int c1 = 0, c2 = 0, c3 = 0;
     const int row = qt * FM_ROWS + tid;
 
     // iteration t: thread 0 issues the MMAs of tile t, then everyone runs the epilogue of tile t-1
@@ -268,11 +295,14 @@ feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const
                         o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3;
                     }
                 }
-                const float mc = fminf(ma, mb);
-                const int chunk = e * 4 + ch;
-                m2 = fminf(m2, fmaxf(m1, mc));
-                c1 = mc < m1 ? chunk : c1;
-                m1 = fminf(m1, mc);
+                float x = fminf(ma, mb);
+                int cx = e * 4 + ch;
+                if (x < m3) {   // sorted insertion; strict compares keep the lowest chunk id first among equals
+                    if (x < m1) { const float t = m1; m1 = x; x = t; const int tc = c1; c1 = cx; cx = tc; }
+                    if (x < m2) { const float t = m2; m2 = x; x = t; const int tc = c2; c2 = cx; cx = tc; }
+                    if (x < m3) { const float t = m3; m3 = x; x = t; c3 = cx; }
+                }
+                m4 = fminf(m4, x);
             }
             tc_fence_before();
             __syncthreads();   // accumulator e&1 and stage s are free again
@@ -286,9 +316,8 @@ feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const
     }
     if (row < nq) {
         const size_t o = (size_t)pair * nq + row;
-        out_m1[o] = m1;
-        out_c1[o] = c1;
-        out_m2[o] = m2;
+        out_m[o] = m1; out_m[o + out_stride] = m2; out_m[o + 2 * out_stride] = m3; out_m[o + 3 * out_stride] = m4;
+        out_c[o] = c1; out_c[o + out_stride] = c2; out_c[o + 2 * out_stride] = c3;
     }
     tc_fence_before();
     __syncthreads();
@@ -296,53 +325,90 @@ feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
 }
 
-// nanoflann L2_Adaptor::evalMetric for dim 33: groups of four summed left to right, then the tail.
-__device__ __forceinline__ double sqdist33(const double *__restrict__ a, const double *__restrict__ b)
+// nanoflann L2_Adaptor::evalMetric for dim 33: groups of four summed left to right, then the tail;
+// b is row (lane) of a feature-major chunk block: feature k at b[k * 32].
+__device__ __forceinline__ double sqdist33_fm(const double *__restrict__ a, const double *__restrict__ b)
 {
     double result = 0.0;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-        const double d0 = a[i] - b[i], d1 = a[i + 1] - b[i + 1], d2 = a[i + 2] - b[i + 2], d3 = a[i + 3] - b[i + 3];
+        const double d0 = a[i] - b[i * 32], d1 = a[i + 1] - b[(i + 1) * 32], d2 = a[i + 2] - b[(i + 2) * 32],
+                     d3 = a[i + 3] - b[(i + 3) * 32];
         result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
     }
-    const double d0 = a[32] - b[32];
+    const double d0 = a[32] - b[32 * 32];
     result += d0 * d0;
     return result;
 }
 
-// One warp per query row: certify the best chunk, exact float64 re-score (or exact scan).
-// stats[0] += rows that needed the exact scan.
+// One warp per query row.  The chunks with the smallest filter minima are re-scored exactly (float64,
+// nanoflann's summation order) in ascending order of their minima until the next minimum provably lies
+// above the best exact distance found so far; a row that exhausts the FM_TOP recorded chunks without
+// reaching that certificate gets the exact scan of the whole set.  Ties -> lowest index.
+// stats[0] += rows that needed the exact scan, stats[1] += chunks re-scored.
+constexpr int FM_TOP = 3;
+
 __global__ void __launch_bounds__(128)
-feat_resolve_kernel(const double *__restrict__ feat_q, int nq, const double *__restrict__ feat_db, int ndb,
-                    const int *__restrict__ pair_q, const int *__restrict__ pair_db,
-                    const float *__restrict__ db_maxnorm, const float *__restrict__ in_m1,
-                    const int *__restrict__ in_c1, const float *__restrict__ in_m2, int force_exact,
+feat_resolve_kernel(const double *__restrict__ feat_q, int nq, const unsigned char *__restrict__ packed_db,
+                    int db_tiles, int ndb, const double *__restrict__ center, const int *__restrict__ pair_q, const int *__restrict__ pair_db,
+                    const float *__restrict__ db_maxnorm, const float *__restrict__ in_m,
+                    const int *__restrict__ in_c, size_t in_stride, int force_exact,
                     int *__restrict__ out_nn, double *__restrict__ out_d2, int *__restrict__ stats)
 {
     const int pair = blockIdx.y, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= nq) return;
     const double *q = feat_q + ((size_t)pair_q[pair] * nq + row) * FM_DIM;
-    const double *db = feat_db + (size_t)pair_db[pair] * ndb * FM_DIM;
+    // feature-major float64 chunk blocks of the database set; lane l scores row (chunk * 32 + l)
+    const double *db = reinterpret_cast<const double *>(packed_db + (size_t)pair_db[pair] * db_tiles * FM_SET_BYTES_PER_TILE +
+                                                        (size_t)db_tiles * FM_TILE_BYTES) + lane;
+    constexpr int CH = FM_CHUNK_F64_BYTES / 8;
     double qv[FM_DIM];
-    double qn = 0.0;
+    double qn = 0.0;   // |q - center|^2: what the filter value is offset by
 #pragma unroll
-    for (int k = 0; k < FM_DIM; ++k) { qv[k] = q[k]; qn += qv[k] * qv[k]; }
+    for (int k = 0; k < FM_DIM; ++k) {
+        qv[k] = q[k];
+        const double qc = center ? qv[k] - center[k] : qv[k];
+        qn += qc * qc;
+    }
     const size_t o = (size_t)pair * nq + row;
-    const float m1 = in_m1[o], m2 = in_m2[o];
-    const int c1 = in_c1[o];
-    // filter error bound (DESIGN.md "feature filter bound"): |v - (d^2 - |q|^2)| <= 2^-15 |q| Dmax + 2^-23 Dmax^2
+    // filter error bound (DESIGN.md "feature filter bound"): |v - (d^2 - |q|^2)| <= E,
+    //   E = 2^-15 |q| Dmax + 2^-23 Dmax^2 on the centred features; float64 rounding of the centring and of
+    //   |q|^2 (2^-52 relative) is folded into the last term
     const double dmax = sqrt((double)db_maxnorm[pair_db[pair]]);
-    const double E = 2.0 * (ldexp(sqrt(qn) * dmax, -15) + ldexp(dmax * dmax, -23));
-    const bool certified = !force_exact && (double)m2 > (double)m1 + E;
+    const double E = (ldexp(sqrt(qn) * dmax, -15) + ldexp(dmax * dmax, -23)) * 1.0001 + ldexp(qn + dmax * dmax, -40);
     double best = CUDART_INF;
     int bj = 0x7fffffff;
-    if (certified) {
-        const int j = c1 * 32 + lane;
-        if (j < ndb) { best = sqdist33(qv, db + (size_t)j * FM_DIM); bj = j; }
-    } else {
+    bool certified = false;
+    int scored = 0;
+    if (!force_exact) {
+#pragma unroll 1
+        for (int k = 0; k < FM_TOP; ++k) {
+            // chunk k holds nothing better than in_m[k] - E; everything not recorded nothing better than in_m[k..]
+            const double lb = (double)in_m[o + (size_t)k * in_stride] - E + qn;
+            double wb = best;
+            for (int s = 16; s > 0; s >>= 1) wb = fmin(wb, __shfl_xor_sync(0xffffffffu, wb, s));
+            if (lb > wb) { certified = true; break; }
+            const int ck = in_c[o + (size_t)k * in_stride];
+            const int j = ck * 32 + lane;
+            if (j < ndb) {
+                const double d = sqdist33_fm(qv, db + (size_t)ck * CH);
+                if (d < best || (d == best && j < bj)) { best = d; bj = j; }
+            }
+            ++scored;
+        }
+        if (!certified) {
+            const double lb = (double)in_m[o + (size_t)FM_TOP * in_stride] - E + qn;
+            double wb = best;
+            for (int s = 16; s > 0; s >>= 1) wb = fmin(wb, __shfl_xor_sync(0xffffffffu, wb, s));
+            certified = lb > wb;
+        }
+    }
+    if (!certified) {
+        best = CUDART_INF;
+        bj = 0x7fffffff;
         for (int j = lane; j < ndb; j += 32) {
-            const double d = sqdist33(qv, db + (size_t)j * FM_DIM);
+            const double d = sqdist33_fm(qv, db + (size_t)(j >> 5) * CH);
             if (d < best) { best = d; bj = j; }
         }
         if (lane == 0 && stats) atomicAdd(stats, 1);
@@ -355,6 +421,7 @@ feat_resolve_kernel(const double *__restrict__ feat_q, int nq, const double *__r
     if (lane == 0) {
         out_nn[o] = bj == 0x7fffffff ? -1 : bj;
         if (out_d2) out_d2[o] = best;
+        if (stats && scored) atomicAdd(stats + 1, scored);
     }
 }
 
@@ -774,18 +841,27 @@ bool fgr_layout(const orpcd_fgr_params *p, FgrLayout &L)
 ORPCD_API size_t orpcd_feature_pack_bytes(int n)
 {
     if (n <= 0) return 0;
-    return (size_t)((n + FM_ROWS - 1) / FM_ROWS) * FM_TILE_BYTES;
+    return (size_t)((n + FM_ROWS - 1) / FM_ROWS) * FM_SET_BYTES_PER_TILE;
 }
 
-ORPCD_API int orpcd_feature_pack(const double *d_features, int n, int n_sets, void *d_packed, float *d_set_maxnorm,
-                                 orpcd_stream_t stream)
+ORPCD_API int orpcd_feature_center(const double *d_features, int n, double *d_center, orpcd_stream_t stream)
+{
+    if (!d_features || !d_center || n <= 0) return ORPCD_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    feat_center_kernel<<<1, 1023, 0, st>>>(d_features, n, d_center);
+    ORPCD_CHECK_LAUNCH();
+    return ORPCD_OK;
+}
+
+ORPCD_API int orpcd_feature_pack(const double *d_features, int n, int n_sets, const double *d_center, void *d_packed,
+                                 float *d_set_maxnorm, orpcd_stream_t stream)
 {
     if (!d_features || !d_packed || !d_set_maxnorm || n <= 0 || n_sets <= 0) return ORPCD_ERR_INVALID;
     if ((uintptr_t)d_packed & 127) return ORPCD_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(d_set_maxnorm, 0, sizeof(float) * n_sets, st) != cudaSuccess) return ORPCD_ERR_CUDA;
     const int tiles = (n + FM_ROWS - 1) / FM_ROWS;
-    feat_pack_kernel<<<dim3(tiles, n_sets), FM_ROWS, 0, st>>>(d_features, n, tiles, (unsigned char *)d_packed,
+    feat_pack_kernel<<<dim3(tiles, n_sets), FM_ROWS, 0, st>>>(d_features, n, tiles, d_center, (unsigned char *)d_packed,
                                                              d_set_maxnorm);
     ORPCD_CHECK_LAUNCH();
     return ORPCD_OK;
@@ -794,12 +870,13 @@ ORPCD_API int orpcd_feature_pack(const double *d_features, int n, int n_sets, vo
 ORPCD_API size_t orpcd_feature_match_workspace_bytes(int n_query, int n_pairs)
 {
     if (n_query <= 0 || n_pairs <= 0) return 0;
-    return 3 * orpcd_align_up((size_t)n_query * n_pairs * 4, 256);
+    return 7 * orpcd_align_up((size_t)n_query * n_pairs * 4, 256);   // 4 chunk minima + 3 chunk ids per row
 }
 
 ORPCD_API int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q, int n_query,
                                   const double *d_feat_db, const void *d_packed_db, const float *d_db_maxnorm,
-                                  int n_db, const int *d_pair_q, const int *d_pair_db, int n_pairs, int mode,
+                                  int n_db, const double *d_center, const int *d_pair_q, const int *d_pair_db,
+                                  int n_pairs, int mode,
                                   void *d_workspace, size_t workspace_bytes, int *d_nn, double *d_nn_d2,
                                   int *d_stats, float *d_debug_v, orpcd_stream_t stream)
 {
@@ -811,9 +888,9 @@ ORPCD_API int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q
         return ORPCD_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t slice = orpcd_align_up((size_t)n_query * n_pairs * 4, 256);
-    float *m1 = (float *)d_workspace;
-    int *c1 = (int *)((unsigned char *)d_workspace + slice);
-    float *m2 = (float *)((unsigned char *)d_workspace + 2 * slice);
+    float *fm = (float *)d_workspace;                                     // [4][pairs * n_query]
+    int *fc = (int *)((unsigned char *)d_workspace + 4 * slice);          // [3][pairs * n_query]
+    const size_t stride = slice / 4;
     const int q_tiles = (n_query + FM_ROWS - 1) / FM_ROWS, db_tiles = (n_db + FM_ROWS - 1) / FM_ROWS;
     if (mode == 0) {
         auto kern = d_debug_v ? feat_match_kernel<true> : feat_match_kernel<false>;
@@ -821,12 +898,14 @@ ORPCD_API int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q
             return ORPCD_ERR_CUDA;
         kern<<<dim3(q_tiles, n_pairs), FM_ROWS, FM_SMEM_BYTES, st>>>(
             (const unsigned char *)d_packed_q, q_tiles, (const unsigned char *)d_packed_db, db_tiles, d_pair_q,
-            d_pair_db, n_query, m1, c1, m2, d_debug_v);
+            d_pair_db, n_query, fm, fc, stride, d_debug_v);
         ORPCD_CHECK_LAUNCH();
     }
-    if (d_stats && cudaMemsetAsync(d_stats, 0, sizeof(int), st) != cudaSuccess) return ORPCD_ERR_CUDA;
-    feat_resolve_kernel<<<dim3((n_query + 3) / 4, n_pairs), 128, 0, st>>>(d_feat_q, n_query, d_feat_db, n_db, d_pair_q,
-                                                                          d_pair_db, d_db_maxnorm, m1, c1, m2,
+    if (d_stats && cudaMemsetAsync(d_stats, 0, 2 * sizeof(int), st) != cudaSuccess) return ORPCD_ERR_CUDA;
+    feat_resolve_kernel<<<dim3((n_query + 3) / 4, n_pairs), 128, 0, st>>>(d_feat_q, n_query,
+                                                                          (const unsigned char *)d_packed_db, db_tiles,
+                                                                          n_db, d_center, d_pair_q,
+                                                                          d_pair_db, d_db_maxnorm, fm, fc, stride,
                                                                           mode == 1, d_nn, d_nn_d2, d_stats);
     ORPCD_CHECK_LAUNCH();
     return ORPCD_OK;

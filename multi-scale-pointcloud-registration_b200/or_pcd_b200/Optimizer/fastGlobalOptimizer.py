@@ -97,6 +97,7 @@ class FastGlobalOptimizer(IOptimizer):
         self._ws = None
         self.last_info = None          # int array (U,4): cross-checked pairs, tuple pairs, trials, swapped
         self.last_exact_scans = None   # feature rows that needed the exact float64 scan
+        self.last_rescored_chunks = None   # 32-row chunks re-scored in float64 by the certificate
 
     # ------------------------------------------------------------------ features
     def _neighbour_lists(self, d_clouds, k: int, rigid_base: Optional[np.ndarray]):
@@ -174,7 +175,7 @@ class FastGlobalOptimizer(IOptimizer):
             scans = st
         else:
             ft, _ = self._fpfh_sets(d_tgt)
-            pf_t = ops.feature_pack(ft)
+            pf_t = ops.feature_pack(ft, center=pf_s.center)
             ij, _, st1, _ = ops.feature_match(pf_s, pf_t, us, ut, mode=self.match_mode)
             ji, _, st2, _ = ops.feature_match(pf_t, pf_s, ut, us, mode=self.match_mode)
             scans = st1 + st2
@@ -196,7 +197,8 @@ class FastGlobalOptimizer(IOptimizer):
         Th = T.cpu().numpy()
         stats = stats.cpu().numpy()
         self.last_info = info.cpu().numpy()
-        self.last_exact_scans = int(scans.item()) if hasattr(scans, "item") else int(scans)
+        self.last_exact_scans = int(scans[0].item()) if hasattr(scans, "cpu") else int(scans)
+        self.last_rescored_chunks = int(scans[1].item()) if hasattr(scans, "cpu") else 0
         Th[:, :3, :3] = np.transpose(Th[:, :3, :3], (0, 2, 1)).copy()       # fastGlobalOptimizer.py:176-178
         return BatchResult(Th, stats[:, 1].copy(), stats[:, 0].copy(), self.last_info[:, 1].astype(np.int64),
                            status.cpu().numpy(), [])

@@ -127,11 +127,13 @@ def lib():
     L.orpcd_feature_pack_bytes.restype = sz
     L.orpcd_feature_pack_bytes.argtypes = [ip]
     L.orpcd_feature_pack.restype = ip
-    L.orpcd_feature_pack.argtypes = [vp, ip, ip, vp, vp, vp]
+    L.orpcd_feature_pack.argtypes = [vp, ip, ip, vp, vp, vp, vp]
+    L.orpcd_feature_center.restype = ip
+    L.orpcd_feature_center.argtypes = [vp, ip, vp, vp]
     L.orpcd_feature_match_workspace_bytes.restype = sz
     L.orpcd_feature_match_workspace_bytes.argtypes = [ip, ip]
     L.orpcd_feature_match.restype = ip
-    L.orpcd_feature_match.argtypes = [vp, vp, ip, vp, vp, vp, ip, vp, vp, ip, ip, vp, sz, vp, vp, vp, vp, vp]
+    L.orpcd_feature_match.argtypes = [vp, vp, ip, vp, vp, vp, ip, vp, vp, vp, ip, ip, vp, sz, vp, vp, vp, vp, vp]
     L.orpcd_fgr_batch_workspace_bytes.restype = sz
     L.orpcd_fgr_batch_workspace_bytes.argtypes = [C.POINTER(FgrParams)]
     L.orpcd_fgr_batch.restype = ip

@@ -316,10 +316,22 @@ def fpfh(points, normals, nn_idx, nn_d2, knn: int, radius: float, want_spfh=Fals
 
 class PackedFeatures:
     """Feature sets [S,N,33] float64 plus their TF32 hi/lo operand-tile images for the tcgen05 filter."""
-    __slots__ = ("features", "packed", "maxnorm", "n", "n_sets")
+    __slots__ = ("features", "packed", "maxnorm", "n", "n_sets", "center")
 
 
-def feature_pack(features) -> PackedFeatures:
+def feature_center(features):
+    """Mean feature [33] of set 0: the centring vector shared by the two sides of a match."""
+    t = _t()
+    features = _f64(features)
+    c = t.empty(33, dtype=t.float64, device="cuda")
+    check(_lib.lib().orpcd_feature_center(features.data_ptr(), features.shape[1], c.data_ptr(), _lib.stream_ptr()),
+          "orpcd_feature_center")
+    launch_counter["kernels"] += 1
+    return c
+
+
+def feature_pack(features, center=None) -> PackedFeatures:
+    """center: None (computed from set 0 of `features`), False (no centring) or the tensor of the other side."""
     t = _t()
     features = _f64(features)
     S, N, D = features.shape
@@ -327,10 +339,11 @@ def feature_pack(features) -> PackedFeatures:
     L = _lib.lib()
     pf = PackedFeatures()
     pf.features, pf.n, pf.n_sets = features, N, S
+    pf.center = None if center is False else (feature_center(features) if center is None else center)
     pf.packed = t.empty(L.orpcd_feature_pack_bytes(N) * S, dtype=t.uint8, device="cuda")
     pf.maxnorm = t.empty(S, dtype=t.float32, device="cuda")
-    check(L.orpcd_feature_pack(features.data_ptr(), N, S, pf.packed.data_ptr(), pf.maxnorm.data_ptr(),
-                               _lib.stream_ptr()), "orpcd_feature_pack")
+    check(L.orpcd_feature_pack(features.data_ptr(), N, S, pf.center.data_ptr() if pf.center is not None else None,
+                               pf.packed.data_ptr(), pf.maxnorm.data_ptr(), _lib.stream_ptr()), "orpcd_feature_pack")
     launch_counter["kernels"] += 1
     return pf
 
@@ -338,20 +351,24 @@ def feature_pack(features) -> PackedFeatures:
 def feature_match(query: PackedFeatures, db: PackedFeatures, pair_q, pair_db, mode: int = 0, want_d2=False,
                   want_debug=False):
     """For pair p: nearest row of db set pair_db[p] for every row of query set pair_q[p].
-    Returns (nn int32 [P,Nq], d2 | None, n_exact_scans (device int32[1]), debug | None)."""
+    Returns (nn int32 [P,Nq], d2 | None, device int32[2] = (rows that needed the exact scan, chunks re-scored),
+    debug | None)."""
     t = _t()
     P = pair_q.shape[0]
     assert pair_q.dtype == t.int32 and pair_db.dtype == t.int32 and pair_q.is_cuda and pair_db.is_cuda
     L = _lib.lib()
+    if query.center is not db.center:
+        raise ValueError("both sides of a feature match must be packed with the same centring vector")
     ws = _lib.workspace(L.orpcd_feature_match_workspace_bytes(query.n, P))
     nn = t.empty((P, query.n), dtype=t.int32, device="cuda")
     d2 = t.empty((P, query.n), dtype=t.float64, device="cuda") if want_d2 else None
-    stats = t.zeros(1, dtype=t.int32, device="cuda")
+    stats = t.zeros(2, dtype=t.int32, device="cuda")
     dbg = None
     if want_debug:
         dbg = t.full((P, query.n, (db.n + 127) // 128 * 128), float("nan"), dtype=t.float32, device="cuda")
     check(L.orpcd_feature_match(query.features.data_ptr(), query.packed.data_ptr(), query.n, db.features.data_ptr(),
-                                db.packed.data_ptr(), db.maxnorm.data_ptr(), db.n, pair_q.data_ptr(),
+                                db.packed.data_ptr(), db.maxnorm.data_ptr(), db.n,
+                                db.center.data_ptr() if db.center is not None else None, pair_q.data_ptr(),
                                 pair_db.data_ptr(), P, int(mode), ws.data_ptr(), ws.numel(), nn.data_ptr(),
                                 d2.data_ptr() if want_d2 else None, stats.data_ptr(),
                                 dbg.data_ptr() if want_debug else None, _lib.stream_ptr()), "orpcd_feature_match")
