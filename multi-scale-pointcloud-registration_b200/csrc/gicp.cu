@@ -467,31 +467,25 @@ __global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c, int round)
 constexpr int CULL_RING = 4;       // chunk buffers per warp (512 B each), filled by cp.async
 constexpr int CULL_LIST = 1024;    // visit-list capacity per pass (chunk ids)
 
-template <int Q, int CULL_WARPS>
-__global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, int round)
+// The sweep of one warp over its patch.  qv[k] = (centred FP32 query, d_ub) of query k*32+lane of the patch
+// (lanes past the end of the cloud carry a copy of another query of the same patch); chunks [cb, ce) of the
+// target table; results per query: best chunk minimum m1, its chunk c1, second-best chunk minimum m2.
+// Returns the number of chunks the warp visited.  `ring` / `vl` are this warp's private shared memory.
+template <int Q>
+__device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__restrict__ tg, const float4 *__restrict__ sph,
+                                               float rmax_tgt, int cb, int ce, const float4 (&qv)[Q],
+                                               float4 (*ring)[NN_CH], unsigned short *vl, float (&m1)[Q], int (&c1)[Q],
+                                               float (&m2)[Q])
 {
     constexpr int TJ = 4;
-    __shared__ __align__(16) float4 ring[CULL_WARPS][CULL_RING][NN_CH];
-    __shared__ unsigned short vlist[CULL_WARPS][CULL_LIST];
-    const int u = blockIdx.z, split = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const UnitState &st = c.state[u];
-    if (st.done && !c.ignore_done) return;
-    const int wbase = (blockIdx.x * CULL_WARPS + warp) * (32 * Q);
-    if (wbase >= c.n_src) return;
-    const float4 *tg = c.tgt4 + (size_t)st.tgt_set * c.nt_pad;
-    const float4 *sph = c.chunk_sph + (size_t)st.tgt_set * c.n_chunks;
-    const float4 *qsrc = c.cur_qf + (size_t)u * c.n_src;
-
+    const int lane = threadIdx.x & 31;
     uint64_t qx[Q / 2], qy[Q / 2], qz[Q / 2];
     float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     float D = 0.f, rw = 0.f, pcx, pcy, pcz;
     float dq[Q];
     {
-        float4 qv[Q];
 #pragma unroll
         for (int k = 0; k < Q; ++k) {
-            const int i = min(wbase + k * 32 + lane, c.n_src - 1);   // tail lanes repeat the last query
-            qv[k] = qsrc[i];
             dq[k] = qv[k].w;
             lo[0] = fminf(lo[0], qv[k].x); hi[0] = fmaxf(hi[0], qv[k].x);
             lo[1] = fminf(lo[1], qv[k].y); hi[1] = fmaxf(hi[1], qv[k].y);
@@ -520,20 +514,15 @@ __global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, i
         for (int o = 16; o > 0; o >>= 1) rw = fmaxf(rw, __shfl_xor_sync(0xffffffffu, rw, o));
     }
     // FP32 slack: every quantity below carries a few ulps of the coordinate magnitude
-    const float mag = fabsf(pcx) + fabsf(pcy) + fabsf(pcz) + rw + (float)c.tgt_meta[st.tgt_set].rmax;
+    const float mag = fabsf(pcx) + fabsf(pcy) + fabsf(pcz) + rw + rmax_tgt;
     const float reach = (rw + D) * (1.f + 4e-6f) + 8e-6f * mag;
 #pragma unroll
     for (int k = 0; k < Q; ++k) dq[k] = dq[k] * (1.f + 4e-6f) + 8e-6f * mag;   // per-query reach, inflated
 
-    float m1[Q], m2[Q];
-    int c1[Q];
 #pragma unroll
     for (int k = 0; k < Q; ++k) { m1[k] = CUDART_INF_F; m2[k] = CUDART_INF_F; c1[k] = 0; }
 
-    const int cb = split * c.chunks_per_split;
-    const int ce = min(c.n_chunks, cb + c.chunks_per_split);
     int visited = 0;
-    unsigned short *vl = vlist[warp];
     for (int pass = cb; pass < ce; pass += CULL_LIST) {
         // 1) visit list of this pass.  Coarse test, lane-parallel over chunks: chunk sphere against the
         //    patch sphere inflated by the largest d_ub.  Survivors get the exact test: a chunk is needed
@@ -577,7 +566,7 @@ __global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, i
         visited += nv;
         // 2) stream the listed chunks through the warp's ring (one 16-byte cp.async per lane per chunk)
         auto issue = [&](int k) {
-            if (k < nv) cp_async16(&ring[warp][k % CULL_RING][lane], tg + (size_t)(pass + vl[k]) * NN_CH + lane);
+            if (k < nv) cp_async16(&ring[k % CULL_RING][lane], tg + (size_t)(pass + vl[k]) * NN_CH + lane);
             cp_async_commit();
         };
 #pragma unroll
@@ -586,7 +575,7 @@ __global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, i
             issue(k + CULL_RING - 1);
             cp_async_wait<CULL_RING - 1>();
             __syncwarp();
-            const float4 *tc = ring[warp][k % CULL_RING];
+            const float4 *tc = ring[k % CULL_RING];
             float mc[Q];
 #pragma unroll
             for (int q = 0; q < Q; ++q) mc[q] = CUDART_INF_F;
@@ -626,6 +615,31 @@ __global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, i
         cp_async_wait<0>();
         __syncwarp();
     }
+    return visited;
+}
+
+template <int Q, int CULL_WARPS>
+__global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, int round)
+{
+    __shared__ __align__(16) float4 ring[CULL_WARPS][CULL_RING][NN_CH];
+    __shared__ unsigned short vlist[CULL_WARPS][CULL_LIST];
+    const int u = blockIdx.z, split = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const UnitState &st = c.state[u];
+    if (st.done && !c.ignore_done) return;
+    const int wbase = (blockIdx.x * CULL_WARPS + warp) * (32 * Q);
+    if (wbase >= c.n_src) return;
+    const float4 *tg = c.tgt4 + (size_t)st.tgt_set * c.nt_pad;
+    const float4 *sph = c.chunk_sph + (size_t)st.tgt_set * c.n_chunks;
+    const float4 *qsrc = c.cur_qf + (size_t)u * c.n_src;
+    float4 qv[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) qv[k] = qsrc[min(wbase + k * 32 + lane, c.n_src - 1)];   // tail lanes repeat the last query
+    float m1[Q], m2[Q];
+    int c1[Q];
+    const int cb = split * c.chunks_per_split;
+    const int ce = min(c.n_chunks, cb + c.chunks_per_split);
+    const int visited = cull_sweep_core<Q>(c, tg, sph, (float)c.tgt_meta[st.tgt_set].rmax, cb, ce, qv, ring[warp],
+                                           vlist[warp], m1, c1, m2);
     const size_t pbase = ((size_t)u * c.splits + split) * c.n_src;
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
@@ -727,10 +741,55 @@ __global__ void __launch_bounds__(128) nn_resolve_kernel(Ctx c, int round)
     c.corr_d2[oi] = ok ? best : 0.0;
 }
 
-// Exact float64 search, one warp per listed query.  The best chunk of the FP32 filter is scored first;
-// every other 32-target chunk is scored only if its bounding sphere comes within that distance of the
-// query (strict test with FP32 slack, so equal-distance candidates are never skipped), lane-parallel
-// over chunks for the test and over the 32 targets for the scoring.  Ties -> lowest original index.
+// Exact float64 search by a whole warp for one query (x, y, z; centred FP32 copy qf).  The best chunk c1 of
+// the FP32 filter is scored first; every other 32-target chunk is scored only if its bounding sphere comes
+// within that distance of the query (strict test with FP32 slack, so equal-distance candidates are never
+// skipped), lane-parallel over chunks for the test and over the 32 targets for the scoring.  Ties -> lowest
+// original index.  All lanes return the same (best, bj); bj = 0x7fffffff if the set is empty.
+__device__ __forceinline__ void exact_search_warp(const Ctx &c, int tgt_set, double x, double y, double z, float qfx,
+                                                  float qfy, float qfz, int c1, double &best, int &bj)
+{
+    const int lane = threadIdx.x & 31;
+    const double *tp = c.tgt_pts + (size_t)tgt_set * c.n_tgt * 3;
+    const int *perm = c.tperm + (size_t)tgt_set * c.nt_pad;
+    const float4 *sph = c.chunk_sph + (size_t)tgt_set * c.n_chunks;
+    best = CUDART_INF;
+    bj = 0x7fffffff;
+    auto score = [&](int chunk) {
+        const int j = perm[(size_t)chunk * NN_CH + lane];
+        if (j >= 0) {
+            const double d = sqdist3_rn(x, y, z, tp[(size_t)j * 3], tp[(size_t)j * 3 + 1], tp[(size_t)j * 3 + 2]);
+            if (d < best || (d == best && j < bj)) { best = d; bj = j; }
+        }
+    };
+    score(c1);
+    double wb = best;
+    for (int o = 16; o > 0; o >>= 1) wb = fmin(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+    const float mag = fabsf(qfx) + fabsf(qfy) + fabsf(qfz) + (float)c.tgt_meta[tgt_set].rmax;
+    const float thr = __double2float_ru(sqrt(wb)) * (1.f + 4e-6f) + 8e-6f * mag;   // inf if chunk c1 was empty
+    for (int base = 0; base < c.n_chunks; base += 32) {
+        const int chunk = base + lane;
+        bool need = false;
+        if (chunk < c.n_chunks && chunk != c1) {
+            const float4 sp = sph[chunk];
+            const float sx = sp.x - qfx, sy = sp.y - qfy, sz = sp.z - qfz;
+            need = !(sqrtf(sx * sx + sy * sy + sz * sz) - sp.w > thr);
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, need);
+        while (bal) {
+            const int l = __ffs(bal) - 1;
+            bal &= bal - 1;
+            score(base + l);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (od < best || (od == best && oj < bj)) { best = od; bj = oj; }
+    }
+}
+
+// one warp per query of the work list written by nn_resolve_kernel
 __global__ void __launch_bounds__(128) nn_fix_kernel(Ctx c, int round)
 {
     const int count = c.worklist_count[round];
@@ -742,46 +801,11 @@ __global__ void __launch_bounds__(128) nn_fix_kernel(Ctx c, int round)
         const int u = item / c.n_src;
         const UnitState &st = c.state[u];
         const double *p = c.cur_pts + (size_t)item * 3;
-        const double x = p[0], y = p[1], z = p[2];
-        const double *tp = c.tgt_pts + (size_t)st.tgt_set * c.n_tgt * 3;
-        const int *perm = c.tperm + (size_t)st.tgt_set * c.nt_pad;
-        const float4 *sph = c.chunk_sph + (size_t)st.tgt_set * c.n_chunks;
         const float4 qf = c.cur_qf[item];
         const int c1 = c.corr[item];   // nn_resolve_kernel parked the filter's best chunk here
-        double best = CUDART_INF;
-        int bj = 0x7fffffff;
-        auto score = [&](int chunk) {
-            const int j = perm[(size_t)chunk * NN_CH + lane];
-            if (j >= 0) {
-                const double d = sqdist3_rn(x, y, z, tp[(size_t)j * 3], tp[(size_t)j * 3 + 1], tp[(size_t)j * 3 + 2]);
-                if (d < best || (d == best && j < bj)) { best = d; bj = j; }
-            }
-        };
-        score(c1);
-        double wb = best;
-        for (int o = 16; o > 0; o >>= 1) wb = fmin(wb, __shfl_xor_sync(0xffffffffu, wb, o));
-        const float mag = fabsf(qf.x) + fabsf(qf.y) + fabsf(qf.z) + (float)c.tgt_meta[st.tgt_set].rmax;
-        const float thr = __double2float_ru(sqrt(wb)) * (1.f + 4e-6f) + 8e-6f * mag;   // inf if chunk c1 was empty
-        for (int base = 0; base < c.n_chunks; base += 32) {
-            const int chunk = base + lane;
-            bool need = false;
-            if (chunk < c.n_chunks && chunk != c1) {
-                const float4 sp = sph[chunk];
-                const float sx = sp.x - qf.x, sy = sp.y - qf.y, sz = sp.z - qf.z;
-                need = !(sqrtf(sx * sx + sy * sy + sz * sz) - sp.w > thr);
-            }
-            unsigned bal = __ballot_sync(0xffffffffu, need);
-            while (bal) {
-                const int l = __ffs(bal) - 1;
-                bal &= bal - 1;
-                score(base + l);
-            }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-            if (od < best || (od == best && oj < bj)) { best = od; bj = oj; }
-        }
+        double best;
+        int bj;
+        exact_search_warp(c, st.tgt_set, p[0], p[1], p[2], qf.x, qf.y, qf.z, c1, best, bj);
         if (lane == 0) {
             const bool ok = bj != 0x7fffffff && best < c.r2;
             c.corr[item] = ok ? bj : -1;
@@ -830,33 +854,6 @@ __device__ __forceinline__ Sym3 inv_sqrt_sym3(const Sym3 &M)
     W.yy = v[1][0] * s0 * v[1][0] + v[1][1] * s1 * v[1][1] + v[1][2] * s2 * v[1][2];
     W.yz = v[1][0] * s0 * v[2][0] + v[1][1] * s1 * v[2][1] + v[1][2] * s2 * v[2][2];
     W.zz = v[2][0] * s0 * v[2][0] + v[2][1] * s1 * v[2][1] + v[2][2] * s2 * v[2][2];
-    return W;
-}
-
-// Closed form of the same W when both covariances are GICP plane covariances
-//   C = R diag(eps,1,1) R^T = I - kappa a a^T,  kappa = 1 - eps,  a = R e1 (unit).
-// M = 2I - kappa (a a^T + b b^T) has eigenvalues 2, 2 - kappa(1 +- |a.b|) with
-// eigenvectors along a +- sgn(a.b) b, so
-//   W = I/sqrt2 + k+ (a + s b)(a + s b)^T + k- (a - s b)(a - s b)^T,
-//   k+- = kappa / (2 sqrt(l+-) sqrt2 (sqrt(l+-) + sqrt2))      (no cancellation, no 0/0)
-__device__ __forceinline__ Sym3 inv_sqrt_plane_pair(const double *a, const double *b, double kappa)
-{
-    const double dot = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
-    const double s = dot >= 0 ? 1.0 : -1.0;
-    const double ac = fmin(fabs(dot), 1.0);
-    const double r2 = 1.4142135623730951;
-    const double lp = sqrt(2.0 - kappa * (1.0 + ac)), lm = sqrt(2.0 - kappa * (1.0 - ac));
-    const double kp = kappa / (2.0 * lp * r2 * (lp + r2)), km = kappa / (2.0 * lm * r2 * (lm + r2));
-    const double px = a[0] + s * b[0], py = a[1] + s * b[1], pz = a[2] + s * b[2];
-    const double mx = a[0] - s * b[0], my = a[1] - s * b[1], mz = a[2] - s * b[2];
-    const double h = 0.70710678118654752;
-    Sym3 W;
-    W.xx = h + kp * px * px + km * mx * mx;
-    W.xy = kp * px * py + km * mx * my;
-    W.xz = kp * px * pz + km * mx * mz;
-    W.yy = h + kp * py * py + km * my * my;
-    W.yz = kp * py * pz + km * my * mz;
-    W.zz = h + kp * pz * pz + km * mz * mz;
     return W;
 }
 
@@ -958,128 +955,118 @@ __device__ void umeyama_from_sums(const double *tot, double n, double *Um)
 // ----------------------------------------------------------------------------
 // residual / Jacobian reduction + solve
 // ----------------------------------------------------------------------------
-template <int COV_MODE>
-__global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
+// One correspondence (source point s with covariance data cs, target point t with ct, squared distance d2)
+// added to the 29 running sums: acc[0..20] upper triangle of J^T J (row-major), acc[21..26] J^T r,
+// acc[27] sum d2, acc[28] count.  EST: 0 Generalized-ICP with full covariances, 1 Generalized-ICP with plane
+// axes, 2 evaluation only, 3 point-to-point (sums for Umeyama), 4 point-to-plane.
+//
+// EST 1 uses J^T J = Jr^T M^-1 Jr and J^T r = Jr^T M^-1 d (W = M^-1/2 is symmetric, Jr = [-skew(s) | I]) with the
+// closed form  M^-1 = I/2 + g+ p p^T + g- m m^T,  p = a + sgn(a.b) b, m = a - sgn(a.b) b, g+- = kappa / (4 l+-),
+// l+- = 2 - kappa (1 +- |a.b|)  (M = 2I - kappa (a a^T + b b^T) has eigenvectors p, m).  So
+//   Jr^T M^-1 Jr = Jr^T Jr / 2 + g+ e+ e+^T + g- e- e-^T,   e+- = Jr^T (p | m) = (s x p, p) | (s x m, m),
+// accumulated as TWICE these sums (finish_round halves them); the identity block of Jr^T Jr is added from the
+// count there.  No square root, one division, DFMA issued explicitly.
+template <int EST>
+__device__ __forceinline__ void accumulate_pair(const Ctx &c, double (&acc)[32], double sx, double sy, double sz,
+                                                double tx, double ty, double tz, const double *__restrict__ cs,
+                                                const double *__restrict__ ct, double d2)
 {
-    __shared__ double sm[RED_THREADS / 32][RED_STRIDE];
-    __shared__ double tot[RED_STRIDE];
-    __shared__ int is_last;
-    const int u = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    UnitState &st = c.state[u];
-    if (st.done) return;
-    double acc[RED_VALS];
+    acc[27] += d2;
+    acc[28] += 1.0;
+    if (EST == 2) return;
+    const double dx = sx - tx, dy = sy - ty, dz = sz - tz;
+    if (EST == 3) {
+        acc[0] += sx; acc[1] += sy; acc[2] += sz;
+        acc[3] += tx; acc[4] += ty; acc[5] += tz;
+        acc[6] += tx * sx; acc[7] += tx * sy; acc[8] += tx * sz;
+        acc[9] += ty * sx; acc[10] += ty * sy; acc[11] += ty * sz;
+        acc[12] += tz * sx; acc[13] += tz * sy; acc[14] += tz * sz;
+    } else if (EST == 4) {
+        // point-to-plane: r = (vs - vt).nt, J = [vs x nt, nt]
+        const double nx = ct[0], ny = ct[1], nz = ct[2];
+        const double r = dx * nx + dy * ny + dz * nz;
+        const double J[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
+        int k = 0;
 #pragma unroll
-    for (int k = 0; k < RED_VALS; ++k) acc[k] = 0.0;
-    // RED_PER_THREAD correspondences per thread (block-strided, so loads stay coalesced): the 29-value
-    // warp-shuffle reduction -- the SHFL pipe is what bounds this kernel -- is paid once per four points
-#pragma unroll 1
-    for (int rep = 0; rep < RED_PER_THREAD; ++rep) {
-        const int i = (blockIdx.x * RED_PER_THREAD + rep) * RED_THREADS + tid;
-        if (i >= c.n_src) break;
-        const size_t oi = (size_t)u * c.n_src + i;
-        const int j = c.corr[oi];
-        if (j >= 0) {
-            const double *ps = c.cur_pts + oi * 3;
-            const double sx = ps[0], sy = ps[1], sz = ps[2];
-            const size_t tj = (size_t)st.tgt_set * c.n_tgt + j;
-            const double *pt = c.tgt_pts + tj * 3;
-            const double dx = sx - pt[0], dy = sy - pt[1], dz = sz - pt[2];
-            Sym3 W;
-            if (COV_MODE == 2) {
-                // EvaluateRegistration only: squared error and count
-                acc[27] += c.corr_d2[oi];
-                acc[28] += 1.0;
-            } else if (COV_MODE == 3) {
-                // point-to-point (Umeyama): sums of s, t and t s^T
-                const double tx = pt[0], ty = pt[1], tz = pt[2];
-                acc[0] += sx; acc[1] += sy; acc[2] += sz;
-                acc[3] += tx; acc[4] += ty; acc[5] += tz;
-                acc[6] += tx * sx; acc[7] += tx * sy; acc[8] += tx * sz;
-                acc[9] += ty * sx; acc[10] += ty * sy; acc[11] += ty * sz;
-                acc[12] += tz * sx; acc[13] += tz * sy; acc[14] += tz * sz;
-                acc[27] += c.corr_d2[oi];
-                acc[28] += 1.0;
-            } else if (COV_MODE == 4) {
-                // point-to-plane: r = (vs - vt).nt, J = [vs x nt, nt]
-                const double *nt = c.tgt_cov + tj * 3;
-                const double nx = nt[0], ny = nt[1], nz = nt[2];
-                const double r = dx * nx + dy * ny + dz * nz;
-                const double J[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
-                int k = 0;
+        for (int a = 0; a < 6; ++a)
 #pragma unroll
-                for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b) acc[k++] += J[a] * J[b];
 #pragma unroll
-                    for (int b = a; b < 6; ++b) acc[k++] += J[a] * J[b];
+        for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
+    } else if (EST == 1) {
+        const double ax = cs[0], ay = cs[1], az = cs[2], bx = ct[0], by = ct[1], bz = ct[2];
+        const double dot = fma(ax, bx, fma(ay, by, az * bz));
+        const double sg = dot >= 0 ? 1.0 : -1.0;
+        const double ac = fmin(fabs(dot), 1.0);
+        const double lp = fma(-c.kappa, 1.0 + ac, 2.0), lm = fma(-c.kappa, 1.0 - ac, 2.0);
+        const double inv = (0.5 * c.kappa) / (lp * lm);
+        const double gp = inv * lm, gm = inv * lp;                      // 2 g+, 2 g-
+        const double px = fma(sg, bx, ax), py = fma(sg, by, ay), pz = fma(sg, bz, az);
+        const double mx = fma(-sg, bx, ax), my = fma(-sg, by, ay), mz = fma(-sg, bz, az);
+        const double e[6] = {fma(sy, pz, -(sz * py)), fma(sz, px, -(sx * pz)), fma(sx, py, -(sy * px)), px, py, pz};
+        const double f[6] = {fma(sy, mz, -(sz * my)), fma(sz, mx, -(sx * mz)), fma(sx, my, -(sy * mx)), mx, my, mz};
+        int k = 0;
 #pragma unroll
-                for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
-                acc[27] += c.corr_d2[oi];
-                acc[28] += 1.0;
-            } else {
-            if (COV_MODE == 0) {
-                const Sym3 Cs = load_sym3(c.cur_cov + oi * 6);
-                const Sym3 Ct = load_sym3(c.tgt_cov + tj * 6);
-                Sym3 M;
-                M.xx = Ct.xx + Cs.xx; M.xy = Ct.xy + Cs.xy; M.xz = Ct.xz + Cs.xz;
-                M.yy = Ct.yy + Cs.yy; M.yz = Ct.yz + Cs.yz; M.zz = Ct.zz + Cs.zz;
-                W = inv_sqrt_sym3(M);
-            } else {
-                W = inv_sqrt_plane_pair(c.cur_cov + oi * 3, c.tgt_cov + tj * 3, c.kappa);
-            }
-            const double Wm[3][3] = {{W.xx, W.xy, W.xz}, {W.xy, W.yy, W.yz}, {W.xz, W.yz, W.zz}};
-            // J = W [ -skew(vs) | I ],  r = W d
-            double J[3][6], rr[3];
+        for (int a = 0; a < 6; ++a) {
+            const double ga = gp * e[a], ha = gm * f[a];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                J[r][0] = Wm[r][1] * (-sz) + Wm[r][2] * sy;
-                J[r][1] = Wm[r][0] * sz + Wm[r][2] * (-sx);
-                J[r][2] = Wm[r][0] * (-sy) + Wm[r][1] * sx;
-                J[r][3] = Wm[r][0]; J[r][4] = Wm[r][1]; J[r][5] = Wm[r][2];
-                rr[r] = Wm[r][0] * dx + Wm[r][1] * dy + Wm[r][2] * dz;
-            }
-            int k = 0;
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-                for (int b = a; b < 6; ++b) acc[k++] += J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b];
-#pragma unroll
-            for (int a = 0; a < 6; ++a) acc[21 + a] += J[0][a] * rr[0] + J[1][a] * rr[1] + J[2][a] * rr[2];
-            acc[27] += c.corr_d2[oi];
-            acc[28] += 1.0;
-            }
+            for (int b = a; b < 6; ++b) { acc[k] = fma(ga, e[b], fma(ha, f[b], acc[k])); ++k; }
         }
-    }
+        const double al = gp * fma(px, dx, fma(py, dy, pz * dz)), be = gm * fma(mx, dx, fma(my, dy, mz * dz));
 #pragma unroll
-    for (int k = 0; k < RED_VALS; ++k) acc[k] = warp_sum(acc[k]);
-    if (lane == 0) {
+        for (int a = 0; a < 6; ++a) acc[21 + a] = fma(al, e[a], fma(be, f[a], acc[21 + a]));
+        // Jr^T Jr (upper triangle, identity block left to finish_round) and Jr^T d
+        acc[0] = fma(sy, sy, fma(sz, sz, acc[0]));
+        acc[1] = fma(-sx, sy, acc[1]);
+        acc[2] = fma(-sx, sz, acc[2]);
+        acc[6] = fma(sx, sx, fma(sz, sz, acc[6]));
+        acc[7] = fma(-sy, sz, acc[7]);
+        acc[11] = fma(sx, sx, fma(sy, sy, acc[11]));
+        acc[4] -= sz; acc[5] += sy;      // (0,4) (0,5)
+        acc[8] += sz; acc[10] -= sx;     // (1,3) (1,5)
+        acc[12] -= sy; acc[13] += sx;    // (2,3) (2,4)
+        acc[21] += fma(sy, dz, -(sz * dy));
+        acc[22] += fma(sz, dx, -(sx * dz));
+        acc[23] += fma(sx, dy, -(sy * dx));
+        acc[24] += dx; acc[25] += dy; acc[26] += dz;
+    } else {
+        const Sym3 Cs = load_sym3(cs);
+        const Sym3 Ct = load_sym3(ct);
+        Sym3 M;
+        M.xx = Ct.xx + Cs.xx; M.xy = Ct.xy + Cs.xy; M.xz = Ct.xz + Cs.xz;
+        M.yy = Ct.yy + Cs.yy; M.yz = Ct.yz + Cs.yz; M.zz = Ct.zz + Cs.zz;
+        const Sym3 W = inv_sqrt_sym3(M);
+        const double Wm[3][3] = {{W.xx, W.xy, W.xz}, {W.xy, W.yy, W.yz}, {W.xz, W.yz, W.zz}};
+        // J = W [ -skew(vs) | I ],  r = W d
+        double J[3][6], rr[3];
 #pragma unroll
-        for (int k = 0; k < RED_VALS; ++k) sm[wid][k] = acc[k];
-    }
-    __syncthreads();
-    if (tid < RED_VALS) {
-        double s = sm[0][tid];
+        for (int r = 0; r < 3; ++r) {
+            J[r][0] = Wm[r][1] * (-sz) + Wm[r][2] * sy;
+            J[r][1] = Wm[r][0] * sz + Wm[r][2] * (-sx);
+            J[r][2] = Wm[r][0] * (-sy) + Wm[r][1] * sx;
+            J[r][3] = Wm[r][0]; J[r][4] = Wm[r][1]; J[r][5] = Wm[r][2];
+            rr[r] = Wm[r][0] * dx + Wm[r][1] * dy + Wm[r][2] * dz;
+        }
+        int k = 0;
 #pragma unroll
-        for (int w = 1; w < RED_THREADS / 32; ++w) s += sm[w][tid];
-        c.red_partial[((size_t)u * c.red_blocks + blockIdx.x) * RED_STRIDE + tid] = s;
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = a; b < 6; ++b) acc[k++] += J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc[21 + a] += J[0][a] * rr[0] + J[1][a] * rr[1] + J[2][a] * rr[2];
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned prev = atomicAdd(&c.red_counter[u], 1u);
-        is_last = (prev == (unsigned)c.red_blocks - 1u);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (tid < RED_VALS) {
-        double s = 0.0;
-        for (int b = 0; b < c.red_blocks; ++b)
-            s += __ldcg(&c.red_partial[((size_t)u * c.red_blocks + b) * RED_STRIDE + tid]);
-        tot[tid] = s;
-    }
-    __syncthreads();
-    if (tid != 0) return;
-    c.red_counter[u] = 0;
+}
+
+// End of a round for one unit, run by a single thread on the unit's 29 totals: Open3D's stopping rule, the
+// 6x6 solve (or Umeyama), T <- U T, results for finished units.
+template <int EST>
+__device__ void finish_round(const Ctx &c, UnitState &st, int u, double *tot, int round)
+{
     const double n = tot[28];
+    if (EST == 1) {   // accumulate_pair<1> sums twice J^T J / J^T r without the identity block
+        tot[15] += n; tot[18] += n; tot[20] += n;
+        for (int k = 0; k < 27; ++k) tot[k] *= 0.5;
+    }
     double fitness = 0.0, rmse = 0.0;
     if (n > 0) { fitness = n / (double)c.n_src; rmse = sqrt(tot[27] / n); }
     if (c.trace) {
@@ -1102,7 +1089,7 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
         return;
     }
     double Um[12];
-    if (COV_MODE == 3) {
+    if (EST == 3) {
         umeyama_from_sums(tot, n, Um);
     } else if (n > 0) {
         double A[36], nb[6], x[6];
@@ -1134,6 +1121,300 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
     st.iters = round + 1;
 }
 
+template <int COV_MODE>
+__global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
+{
+    __shared__ double sm[RED_THREADS / 32][RED_STRIDE];
+    __shared__ double tot[RED_STRIDE];
+    __shared__ int is_last;
+    const int u = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    UnitState &st = c.state[u];
+    if (st.done) return;
+    double acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+    // RED_PER_THREAD correspondences per thread (block-strided, so loads stay coalesced) before the shuffles
+#pragma unroll 1
+    for (int rep = 0; rep < RED_PER_THREAD; ++rep) {
+        const int i = (blockIdx.x * RED_PER_THREAD + rep) * RED_THREADS + tid;
+        if (i >= c.n_src) break;
+        const size_t oi = (size_t)u * c.n_src + i;
+        const int j = c.corr[oi];
+        if (j >= 0) {
+            const double *ps = c.cur_pts + oi * 3;
+            const size_t tj = (size_t)st.tgt_set * c.n_tgt + j;
+            const double *pt = c.tgt_pts + tj * 3;
+            const int cst = COV_MODE == 0 ? 6 : 3;
+            accumulate_pair<COV_MODE>(c, acc, ps[0], ps[1], ps[2], pt[0], pt[1], pt[2], c.cur_cov + oi * cst,
+                                      c.tgt_cov + tj * cst, c.corr_d2[oi]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RED_VALS; ++k) acc[k] = warp_sum(acc[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < RED_VALS; ++k) sm[wid][k] = acc[k];
+    }
+    __syncthreads();
+    if (tid < RED_VALS) {
+        double s = sm[0][tid];
+#pragma unroll
+        for (int w = 1; w < RED_THREADS / 32; ++w) s += sm[w][tid];
+        c.red_partial[((size_t)u * c.red_blocks + blockIdx.x) * RED_STRIDE + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(&c.red_counter[u], 1u);
+        is_last = (prev == (unsigned)gridDim.x - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid < RED_VALS) {
+        double s = 0.0;
+        for (int b = 0; b < (int)gridDim.x; ++b)
+            s += __ldcg(&c.red_partial[((size_t)u * c.red_blocks + b) * RED_STRIDE + tid]);
+        tot[tid] = s;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    c.red_counter[u] = 0;
+    finish_round<COV_MODE>(c, st, u, tot, round);
+}
+
+// ----------------------------------------------------------------------------
+// One Gauss-Newton round of every unit in ONE launch (the default path): each warp owns a patch of 32*Q
+// spatially consecutive source points and runs, for them,
+//   1. the pending rigid update (update_kernel's arithmetic) and the bound d_ub from the previous match,
+//   2. the chunk-culled FP32 sweep (cull_sweep_core),
+//   3. the certificate of nn_resolve_kernel with the warp-wide ballot over the best chunk,
+//   4. the exact float64 search for the few uncertified queries (exact_search_warp),
+//   5. the residual / Jacobian sums (accumulate_pair), a transposing butterfly that leaves total k in lane k,
+//      one 256-byte partial per warp; the last warp of the unit to finish adds the partials in warp order
+//      (fixed order: run-to-run deterministic) and closes the round (finish_round).
+// The float64 phases of one warp overlap the FP32 sweep of the others on the same SM.
+// ----------------------------------------------------------------------------
+// after the call lane L holds the warp total of v[L]
+__device__ __forceinline__ double warp_transpose_sum32(double (&v)[32], int lane)
+{
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double send = up ? v[i] : v[i + half];
+            const double keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+template <int Q, int EST>
+__device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, int wi, int round,
+                                           float4 (*ring)[NN_CH], unsigned short *vl)
+{
+    const int lane = threadIdx.x & 31;
+    const int wbase = wi * (32 * Q);
+    if (wbase >= c.n_src) return;
+    const int tgt_set = st.tgt_set;
+    if (wi == 0 && lane == 0) atomicAdd(&c.round_active[round], 1);
+    const TgtMeta tm = c.tgt_meta[tgt_set];
+    const double *tpts = c.tgt_pts + (size_t)tgt_set * c.n_tgt * 3;
+    const float4 *tg = c.tgt4 + (size_t)tgt_set * c.nt_pad;
+    constexpr int CST = EST == 0 ? 6 : 3;
+
+    // ---- 1. pending update, d_ub, centred FP32 copy
+    float4 qv[Q];
+    {
+        const bool has_update = st.has_update != 0;
+        double U[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) U[k] = st.U[k];
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+            const int i = wbase + k * 32 + lane;
+            qv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < c.n_src) {
+                const size_t oi = (size_t)u * c.n_src + i;
+                double *p = c.cur_pts + oi * 3;
+                double x = p[0], y = p[1], z = p[2];
+                if (has_update) {
+                    transform_point(U, x, y, z);
+                    p[0] = x; p[1] = y; p[2] = z;
+                    if (EST == 0) {
+                        double *cp = c.cur_cov + oi * 6;
+                        store_sym3(cp, rotate_sym3(U, load_sym3(cp)));
+                    } else if (EST == 1) {
+                        double *ap = c.cur_cov + oi * 3;
+                        const double ax = ap[0], ay = ap[1], az = ap[2];
+                        ap[0] = U[0] * ax + U[1] * ay + U[2] * az;
+                        ap[1] = U[4] * ax + U[5] * ay + U[6] * az;
+                        ap[2] = U[8] * ax + U[9] * ay + U[10] * az;
+                    }
+                }
+                float dub = c.dcap;
+                if (round >= 1) {
+                    const int j = c.corr[oi];
+                    if (j >= 0) {
+                        const double *tp = tpts + (size_t)j * 3;
+                        const double dx = x - tp[0], dy = y - tp[1], dz = z - tp[2];
+                        dub = fminf(dub, __double2float_ru(sqrt(dx * dx + dy * dy + dz * dz)) * (1.f + 1e-6f));
+                    }
+                }
+                qv[k] = make_float4((float)(x - tm.cx), (float)(y - tm.cy), (float)(z - tm.cz), dub);
+            }
+        }
+        // lanes past the end of the cloud carry the patch's first query (always a real one)
+        const float fx = __shfl_sync(0xffffffffu, qv[0].x, 0), fy = __shfl_sync(0xffffffffu, qv[0].y, 0);
+        const float fz = __shfl_sync(0xffffffffu, qv[0].z, 0), fw = __shfl_sync(0xffffffffu, qv[0].w, 0);
+#pragma unroll
+        for (int k = 0; k < Q; ++k)
+            if (wbase + k * 32 + lane >= c.n_src) qv[k] = make_float4(fx, fy, fz, fw);
+    }
+
+    // ---- 2. sweep
+    float m1[Q], m2[Q];
+    int c1[Q];
+    const int visited = cull_sweep_core<Q>(c, tg, c.chunk_sph + (size_t)tgt_set * c.n_chunks, (float)tm.rmax, 0,
+                                           c.n_chunks, qv, ring, vl, m1, c1, m2);
+    if (lane == 0)
+        atomicAdd(c.visit_count + round, (unsigned long long)visited * NN_CH * min(32 * Q, c.n_src - wbase));
+
+    // ---- 3. certificate (nn_resolve_kernel's bound), then each lane scans the best chunk of its own queries:
+    //         the FP32 values are recomputed with the sweep's FMA chain (bit-identical), and the chunk decides
+    //         the query iff exactly one target lies within the certified margin of the minimum
+    int tj[Q];          // matched target (original index); -1 none within the cut-off; -2 exact search needed
+    const int *tperm = c.tperm + (size_t)tgt_set * c.nt_pad;
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+        const float fx = qv[k].x, fy = qv[k].y, fz = qv[k].z;
+        const double qn = (double)fx * fx + (double)fy * fy + (double)fz * fz;
+        const double qnorm = sqrt(qn);
+        const double rho_max = qnorm + tm.rmax;
+        const double e_glob = (double)F32_EPS * 6.0 * rho_max * rho_max * 1.001;
+        const double d_ub = sqrt(fmax((double)m1[k] + qn, 0.0) + e_glob) * (1.0 + 1e-6);
+        const double rho = 2.0 * qnorm + d_ub + 4.0 * (double)F32_EPS * rho_max;
+        const double margin = 2.02 * (double)F32_EPS * (4.0 * rho * rho + 2.0 * d_ub * rho) * 1.001 + 1e-300;
+        const double lim = (double)m1[k] + margin;
+        const bool none = !(m1[k] < CUDART_INF_F);        // no chunk visited: nothing within the cut-off
+        const bool cross = !((double)m2[k] > lim);        // another chunk may hold the true neighbour
+        const float thr = __double2float_ru(lim);
+        const float4 *tc = tg + (size_t)c1[k] * NN_CH;
+        int cnt = 0, first = 0;
+#pragma unroll 8
+        for (int j = 0; j < NN_CH; ++j) {
+            const float4 t = __ldg(tc + j);
+            const float sv = __fmaf_rn(fx, t.x, __fmaf_rn(fy, t.y, __fmaf_rn(fz, t.z, t.w)));
+            const bool in = sv <= thr;
+            first = (in && cnt == 0) ? j : first;
+            cnt += in ? 1 : 0;
+        }
+        tj[k] = none ? -1 : ((cross || cnt != 1) ? -2 : tperm[(size_t)c1[k] * NN_CH + first]);
+        if (wbase + k * 32 + lane >= c.n_src) tj[k] = -1;
+    }
+
+    // ---- 4. exact search for what the FP32 filter could not decide
+    double fd2[Q];
+    int n_fix = 0;
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+        fd2[k] = -1.0;
+        unsigned fb = __ballot_sync(0xffffffffu, tj[k] == -2);
+        n_fix += __popc(fb);
+        while (fb) {
+            const int l = __ffs(fb) - 1;
+            fb &= fb - 1;
+            const double *p = c.cur_pts + ((size_t)u * c.n_src + wbase + k * 32 + l) * 3;
+            const float qfx = __shfl_sync(0xffffffffu, qv[k].x, l), qfy = __shfl_sync(0xffffffffu, qv[k].y, l);
+            const float qfz = __shfl_sync(0xffffffffu, qv[k].z, l);
+            double best;
+            int bj;
+            exact_search_warp(c, tgt_set, p[0], p[1], p[2], qfx, qfy, qfz, __shfl_sync(0xffffffffu, c1[k], l), best, bj);
+            if (lane == l) { tj[k] = bj == 0x7fffffff ? -1 : bj; fd2[k] = best; }
+        }
+    }
+    if (lane == 0 && n_fix) atomicAdd(&c.worklist_count[round], n_fix);
+
+    // ---- 5. sums over this warp's correspondences
+    double acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+        const int i = wbase + k * 32 + lane;
+        if (i < c.n_src) {
+            const size_t oi = (size_t)u * c.n_src + i;
+            int j = tj[k];
+            if (j >= 0) {
+                const double *ps = c.cur_pts + oi * 3;
+                const double *pt = tpts + (size_t)j * 3;
+                const double sx = ps[0], sy = ps[1], sz = ps[2], tx = pt[0], ty = pt[1], tz = pt[2];
+                const double d2 = fd2[k] >= 0.0 ? fd2[k] : sqdist3_rn(sx, sy, sz, tx, ty, tz);
+                if (d2 < c.r2)
+                    accumulate_pair<EST>(c, acc, sx, sy, sz, tx, ty, tz, c.cur_cov + oi * CST,
+                                         c.tgt_cov + ((size_t)tgt_set * c.n_tgt + j) * CST, d2);
+                else
+                    j = -1;
+            }
+            c.corr[oi] = j;
+        }
+    }
+    const double mine = warp_transpose_sum32(acc, lane);
+    const int n_warps = (c.n_src + 32 * Q - 1) / (32 * Q);
+    double *part = c.red_partial + (size_t)u * c.red_blocks * RED_STRIDE;
+    __stcg(part + (size_t)wi * RED_STRIDE + lane, mine);
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = atomicAdd(&c.red_counter[u], 1u) == (unsigned)n_warps - 1u;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    // totals in warp order, four interleaved chains (fixed order)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = 0;
+    for (; b + 3 < n_warps; b += 4) {
+        s0 += __ldcg(part + (size_t)b * RED_STRIDE + lane);
+        s1 += __ldcg(part + (size_t)(b + 1) * RED_STRIDE + lane);
+        s2 += __ldcg(part + (size_t)(b + 2) * RED_STRIDE + lane);
+        s3 += __ldcg(part + (size_t)(b + 3) * RED_STRIDE + lane);
+    }
+    for (; b < n_warps; ++b) s0 += __ldcg(part + (size_t)b * RED_STRIDE + lane);
+    double *tot = reinterpret_cast<double *>(vl);   // the visit list is free now
+    tot[lane] = (s0 + s1) + (s2 + s3);
+    __syncwarp();
+    if (lane != 0) return;
+    c.red_counter[u] = 0;
+    finish_round<EST>(c, st, u, tot, round);
+}
+
+// 64 source points per warp (Q = 2): the smaller the patch, the tighter its sphere and the fewer chunks it
+// visits, and the more warps a unit spreads over -- late rounds, when few units are still running, are bound by
+// the latency of one warp's patch, not by throughput (measured: 128-point patches 16.3 ms, 64-point 13.8 ms
+// of round kernels per 180-unit batch).
+#ifndef ROUND_MIN_BLOCKS
+#define ROUND_MIN_BLOCKS 6
+#endif
+#ifndef ROUND_W
+#define ROUND_W 4            // warps per block (independent workers)
+#endif
+#ifndef ROUND_Q
+#define ROUND_Q 2
+#endif
+
+template <int EST>
+__global__ void __launch_bounds__(ROUND_W * 32, ROUND_MIN_BLOCKS) gicp_round_kernel(Ctx c, int round)
+{
+    __shared__ __align__(16) float4 ring[ROUND_W][CULL_RING][NN_CH];     // 2 KB per warp
+    __shared__ __align__(16) unsigned short vlist[ROUND_W][CULL_LIST];   // 2 KB per warp; reused for the unit totals
+    const int u = blockIdx.z, warp = threadIdx.x >> 5;
+    UnitState &st = c.state[u];
+    if (st.done) return;
+    round_body<ROUND_Q, EST>(c, st, u, blockIdx.x * ROUND_W + warp, round, ring[warp], vlist[warp]);
+}
+
 // correspondences of unit u in the caller's source order (the unit arrays are spatially sorted)
 __global__ void __launch_bounds__(256) unpermute_corr_kernel(Ctx c, int *__restrict__ out)
 {
@@ -1152,6 +1433,8 @@ struct Layout {
         off_sph, off_sort, off_bbox, total;
     int nt_pad, n_chunks, splits, chunks_per_split, red_blocks, q_tiles, nn_q, nn_tj, cov_stride, smem_pad, nn_mode;
     int cull;
+    int fused;       // one gicp_round_kernel launch per round instead of update / sweep / resolve / fix / reduce
+    int red_grid;    // blocks per unit of reduce_kernel (red_blocks is the partial-sum stride, >= patches per unit)
 };
 
 bool make_layout(const orpcd_gicp_params *p, Layout &L)
@@ -1169,8 +1452,9 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     L.smem_pad = p->sweep_smem_pad > 0 && p->sweep_smem_pad <= 190000 ? p->sweep_smem_pad : 0;
     L.nn_tj = (p->sweep_tj == 2 || p->sweep_tj == 4 || p->sweep_tj == 8) ? p->sweep_tj : 4;
     L.nn_mode = (p->sweep_mode >= 1 && p->sweep_mode <= 3) ? p->sweep_mode - 1 : 0;
-    L.cull = !(p->sweep_mode >= 1 && p->sweep_mode <= 3);   // 0 (auto): culled sweep; 1..3: dense variants
+    L.cull = !(p->sweep_mode >= 1 && p->sweep_mode <= 3);   // 0 (auto), 4: culled sweep; 1..3: dense variants
     if (L.cull && !(p->sweep_q == 4 || p->sweep_q == 8)) L.nn_q = 4;   // smaller patches cull better
+    L.fused = L.cull && p->sweep_mode != 4;  // 4: culled sweep with the five separate kernels
     L.q_tiles = (p->n_src + NN_THREADS * L.nn_q - 1) / (NN_THREADS * L.nn_q);
     int s = p->target_splits;
     if (s <= 0) {
@@ -1186,7 +1470,10 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     if (s < 1) s = 1;
     L.chunks_per_split = (L.n_chunks + s - 1) / s;
     L.splits = (L.n_chunks + L.chunks_per_split - 1) / L.chunks_per_split;
-    L.red_blocks = (p->n_src + RED_THREADS * RED_PER_THREAD - 1) / (RED_THREADS * RED_PER_THREAD);
+    L.red_grid = (p->n_src + RED_THREADS * RED_PER_THREAD - 1) / (RED_THREADS * RED_PER_THREAD);
+    const int patches = (p->n_src + 32 * ROUND_Q - 1) / (32 * ROUND_Q);   // fused rounds: one partial per patch
+    L.red_blocks = L.red_grid > patches ? L.red_grid : patches;
+    if (L.fused) { L.chunks_per_split = L.n_chunks; L.splits = 1; }
     const size_t U = p->n_units, ns = p->n_src;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += orpcd_align_up(bytes, 256); return r; };
@@ -1302,6 +1589,23 @@ void launch_sweep(const Ctx &c, const Layout &L, int n_units, int round, cudaStr
     }
 }
 
+template <int EST>
+void launch_round_e(const Ctx &c, int n_units, int round, cudaStream_t st)
+{
+    const dim3 g((c.n_src + ROUND_W * 32 * ROUND_Q - 1) / (ROUND_W * 32 * ROUND_Q), 1, n_units);
+    gicp_round_kernel<EST><<<g, ROUND_W * 32, 0, st>>>(c, round);
+}
+
+// one fused round; est: 0 / 1 Generalized-ICP, 2 evaluation, 3 point-to-point, 4 point-to-plane
+void launch_round(const Ctx &c, int est, int n_units, int round, cudaStream_t st)
+{
+    if (est == 0) launch_round_e<0>(c, n_units, round, st);
+    else if (est == 1) launch_round_e<1>(c, n_units, round, st);
+    else if (est == 2) launch_round_e<2>(c, n_units, round, st);
+    else if (est == 3) launch_round_e<3>(c, n_units, round, st);
+    else launch_round_e<4>(c, n_units, round, st);
+}
+
 // Morton permutations of all source and target sets, the sorted FP32 target tables and the unit state
 int prepare_batch(const Ctx &c, const Layout &L, const orpcd_gicp_params *p, const double *d_src_points,
                   const double *d_src_cov, const int *d_unit_src, const int *d_unit_tgt, const double *d_init_T,
@@ -1366,7 +1670,7 @@ int run_registration(const orpcd_gicp_params *p, int est_mode, const double *d_s
         return ORPCD_ERR_CUDA;
     const dim3 g_upd((p->n_src + 255) / 256, p->n_units);
     const dim3 g_res((p->n_src + 127) / 128, p->n_units);
-    const dim3 g_red(L.red_blocks, p->n_units);
+    const dim3 g_red(L.red_grid, p->n_units);
     const int fix_blocks = 148 * 4;
     // profiling mode: CUDA events around every sweep launch on the caller's stream
     const bool prof = p->profile != 0 && h_profile != nullptr;
@@ -1380,18 +1684,25 @@ int run_registration(const orpcd_gicp_params *p, int est_mode, const double *d_s
     }
     int rounds = 0;
     for (int round = 0; round <= p->max_iterations; ++round) {
-        update_kernel<<<g_upd, 256, 0, st>>>(c, round);
-        if (prof) cudaEventRecord(ev[2 * round], st);
-        launch_sweep(c, L, p->n_units, round, st);
-        if (prof) cudaEventRecord(ev[2 * round + 1], st);
-        nn_resolve_kernel<<<g_res, 128, 0, st>>>(c, round);
-        nn_fix_kernel<<<fix_blocks, 128, 0, st>>>(c, round);
-        if (est_mode == 0) reduce_kernel<0><<<g_red, RED_THREADS, 0, st>>>(c, round);
-        else if (est_mode == 1) reduce_kernel<1><<<g_red, RED_THREADS, 0, st>>>(c, round);
-        else if (est_mode == 3) reduce_kernel<3><<<g_red, RED_THREADS, 0, st>>>(c, round);
-        else reduce_kernel<4><<<g_red, RED_THREADS, 0, st>>>(c, round);
+        if (L.fused) {
+            if (prof) cudaEventRecord(ev[2 * round], st);
+            launch_round(c, est_mode, p->n_units, round, st);
+            if (prof) cudaEventRecord(ev[2 * round + 1], st);
+            launches += 1;
+        } else {
+            update_kernel<<<g_upd, 256, 0, st>>>(c, round);
+            if (prof) cudaEventRecord(ev[2 * round], st);
+            launch_sweep(c, L, p->n_units, round, st);
+            if (prof) cudaEventRecord(ev[2 * round + 1], st);
+            nn_resolve_kernel<<<g_res, 128, 0, st>>>(c, round);
+            nn_fix_kernel<<<fix_blocks, 128, 0, st>>>(c, round);
+            if (est_mode == 0) reduce_kernel<0><<<g_red, RED_THREADS, 0, st>>>(c, round);
+            else if (est_mode == 1) reduce_kernel<1><<<g_red, RED_THREADS, 0, st>>>(c, round);
+            else if (est_mode == 3) reduce_kernel<3><<<g_red, RED_THREADS, 0, st>>>(c, round);
+            else reduce_kernel<4><<<g_red, RED_THREADS, 0, st>>>(c, round);
+            launches += 5;
+        }
         ORPCD_CHECK_LAUNCH();
-        launches += 5;
         rounds = round + 1;
         if (p->poll_interval > 0 && round < p->max_iterations && (round + 1) % p->poll_interval == 0) {
             int done = 0;
@@ -1511,11 +1822,15 @@ ORPCD_API int orpcd_evaluate_batch(const orpcd_gicp_params *p_in, const double *
     if ((size_t)q.n_units * 16 > (size_t)q.n_units * q.n_src * 3) return ORPCD_ERR_INVALID;
     if (prepare_batch(c, L, &q, d_src_points, nullptr, d_unit_src, d_unit_tgt, d_T, st, nullptr) != 0)
         return ORPCD_ERR_CUDA;
-    update_kernel<<<dim3((q.n_src + 255) / 256, q.n_units), 256, 0, st>>>(c, 0);
-    launch_sweep(c, L, q.n_units, 0, st);
-    nn_resolve_kernel<<<dim3((q.n_src + 127) / 128, q.n_units), 128, 0, st>>>(c, 0);
-    nn_fix_kernel<<<148 * 4, 128, 0, st>>>(c, 0);
-    reduce_kernel<2><<<dim3(L.red_blocks, q.n_units), RED_THREADS, 0, st>>>(c, 0);
+    if (L.fused) {
+        launch_round(c, 2, q.n_units, 0, st);
+    } else {
+        update_kernel<<<dim3((q.n_src + 255) / 256, q.n_units), 256, 0, st>>>(c, 0);
+        launch_sweep(c, L, q.n_units, 0, st);
+        nn_resolve_kernel<<<dim3((q.n_src + 127) / 128, q.n_units), 128, 0, st>>>(c, 0);
+        nn_fix_kernel<<<148 * 4, 128, 0, st>>>(c, 0);
+        reduce_kernel<2><<<dim3(L.red_grid, q.n_units), RED_THREADS, 0, st>>>(c, 0);
+    }
     if (d_out_corr)   // back to the caller's source order
         unpermute_corr_kernel<<<dim3((q.n_src + 255) / 256, q.n_units), 256, 0, st>>>(c, d_out_corr);
     ORPCD_CHECK_LAUNCH();

@@ -46,10 +46,11 @@ class GeneralizedICP(IOptimizer):
         # generic 3x3 covariance path with a Jacobi eigen-solve per correspondence
         self.analytic_whitening = True
         self.profile = False          # set True to collect sweep timings in BatchResult.profile
-        self.sweep_mode = 0           # tuning: 0 = chunk-culled 1-NN sweep, 1..3 = dense sweep variants
+        self.sweep_mode = 0           # tuning: 0 = fused culled rounds, 4 = culled sweep + separate kernels, 1..3 = dense sweeps
         self.sweep_q = 0              # tuning: queries per thread (4 | 8), 0 = auto
         self.target_splits = 0        # tuning: target splits per sweep, 0 = auto
         self.sweep_tj = 0             # tuning: dense sweep targets per step; culled sweep warps per block (2->1, 4->2, 8->4)
+        self.sweep_smem_pad = 0       # tuning: dense sweep occupancy pad; negative -(n+1): small patches below n
         self.last_profile = None
 
     # ------------------------------------------------------------------ reference API
@@ -129,7 +130,7 @@ class GeneralizedICP(IOptimizer):
                              relative_rmse=ICP_RELATIVE_RMSE, poll_interval=poll_interval, profile=self.profile,
                              want_trace=want_trace, ws=self._ws, gicp_epsilon=GICP_EPSILON,
                              sweep_mode=self.sweep_mode, sweep_q=self.sweep_q, target_splits=self.target_splits,
-                             sweep_tj=self.sweep_tj)
+                             sweep_tj=self.sweep_tj, sweep_smem_pad=self.sweep_smem_pad)
         self._ws = res.workspace
         return res
 

@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "liborpcd_b200.so")
+LIB_PATH = os.environ.get("ORPCD_B200_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "liborpcd_b200.so")
 
 ORPCD_OK = 0
 MAX_KNN = 64

@@ -35,6 +35,7 @@ def main():
     opt.sweep_q = int(os.environ.get("SWEEP_Q", "0"))
     opt.target_splits = int(os.environ.get("SPLITS", "0"))
     opt.sweep_tj = int(os.environ.get("SWEEP_TJ", "0"))
+    opt.sweep_smem_pad = int(os.environ.get("PAD", "0"))
     d_s, d_t = _lib.to_device(sources), _lib.to_device(targets)
     us = torch.arange(n_units, dtype=torch.int32, device="cuda")
     ut = (torch.arange(n_units, dtype=torch.int32, device="cuda") * 6 // n_units).to(torch.int32)
