@@ -11,10 +11,12 @@ SURVEY.md 8(e)) and a tiny all-gather collects the (rmse, transform) records.
   value  : inner registrations per second, inputs resident in HBM, CUDA-event timed.
   e2e    : same through the plugin API (GeneralizedICP.optimize_batch) with HOST buffers:
            H2D of the step's clouds and D2H of its results inside the timed region.
-  roofline: the dominant kernel (nn_sweep_cull_kernel, FP32 FMA pipe bound) -- 8 FLOP per
-           (query,target) pair the kernel actually evaluated (chunks it culls are not counted;
-           the brute-force equivalent is reported beside it) over the CUDA-event time spent
-           in that kernel during the timed steps, against the FFMA peak measured in this run.
+  roofline: the dominant kernel (gicp_round_kernel: one launch per Gauss-Newton round = pending update +
+           chunk-culled FP32 1-NN sweep + certificate + exact float64 re-rank + Jacobian sums + solve) --
+           8 FLOP per (query,target) pair the kernel actually evaluated (chunks it culls are not counted;
+           the brute-force equivalent is reported beside it) over the CUDA-event time spent in that kernel
+           during the timed steps, against the FFMA peak measured in this run.  The dense (un-culled)
+           sweep kernel, which is purely FMA-pipe work, is timed beside it as `dense_sweep_reference`.
   cpu_baseline: the restated CPU path (oracle/, C + OpenMP, KD-tree) on the host cores.
 
 `--impl reference` times that CPU path alone (Open3D, the reference's arithmetic, is an
@@ -250,8 +252,10 @@ def run_b200(args):
 
     # ---- second half of the metric: Aligner.align() wall seconds on BASELINE config 1 (rank 0, N = 1)
     align_info = None
+    fgr_info = None
     if world == 1:
         align_info = align_config1()
+        fgr_info = fgr_throughput(src, sources, targets, unit_src, unit_tgt)
 
     # ---- max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -275,6 +279,25 @@ def run_b200(args):
 
         ffma_peak = max(peak(False), peak(True))
         achieved = 8.0 * pairs / (sweep_ms * 1e-3) / 1e12
+
+        # the brute-force sweep kernel alone (sweep_mode 1: every (query, target) pair), same clouds
+        def dense_sweep():
+            ax_s = ops.normals_cov(d_src, want_gicp_cov=False, want_gicp_axis=True)["gicp_axis"]
+            ax_t = ops.normals_cov(d_tgt, want_gicp_cov=False, want_gicp_axis=True)["gicp_axis"]
+            r0 = ops.gicp_batch(d_src, ax_s, d_tgt, ax_t, us, ut, max_iterations=0, sweep_mode=1)
+            for _ in range(2):
+                ops.gicp_sweep_only(r0.params, r0.workspace)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                ops.gicp_sweep_only(r0.params, r0.workspace)
+            b.record()
+            torch.cuda.synchronize()
+            tf = 8.0 * n_units * N_POINTS * N_POINTS * 5 / (a.elapsed_time(b) * 1e-3) / 1e12
+            return {"kernel": "nn_sweep_kernel (dense, not on the default path)", "achieved": tf, "unit": "TFLOP/s",
+                    "frac": tf / ffma_peak, "us_per_launch": a.elapsed_time(b) * 1e3 / 5}
+
+        dense_ref = dense_sweep()
         # CPU baseline on this box's host cores: a bounded sample of the same step (N = 1 only)
         cpu_units = [c * ATTEMPTS + k for k in range(2) for c in range(len(SCALES))]
         if world == 1:
@@ -298,11 +321,15 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
                          "frac": achieved / ffma_peak, "traffic": None,
-                         "kernel": "nn_sweep_cull_kernel", "avg_launch_us": 1e3 * sweep_ms / max(sweep_launches * args.steps, 1),
+                         "kernel": "gicp_round_kernel", "avg_launch_us": 1e3 * sweep_ms / max(sweep_launches * args.steps, 1),
                          "share_of_step": sweep_ms / dev_ms,
                          "note": "8 FLOP per (query,target) pair x pairs the kernel evaluated / CUDA-event time inside the "
                                  "kernel; peak = FFMA/FFMA2 micro-benchmark measured in this run (MEASURED_PEAKS.json has "
-                                 "no FP32 figure); brute force would evaluate pairs_brute_force_per_step",
+                                 "no FP32 figure); brute force would evaluate pairs_brute_force_per_step.  The kernel "
+                                 "fuses the whole round (float64 update, certificate, exact re-rank, Jacobian sums, "
+                                 "6x6 solve) around the FP32 sweep, so its time is not FMA-pipe time alone: see "
+                                 "profiles/ for the per-phase split",
+                         "dense_sweep_reference": dense_ref,
                          "pairs_per_step": pairs / args.steps,
                          "pairs_brute_force_per_step": unit_rounds * N_POINTS * N_POINTS / args.steps,
                          "culled_fraction": 1.0 - pairs / max(unit_rounds * N_POINTS * N_POINTS, 1),
@@ -313,10 +340,37 @@ def run_b200(args):
             line["cpu_baseline"] = cpu_baseline
         if align_info is not None:
             line["align"] = align_info
+        if fgr_info is not None:
+            line["fgr"] = fgr_info
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def fgr_throughput(src, sources, targets, unit_src, unit_tgt):
+    """The same 180-unit batch through FastGlobalOptimizer.optimize_batch (host buffers in, host results out):
+    FPFH of every source copy and target set, tcgen05 feature matching both ways, tuple test, GNC solve,
+    evaluation.  Secondary figure (BASELINE config 2's optimizer on the bench clouds)."""
+    import torch
+
+    from or_pcd_b200.Optimizer import FastGlobalOptimizer
+
+    out = {}
+    for mode in ("fixed", "reference_compat"):
+        opt = FastGlobalOptimizer(feature_mode=mode)
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            opt.optimize_batch(sources, targets, unit_src, unit_tgt, rigid_base=src)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        out[mode] = {"registrations_per_s": len(unit_src) / best, "wall_s": best,
+                     "feature_rows_exact_scanned": opt.last_exact_scans}
+    out["note"] = "FastGlobalOptimizer.optimize_batch on the bench batch, host buffers, best of 3"
+    return out
 
 
 def align_config1():

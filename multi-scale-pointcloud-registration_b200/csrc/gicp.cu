@@ -515,7 +515,7 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
     }
     // FP32 slack: every quantity below carries a few ulps of the coordinate magnitude
     const float mag = fabsf(pcx) + fabsf(pcy) + fabsf(pcz) + rw + rmax_tgt;
-    const float reach = (rw + D) * (1.f + 4e-6f) + 8e-6f * mag;
+    const float reach_box = D * (1.f + 4e-6f) + 8e-6f * mag;   // a query is inside the box: only its own reach counts
 #pragma unroll
     for (int k = 0; k < Q; ++k) dq[k] = dq[k] * (1.f + 4e-6f) + 8e-6f * mag;   // per-query reach, inflated
 
@@ -535,8 +535,10 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
             float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
             if (chunk < pe) {
                 sp = __ldg(sph + chunk);
-                const float sx = sp.x - pcx, sy = sp.y - pcy, sz = sp.z - pcz;
-                need = !(sqrtf(sx * sx + sy * sy + sz * sz) - sp.w > reach);
+                // distance from the chunk centre to the patch's bounding box (tighter than its bounding sphere)
+                const float bx = fmaxf(fmaxf(lo[0] - sp.x, sp.x - hi[0]), 0.f), by = fmaxf(fmaxf(lo[1] - sp.y, sp.y - hi[1]), 0.f);
+                const float bz = fmaxf(fmaxf(lo[2] - sp.z, sp.z - hi[2]), 0.f);
+                need = !(sqrtf(bx * bx + by * by + bz * bz) - sp.w > reach_box);
             }
             unsigned bal = __ballot_sync(0xffffffffu, need);
             while (bal) {
