@@ -59,10 +59,16 @@ const char *orpcd_error_string(int code);
  * d_idx    : [batch][m][k] int32, -1 where fewer than k points exist
  * d_d2     : [batch][m][k] float64, +inf where fewer than k points exist
  * 1 <= k <= ORPCD_MAX_KNN.
+ * d_workspace (orpcd_knn_exact_workspace_bytes, may be 0 bytes / NULL): with few
+ * queries the point range of each query is split over several blocks and the
+ * per-split lists are merged (exact: the (d2, index) order is total); without
+ * a workspace the search runs unsplit.
  * ---------------------------------------------------------------------- */
+size_t orpcd_knn_exact_workspace_bytes(int n, int m, int batch, int k);
 int orpcd_knn_exact(const double *d_points, int n, long long points_stride,
                     const double *d_queries, int m, long long queries_stride,
-                    int batch, int k, int *d_idx, double *d_d2, orpcd_stream_t stream);
+                    int batch, int k, int *d_idx, double *d_d2, void *d_workspace,
+                    size_t workspace_bytes, orpcd_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * k-NN of a moved copy of a cloud, re-ranked from the base cloud's lists.

@@ -10,7 +10,8 @@
 
 int orpcd_launch_knn(const double *d_points, int n, long long points_stride, const double *d_queries,
                      int m, long long queries_stride, int batch, int k, int *d_idx, double *d_d2,
-                     cudaStream_t st);
+                     void *d_scratch, size_t scratch_bytes, cudaStream_t st);
+size_t orpcd_knn_scratch_bytes(int n, int m, int batch, int k);
 
 namespace {
 
@@ -232,7 +233,8 @@ ORPCD_API size_t orpcd_normals_workspace_bytes(int n, int batch, int knn)
 {
     if (n <= 0 || batch <= 0 || knn < 1) return 0;
     const size_t nn = (size_t)n * batch * knn;
-    return orpcd_align_up(nn * sizeof(double), 256) + orpcd_align_up(nn * sizeof(int), 256);
+    return orpcd_align_up(nn * sizeof(double), 256) + orpcd_align_up(nn * sizeof(int), 256) +
+           orpcd_knn_scratch_bytes(n, n, batch, knn);
 }
 
 ORPCD_API int orpcd_normals_cov(const double *d_points, int n, long long points_stride, int batch,
@@ -250,7 +252,9 @@ ORPCD_API int orpcd_normals_cov(const double *d_points, int n, long long points_
     const size_t nn = (size_t)n * batch * knn;
     double *d2 = (double *)d_workspace;
     int *idx = (int *)((unsigned char *)d_workspace + orpcd_align_up(nn * sizeof(double), 256));
-    int rc = orpcd_launch_knn(d_points, n, points_stride, d_points, n, points_stride, batch, knn, idx, d2, st);
+    unsigned char *scratch = (unsigned char *)idx + orpcd_align_up(nn * sizeof(int), 256);
+    int rc = orpcd_launch_knn(d_points, n, points_stride, d_points, n, points_stride, batch, knn, idx, d2, scratch,
+                              orpcd_knn_scratch_bytes(n, n, batch, knn), st);
     if (rc != ORPCD_OK) return rc;
     dim3 grid((n + 127) / 128, batch);
     normals_cov_kernel<<<grid, 128, 0, st>>>(d_points, n, points_stride, idx, d2, knn,

@@ -9,6 +9,7 @@
 // k > 1 searches are a few percent of a registration, the 1-NN correspondence
 // sweep (gicp.cu) is the hot one and has its own FP32-filter kernel.
 #include "common.cuh"
+#include "sort.cuh"
 
 namespace {
 
@@ -25,7 +26,7 @@ constexpr int KNN_TILE = 512;   // points staged per shared-memory tile
 __global__ void __launch_bounds__(KNN_BLOCK)
 knn_f64_kernel(const double *__restrict__ points, int n, long long points_stride,
                const double *__restrict__ queries, int m, long long queries_stride, int k,
-               int *__restrict__ out_idx, double *__restrict__ out_d2)
+               int split_len, int *__restrict__ out_idx, double *__restrict__ out_d2)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *tx = reinterpret_cast<double *>(smem_raw);
@@ -49,8 +50,12 @@ knn_f64_kernel(const double *__restrict__ points, int n, long long points_stride
     int cnt = 0, wpos = 0;
     double worst = CUDART_INF;
 
-    for (int base = 0; base < n; base += KNN_TILE) {
-        const int tn = min(KNN_TILE, n - base);
+    // blockIdx.z = split: this block scans points [p0, p1) and writes list (query, split); the lists of a
+    // query are merged by knn_merge_kernel (the (d2, idx) order is total, so split + merge is exact)
+    const int n_splits = gridDim.z, split = blockIdx.z;
+    const int p0 = split * split_len, p1 = min(n, p0 + split_len);
+    for (int base = p0; base < p1; base += KNN_TILE) {
+        const int tn = min(KNN_TILE, p1 - base);
         __syncthreads();
         for (int e = tid; e < tn * 3; e += KNN_BLOCK) {
             const double v = pts[(size_t)base * 3 + e];
@@ -112,13 +117,232 @@ knn_f64_kernel(const double *__restrict__ points, int n, long long points_stride
         ld[(size_t)pos * KNN_BLOCK + tid] = d;
         li[(size_t)pos * KNN_BLOCK + tid] = id;
     }
-    int *oi = out_idx + ((size_t)b * m + qi) * k;
-    double *od = out_d2 + ((size_t)b * m + qi) * k;
+    int *oi = out_idx + (((size_t)b * m + qi) * n_splits + split) * k;
+    double *od = out_d2 + (((size_t)b * m + qi) * n_splits + split) * k;
     for (int s = 0; s < k; ++s) {
         oi[s] = s < cnt ? li[(size_t)s * KNN_BLOCK + tid] : -1;
         od[s] = s < cnt ? ld[(size_t)s * KNN_BLOCK + tid] : CUDART_INF;
     }
 }
+
+// S sorted lists per query -> the k smallest under (d2, idx), sorted.  One thread per query.
+constexpr int KNN_MAX_SPLITS = 8;
+__global__ void __launch_bounds__(128)
+knn_merge_kernel(const int *__restrict__ part_idx, const double *__restrict__ part_d2, long long n_queries, int n_splits,
+                 int k, int *__restrict__ out_idx, double *__restrict__ out_d2)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries) return;
+    const int *pi = part_idx + (size_t)q * n_splits * k;
+    const double *pd = part_d2 + (size_t)q * n_splits * k;
+    int head[KNN_MAX_SPLITS], hi[KNN_MAX_SPLITS];
+    double hd[KNN_MAX_SPLITS];
+#pragma unroll
+    for (int s = 0; s < KNN_MAX_SPLITS; ++s) {
+        head[s] = 0;
+        hi[s] = s < n_splits ? pi[(size_t)s * k] : -1;
+        hd[s] = s < n_splits ? pd[(size_t)s * k] : CUDART_INF;
+    }
+    for (int r = 0; r < k; ++r) {
+        int bs = -1, bi = -1;
+        double bd = CUDART_INF;
+#pragma unroll
+        for (int s = 0; s < KNN_MAX_SPLITS; ++s)
+            if (hi[s] >= 0 && (bs < 0 || hd[s] < bd || (hd[s] == bd && hi[s] < bi))) { bs = s; bd = hd[s]; bi = hi[s]; }
+        out_idx[(size_t)q * k + r] = bi;
+        out_d2[(size_t)q * k + r] = bd;
+        if (bs < 0) continue;
+#pragma unroll
+        for (int s = 0; s < KNN_MAX_SPLITS; ++s)
+            if (s == bs) {
+                ++head[s];
+                hi[s] = head[s] < k ? pi[(size_t)s * k + head[s]] : -1;
+                hd[s] = head[s] < k ? pd[(size_t)s * k + head[s]] : CUDART_INF;
+            }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// Self k-NN with chunk culling (queries == points, the case of SOR, normals, GICP covariances and FPFH).
+// The cloud is put in Hilbert order (sort.cuh); every 32 consecutive points form a chunk with a bounding
+// sphere.  One warp owns the 32 queries of one chunk, one query per lane, k-best lists in shared memory as
+// in knn_f64_kernel.  It scans its own chunk and its neighbours along the curve until every list is full,
+// then walks outwards over the remaining chunks and skips every chunk whose sphere lies farther from the
+// patch than the worst kept distance of any lane (and, per lane, farther than that lane's own worst).  Skips
+// are strict with slack, so a skipped chunk holds no point that could enter a list -- not even on an exact
+// tie -- and the lists equal the brute-force result under the (d2, original index) order.
+// ----------------------------------------------------------------------------
+constexpr int KC_WARPS = 4;
+
+// sorted copy of the cloud + chunk spheres.  grid (chunks, batch), 32 threads.
+__global__ void __launch_bounds__(32)
+knn_cull_prep_kernel(const double *__restrict__ points, int n, const int *__restrict__ perm, int n_pad,
+                     double *__restrict__ sorted, double4 *__restrict__ spheres)
+{
+    const int b = blockIdx.y, ch = blockIdx.x, lane = threadIdx.x;
+    const int pos = ch * 32 + lane;
+    const int i = perm[(size_t)b * n_pad + pos];
+    double x = 0, y = 0, z = 0;
+    if (i >= 0) {
+        const double *p = points + ((size_t)b * n + i) * 3;
+        x = p[0]; y = p[1]; z = p[2];
+    }
+    double *o = sorted + ((size_t)b * n_pad + pos) * 3;
+    o[0] = x; o[1] = y; o[2] = z;
+    double lo[3] = {i >= 0 ? x : CUDART_INF, i >= 0 ? y : CUDART_INF, i >= 0 ? z : CUDART_INF};
+    double hi[3] = {i >= 0 ? x : -CUDART_INF, i >= 0 ? y : -CUDART_INF, i >= 0 ? z : -CUDART_INF};
+    for (int k = 0; k < 3; ++k)
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o2));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o2));
+        }
+    const double cx = 0.5 * (lo[0] + hi[0]), cy = 0.5 * (lo[1] + hi[1]), cz = 0.5 * (lo[2] + hi[2]);
+    double r = i >= 0 ? sqrt((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz)) : 0.0;
+    for (int o2 = 16; o2 > 0; o2 >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o2));
+    if (lane == 0) spheres[(size_t)b * (n_pad / 32) + ch] = make_double4(cx, cy, cz, r * (1.0 + 1e-12) + 1e-300);
+}
+
+__global__ void __launch_bounds__(KC_WARPS * 32)
+knn_cull_kernel(const double *__restrict__ sorted, const double4 *__restrict__ spheres, const int *__restrict__ perm,
+                int n, int n_pad, int k, int *__restrict__ out_idx, double *__restrict__ out_d2)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, n_chunks = n_pad / 32;
+    const int c0 = blockIdx.x * KC_WARPS + warp;   // this warp's chunk = its 32 queries
+    if (c0 >= n_chunks) return;
+    double *ld = reinterpret_cast<double *>(smem_raw) + (size_t)warp * k * 32;                        // [k][32]
+    int *li = reinterpret_cast<int *>(smem_raw + (size_t)KC_WARPS * k * 32 * sizeof(double)) + (size_t)warp * k * 32;
+    const double *pts = sorted + (size_t)b * n_pad * 3;
+    const int *pm = perm + (size_t)b * n_pad;
+    const double4 *sph = spheres + (size_t)b * n_chunks;
+    const int qorig = pm[c0 * 32 + lane];
+    const bool active = qorig >= 0;
+    const double qx = pts[(size_t)(c0 * 32 + lane) * 3], qy = pts[(size_t)(c0 * 32 + lane) * 3 + 1],
+                 qz = pts[(size_t)(c0 * 32 + lane) * 3 + 2];
+    int cnt = 0, wpos = 0, worst_i = 0x7fffffff;
+    double worst = CUDART_INF;
+
+    // all 32 points of chunk ch against this lane's query (broadcast loads)
+    auto scan = [&](int ch) {
+        const double *cp = pts + (size_t)ch * 96;
+        const int *ci = pm + ch * 32;
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+            const int id = ci[j];
+            const double d = sqdist3_rn(qx, qy, qz, cp[j * 3], cp[j * 3 + 1], cp[j * 3 + 2]);
+            if (id < 0 || !active) continue;
+            if (cnt < k) {
+                ld[cnt * 32 + lane] = d;
+                li[cnt * 32 + lane] = id;
+                ++cnt;
+                if (cnt < k) continue;
+            } else if (d < worst || (d == worst && id < worst_i)) {
+                ld[wpos * 32 + lane] = d;
+                li[wpos * 32 + lane] = id;
+            } else {
+                continue;
+            }
+            // rescan for the lexicographically largest (d2, idx) member
+            double wd = ld[lane];
+            int wi = li[lane], wp = 0;
+            for (int s = 1; s < k; ++s) {
+                const double sd = ld[s * 32 + lane];
+                const int si = li[s * 32 + lane];
+                if (sd > wd || (sd == wd && si > wi)) { wd = sd; wi = si; wp = s; }
+            }
+            worst = wd; worst_i = wi; wpos = wp;
+        }
+    };
+
+    // 1) own chunk and its neighbours along the curve until every list is full (or the cloud is exhausted)
+    int lo = c0, hi = c0;   // chunks [lo, hi] are done
+    scan(c0);
+    while ((hi - lo + 1) * 32 < k + 32 && (lo > 0 || hi < n_chunks - 1)) {
+        if (hi < n_chunks - 1) scan(++hi);
+        if (lo > 0) scan(--lo);
+    }
+    // 2) outwards, 32 chunks per step on each side, culled
+    const double4 ps = sph[c0];
+    auto side = [&](int first, int count, int step) {   // chunks first, first+step, ... (count of them)
+        double wmax = active && cnt >= k ? worst : (active ? CUDART_INF : 0.0);
+        for (int o = 16; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        bool need = false;
+        double4 sc = make_double4(0, 0, 0, 0);
+        if (lane < count) {
+            sc = sph[first + lane * step];
+            const double dx = sc.x - ps.x, dy = sc.y - ps.y, dz = sc.z - ps.z;
+            const double lb = sqrt(dx * dx + dy * dy + dz * dz) - sc.w - ps.w;
+            need = !(lb > 0.0 && lb * lb * (1.0 - 1e-9) > wmax);
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, need);
+        while (bal) {
+            const int l = __ffs(bal) - 1;
+            bal &= bal - 1;
+            const double sx = __shfl_sync(0xffffffffu, sc.x, l), sy = __shfl_sync(0xffffffffu, sc.y, l);
+            const double sz = __shfl_sync(0xffffffffu, sc.z, l), sr = __shfl_sync(0xffffffffu, sc.w, l);
+            const double dx = sx - qx, dy = sy - qy, dz = sz - qz;
+            const double lb = sqrt(dx * dx + dy * dy + dz * dz) - sr;
+            const bool mine = active && !(cnt >= k && lb > 0.0 && lb * lb * (1.0 - 1e-9) > worst);
+            if (__any_sync(0xffffffffu, mine)) scan(first + l * step);
+        }
+    };
+    while (lo > 0 || hi < n_chunks - 1) {
+        if (hi < n_chunks - 1) {
+            const int cntr = min(32, n_chunks - 1 - hi);
+            side(hi + 1, cntr, 1);
+            hi += cntr;
+        }
+        if (lo > 0) {
+            const int cntl = min(32, lo);
+            side(lo - 1, cntl, -1);
+            lo -= cntl;
+        }
+    }
+    if (!active) return;
+    // sort the kept set by (d2, idx)
+    for (int a = 1; a < cnt; ++a) {
+        const double d = ld[a * 32 + lane];
+        const int id = li[a * 32 + lane];
+        int pos = a;
+        while (pos > 0) {
+            const double pd = ld[(pos - 1) * 32 + lane];
+            const int pj = li[(pos - 1) * 32 + lane];
+            if (!(d < pd || (d == pd && id < pj))) break;
+            ld[pos * 32 + lane] = pd;
+            li[pos * 32 + lane] = pj;
+            --pos;
+        }
+        ld[pos * 32 + lane] = d;
+        li[pos * 32 + lane] = id;
+    }
+    int *oi = out_idx + ((size_t)b * n + qorig) * k;
+    double *od = out_d2 + ((size_t)b * n + qorig) * k;
+    for (int s = 0; s < k; ++s) {
+        oi[s] = s < cnt ? li[s * 32 + lane] : -1;
+        od[s] = s < cnt ? ld[s * 32 + lane] : CUDART_INF;
+    }
+}
+
+struct CullLayout {
+    size_t off_perm, off_sorted, off_sph, off_keys, off_bbox, total;
+    int n_pad;
+};
+CullLayout knn_cull_layout(int n, int batch)
+{
+    CullLayout L;
+    L.n_pad = (n + 31) / 32 * 32;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += orpcd_align_up(bytes, 256); return r; };
+    L.off_perm = take((size_t)batch * L.n_pad * sizeof(int));
+    L.off_sorted = take((size_t)batch * L.n_pad * 3 * sizeof(double));
+    L.off_sph = take((size_t)batch * (L.n_pad / 32) * sizeof(double4));
+    L.off_keys = take((size_t)batch * sort_pad(n) * sizeof(unsigned long long));
+    L.off_bbox = take((size_t)batch * 6 * sizeof(double));
+    L.total = o;
+    return L;
+}
+constexpr int KNN_CULL_MIN_N = 2048;   // below this the brute-force kernel is as fast
 
 size_t knn_smem_bytes(int k)
 {
@@ -308,9 +532,33 @@ __global__ void knn_bound_kernel(const int *__restrict__ cand, const double *__r
 
 }  // namespace
 
+// Splits of the point range per query: enough blocks to fill the GPU when there are few queries
+// (one 5000-point cloud is 157 warps for 148 SMs), at least 512 points per split.
+int orpcd_knn_splits(int n, int m, int batch)
+{
+    const long long warps = ((long long)m * batch + 31) / 32;
+    long long s = (148LL * 24 + warps - 1) / (warps > 0 ? warps : 1);
+    if (s > KNN_MAX_SPLITS) s = KNN_MAX_SPLITS;
+    if (s > n / 512) s = n / 512;
+    return s < 1 ? 1 : (int)s;
+}
+
+size_t orpcd_knn_scratch_bytes(int n, int m, int batch, int k)
+{
+    const int s = orpcd_knn_splits(n, m, batch);
+    size_t split = 0;
+    if (s > 1) {
+        const size_t e = (size_t)m * batch * s * k;
+        split = orpcd_align_up(e * sizeof(double), 256) + orpcd_align_up(e * sizeof(int), 256);
+    }
+    const size_t cull = (n == m && n >= KNN_CULL_MIN_N) ? knn_cull_layout(n, batch).total : 0;
+    return split > cull ? split : cull;
+}
+
+// d_scratch (orpcd_knn_scratch_bytes) may be NULL: the search then runs unsplit.
 int orpcd_launch_knn(const double *d_points, int n, long long points_stride, const double *d_queries,
                      int m, long long queries_stride, int batch, int k, int *d_idx, double *d_d2,
-                     cudaStream_t st)
+                     void *d_scratch, size_t scratch_bytes, cudaStream_t st)
 {
     if (!d_points || !d_queries || !d_idx || !d_d2 || n < 0 || m < 0 || batch < 0 || k < 1 ||
         k > ORPCD_MAX_KNN)
@@ -320,19 +568,64 @@ int orpcd_launch_knn(const double *d_points, int n, long long points_stride, con
     if (cudaFuncSetAttribute(knn_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess)
         return ORPCD_ERR_CUDA;
-    dim3 grid((m + KNN_BLOCK - 1) / KNN_BLOCK, batch);
-    knn_f64_kernel<<<grid, KNN_BLOCK, smem, st>>>(d_points, n, points_stride, d_queries, m,
-                                                  queries_stride, k, d_idx, d_d2);
+    const bool have_scratch = d_scratch && scratch_bytes >= orpcd_knn_scratch_bytes(n, m, batch, k) &&
+                              !((uintptr_t)d_scratch & 255);
+    if (have_scratch && d_queries == d_points && m == n && queries_stride == points_stride && n >= KNN_CULL_MIN_N &&
+        (batch == 1 || points_stride == (long long)n * 3)) {
+        // self query: Hilbert order, chunk spheres, culled scan
+        const CullLayout L = knn_cull_layout(n, batch);
+        unsigned char *w = (unsigned char *)d_scratch;
+        int *perm = (int *)(w + L.off_perm);
+        double *sorted = (double *)(w + L.off_sorted);
+        double4 *sph = (double4 *)(w + L.off_sph);
+        if (spatial_perm(d_points, n, batch, L.n_pad, (double *)(w + L.off_bbox), (unsigned long long *)(w + L.off_keys),
+                         perm, st) != 0)
+            return ORPCD_ERR_CUDA;
+        const int n_chunks = L.n_pad / 32;
+        knn_cull_prep_kernel<<<dim3(n_chunks, batch), 32, 0, st>>>(d_points, n, perm, L.n_pad, sorted, sph);
+        const size_t sm = (size_t)KC_WARPS * k * 32 * (sizeof(double) + sizeof(int));
+        if (cudaFuncSetAttribute(knn_cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+            return ORPCD_ERR_CUDA;
+        knn_cull_kernel<<<dim3((n_chunks + KC_WARPS - 1) / KC_WARPS, batch), KC_WARPS * 32, sm, st>>>(
+            sorted, sph, perm, n, L.n_pad, k, d_idx, d_d2);
+        ORPCD_CHECK_LAUNCH();
+        return ORPCD_OK;
+    }
+    int splits = orpcd_knn_splits(n, m, batch);
+    if (!d_scratch || scratch_bytes < orpcd_knn_scratch_bytes(n, m, batch, k) || ((uintptr_t)d_scratch & 255)) splits = 1;
+    if (splits <= 1) {
+        dim3 grid((m + KNN_BLOCK - 1) / KNN_BLOCK, batch, 1);
+        knn_f64_kernel<<<grid, KNN_BLOCK, smem, st>>>(d_points, n, points_stride, d_queries, m, queries_stride, k,
+                                                      n > 0 ? n : 1, d_idx, d_d2);
+        ORPCD_CHECK_LAUNCH();
+        return ORPCD_OK;
+    }
+    const size_t e = (size_t)m * batch * splits * k;
+    double *pd = (double *)d_scratch;
+    int *pi = (int *)((unsigned char *)d_scratch + orpcd_align_up(e * sizeof(double), 256));
+    dim3 grid((m + KNN_BLOCK - 1) / KNN_BLOCK, batch, splits);
+    knn_f64_kernel<<<grid, KNN_BLOCK, smem, st>>>(d_points, n, points_stride, d_queries, m, queries_stride, k,
+                                                  (n + splits - 1) / splits, pi, pd);
+    ORPCD_CHECK_LAUNCH();
+    const long long nq = (long long)m * batch;
+    knn_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(pi, pd, nq, splits, k, d_idx, d_d2);
     ORPCD_CHECK_LAUNCH();
     return ORPCD_OK;
 }
 
+ORPCD_API size_t orpcd_knn_exact_workspace_bytes(int n, int m, int batch, int k)
+{
+    if (n <= 0 || m <= 0 || batch <= 0 || k < 1) return 0;
+    return orpcd_knn_scratch_bytes(n, m, batch, k);
+}
+
 ORPCD_API int orpcd_knn_exact(const double *d_points, int n, long long points_stride,
                               const double *d_queries, int m, long long queries_stride, int batch,
-                              int k, int *d_idx, double *d_d2, orpcd_stream_t stream)
+                              int k, int *d_idx, double *d_d2, void *d_workspace, size_t workspace_bytes,
+                              orpcd_stream_t stream)
 {
     return orpcd_launch_knn(d_points, n, points_stride, d_queries, m, queries_stride, batch, k, d_idx,
-                            d_d2, (cudaStream_t)stream);
+                            d_d2, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 ORPCD_API size_t orpcd_sor_workspace_bytes(int n, int nb_neighbors)
@@ -340,7 +633,7 @@ ORPCD_API size_t orpcd_sor_workspace_bytes(int n, int nb_neighbors)
     if (n <= 0 || nb_neighbors < 1) return 0;
     const size_t nn = (size_t)n * nb_neighbors;
     return orpcd_align_up(nn * sizeof(double), 256) + orpcd_align_up(nn * sizeof(int), 256) +
-           orpcd_align_up((size_t)n * sizeof(double), 256);
+           orpcd_align_up((size_t)n * sizeof(double), 256) + orpcd_knn_scratch_bytes(n, n, 1, nb_neighbors);
 }
 
 ORPCD_API int orpcd_sor_mask(const double *d_points, int n, int nb_neighbors, double std_ratio,
@@ -361,7 +654,9 @@ ORPCD_API int orpcd_sor_mask(const double *d_points, int n, int nb_neighbors, do
     int *idx = (int *)w;
     w += orpcd_align_up(nn * sizeof(int), 256);
     double *avg = d_avg ? d_avg : (double *)w;
-    int rc = orpcd_launch_knn(d_points, n, 0, d_points, n, 0, 1, nb_neighbors, idx, d2, st);
+    w += orpcd_align_up((size_t)n * sizeof(double), 256);
+    int rc = orpcd_launch_knn(d_points, n, 0, d_points, n, 0, 1, nb_neighbors, idx, d2, w,
+                              orpcd_knn_scratch_bytes(n, n, 1, nb_neighbors), st);
     if (rc != ORPCD_OK) return rc;
     const int tb = 128, gb = (n + tb - 1) / tb;
     sor_avg_kernel<<<gb, tb, 0, st>>>(d2, n, nb_neighbors, avg);

@@ -86,7 +86,9 @@ def lib():
     L.orpcd_error_string.restype = C.c_char_p
     L.orpcd_error_string.argtypes = [ip]
     L.orpcd_knn_exact.restype = ip
-    L.orpcd_knn_exact.argtypes = [vp, ip, ll, vp, ip, ll, ip, ip, vp, vp, vp]
+    L.orpcd_knn_exact.argtypes = [vp, ip, ll, vp, ip, ll, ip, ip, vp, vp, vp, sz, vp]
+    L.orpcd_knn_exact_workspace_bytes.restype = sz
+    L.orpcd_knn_exact_workspace_bytes.argtypes = [ip, ip, ip, ip]
     L.orpcd_knn_candidate_bound.restype = ip
     L.orpcd_knn_candidate_bound.argtypes = [vp, vp, ip, ip, vp, vp]
     L.orpcd_knn_rerank_workspace_bytes.restype = sz

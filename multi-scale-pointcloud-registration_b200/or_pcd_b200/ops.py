@@ -36,9 +36,12 @@ def knn_exact(points, queries, k: int):
     M = queries.shape[1]
     idx = t.empty((B, M, k), dtype=t.int32, device="cuda")
     d2 = t.empty((B, M, k), dtype=t.float64, device="cuda")
-    check(_lib.lib().orpcd_knn_exact(points.data_ptr(), N, N * 3, queries.data_ptr(), M, M * 3, B, k,
-                                     idx.data_ptr(), d2.data_ptr(), _lib.stream_ptr()), "orpcd_knn_exact")
-    launch_counter["kernels"] += 1
+    L = _lib.lib()
+    nws = L.orpcd_knn_exact_workspace_bytes(N, M, B, k)
+    ws = _lib.workspace(nws) if nws else None
+    check(L.orpcd_knn_exact(points.data_ptr(), N, N * 3, queries.data_ptr(), M, M * 3, B, k, idx.data_ptr(),
+                            d2.data_ptr(), ws.data_ptr() if nws else None, nws, _lib.stream_ptr()), "orpcd_knn_exact")
+    launch_counter["kernels"] += 2 if nws else 1
     return (idx[0], d2[0]) if squeeze else (idx, d2)
 
 

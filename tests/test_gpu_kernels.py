@@ -38,6 +38,32 @@ def test_knn_ties_duplicates_and_small_clouds(oracle):
             assert np.array_equal(d2.cpu().numpy(), od)
 
 
+@pytest.mark.parametrize("k", [20, 48, 64])
+def test_knn_self_query_culled_path(oracle, armadillo_pair, k):
+    """Self query on clouds >= 2048 points runs the Hilbert-ordered, chunk-culled kernel: same lists as the
+    oracle, on a real scan, on a lattice (every distance tied many times) and with duplicated points; batched
+    launches of several clouds too."""
+    from or_pcd_b200 import ops
+
+    s, t, _ = armadillo_pair
+    g = np.stack(np.meshgrid(np.arange(16.0), np.arange(16.0), np.arange(9.0), indexing="ij"), -1).reshape(-1, 3)
+    rng = np.random.default_rng(11)
+    dup = np.concatenate([s[:1500], s[:1500], s[200:300], rng.standard_normal((37, 3)) * 0.3])
+    for pts in (s, g[rng.permutation(len(g))], dup):
+        d = _dev(pts)
+        idx, d2 = ops.knn_exact(d, d, k)
+        oi, od = oracle.knn(pts, pts, k, method="brute")
+        assert np.array_equal(idx.cpu().numpy(), oi), (len(pts), k)
+        assert np.array_equal(d2.cpu().numpy(), od)
+    if k == 20:
+        batch = np.stack([t[:4900] * sc for sc in ([1, 1, 1], [1.2, 1, 1], [1, 0.8, 1])])
+        d = _dev(batch)
+        idx, d2 = ops.knn_exact(d, d, k)
+        for b in range(3):
+            oi, od = oracle.knn(batch[b], batch[b], k)
+            assert np.array_equal(idx[b].cpu().numpy(), oi) and np.array_equal(d2[b].cpu().numpy(), od)
+
+
 def test_knn_batched(oracle):
     from or_pcd_b200 import ops
 
