@@ -538,7 +538,7 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                 // distance from the chunk centre to the patch's bounding box (tighter than its bounding sphere)
                 const float bx = fmaxf(fmaxf(lo[0] - sp.x, sp.x - hi[0]), 0.f), by = fmaxf(fmaxf(lo[1] - sp.y, sp.y - hi[1]), 0.f);
                 const float bz = fmaxf(fmaxf(lo[2] - sp.z, sp.z - hi[2]), 0.f);
-                need = !(sqrtf(bx * bx + by * by + bz * bz) - sp.w > reach_box);
+                need = !(sqrtf(__fmaf_rn(bx, bx, __fmaf_rn(by, by, bz * bz))) - sp.w > reach_box);
             }
             unsigned bal = __ballot_sync(0xffffffffu, need);
             while (bal) {
@@ -555,8 +555,9 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                     unpack_f2(qz[h], z0, z1);
                     const float ax = x0 - sx, ay = y0 - sy, az = z0 - sz, bx = x1 - sx, by = y1 - sy, bz = z1 - sz;
                     const float ta = dq[2 * h] + sr, tb = dq[2 * h + 1] + sr;
-                    mine |= (ax * ax + ay * ay + az * az) <= ta * ta * (1.f + 1e-6f);
-                    mine |= (bx * bx + by * by + bz * bz) <= tb * tb * (1.f + 1e-6f);
+                    // (the library is built -fmad=false for the float64 code: FP32 FMAs are written out)
+                    mine |= __fmaf_rn(ax, ax, __fmaf_rn(ay, ay, az * az)) <= ta * ta * (1.f + 1e-6f);
+                    mine |= __fmaf_rn(bx, bx, __fmaf_rn(by, by, bz * bz)) <= tb * tb * (1.f + 1e-6f);
                 }
                 if (__any_sync(0xffffffffu, mine)) {
                     if (lane == 0) vl[nv] = (unsigned short)(base + l - pass);
