@@ -92,6 +92,8 @@ struct Ctx {
     int *sperm;          // [src_sets][n_src]  spatially sorted position -> original source index
     int *tperm;          // [tgt_sets][nt_pad] spatially sorted position -> original target index (-1 = padding)
     float4 *chunk_sph;   // [tgt_sets][n_chunks] bounding sphere (centre, radius) of each 32-target chunk, centred coords
+    float4 *super_sph;   // [tgt_sets][n_super] bounding sphere of each group of 32 chunks (1024 targets)
+    int n_super;
     unsigned long long *sortbuf;  // Morton keys being sorted
     double *bbox;        // [max(src_sets, tgt_sets)][6]
     float dcap;          // max correspondence distance (inflated): nothing farther is ever needed
@@ -259,6 +261,25 @@ __global__ void __launch_bounds__(1024) prep_targets_kernel(Ctx c)
         float r = valid ? sqrtf((x - mx) * (x - mx) + (y - my) * (y - my) + (z - mz) * (z - mz)) : 0.f;
         for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
         if (lane == 0) sph[ch] = make_float4(mx, my, mz, r * (1.f + 1e-5f) + 1e-30f);
+    }
+    __syncthreads();
+    // second level: one sphere around each group of 32 chunk spheres
+    float4 *ssph = c.super_sph + (size_t)s * c.n_super;
+    for (int g = wid; g < c.n_super; g += (int)(blockDim.x >> 5)) {
+        const int ch = g * 32 + lane;
+        const bool valid = ch < c.n_chunks;
+        const float4 t = valid ? sph[ch] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float lo[3] = {valid ? t.x - t.w : CUDART_INF_F, valid ? t.y - t.w : CUDART_INF_F, valid ? t.z - t.w : CUDART_INF_F};
+        float hi[3] = {valid ? t.x + t.w : -CUDART_INF_F, valid ? t.y + t.w : -CUDART_INF_F, valid ? t.z + t.w : -CUDART_INF_F};
+        for (int k = 0; k < 3; ++k)
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+                hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+            }
+        const float mx = 0.5f * (lo[0] + hi[0]), my = 0.5f * (lo[1] + hi[1]), mz = 0.5f * (lo[2] + hi[2]);
+        float r = valid ? sqrtf((t.x - mx) * (t.x - mx) + (t.y - my) * (t.y - my) + (t.z - mz) * (t.z - mz)) + t.w : 0.f;
+        for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+        if (lane == 0) ssph[g] = make_float4(mx, my, mz, r * (1.f + 1e-5f) + 1e-30f);
     }
 }
 
@@ -473,7 +494,8 @@ constexpr int CULL_LIST = 1024;    // visit-list capacity per pass (chunk ids)
 // Returns the number of chunks the warp visited.  `ring` / `vl` are this warp's private shared memory.
 template <int Q>
 __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__restrict__ tg, const float4 *__restrict__ sph,
-                                               float rmax_tgt, int cb, int ce, const float4 (&qv)[Q],
+                                               const float4 *__restrict__ ssph, int n_super, float rmax_tgt, int cb,
+                                               int ce, const float4 (&qv)[Q],
                                                float4 (*ring)[NN_CH], unsigned short *vl, float (&m1)[Q], int (&c1)[Q],
                                                float (&m2)[Q])
 {
@@ -529,7 +551,22 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
         //    iff SOME query q of the patch has it within reach, dist(q, chunk centre) <= d_ub(q) + r_chunk.
         const int pe = min(ce, pass + CULL_LIST);
         int nv = 0;
-        for (int base = pass; base < pe; base += 32) {
+        // level 1: the 32 groups of 32 chunks of this pass (pass boundaries are multiples of 1024 chunks)
+        bool gneed = false;
+        {
+            const int g = pass / 32 + lane;
+            if (g < n_super && g * 32 < pe) {
+                const float4 sp = __ldg(ssph + g);
+                const float bx = fmaxf(fmaxf(lo[0] - sp.x, sp.x - hi[0]), 0.f), by = fmaxf(fmaxf(lo[1] - sp.y, sp.y - hi[1]), 0.f);
+                const float bz = fmaxf(fmaxf(lo[2] - sp.z, sp.z - hi[2]), 0.f);
+                gneed = !(sqrtf(__fmaf_rn(bx, bx, __fmaf_rn(by, by, bz * bz))) - sp.w > reach_box);
+            }
+        }
+        unsigned gbal = __ballot_sync(0xffffffffu, gneed);
+        while (gbal) {
+            const int gl = __ffs(gbal) - 1;
+            gbal &= gbal - 1;
+            const int base = pass + gl * 32;
             const int chunk = base + lane;
             bool need = false;
             float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -641,8 +678,9 @@ __global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, i
     int c1[Q];
     const int cb = split * c.chunks_per_split;
     const int ce = min(c.n_chunks, cb + c.chunks_per_split);
-    const int visited = cull_sweep_core<Q>(c, tg, sph, (float)c.tgt_meta[st.tgt_set].rmax, cb, ce, qv, ring[warp],
-                                           vlist[warp], m1, c1, m2);
+    const int visited = cull_sweep_core<Q>(c, tg, sph, c.super_sph + (size_t)st.tgt_set * c.n_super, c.n_super,
+                                           (float)c.tgt_meta[st.tgt_set].rmax, cb, ce, qv, ring[warp], vlist[warp], m1,
+                                           c1, m2);
     const size_t pbase = ((size_t)u * c.splits + split) * c.n_src;
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
@@ -770,19 +808,33 @@ __device__ __forceinline__ void exact_search_warp(const Ctx &c, int tgt_set, dou
     for (int o = 16; o > 0; o >>= 1) wb = fmin(wb, __shfl_xor_sync(0xffffffffu, wb, o));
     const float mag = fabsf(qfx) + fabsf(qfy) + fabsf(qfz) + (float)c.tgt_meta[tgt_set].rmax;
     const float thr = __double2float_ru(sqrt(wb)) * (1.f + 4e-6f) + 8e-6f * mag;   // inf if chunk c1 was empty
-    for (int base = 0; base < c.n_chunks; base += 32) {
-        const int chunk = base + lane;
-        bool need = false;
-        if (chunk < c.n_chunks && chunk != c1) {
-            const float4 sp = sph[chunk];
+    const float4 *ssph = c.super_sph + (size_t)tgt_set * c.n_super;
+    for (int gbase = 0; gbase < c.n_super; gbase += 32) {
+        // level 1: groups of 32 chunks
+        bool gneed = false;
+        if (gbase + lane < c.n_super) {
+            const float4 sp = ssph[gbase + lane];
             const float sx = sp.x - qfx, sy = sp.y - qfy, sz = sp.z - qfz;
-            need = !(sqrtf(sx * sx + sy * sy + sz * sz) - sp.w > thr);
+            gneed = !(sqrtf(sx * sx + sy * sy + sz * sz) - sp.w > thr);
         }
-        unsigned bal = __ballot_sync(0xffffffffu, need);
-        while (bal) {
-            const int l = __ffs(bal) - 1;
-            bal &= bal - 1;
-            score(base + l);
+        unsigned gbal = __ballot_sync(0xffffffffu, gneed);
+        while (gbal) {
+            const int gl = __ffs(gbal) - 1;
+            gbal &= gbal - 1;
+            const int base = (gbase + gl) * 32;
+            const int chunk = base + lane;
+            bool need = false;
+            if (chunk < c.n_chunks && chunk != c1) {
+                const float4 sp = sph[chunk];
+                const float sx = sp.x - qfx, sy = sp.y - qfy, sz = sp.z - qfz;
+                need = !(sqrtf(sx * sx + sy * sy + sz * sz) - sp.w > thr);
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, need);
+            while (bal) {
+                const int l = __ffs(bal) - 1;
+                bal &= bal - 1;
+                score(base + l);
+            }
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -1280,7 +1332,8 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     // ---- 2. sweep
     float m1[Q], m2[Q];
     int c1[Q];
-    const int visited = cull_sweep_core<Q>(c, tg, c.chunk_sph + (size_t)tgt_set * c.n_chunks, (float)tm.rmax, 0,
+    const int visited = cull_sweep_core<Q>(c, tg, c.chunk_sph + (size_t)tgt_set * c.n_chunks,
+                                           c.super_sph + (size_t)tgt_set * c.n_super, c.n_super, (float)tm.rmax, 0,
                                            c.n_chunks, qv, ring, vl, m1, c1, m2);
     if (lane == 0)
         atomicAdd(c.visit_count + round, (unsigned long long)visited * NN_CH * min(32 * Q, c.n_src - wbase));
@@ -1433,7 +1486,7 @@ __global__ void __launch_bounds__(256) unpermute_corr_kernel(Ctx c, int *__restr
 struct Layout {
     size_t off_state, off_pts, off_cov, off_qf, off_corr, off_d2, off_m1, off_c1, off_m2, off_tgt4, off_meta,
         off_partial, off_counter, off_worklist, off_wcount, off_ract, off_done, off_visit, off_sperm, off_tperm,
-        off_sph, off_sort, off_bbox, total;
+        off_sph, off_ssph, off_sort, off_bbox, total;
     int nt_pad, n_chunks, splits, chunks_per_split, red_blocks, q_tiles, nn_q, nn_tj, cov_stride, smem_pad, nn_mode;
     int cull;
     int fused;       // one gicp_round_kernel launch per round instead of update / sweep / resolve / fix / reduce
@@ -1468,6 +1521,7 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
         s = (int)((want + blocks - 1) / blocks);
         if (s > 8) s = 8;
     }
+    if (L.cull) s = 1;   // the culled sweep walks whole groups of 32 chunks: one split
     const int s_max = L.n_chunks / 8 > 1 ? L.n_chunks / 8 : 1;
     if (s > s_max) s = s_max;
     if (s < 1) s = 1;
@@ -1501,6 +1555,7 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     L.off_sperm = take((size_t)p->n_src_sets * ns * sizeof(int));
     L.off_tperm = take((size_t)p->n_tgt_sets * L.nt_pad * sizeof(int));
     L.off_sph = take((size_t)p->n_tgt_sets * L.n_chunks * sizeof(float4));
+    L.off_ssph = take((size_t)p->n_tgt_sets * ((L.n_chunks + 31) / 32) * sizeof(float4));
     const size_t sort_s = (size_t)p->n_src_sets * sort_pad(p->n_src), sort_t = (size_t)p->n_tgt_sets * sort_pad(p->n_tgt);
     L.off_sort = take((sort_s > sort_t ? sort_s : sort_t) * sizeof(unsigned long long));
     L.off_bbox = take((size_t)(p->n_src_sets > p->n_tgt_sets ? p->n_src_sets : p->n_tgt_sets) * 6 * sizeof(double));
@@ -1539,6 +1594,8 @@ void fill_ctx(const orpcd_gicp_params *p, const Layout &L, void *ws, Ctx &c)
     c.sperm = (int *)(w + L.off_sperm);
     c.tperm = (int *)(w + L.off_tperm);
     c.chunk_sph = (float4 *)(w + L.off_sph);
+    c.super_sph = (float4 *)(w + L.off_ssph);
+    c.n_super = (L.n_chunks + 31) / 32;
     c.sortbuf = (unsigned long long *)(w + L.off_sort);
     c.bbox = (double *)(w + L.off_bbox);
     c.dcap = (float)(p->max_correspondence_distance * (1.0 + 1e-5)) * (1.f + 1e-6f) + 1e-30f;

@@ -1,0 +1,135 @@
+"""BASELINE configs 4 and 5 at their full sizes: synthetic anisotropically scaled + SE(3)-perturbed cloud
+pairs, one poll round of many scale candidates, batched GICP (and optionally FGR); wall time, registrations/s and
+size-independent checks of the results (exact correspondences on a sample, fitness/rmse recomputed independently).
+
+  python tools/scale_check.py 50000 256 1        # config 4: 50k points, 256 scale candidates x 1 start
+  python tools/scale_check.py 200000 32 32       # config 5: 200k points, 32 scales x 32 starts = 1024 units
+  python tools/scale_check.py 200000 32 32 fgr   # same through FastGlobalOptimizer
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "multi-scale-pointcloud-registration_b200"))
+sys.path.insert(0, ROOT)
+
+
+def make_pair(n, rng):
+    """SURVEY 8(d) config 4 generator: independent samples of one surface, target moved and scaled per axis."""
+    import bench
+
+    src = bench.synthetic_cloud(n, rng)
+    tgt = bench.synthetic_cloud(n, rng)
+    th = rng.uniform(-0.3, 0.3, 3)
+    cx, cy, cz = np.cos(th)
+    sx, sy, sz = np.sin(th)
+    R = (np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+         @ np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]))
+    true_scale = rng.uniform(0.5, 2.0, 3)
+    tgt = (tgt @ R + rng.normal(0, 0.05, 3)) * true_scale
+    return bench.radius_scale(src), bench.radius_scale(tgt), true_scale
+
+
+def latin_hypercube(n, rng, lo=0.5, hi=2.0):
+    u = (np.stack([rng.permutation(n) for _ in range(3)], 1) + rng.uniform(size=(n, 3))) / n
+    return lo + (hi - lo) * u
+
+
+def brute_nn_sample(moved, tgt, sample):
+    """Exact nearest target (float64, lowest index on ties) of moved[sample] by plain torch, in slabs."""
+    import torch
+
+    out_i = torch.empty(len(sample), dtype=torch.int64, device="cuda")
+    out_d = torch.empty(len(sample), dtype=torch.float64, device="cuda")
+    q = moved[sample]
+    for a in range(0, len(sample), 256):
+        d = ((q[a:a + 256, None, :] - tgt[None, :, :]) ** 2)
+        d2 = (d[..., 0] + d[..., 1]) + d[..., 2]
+        m, i = d2.min(1)
+        # lowest index among exact ties
+        first = (d2 == m[:, None]).to(torch.int8).argmax(1)
+        out_i[a:a + 256] = first
+        out_d[a:a + 256] = m
+    return out_i, out_d
+
+
+def main():
+    import torch
+
+    from or_pcd_b200 import _lib, ops
+    from or_pcd_b200.Optimizer import FastGlobalOptimizer, GeneralizedICP
+
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
+    n_scales = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+    n_starts = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    which = sys.argv[4] if len(sys.argv) > 4 else "gicp"
+    rng = np.random.default_rng(1234)
+    src, tgt, true_scale = make_pair(n, rng)
+    scales = latin_hypercube(n_scales, np.random.default_rng(7)) if n_scales > 1 else np.ones((1, 3))
+    import bench
+
+    rs = np.random.RandomState(11)
+    sources = np.empty((n_starts, n, 3))
+    for k in range(n_starts):
+        r, t = bench.start_pose(rs, 0.3, 0.05) if n_starts > 1 else (np.eye(3), np.zeros(3))
+        sources[k] = src @ r + t
+    targets = np.stack([tgt * s[None, :] for s in scales])
+    unit_src = np.tile(np.arange(n_starts, dtype=np.int32), n_scales)
+    unit_tgt = np.repeat(np.arange(n_scales, dtype=np.int32), n_starts)
+    U = len(unit_src)
+    d_src, d_tgt = _lib.to_device(sources), _lib.to_device(targets)
+    opt = GeneralizedICP() if which == "gicp" else FastGlobalOptimizer(feature_mode="fixed")
+    if which == "gicp":
+        opt.profile = True
+    torch.cuda.synchronize()
+    times = []
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = opt.optimize_batch(d_src, d_tgt, unit_src, unit_tgt, rigid_base=src)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    wall = min(times)
+    out = dict(optimizer=which, n_points=n, scales=n_scales, starts=n_starts, units=U, wall_s=wall,
+               registrations_per_s=U / wall, rmse_min=float(res.rmse[res.status == 0].min()) if (res.status == 0).any() else None,
+               failed_units=int((res.status != 0).sum()), mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
+    if which == "gicp":
+        p = res.profile
+        out.update(mean_iterations=float(res.iterations.mean()), round_kernel_ms=p[1], pairs_visited=p[2],
+                   visited_fraction=p[2] / max(p[7] * float(n) * n, 1), exact_fallback_fraction=p[4] / max(p[7] * n, 1))
+
+    # ---- checks on the best unit and on a few others: evaluate at the returned transform, compare a sample of the
+    # correspondences with a plain-torch exact search, and the fitness / rmse with sums taken here
+    ok = True
+    good = np.flatnonzero(res.status == 0)
+    check_units = list(dict.fromkeys([int(good[np.argmin(res.rmse[good])]), int(good[0]), int(good[-1])])) if len(good) else []
+    for u in check_units:
+        T = res.transforms[u].copy()
+        T[:3, :3] = T[:3, :3].T                                  # plugin convention -> column convention
+        us, ut = int(unit_src[u]), int(unit_tgt[u])
+        stats, status, corr, _ = ops.evaluate_batch(d_src[us:us + 1], d_tgt[ut:ut + 1], torch.zeros(1, dtype=torch.int32, device="cuda"),
+                                                    torch.zeros(1, dtype=torch.int32, device="cuda"),
+                                                    _lib.to_device(T[None]), 0.5, want_corr=True)
+        moved = d_src[us] @ _lib.to_device(T[:3, :3].T.copy()) + _lib.to_device(T[:3, 3].copy())
+        sample = torch.as_tensor(np.random.default_rng(u).choice(n, 2048, replace=False)).cuda()
+        bi, bd = brute_nn_sample(moved, d_tgt[ut], sample)
+        got = corr[0][sample].to(torch.int64)
+        within = bd < 0.25
+        # the device moves the cloud with the same un-fused arithmetic; allow the sample to disagree only where the
+        # two nearest targets are tied to rounding (none expected)
+        mism = int(((got != bi) & within).sum().item()) + int(((got != -1) & ~within).sum().item())
+        st = stats.cpu().numpy()[0]
+        rel_rmse = abs(st[1] - res.rmse[u]) / max(res.rmse[u], 1e-300)
+        out.setdefault("checks", []).append(dict(unit=u, sample_mismatches=mism, fitness=float(st[0]),
+                                                  rmse_eval=float(st[1]), rmse_reported=float(res.rmse[u]), rel=float(rel_rmse)))
+        ok = ok and mism == 0 and rel_rmse < 1e-9
+    out["ok"] = bool(ok)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
