@@ -133,6 +133,25 @@ __device__ __forceinline__ uint64_t fma2_sv(uint64_t a, float b, uint64_t c)
         : "=l"(d) : "l"(a), "f"(b), "l"(c));
     return d;
 }
+// packed FP32 pairs: a + {b,b}, a * b, a * b + c
+__device__ __forceinline__ uint64_t add2_s(uint64_t a, float b)
+{
+    uint64_t d;
+    asm("{\n\t.reg .b64 rb;\n\tmov.b64 rb, {%2, %2};\n\tadd.rn.f32x2 %0, %1, rb;\n\t}" : "=l"(d) : "l"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 __device__ __forceinline__ float min3f(float a, float b, float c)
 {
     float d;
@@ -540,6 +559,9 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
     const float reach_box = D * (1.f + 4e-6f) + 8e-6f * mag;   // a query is inside the box: only its own reach counts
 #pragma unroll
     for (int k = 0; k < Q; ++k) dq[k] = dq[k] * (1.f + 4e-6f) + 8e-6f * mag;   // per-query reach, inflated
+    uint64_t dq2[Q / 2];
+#pragma unroll
+    for (int h = 0; h < Q / 2; ++h) dq2[h] = pack_f2(dq[2 * h], dq[2 * h + 1]);
 
 #pragma unroll
     for (int k = 0; k < Q; ++k) { m1[k] = CUDART_INF_F; m2[k] = CUDART_INF_F; c1[k] = 0; }
@@ -586,15 +608,15 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                 bool mine = false;
 #pragma unroll
                 for (int h = 0; h < Q / 2; ++h) {
-                    float x0, x1, y0, y1, z0, z1;
-                    unpack_f2(qx[h], x0, x1);
-                    unpack_f2(qy[h], y0, y1);
-                    unpack_f2(qz[h], z0, z1);
-                    const float ax = x0 - sx, ay = y0 - sy, az = z0 - sz, bx = x1 - sx, by = y1 - sy, bz = z1 - sz;
-                    const float ta = dq[2 * h] + sr, tb = dq[2 * h + 1] + sr;
-                    // (the library is built -fmad=false for the float64 code: FP32 FMAs are written out)
-                    mine |= __fmaf_rn(ax, ax, __fmaf_rn(ay, ay, az * az)) <= ta * ta * (1.f + 1e-6f);
-                    mine |= __fmaf_rn(bx, bx, __fmaf_rn(by, by, bz * bz)) <= tb * tb * (1.f + 1e-6f);
+                    // both queries of the pair at once: |q - s|^2 <= (d_ub(q) + r)^2 (1 + 1e-6), packed FP32
+                    const uint64_t ax = add2_s(qx[h], -sx), ay = add2_s(qy[h], -sy), az = add2_s(qz[h], -sz);
+                    const uint64_t d2 = fma2(ax, ax, fma2(ay, ay, mul2(az, az)));
+                    const uint64_t tt = add2_s(dq2[h], sr);
+                    const uint64_t lim = mul2(mul2(tt, tt), pack_f2(1.f + 1e-6f, 1.f + 1e-6f));
+                    float d0, d1, l0, l1;
+                    unpack_f2(d2, d0, d1);
+                    unpack_f2(lim, l0, l1);
+                    mine |= (d0 <= l0) | (d1 <= l1);
                 }
                 if (__any_sync(0xffffffffu, mine)) {
                     if (lane == 0) vl[nv] = (unsigned short)(base + l - pass);
