@@ -511,7 +511,10 @@ constexpr int CULL_LIST = 1024;    // visit-list capacity per pass (chunk ids)
 // (lanes past the end of the cloud carry a copy of another query of the same patch); chunks [cb, ce) of the
 // target table; results per query: best chunk minimum m1, its chunk c1, second-best chunk minimum m2.
 // Returns the number of chunks the warp visited.  `ring` / `vl` are this warp's private shared memory.
-template <int Q>
+// SUB = false: (m1, c1, m2) fold per 32-target chunk, c1 = chunk id.  SUB = true: fold per 8-target sub-chunk,
+// c1 = chunk * 4 + sub-chunk, m2 = second-best sub-chunk minimum (the certificate works at either granularity; the
+// finer one leaves the caller 8 candidates to re-score instead of 32).
+template <int Q, bool SUB>
 __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__restrict__ tg, const float4 *__restrict__ sph,
                                                const float4 *__restrict__ ssph, int n_super, float rmax_tgt, int cb,
                                                int ce, const float4 (&qv)[Q],
@@ -638,6 +641,7 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
             cp_async_wait<CULL_RING - 1>();
             __syncwarp();
             const float4 *tc = ring[k % CULL_RING];
+            const int chunk = pass + vl[k];
             float mc[Q];
 #pragma unroll
             for (int q = 0; q < Q; ++q) mc[q] = CUDART_INF_F;
@@ -664,13 +668,24 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                         mc[2 * h + 1] = min3f(mc[2 * h + 1], h0, h1);
                     }
                 }
-            }
-            const int chunk = pass + vl[k];
+                if (SUB && ((j + TJ) & 7) == 0) {   // end of an 8-target sub-chunk
+                    const int id = chunk * 4 + (j >> 3);
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                m2[q] = fminf(m2[q], fmaxf(m1[q], mc[q]));
-                c1[q] = mc[q] < m1[q] ? chunk : c1[q];
-                m1[q] = fminf(m1[q], mc[q]);
+                    for (int q = 0; q < Q; ++q) {
+                        m2[q] = fminf(m2[q], fmaxf(m1[q], mc[q]));
+                        c1[q] = mc[q] < m1[q] ? id : c1[q];
+                        m1[q] = fminf(m1[q], mc[q]);
+                        mc[q] = CUDART_INF_F;
+                    }
+                }
+            }
+            if (!SUB) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    m2[q] = fminf(m2[q], fmaxf(m1[q], mc[q]));
+                    c1[q] = mc[q] < m1[q] ? chunk : c1[q];
+                    m1[q] = fminf(m1[q], mc[q]);
+                }
             }
             __syncwarp();   // everyone is done with this slot before it is refilled
         }
@@ -700,7 +715,7 @@ __global__ void __launch_bounds__(CULL_WARPS * 32) nn_sweep_cull_kernel(Ctx c, i
     int c1[Q];
     const int cb = split * c.chunks_per_split;
     const int ce = min(c.n_chunks, cb + c.chunks_per_split);
-    const int visited = cull_sweep_core<Q>(c, tg, sph, c.super_sph + (size_t)st.tgt_set * c.n_super, c.n_super,
+    const int visited = cull_sweep_core<Q, false>(c, tg, sph, c.super_sph + (size_t)st.tgt_set * c.n_super, c.n_super,
                                            (float)c.tgt_meta[st.tgt_set].rmax, cb, ce, qv, ring[warp], vlist[warp], m1,
                                            c1, m2);
     const size_t pbase = ((size_t)u * c.splits + split) * c.n_src;
@@ -1354,13 +1369,13 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     // ---- 2. sweep
     float m1[Q], m2[Q];
     int c1[Q];
-    const int visited = cull_sweep_core<Q>(c, tg, c.chunk_sph + (size_t)tgt_set * c.n_chunks,
+    const int visited = cull_sweep_core<Q, true>(c, tg, c.chunk_sph + (size_t)tgt_set * c.n_chunks,
                                            c.super_sph + (size_t)tgt_set * c.n_super, c.n_super, (float)tm.rmax, 0,
                                            c.n_chunks, qv, ring, vl, m1, c1, m2);
     if (lane == 0)
         atomicAdd(c.visit_count + round, (unsigned long long)visited * NN_CH * min(32 * Q, c.n_src - wbase));
 
-    // ---- 3. certificate (nn_resolve_kernel's bound), then each lane scans the best chunk of its own queries:
+    // ---- 3. certificate (nn_resolve_kernel's bound), then each lane scans the best 8-target sub-chunk of its own queries:
     //         the FP32 values are recomputed with the sweep's FMA chain (bit-identical), and the chunk decides
     //         the query iff exactly one target lies within the certified margin of the minimum
     int tj[Q];          // matched target (original index); -1 none within the cut-off; -2 exact search needed
@@ -1379,17 +1394,17 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
         const bool none = !(m1[k] < CUDART_INF_F);        // no chunk visited: nothing within the cut-off
         const bool cross = !((double)m2[k] > lim);        // another chunk may hold the true neighbour
         const float thr = __double2float_ru(lim);
-        const float4 *tc = tg + (size_t)c1[k] * NN_CH;
+        const float4 *tc = tg + (size_t)c1[k] * 8;   // c1 = 8-target sub-chunk (cull_sweep_core<Q, true>)
         int cnt = 0, first = 0;
-#pragma unroll 8
-        for (int j = 0; j < NN_CH; ++j) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
             const float4 t = __ldg(tc + j);
             const float sv = __fmaf_rn(fx, t.x, __fmaf_rn(fy, t.y, __fmaf_rn(fz, t.z, t.w)));
             const bool in = sv <= thr;
             first = (in && cnt == 0) ? j : first;
             cnt += in ? 1 : 0;
         }
-        tj[k] = none ? -1 : ((cross || cnt != 1) ? -2 : tperm[(size_t)c1[k] * NN_CH + first]);
+        tj[k] = none ? -1 : ((cross || cnt != 1) ? -2 : tperm[(size_t)c1[k] * 8 + first]);
         if (wbase + k * 32 + lane >= c.n_src) tj[k] = -1;
     }
 
@@ -1409,7 +1424,7 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
             const float qfz = __shfl_sync(0xffffffffu, qv[k].z, l);
             double best;
             int bj;
-            exact_search_warp(c, tgt_set, p[0], p[1], p[2], qfx, qfy, qfz, __shfl_sync(0xffffffffu, c1[k], l), best, bj);
+            exact_search_warp(c, tgt_set, p[0], p[1], p[2], qfx, qfy, qfz, __shfl_sync(0xffffffffu, c1[k], l) >> 2, best, bj);
             if (lane == l) { tj[k] = bj == 0x7fffffff ? -1 : bj; fd2[k] = best; }
         }
     }
