@@ -141,6 +141,18 @@ int orpcd_apply_scale_batch(const double *d_points, int n, const double *d_scale
                             int n_scales, double *d_out, orpcd_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * source @ R_u + t_u for a batch of random starts (row-vector convention of
+ * Aligner/Aligner.py:183-185, `np.dot(source, rotation) + translation`).
+ * d_rot: [n_units][3][3] row-major; d_trans: [n_units][3]; d_out: [n_units][n][3].
+ * Same arithmetic as numpy's expression (OpenBLAS dgemm: x R0j, then two fused
+ * multiply-adds over k, then one rounded add of t_j), so the clouds are bit-identical
+ * to the host's; the Aligner verifies that once before relying on it.
+ * ---------------------------------------------------------------------- */
+int orpcd_apply_rigid_batch(const double *d_points, int n, const double *d_rot,
+                            const double *d_trans, int n_units, double *d_out,
+                            orpcd_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Batched Generalized-ICP: n_units independent inner registrations
  * (one per multi-start x scale candidate) advanced together, one launch
  * sequence per Gauss-Newton iteration for all of them.

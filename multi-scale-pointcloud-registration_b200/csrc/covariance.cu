@@ -280,6 +280,34 @@ ORPCD_API int orpcd_normals_cov_from_knn(const double *d_points, int n, long lon
     return ORPCD_OK;
 }
 
+// out[u][i] = points[i] @ R_u + t_u (row-vector convention of Aligner/Aligner.py:183-185) with the arithmetic of
+// numpy's np.dot(source, rotation) + translation: OpenBLAS' dgemm micro-kernels accumulate over k with fused
+// multiply-adds, acc = x R0j; acc = fma(y, R1j, acc); acc = fma(z, R2j, acc), then one rounded add of t_j
+// (checked bit for bit against numpy in tests/ and by the Aligner before it relies on it).  One thread per point.
+__global__ void __launch_bounds__(256)
+apply_rigid_kernel(const double *__restrict__ pts, int n, const double *__restrict__ rot, const double *__restrict__ trans,
+                   double *__restrict__ out)
+{
+    const int u = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *R = rot + (size_t)u * 9, *t = trans + (size_t)u * 3;
+    const double x = pts[(size_t)i * 3], y = pts[(size_t)i * 3 + 1], z = pts[(size_t)i * 3 + 2];
+    double *o = out + ((size_t)u * n + i) * 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        o[j] = __dadd_rn(fma(z, R[6 + j], fma(y, R[3 + j], __dmul_rn(x, R[j]))), t[j]);
+}
+
+ORPCD_API int orpcd_apply_rigid_batch(const double *d_points, int n, const double *d_rot, const double *d_trans,
+                                      int n_units, double *d_out, orpcd_stream_t stream)
+{
+    if (!d_points || !d_rot || !d_trans || !d_out || n < 0 || n_units < 0 || n_units > 65535) return ORPCD_ERR_INVALID;
+    if (n == 0 || n_units == 0) return ORPCD_OK;
+    apply_rigid_kernel<<<dim3((n + 255) / 256, n_units), 256, 0, (cudaStream_t)stream>>>(d_points, n, d_rot, d_trans, d_out);
+    ORPCD_CHECK_LAUNCH();
+    return ORPCD_OK;
+}
+
 ORPCD_API int orpcd_apply_scale_batch(const double *d_points, int n, const double *d_scales,
                                       int n_scales, double *d_out, orpcd_stream_t stream)
 {

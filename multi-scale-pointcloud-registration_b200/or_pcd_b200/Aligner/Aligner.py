@@ -82,6 +82,9 @@ class Aligner:
         self.decision_log: List[dict] = []
         self.n_optimize_calls = 0          # inner registrations the sequential reference would have run
         self.n_units_evaluated = 0         # inner registrations actually run (speculation included)
+        self.device_starts = True          # build the start clouds on the GPU when the optimizer allows it
+        self._d_source, self._d_source_key = None, None
+        self._device_starts_verified = False
 
     # ------------------------------------------------------------------ starts
     def initialize_rotation(self) -> Tuple[np.ndarray, np.ndarray]:
@@ -97,16 +100,48 @@ class Aligner:
         translation = self._mu + np.random.randn(3) * self._std
         return rotation, translation
 
+    def _device_starts(self) -> bool:
+        """True when the optimizer takes start clouds built on the GPU: ``source @ R + t`` evaluated by
+        orpcd_apply_rigid_batch with the arithmetic of numpy's BLAS (k-ordered fused multiply-adds), verified
+        bit for bit against the host expression on the first batch -- a 1-ulp difference in a start cloud
+        is enough to move a non-converged registration to another local minimum."""
+        return self.device_starts and bool(getattr(self._optimizer, "accepts_device_sources", False))
+
     def _draw_starts(self, source: np.ndarray):
-        """Draw ``attempts`` starts and build their initial source clouds on the host with
-        the reference's own expression (Aligner.py:183-185) so inputs are bit-identical."""
-        rots, trans, clouds = [], [], np.empty((self._attempts,) + source.shape, dtype=np.float64)
+        """Draw ``attempts`` starts.  Host path: their initial source clouds are built with the reference's
+        own expression (Aligner.py:183-185) so inputs are bit-identical; device path: clouds is None and
+        ``_start_clouds`` builds the whole batch on the GPU."""
+        rots, trans = [], []
+        device = self._device_starts()
+        clouds = None if device else np.empty((self._attempts,) + source.shape, dtype=np.float64)
         for n in range(self._attempts):
             r, t = self.initialize_rotation()
             rots.append(r)
             trans.append(t)
-            clouds[n] = np.dot(source, r) + t
+            if not device:
+                clouds[n] = np.dot(source, r) + t
         return rots, trans, clouds
+
+    def _start_clouds(self, source: np.ndarray, starts):
+        """Initial source clouds of a list of ``_draw_starts`` results, one batch: host ndarray, or a CUDA
+        tensor when the optimizer accepts device sources."""
+        if not self._device_starts():
+            return np.concatenate([s[2] for s in starts], axis=0)
+        from .. import _lib, ops
+
+        if self._d_source_key is not source:   # the array itself is kept, so the identity cannot be recycled
+            self._d_source, self._d_source_key = _lib.to_device(source), source
+        rots = np.stack([r for s in starts for r in s[0]])
+        trans = np.stack([t for s in starts for t in s[1]])
+        clouds = ops.apply_rigid_batch(self._d_source, _lib.to_device(rots), _lib.to_device(trans))
+        if not self._device_starts_verified:
+            k = len(rots) - 1
+            if not np.array_equal(clouds[k].cpu().numpy(), np.dot(source, rots[k]) + trans[k]):
+                self._LOG.warning("device start clouds differ from numpy's on this host: building them on the host")
+                self.device_starts = False
+                return np.stack([np.dot(source, r) + t for r, t in zip(rots, trans)])
+            self._device_starts_verified = True
+        return clouds
 
     def _batch_kwargs(self, source):
         """Tell optimizers that understand it that every start is a rigid image of ``source``."""
@@ -151,6 +186,7 @@ class Aligner:
         if not hasattr(self._optimizer, "optimize_batch"):
             return self._multistart_sequential(source, target)
         rots, trans, clouds = self._draw_starts(source)
+        clouds = self._start_clouds(source, [(rots, trans, clouds)])
         res = self._optimizer.optimize_batch(clouds, np.asarray(target, dtype=np.float64)[None],
                                              np.arange(self._attempts), np.zeros(self._attempts, dtype=np.int32),
                                              **self._batch_kwargs(source))
@@ -189,7 +225,7 @@ class Aligner:
             starts.append(self._draw_starts(source))
             states.append(np.random.get_state())
         A = self._attempts
-        sources = np.concatenate([s[2] for s in starts], axis=0)
+        sources = self._start_clouds(source, starts)
         targets = np.stack([target * (scale + st) for st in steps], axis=0)   # Aligner.py:221-222
         unit_src = np.arange(6 * A, dtype=np.int32)
         unit_tgt = np.repeat(np.arange(6, dtype=np.int32), A)

@@ -94,6 +94,7 @@ class GeneralizedICP(IOptimizer):
                            d_res.profile)
 
     RERANK_KC = 48   # candidates kept per point of the base cloud (k = 20 are needed)
+    accepts_device_sources = True   # the Aligner may hand over start clouds built on the GPU (CUDA tensors)
 
     def _rigid_source_covariances(self, rigid_base: np.ndarray, d_src):
         """GICP covariances of rigid images of ``rigid_base`` via re-ranked neighbour lists."""

@@ -105,6 +105,8 @@ def lib():
     L.orpcd_normals_workspace_bytes.argtypes = [ip, ip, ip]
     L.orpcd_normals_cov.restype = ip
     L.orpcd_normals_cov.argtypes = [vp, ip, ll, ip, ip, dp, dp, vp, sz, vp, vp, vp, vp, vp, vp]
+    L.orpcd_apply_rigid_batch.restype = ip
+    L.orpcd_apply_rigid_batch.argtypes = [vp, ip, vp, vp, ip, vp, vp]
     L.orpcd_apply_scale_batch.restype = ip
     L.orpcd_apply_scale_batch.argtypes = [vp, ip, vp, ip, vp, vp]
     L.orpcd_gicp_batch_workspace_bytes.restype = sz

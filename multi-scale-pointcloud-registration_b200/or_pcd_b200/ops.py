@@ -155,6 +155,18 @@ def apply_scale_batch(points, scales):
     return out
 
 
+def apply_rigid_batch(points, rotations, translations):
+    """points [N,3] @ rotations [U,3,3] + translations [U,3] -> [U,N,3] (row-vector convention)."""
+    t = _t()
+    points, rotations, translations = _f64(points), _f64(rotations), _f64(translations)
+    N, U = points.shape[0], rotations.shape[0]
+    out = t.empty((U, N, 3), dtype=t.float64, device="cuda")
+    check(_lib.lib().orpcd_apply_rigid_batch(points.data_ptr(), N, rotations.data_ptr(), translations.data_ptr(), U,
+                                             out.data_ptr(), _lib.stream_ptr()), "orpcd_apply_rigid_batch")
+    launch_counter["kernels"] += 1
+    return out
+
+
 class GicpBatchResult:
     __slots__ = ("T", "stats", "status", "trace", "profile", "workspace", "params")
 

@@ -169,3 +169,20 @@ def test_refine_registration_icp(oracle, armadillo_pair):
         al.refine_registration(s, t, np.eye(4), icp_type="PointToPlane")
     with pytest.raises(RuntimeError):
         oracle.icp(s, t, mode="PointToPlane")
+
+
+def test_device_start_clouds_equal_numpy_bit_for_bit(armadillo_pair):
+    """orpcd_apply_rigid_batch reproduces np.dot(source, R) + t (Aligner.py:183-185) exactly: the Aligner builds
+    its start clouds on the GPU only under that condition."""
+    from or_pcd_b200 import _lib, ops
+    from or_pcd_b200.Aligner.Aligner import Aligner
+    from or_pcd_b200.Optimizer import GeneralizedICP
+    from or_pcd_b200.Preprocessor import Preprocessor
+
+    s, _, _ = armadillo_pair
+    np.random.seed(5)
+    al = Aligner(Preprocessor([]), Preprocessor([]), GeneralizedICP(), attempts=40)
+    rots, trans = zip(*[al.initialize_rotation() for _ in range(40)])
+    dev = ops.apply_rigid_batch(_lib.to_device(s), _lib.to_device(np.stack(rots)), _lib.to_device(np.stack(trans)))
+    host = np.stack([np.dot(s, r) + t for r, t in zip(rots, trans)])
+    assert np.array_equal(dev.cpu().numpy(), host)
