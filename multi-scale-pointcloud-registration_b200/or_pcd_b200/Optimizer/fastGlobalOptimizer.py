@@ -153,6 +153,8 @@ class FastGlobalOptimizer(IOptimizer):
         raise Warning(_NO_CORR_MSG)
 
     # ------------------------------------------------------------------ batched API
+    accepts_device_sources = True   # start clouds built on the GPU are bit-identical to the host's (Aligner verifies)
+
     def optimize_batch(self, sources, targets, unit_src: Sequence[int], unit_tgt: Sequence[int],
                        rigid_base: Optional[np.ndarray] = None) -> BatchResult:
         t = _lib.torch()
