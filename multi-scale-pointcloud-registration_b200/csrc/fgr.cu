@@ -446,7 +446,7 @@ struct FgrCtx {
     const unsigned long long *keys;     // [U]
     FgrUnit *unit;
     int2 *corres_init, *corres;         // [U][cap]
-    double *qcur;                       // [U][cap][3]
+    double *qcur, *pcur;                // [U][cap][3] each
     double *out_T;
     int *out_info;
 };
@@ -483,7 +483,7 @@ __device__ __forceinline__ int block_scan_flag(int flag, int *sh, int &total)
     if (lane == 0) sh[wid] = __popc(bal);
     __syncthreads();
     int base = 0, tot = 0;
-    for (int w = 0; w < FG_THREADS / 32; ++w) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
         if (w < wid) base += sh[w];
         tot += sh[w];
     }
@@ -582,9 +582,11 @@ __device__ __forceinline__ double dist3(const double a[3], const double b[3])
 
 // AdvancedMatching's tuple test: trials are independent given the counter-based stream, so a block
 // evaluates 256 at a time and keeps the accepted ones in trial order (= the sequential semantics).
-__global__ void __launch_bounds__(FG_THREADS) fgr_tuple_kernel(FgrCtx c)
+// (1024 threads: the kernel is bound by the latency of one batch of trials, not by throughput)
+constexpr int FG_WIDE = 1024;
+__global__ void __launch_bounds__(FG_WIDE) fgr_tuple_kernel(FgrCtx c)
 {
-    __shared__ int shi[FG_THREADS / 32];
+    __shared__ int shi[FG_WIDE / 32];
     __shared__ int s_cnt;
     const int u = blockIdx.x, tid = threadIdx.x;
     FgrUnit &fu = c.unit[u];
@@ -592,7 +594,7 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_tuple_kernel(FgrCtx c)
     const int2 *in = c.corres_init + (size_t)u * c.cap;
     int2 *out = c.corres + (size_t)u * c.cap;
     if (!c.tuple_test) {
-        for (int i = tid; i < ncorr; i += FG_THREADS) out[i] = in[i];
+        for (int i = tid; i < ncorr; i += FG_WIDE) out[i] = in[i];
         if (tid == 0) { fu.n_pairs = ncorr; fu.trials = 0; }
         return;
     }
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_tuple_kernel(FgrCtx c)
     if (tid == 0) s_cnt = 0;
     __syncthreads();
     long long done = 0;
-    for (long long base = 0; base < n_trials; base += FG_THREADS) {
+    for (long long base = 0; base < n_trials; base += FG_WIDE) {
         const long long t = base + tid;
         int flag = 0;
         int2 pr[3];
@@ -653,7 +655,7 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_tuple_kernel(FgrCtx c)
         }
         if (tid == 0) s_cnt = cnt0 + total;
         __syncthreads();
-        done = base + FG_THREADS < n_trials ? base + FG_THREADS : n_trials;
+        done = base + FG_WIDE < n_trials ? base + FG_WIDE : n_trials;
     }
     if (tid == 0) {
         fu.n_pairs = s_cnt * 3;
@@ -709,6 +711,7 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_gnc_kernel(FgrCtx c)
     const int ncorr = fu.n_pairs;
     const int2 *cor = c.corres + (size_t)u * c.cap;
     double *qc = c.qcur + (size_t)u * c.cap * 3;
+    double *pc = c.pcur + (size_t)u * c.cap * 3;   // normalised source point of every pair (constant over the iterations)
     const double *sp = c.src_pts + (size_t)c.unit_src[u] * c.n_src * 3;
     const double *tp = c.tgt_pts + (size_t)c.unit_tgt[u] * c.n_tgt * 3;
     double trans[16];
@@ -718,15 +721,18 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_gnc_kernel(FgrCtx c)
             double q[3];
             norm_point(tp, cor[i].y, fu.mean_t, fu.scale, q);
             qc[(size_t)i * 3] = q[0]; qc[(size_t)i * 3 + 1] = q[1]; qc[(size_t)i * 3 + 2] = q[2];
+            norm_point(sp, cor[i].x, fu.mean_s, fu.scale, q);
+            pc[(size_t)i * 3] = q[0]; pc[(size_t)i * 3 + 1] = q[1]; pc[(size_t)i * 3 + 2] = q[2];
         }
+        __syncthreads();
         double par = 1.0;   // scale_start (use_absolute_scale = false)
         for (int itr = 0; itr < c.iteration_number; ++itr) {
             double acc[27];
 #pragma unroll
             for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+#pragma unroll 4
             for (int i = tid; i < ncorr; i += FG_THREADS) {
-                double p[3];
-                norm_point(sp, cor[i].x, fu.mean_s, fu.scale, p);
+                const double p[3] = {pc[(size_t)i * 3], pc[(size_t)i * 3 + 1], pc[(size_t)i * 3 + 2]};
                 const double qx = qc[(size_t)i * 3], qy = qc[(size_t)i * 3 + 1], qz = qc[(size_t)i * 3 + 2];
                 const double rx = p[0] - qx, ry = p[1] - qy, rz = p[2] - qz;
                 const double temp = par / ((rx * rx + ry * ry + rz * rz) + par);
@@ -812,7 +818,7 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_gnc_kernel(FgrCtx c)
 }
 
 struct FgrLayout {
-    size_t off_unit, off_init, off_cor, off_q, total;
+    size_t off_unit, off_init, off_cor, off_q, off_p, total;
     int cap;
 };
 
@@ -832,6 +838,7 @@ bool fgr_layout(const orpcd_fgr_params *p, FgrLayout &L)
     L.off_init = take(U * L.cap * sizeof(int2));
     L.off_cor = take(U * L.cap * sizeof(int2));
     L.off_q = take(U * L.cap * 3 * sizeof(double));
+    L.off_p = take(U * L.cap * 3 * sizeof(double));
     L.total = o;
     return true;
 }
@@ -943,9 +950,10 @@ ORPCD_API int orpcd_fgr_batch(const orpcd_fgr_params *p, const double *d_src_poi
     c.corres_init = (int2 *)(w + L.off_init);
     c.corres = (int2 *)(w + L.off_cor);
     c.qcur = (double *)(w + L.off_q);
+    c.pcur = (double *)(w + L.off_p);
     c.out_T = d_out_T; c.out_info = d_out_info;
     fgr_prepare_kernel<<<p->n_units, FG_THREADS, 0, st>>>(c);
-    fgr_tuple_kernel<<<p->n_units, FG_THREADS, 0, st>>>(c);
+    fgr_tuple_kernel<<<p->n_units, FG_WIDE, 0, st>>>(c);
     fgr_gnc_kernel<<<p->n_units, FG_THREADS, 0, st>>>(c);
     ORPCD_CHECK_LAUNCH();
     return ORPCD_OK;
