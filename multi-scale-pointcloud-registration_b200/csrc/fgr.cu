@@ -45,7 +45,10 @@ constexpr int FM_STAGES = 3;
 // per feature.
 constexpr int FM_CHUNK_F64_BYTES = 33 * 32 * 8;         // 8448
 constexpr int FM_SET_BYTES_PER_TILE = FM_TILE_BYTES + 4 * FM_CHUNK_F64_BYTES;   // 75264
-constexpr int FM_SMEM_BYTES = (1 + FM_STAGES) * FM_TILE_BYTES + 128 /*barriers*/ + 128 /*alignment*/;
+constexpr int FM_ATILES = 2;                          // query tiles per CTA: every B tile brought in is used twice
+constexpr int FM_EPI_WARPS = FM_ATILES * 4;           // warps 0-3 own the rows of A tile 0, warps 4-7 those of A tile 1
+constexpr int FM_THREADS = (FM_EPI_WARPS + 1) * 32;   // + one warp that only drives TMA and tcgen05.mma
+constexpr int FM_SMEM_BYTES = (FM_ATILES + FM_STAGES) * FM_TILE_BYTES + 128 /*barriers*/ + 128 /*alignment*/;
 constexpr float FM_PAD_NORM = 3.0e38f;
 
 __device__ __forceinline__ int fm_image_offset(int r, int c)
@@ -126,6 +129,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile(
@@ -177,6 +184,7 @@ __device__ __forceinline__ float min3f(float a, float b, float c)
     asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
+// issue only: tmem_wait_ld() before the registers are read
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile(
@@ -188,42 +196,51 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------
 // tensor-core filter: per query row (best chunk min, chunk id, second-best chunk min) of
 //   v(row, col) = |d_col|^2 - 2 q_row . d_col          (= dist^2 - |q_row|^2)
-// grid (query tiles, pairs); 128 threads; thread t owns query row t of the tile.
+// grid (pairs of query tiles, pairs of sets); 288 threads: warps 0-3 own the 128 rows of the CTA's first query tile,
+// warps 4-7 those of the second, warp 8 only drives the TMA copies and the MMAs (warp-specialised: the epilogue of
+// tile e overlaps the issue and execution of tile e+1); every database tile staged in shared memory feeds the MMAs
+// of both query tiles.
 // ----------------------------------------------------------------------------
 template <bool DEBUG>
-__global__ void __launch_bounds__(FM_ROWS, 1)
+__global__ void __launch_bounds__(FM_THREADS, 1)
 feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const unsigned char *__restrict__ packed_db,
                   int db_tiles, const int *__restrict__ pair_q, const int *__restrict__ pair_db, int nq,
                   float *__restrict__ out_m, int *__restrict__ out_c, size_t out_stride, float *__restrict__ dbg_v)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    unsigned char *sA = smem;
-    unsigned char *sB = smem + FM_TILE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (1 + FM_STAGES) * FM_TILE_BYTES);
-    // bars[0]: A landed; bars[1..3]: B stage landed; bars[4..5]: accumulator complete; bars[6] low word: TMEM base
+    unsigned char *sA = smem;                                  // FM_ATILES query tiles
+    unsigned char *sB = smem + FM_ATILES * FM_TILE_BYTES;      // FM_STAGES database tiles
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (FM_ATILES + FM_STAGES) * FM_TILE_BYTES);
+    // bars[0]: A landed; bars[1..3]: B stage landed; bars[4..5]: accumulators complete; bars[6] low word: TMEM base;
+    // bars[7..8]: accumulator buffer released by the epilogue warps
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int pair = blockIdx.y, qt = blockIdx.x;
-    const unsigned char *gA = packed_q + (size_t)pair_q[pair] * q_tiles * FM_SET_BYTES_PER_TILE + (size_t)qt * FM_TILE_BYTES;
+    const int atile = warp >> 2, quarter = warp & 3;           // TMEM lanes 32*quarter.. belong to warps quarter, quarter+4
+    const int pair = blockIdx.y, qt0 = blockIdx.x * FM_ATILES;
+    const int n_at = min(FM_ATILES, q_tiles - qt0);            // query tiles this CTA really has
+    const unsigned char *gA = packed_q + (size_t)pair_q[pair] * q_tiles * FM_SET_BYTES_PER_TILE + (size_t)qt0 * FM_TILE_BYTES;
     const unsigned char *gB = packed_db + (size_t)pair_db[pair] * db_tiles * FM_SET_BYTES_PER_TILE;
     const uint32_t bar_a = smem_u32(bars), bar_full0 = smem_u32(bars + 1), bar_mma0 = smem_u32(bars + 4);
+    const uint32_t bar_free0 = smem_u32(bars + 7);   // bars[7..8]: accumulator buffer (and the stage of its tile) free again
 
     if (tid == 0) {
         mbar_init(bar_a, 1);
         for (int s = 0; s < FM_STAGES; ++s) mbar_init(bar_full0 + 8 * s, 1);
         mbar_init(bar_mma0, 1);
         mbar_init(bar_mma0 + 8, 1);
+        mbar_init(bar_free0, FM_EPI_WARPS);
+        mbar_init(bar_free0 + 8, FM_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {   // 256 TMEM columns: two 128 x 128 FP32 accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    if (warp == 0) {   // all 512 TMEM columns: (2 buffers) x (2 query tiles) 128 x 128 FP32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -231,90 +248,105 @@ feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (tid == 0) {
-        mbar_expect_tx(bar_a, FM_TILE_BYTES);
-        tma_bulk_g2s(smem_u32(sA), gA, FM_TILE_BYTES, bar_a);
-        for (int s = 0; s < FM_STAGES && s < db_tiles; ++s) {
-            mbar_expect_tx(bar_full0 + 8 * s, FM_TILE_BYTES);
-            tma_bulk_g2s(smem_u32(sB + (size_t)s * FM_TILE_BYTES), gB + (size_t)s * FM_TILE_BYTES, FM_TILE_BYTES,
-                         bar_full0 + 8 * s);
-        }
-    }
-
     // the FM_TOP smallest chunk minima (ascending, with chunk ids) and the next one as the bound for the rest
     float m1 = CUDART_INF_F, m2 = CUDART_INF_F, m3 = CUDART_INF_F, m4 = CUDART_INF_F;
     int c1 = 0, c2 = 0, c3 = 0;
-    const int row = qt * FM_ROWS + tid;
+    const int row = (qt0 + atile) * FM_ROWS + quarter * 32 + (tid & 31);
+    const bool have_tile = warp < FM_EPI_WARPS && atile < n_at;
 
-    // iteration t: thread 0 issues the MMAs of tile t, then everyone runs the epilogue of tile t-1
-    for (int t = 0; t <= db_tiles; ++t) {
-        if (t < db_tiles && tid == 0) {
-            if (t == 0) mbar_wait(bar_a, 0);
-            const int s = t % FM_STAGES;
-            mbar_wait(bar_full0 + 8 * s, (t / FM_STAGES) & 1);
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + FM_PLANE_BYTES;
-            const uint32_t b_hi = smem_u32(sB + (size_t)s * FM_TILE_BYTES), b_lo = b_hi + FM_PLANE_BYTES;
-            const uint32_t acc = tmem_base + (uint32_t)(t & 1) * FM_ROWS;
-#pragma unroll
-            for (int k = 0; k < FM_K / 8; ++k) {
-                const uint32_t ko = (uint32_t)k * 2 * FM_LBO;   // two 16-byte K chunks per MMA (K = 8 tf32)
-                umma_tf32(acc, umma_desc(a_hi + ko), umma_desc(b_hi + ko), k > 0);
-                umma_tf32(acc, umma_desc(a_hi + ko), umma_desc(b_lo + ko), 1);
-                umma_tf32(acc, umma_desc(a_lo + ko), umma_desc(b_hi + ko), 1);
+    if (warp == FM_EPI_WARPS) {
+        // ---- producer warp: one thread brings the tiles in with TMA bulk copies and issues the MMAs
+        if ((tid & 31) == 0) {
+            mbar_expect_tx(bar_a, (uint32_t)n_at * FM_TILE_BYTES);
+            tma_bulk_g2s(smem_u32(sA), gA, (uint32_t)n_at * FM_TILE_BYTES, bar_a);   // the tiles of a set are contiguous
+            for (int s = 0; s < FM_STAGES && s < db_tiles; ++s) {
+                mbar_expect_tx(bar_full0 + 8 * s, FM_TILE_BYTES);
+                tma_bulk_g2s(smem_u32(sB + (size_t)s * FM_TILE_BYTES), gB + (size_t)s * FM_TILE_BYTES, FM_TILE_BYTES,
+                             bar_full0 + 8 * s);
             }
-            umma_commit(bar_mma0 + 8 * (t & 1));   // implies tcgen05.fence::before_thread_sync
+            mbar_wait(bar_a, 0);
+            for (int t = 0; t < db_tiles; ++t) {
+                if (t >= 2) {
+                    // the epilogue of tile t-2 is done: its accumulators (buffer t&1) and its stage are free
+                    mbar_wait(bar_free0 + 8 * (t & 1), ((t - 2) >> 1) & 1);
+                    const int nt = t + 1;   // stage (t - 2) % 3 == (t + 1) % 3
+                    if (nt < db_tiles) {
+                        const int ns = nt % FM_STAGES;
+                        mbar_expect_tx(bar_full0 + 8 * ns, FM_TILE_BYTES);
+                        tma_bulk_g2s(smem_u32(sB + (size_t)ns * FM_TILE_BYTES), gB + (size_t)nt * FM_TILE_BYTES,
+                                     FM_TILE_BYTES, bar_full0 + 8 * ns);
+                    }
+                }
+                const int s = t % FM_STAGES;
+                mbar_wait(bar_full0 + 8 * s, (t / FM_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t b_hi = smem_u32(sB + (size_t)s * FM_TILE_BYTES), b_lo = b_hi + FM_PLANE_BYTES;
+                for (int at = 0; at < n_at; ++at) {
+                    const uint32_t a_hi = smem_u32(sA + (size_t)at * FM_TILE_BYTES), a_lo = a_hi + FM_PLANE_BYTES;
+                    const uint32_t acc = tmem_base + (uint32_t)((t & 1) * FM_ATILES + at) * FM_ROWS;
+#pragma unroll
+                    for (int k = 0; k < FM_K / 8; ++k) {
+                        const uint32_t ko = (uint32_t)k * 2 * FM_LBO;   // two 16-byte K chunks per MMA (K = 8 tf32)
+                        umma_tf32(acc, umma_desc(a_hi + ko), umma_desc(b_hi + ko), k > 0);
+                        umma_tf32(acc, umma_desc(a_hi + ko), umma_desc(b_lo + ko), 1);
+                        umma_tf32(acc, umma_desc(a_lo + ko), umma_desc(b_hi + ko), 1);
+                    }
+                }
+                umma_commit(bar_mma0 + 8 * (t & 1));   // implies tcgen05.fence::before_thread_sync
+            }
         }
-        __syncwarp();   // warp 0 must be converged again for the .sync.aligned TMEM loads below
-        if (t >= 1) {
-            const int e = t - 1, s = e % FM_STAGES;
+    } else {
+        // ---- epilogue warps: tile e while the tensor core works on tile e+1
+        for (int e = 0; e < db_tiles; ++e) {
+            const int s = e % FM_STAGES;
             mbar_wait(bar_full0 + 8 * s, (e / FM_STAGES) & 1);   // tile e's norms (TMA-written) visible to this thread
             mbar_wait(bar_mma0 + 8 * (e & 1), (e >> 1) & 1);
             tc_fence_after();
-            const uint32_t dn_addr = smem_u32(sB + (size_t)s * FM_TILE_BYTES + FM_NORM_OFF);
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(e & 1) * FM_ROWS;
-#pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(taddr + ch * 32, v);
-                float ma = CUDART_INF_F, mb = CUDART_INF_F;
+            if (have_tile) {
+                const uint32_t dn_addr = smem_u32(sB + (size_t)s * FM_TILE_BYTES + FM_NORM_OFF);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                       (uint32_t)((e & 1) * FM_ATILES + atile) * FM_ROWS;
+                uint32_t v[4][32];   // this row's 128 columns: four loads in flight, one wait
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float d0, d1, d2, d3;   // |d|^2 of four columns: one broadcast 16-byte shared load
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(d0), "=f"(d1), "=f"(d2), "=f"(d3) : "r"(dn_addr + (uint32_t)(ch * 32 + j) * 4));
-                    const float v0 = __fmaf_rn(-2.f, __uint_as_float(v[j]), d0);
-                    const float v1 = __fmaf_rn(-2.f, __uint_as_float(v[j + 1]), d1);
-                    const float v2 = __fmaf_rn(-2.f, __uint_as_float(v[j + 2]), d2);
-                    const float v3 = __fmaf_rn(-2.f, __uint_as_float(v[j + 3]), d3);
-                    ma = min3f(ma, v0, v1);
-                    mb = min3f(mb, v2, v3);
-                    if (DEBUG && row < nq) {
-                        float *o = dbg_v + ((size_t)pair * nq + row) * ((size_t)db_tiles * FM_ROWS) + (size_t)e * FM_ROWS +
-                                   ch * 32 + j;
-                        o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3;
+                for (int ch = 0; ch < 4; ++ch) tmem_ld32(taddr + ch * 32, v[ch]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    float ma = CUDART_INF_F, mb = CUDART_INF_F;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float d0, d1, d2, d3;   // |d|^2 of four columns: one broadcast 16-byte shared load
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(d0), "=f"(d1), "=f"(d2), "=f"(d3) : "r"(dn_addr + (uint32_t)(ch * 32 + j) * 4));
+                        const float v0 = __fmaf_rn(-2.f, __uint_as_float(v[ch][j]), d0);
+                        const float v1 = __fmaf_rn(-2.f, __uint_as_float(v[ch][j + 1]), d1);
+                        const float v2 = __fmaf_rn(-2.f, __uint_as_float(v[ch][j + 2]), d2);
+                        const float v3 = __fmaf_rn(-2.f, __uint_as_float(v[ch][j + 3]), d3);
+                        ma = min3f(ma, v0, v1);
+                        mb = min3f(mb, v2, v3);
+                        if (DEBUG && row < nq) {
+                            float *o = dbg_v + ((size_t)pair * nq + row) * ((size_t)db_tiles * FM_ROWS) + (size_t)e * FM_ROWS +
+                                       ch * 32 + j;
+                            o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3;
+                        }
                     }
+                    float x = fminf(ma, mb);
+                    int cx = e * 4 + ch;
+                    if (x < m3) {   // sorted insertion; strict compares keep the lowest chunk id first among equals
+                        if (x < m1) { const float tt = m1; m1 = x; x = tt; const int tc = c1; c1 = cx; cx = tc; }
+                        if (x < m2) { const float tt = m2; m2 = x; x = tt; const int tc = c2; c2 = cx; cx = tc; }
+                        if (x < m3) { const float tt = m3; m3 = x; x = tt; c3 = cx; }
+                    }
+                    m4 = fminf(m4, x);
                 }
-                float x = fminf(ma, mb);
-                int cx = e * 4 + ch;
-                if (x < m3) {   // sorted insertion; strict compares keep the lowest chunk id first among equals
-                    if (x < m1) { const float t = m1; m1 = x; x = t; const int tc = c1; c1 = cx; cx = tc; }
-                    if (x < m2) { const float t = m2; m2 = x; x = t; const int tc = c2; c2 = cx; cx = tc; }
-                    if (x < m3) { const float t = m3; m3 = x; x = t; c3 = cx; }
-                }
-                m4 = fminf(m4, x);
             }
+            // this warp is done with accumulator buffer e&1 and with stage s (the norms)
             tc_fence_before();
-            __syncthreads();   // accumulator e&1 and stage s are free again
-            if (tid == 0 && e + FM_STAGES < db_tiles) {
-                const int nt = e + FM_STAGES;
-                mbar_expect_tx(bar_full0 + 8 * s, FM_TILE_BYTES);
-                tma_bulk_g2s(smem_u32(sB + (size_t)s * FM_TILE_BYTES), gB + (size_t)nt * FM_TILE_BYTES, FM_TILE_BYTES,
-                             bar_full0 + 8 * s);
-            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar_free0 + 8 * (e & 1));
         }
     }
-    if (row < nq) {
+    if (have_tile && row < nq) {
         const size_t o = (size_t)pair * nq + row;
         out_m[o] = m1; out_m[o + out_stride] = m2; out_m[o + 2 * out_stride] = m3; out_m[o + 3 * out_stride] = m4;
         out_c[o] = c1; out_c[o + out_stride] = c2; out_c[o + 2 * out_stride] = c3;
@@ -322,7 +354,7 @@ feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const
     tc_fence_before();
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 // nanoflann L2_Adaptor::evalMetric for dim 33: groups of four summed left to right, then the tail;
@@ -903,7 +935,7 @@ ORPCD_API int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q
         auto kern = d_debug_v ? feat_match_kernel<true> : feat_match_kernel<false>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FM_SMEM_BYTES) != cudaSuccess)
             return ORPCD_ERR_CUDA;
-        kern<<<dim3(q_tiles, n_pairs), FM_ROWS, FM_SMEM_BYTES, st>>>(
+        kern<<<dim3((q_tiles + FM_ATILES - 1) / FM_ATILES, n_pairs), FM_THREADS, FM_SMEM_BYTES, st>>>(
             (const unsigned char *)d_packed_q, q_tiles, (const unsigned char *)d_packed_db, db_tiles, d_pair_q,
             d_pair_db, n_query, fm, fc, stride, d_debug_v);
         ORPCD_CHECK_LAUNCH();
