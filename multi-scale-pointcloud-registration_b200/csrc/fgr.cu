@@ -380,7 +380,10 @@ __device__ __forceinline__ double sqdist33_fm(const double *__restrict__ a, cons
 // stats[0] += rows that needed the exact scan, stats[1] += chunks re-scored.
 constexpr int FM_TOP = 3;
 
-__global__ void __launch_bounds__(128)
+#ifndef FR_MIN_BLOCKS
+#define FR_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, FR_MIN_BLOCKS)
 feat_resolve_kernel(const double *__restrict__ feat_q, int nq, const unsigned char *__restrict__ packed_db,
                     int db_tiles, int ndb, const double *__restrict__ center, const int *__restrict__ pair_q, const int *__restrict__ pair_db,
                     const float *__restrict__ db_maxnorm, const float *__restrict__ in_m,
@@ -395,11 +398,15 @@ feat_resolve_kernel(const double *__restrict__ feat_q, int nq, const unsigned ch
     const double *db = reinterpret_cast<const double *>(packed_db + (size_t)pair_db[pair] * db_tiles * FM_SET_BYTES_PER_TILE +
                                                         (size_t)db_tiles * FM_TILE_BYTES) + lane;
     constexpr int CH = FM_CHUNK_F64_BYTES / 8;
-    double qv[FM_DIM];
+    // the query row lives in shared memory (broadcast reads): 66 registers less per thread, 2.4x the resident warps
+    __shared__ double qsh[4][FM_DIM + 3];
+    double *qv = qsh[threadIdx.x >> 5];
+    qv[lane] = q[lane];
+    if (lane == 0) qv[32] = q[32];
+    __syncwarp();
     double qn = 0.0;   // |q - center|^2: what the filter value is offset by
 #pragma unroll
     for (int k = 0; k < FM_DIM; ++k) {
-        qv[k] = q[k];
         const double qc = center ? qv[k] - center[k] : qv[k];
         qn += qc * qc;
     }
