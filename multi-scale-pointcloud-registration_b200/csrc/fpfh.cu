@@ -126,9 +126,18 @@ fpfh_kernel(int n, const int *__restrict__ nn_idx, const double *__restrict__ nn
             const double dist = d2[k];
             if (dist == 0.0) continue;
             const double *s = sp + (size_t)idx[k] * FP_DIM;
+            // 33 correctly rounded quotients s[j] / dist from ONE division: with y = RN(1 / dist), q = s y,
+            // r = s - q dist (exact in an FMA), q' = q + r y is RN(s / dist) (Markstein) unless dist's significand
+            // is all ones -- that case takes the plain division.  Histogram values and distances are far from
+            // the overflow / subnormal ranges.
+            const double y = 1.0 / dist;
+            const bool plain = (__double2hiint(dist) & 0x000fffff) == 0x000fffff && (unsigned)__double2loint(dist) == 0xffffffffu;
 #pragma unroll
             for (int j = 0; j < FP_DIM; ++j) {
-                const double val = s[j] / dist;
+                const double sj = s[j];
+                const double q = __dmul_rn(sj, y);
+                double val = fma(fma(-q, dist, sj), y, q);
+                if (plain) val = sj / dist;
                 sum[j / 11] += val;
                 acc[j] += val;
             }

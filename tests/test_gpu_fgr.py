@@ -38,6 +38,8 @@ def test_fpfh_matches_oracle(oracle, armadillo_pair):
         # at most one point in thousands may land in a neighbouring bin
         assert (np.abs(sp - ref_sp).max(1) > 1e-9).sum() <= 1
         assert (np.abs(out - ref).max(1) > 1e-9).sum() <= 25
+        # everything else is bit-identical (the device forms its 33 quotients per neighbour from one division)
+        assert (out != ref).any(1).sum() == (np.abs(out - ref).max(1) > 1e-9).sum()
         assert np.allclose(sp.sum(1), ref_sp.sum(1), atol=1e-9)             # three histograms of 100 each
         # device normals (bit-identical to the oracle's) through the plugin class
         from or_pcd_b200.Optimizer import FastGlobalOptimizer
