@@ -440,10 +440,25 @@ knn_rerank_kernel(const int *__restrict__ cand, const double *__restrict__ bound
     const double qx = pts[(size_t)i * 3], qy = pts[(size_t)i * 3 + 1], qz = pts[(size_t)i * 3 + 2];
     const int *row = cand + (size_t)i * kc;
     int cnt = 0;
-    for (int s = 0; s < kc; ++s) {
-        const int j = row[s];
-        if (j < 0) break;
-        const double d = sqdist3_rn(qx, qy, qz, pts[(size_t)j * 3], pts[(size_t)j * 3 + 1], pts[(size_t)j * 3 + 2]);
+    // four candidates per step: their indices and coordinates are fetched together (the gathers are what this
+    // kernel waits for), then inserted one after the other in list order
+    for (int s0 = 0; s0 < kc; s0 += 4) {
+        int jj[4];
+        double cx[4], cy[4], cz[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) jj[r] = s0 + r < kc ? row[s0 + r] : -1;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int jr = jj[r] < 0 ? 0 : jj[r];
+            cx[r] = pts[(size_t)jr * 3]; cy[r] = pts[(size_t)jr * 3 + 1]; cz[r] = pts[(size_t)jr * 3 + 2];
+        }
+        bool stop = false;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+        const int j = jj[r];
+        if (j < 0) stop = true;
+        if (stop) continue;
+        const double d = sqdist3_rn(qx, qy, qz, cx[r], cy[r], cz[r]);
         if (cnt == k) {
             const double wd = ld[(size_t)(k - 1) * RR_BLOCK + tid];
             const int wj = li[(size_t)(k - 1) * RR_BLOCK + tid];
@@ -460,6 +475,8 @@ knn_rerank_kernel(const int *__restrict__ cand, const double *__restrict__ bound
         }
         ld[(size_t)pos * RR_BLOCK + tid] = d;
         li[(size_t)pos * RR_BLOCK + tid] = j;
+        }
+        if (stop) break;
     }
     const size_t o = ((size_t)b * n + i) * k;
     for (int s = 0; s < k; ++s) {
