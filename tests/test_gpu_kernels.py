@@ -247,3 +247,26 @@ def test_optimize_batch_rigid_base_same_result(oracle, armadillo_pair):
     b = opt.optimize_batch(srcs, t[None], [0, 1, 2, 3], [0, 0, 0, 0], rigid_base=s)
     assert np.array_equal(a.transforms, b.transforms) and np.array_equal(a.rmse, b.rmse)
     assert np.array_equal(a.iterations, b.iterations)
+
+
+def test_fused_round_kernel_agrees_with_the_unfused_and_dense_paths(oracle, armadillo_pair):
+    """Three implementations of the same round -- one fused kernel (default), culled sweep + separate kernels
+    (sweep_mode 4), dense sweep + separate kernels (sweep_mode 1) -- find the same correspondences, so they differ
+    only by the order of the float64 sums: same iteration counts, rmse and transforms to 1e-9."""
+    from or_pcd_b200.Optimizer import GeneralizedICP
+
+    s, t, _ = armadillo_pair
+    np.random.seed(3)
+    starts = [oracle.initialize_rotation(0.6, 0.0, 0.05) for _ in range(4)]
+    sources = np.stack([s @ r + tr for r, tr in starts])
+    targets = np.stack([t, t * np.array([1.0, 1.15, 1.0])])
+    us, ut = [0, 1, 2, 3, 0, 1], [0, 0, 0, 0, 1, 1]
+    res = []
+    for mode in (0, 4, 1):
+        opt = GeneralizedICP()
+        opt.sweep_mode = mode
+        res.append(opt.optimize_batch(sources, targets, us, ut))
+    for other in res[1:]:
+        assert np.array_equal(res[0].iterations, other.iterations)
+        assert np.allclose(res[0].rmse, other.rmse, rtol=1e-9, atol=0)
+        assert np.allclose(res[0].transforms, other.transforms, rtol=0, atol=1e-9)
