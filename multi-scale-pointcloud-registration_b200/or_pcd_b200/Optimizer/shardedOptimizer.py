@@ -70,6 +70,8 @@ class ShardedOptimizer(IOptimizer):
         self._inner = inner
         self._group = group
         self._takes_rigid_base = "rigid_base" in inspect.signature(inner.optimize_batch).parameters
+        # start clouds built on the GPU by the Aligner (CUDA tensors) are passed through when the inner optimizer takes them
+        self.accepts_device_sources = bool(getattr(inner, "accepts_device_sources", False))
         self.last_local_units = 0
 
     def _dist(self):
@@ -102,7 +104,12 @@ class ShardedOptimizer(IOptimizer):
         tgt_sets, local_tgt = np.unique(unit_tgt[mine], return_inverse=True)
         n_slots = (n_units + world - 1) // world
         if len(mine):
-            res = self._inner.optimize_batch(np.asarray(sources)[src_sets], np.asarray(targets)[tgt_sets],
+            def pick(sets, idx):
+                if hasattr(sets, "is_cuda"):
+                    return sets.index_select(0, torch.as_tensor(idx, dtype=torch.int64, device=sets.device))
+                return np.asarray(sets)[idx]
+
+            res = self._inner.optimize_batch(pick(sources, src_sets), pick(targets, tgt_sets),
                                              local_src.astype(np.int32), local_tgt.astype(np.int32), **kwargs)
             rec = pack_records(res, n_slots)
         else:
