@@ -197,8 +197,8 @@ def run_b200(args):
     def device_step():
         """Hot path with inputs resident in HBM: source covariances, target covariances, batched GICP."""
         opt._base_key = None   # no neighbour lists carried over from the previous step: every step does all its work
-        sc = opt._rigid_source_covariances(src, d_src)
-        res = opt.optimize_batch_device(d_src, d_tgt, us, ut, src_cov=sc)
+        sc, tc = opt.covariances(d_src, d_tgt, src)
+        res = opt.optimize_batch_device(d_src, d_tgt, us, ut, src_cov=sc, tgt_cov=tc)
         if world > 1:   # (rmse, fitness, iters, status, T) record per unit, one small all-gather
             rec = torch.cat([res.stats, res.status.to(torch.float64)[:, None], res.T.reshape(n_units, 16)], 1)[:, :20]
             dist.all_gather_into_tensor(gather_buf, rec.contiguous())

@@ -52,6 +52,7 @@ class GeneralizedICP(IOptimizer):
         self.sweep_tj = 0             # tuning: dense sweep targets per step; culled sweep warps per block (2->1, 4->2, 8->4)
         self.sweep_smem_pad = 0       # tuning: dense sweep occupancy pad; negative -(n+1): small patches below n
         self.last_profile = None
+        self._side_stream = None
 
     # ------------------------------------------------------------------ reference API
     def optimize(self, source: np.ndarray, target: np.ndarray, **kwargs) -> Tuple[np.ndarray, float]:
@@ -81,10 +82,9 @@ class GeneralizedICP(IOptimizer):
         d_tgt = targets if hasattr(targets, "is_cuda") else _lib.to_device(np.asarray(targets))
         us = t.as_tensor(np.asarray(unit_src, dtype=np.int32)).to("cuda")
         ut = t.as_tensor(np.asarray(unit_tgt, dtype=np.int32)).to("cuda")
-        src_cov = None
-        if rigid_base is not None and d_src.shape[1] > self.RERANK_KC:
-            src_cov = self._rigid_source_covariances(rigid_base, d_src)
-        d_res = self.optimize_batch_device(d_src, d_tgt, us, ut, poll_interval=poll_interval, src_cov=src_cov)
+        src_cov, tgt_cov = self.covariances(d_src, d_tgt, rigid_base)
+        d_res = self.optimize_batch_device(d_src, d_tgt, us, ut, poll_interval=poll_interval, src_cov=src_cov,
+                                           tgt_cov=tgt_cov)
         T = d_res.T.cpu().numpy()
         stats = d_res.stats.cpu().numpy()
         status = d_res.status.cpu().numpy()
@@ -95,6 +95,29 @@ class GeneralizedICP(IOptimizer):
 
     RERANK_KC = 48   # candidates kept per point of the base cloud (k = 20 are needed)
     accepts_device_sources = True   # the Aligner may hand over start clouds built on the GPU (CUDA tensors)
+
+    def covariances(self, d_src, d_tgt, rigid_base: Optional[np.ndarray] = None):
+        """GICP covariance data (plane axes or 3x3 covariances) of every source and target set.  The two sides are
+        independent: the target side runs on a second CUDA stream next to the source side."""
+        t = _lib.torch()
+        ax = self.analytic_whitening
+        key = "gicp_axis" if ax else "gicp_cov"
+        main = t.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = t.cuda.Stream()
+        side = self._side_stream
+        side.wait_stream(main)
+        with t.cuda.stream(side):
+            tgt_cov = ops.normals_cov(d_tgt, knn=GICP_COVARIANCE_KNN, gicp_eps=GICP_EPSILON, want_gicp_cov=not ax,
+                                      want_gicp_axis=ax)[key]
+        if rigid_base is not None and d_src.shape[1] > self.RERANK_KC:
+            src_cov = self._rigid_source_covariances(rigid_base, d_src)
+        else:
+            src_cov = ops.normals_cov(d_src, knn=GICP_COVARIANCE_KNN, gicp_eps=GICP_EPSILON, want_gicp_cov=not ax,
+                                      want_gicp_axis=ax)[key]
+        main.wait_stream(side)
+        tgt_cov.record_stream(main)
+        return src_cov, tgt_cov
 
     def _rigid_source_covariances(self, rigid_base: np.ndarray, d_src):
         """GICP covariances of rigid images of ``rigid_base`` via re-ranked neighbour lists."""

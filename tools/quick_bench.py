@@ -42,8 +42,9 @@ def main():
     for rep in range(int(os.environ.get("REPS", "3"))):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        sc = opt._rigid_source_covariances(src, d_s) if os.environ.get('RIGID', '1') == '1' else None
-        res = opt.optimize_batch_device(d_s, d_t, us, ut, src_cov=sc)
+        opt._base_key = None
+        sc, tc = opt.covariances(d_s, d_t, src if os.environ.get('RIGID', '1') == '1' else None)
+        res = opt.optimize_batch_device(d_s, d_t, us, ut, src_cov=sc, tgt_cov=tc)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         p = res.profile
