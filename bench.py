@@ -324,8 +324,8 @@ def run_b200(args):
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s",
                          "frac": achieved / ffma_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch with all 180 units active, from the
-                         # ncu --set full capture in profiles/r1_04 (48.7 MB + 25.5 MB; the working set is L2-resident)
-                         "traffic": 74.1e6, "traffic_unit": "bytes/launch (ncu, profiles/r1_04_gicp_round_ncu_full_details.csv)",
+                         # ncu --set full capture in profiles/r1_05 (48.7 MB + 22.7 MB; the working set is L2-resident)
+                         "traffic": 71.4e6, "traffic_unit": "bytes/launch (ncu, profiles/r1_05_gicp_round_ncu_full_details.csv)",
                          "kernel": "gicp_round_kernel", "avg_launch_us": 1e3 * sweep_ms / max(sweep_launches * args.steps, 1),
                          "share_of_step": sweep_ms / dev_ms,
                          "note": "8 FLOP per (query,target) pair x pairs the kernel evaluated / CUDA-event time inside the "
