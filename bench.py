@@ -300,6 +300,11 @@ def run_b200(args):
                     "frac": tf / ffma_peak, "us_per_launch": a.elapsed_time(b) * 1e3 / 5}
 
         dense_ref = dense_sweep()
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            hbm_src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            hbm_peak, hbm_src = 6549.8, "fallback: MEASURED_PEAKS.json of this pool (6549.8 GB/s)"
         # CPU baseline on this box's host cores: a bounded sample of the same step (N = 1 only)
         cpu_units = [c * ATTEMPTS + k for k in range(2) for c in range(len(SCALES))]
         if world == 1:
@@ -335,6 +340,14 @@ def run_b200(args):
                                  "6x6 solve) around the FP32 sweep, so its time is not FMA-pipe time alone: see "
                                  "profiles/ for the per-phase split",
                          "dense_sweep_reference": dense_ref,
+                         # the same kernel against the HBM roofline: per source point and round it reads point, plane
+                         # axis, previous match and that match's target point (76 B), writes point, axis and match
+                         # (52 B), gathers the new match's point and axis (48 B) and streams pairs/32 chunks of 512 B per
+                         # 64-point patch -- all of it L2-resident, which is why DRAM traffic is a quarter of it
+                         "hbm_view": {"algorithmic_bytes_per_step": unit_rounds * N_POINTS * 176.0 / args.steps + pairs / args.steps / 64.0 * 16.0,
+                                      "achieved_GBps": (unit_rounds * N_POINTS * 176.0 + pairs / 64.0 * 16.0) / (sweep_ms * 1e-3) / 1e9,
+                                      "peak_GBps": hbm_peak, "peak_source": hbm_src,
+                                      "frac": (unit_rounds * N_POINTS * 176.0 + pairs / 64.0 * 16.0) / (sweep_ms * 1e-3) / 1e9 / hbm_peak},
                          "pairs_per_step": pairs / args.steps,
                          "pairs_brute_force_per_step": unit_rounds * N_POINTS * N_POINTS / args.steps,
                          "culled_fraction": 1.0 - pairs / max(unit_rounds * N_POINTS * N_POINTS, 1),
