@@ -20,6 +20,9 @@ class RandomDownsampler(IProcessBlock):
         self._replace = replace
 
     def process(self, cloud: np.ndarray) -> np.ndarray:
+        """``sample_size`` rows of ``cloud`` in the order of the permutation numpy drew (legacy global
+        MT19937 stream: ``choice`` without replacement is ``permutation(N)[:k]``); the indices are kept in
+        ``last_indices`` for the parity tests."""
         keep = np.random.choice(cloud.shape[0], self._sample_size, replace=self._replace)
         self.last_indices = keep
         return cloud[keep]

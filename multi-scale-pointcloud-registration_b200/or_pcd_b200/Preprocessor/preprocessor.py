@@ -1,4 +1,8 @@
-"""Sequential block runner (reference: Preprocessor/preprocessor.py:12-31)."""
+"""Sequential block runner (reference: Preprocessor/preprocessor.py:12-31).
+
+One ``Preprocessor`` instance per cloud: the scaler inside it remembers that cloud's mean and scale.  The
+Aligner runs ``source_preprocessor.preprocess(source)`` first and ``target_preprocessor.preprocess(target)``
+second, which also fixes the order of the ``np.random`` draws of the down-samplers."""
 from typing import List
 
 import numpy as np
@@ -19,6 +23,7 @@ class Preprocessor:
         self.preprocessor_blocks = preprocessor_blocks
 
     def preprocess(self, cloud: np.ndarray) -> np.ndarray:
+        """Run every block in list order on the (N,3) cloud; returns the last block's output."""
         for block in self.preprocessor_blocks:
             cloud = block.process(cloud)
         return cloud
