@@ -52,7 +52,6 @@ class GeneralizedICP(IOptimizer):
         self.sweep_tj = 0             # tuning: dense sweep targets per step; culled sweep warps per block (2->1, 4->2, 8->4)
         self.sweep_smem_pad = 0       # tuning: dense sweep occupancy pad; negative -(n+1): small patches below n
         self.last_profile = None
-        self._side_stream = None
 
     # ------------------------------------------------------------------ reference API
     def optimize(self, source: np.ndarray, target: np.ndarray, **kwargs) -> Tuple[np.ndarray, float]:
@@ -103,9 +102,7 @@ class GeneralizedICP(IOptimizer):
         ax = self.analytic_whitening
         key = "gicp_axis" if ax else "gicp_cov"
         main = t.cuda.current_stream()
-        if self._side_stream is None:
-            self._side_stream = t.cuda.Stream()
-        side = self._side_stream
+        side = _lib.side_stream()
         side.wait_stream(main)
         with t.cuda.stream(side):
             tgt_cov = ops.normals_cov(d_tgt, knn=GICP_COVARIANCE_KNN, gicp_eps=GICP_EPSILON, want_gicp_cov=not ax,

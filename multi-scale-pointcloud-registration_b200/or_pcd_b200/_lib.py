@@ -174,6 +174,20 @@ def torch():
     return _torch
 
 
+_side = {}
+
+
+def side_stream():
+    """One extra CUDA stream per device for work that runs next to the current stream.  Shared by every optimizer
+    instance: the caching allocator keeps a pool per stream, so a stream per instance would turn every new
+    instance's temporaries into fresh cudaMalloc calls."""
+    t = torch()
+    dev = t.cuda.current_device()
+    if dev not in _side:
+        _side[dev] = t.cuda.Stream(device=dev)
+    return _side[dev]
+
+
 def stream_ptr() -> int:
     return int(torch().cuda.current_stream().cuda_stream)
 
