@@ -61,7 +61,15 @@ def main():
     import torch
 
     from or_pcd_b200 import _lib, ops
-    from or_pcd_b200.Optimizer import FastGlobalOptimizer, GeneralizedICP
+    from or_pcd_b200.Optimizer import FastGlobalOptimizer, GeneralizedICP, ShardedOptimizer
+
+    # under torchrun the units are sharded over the ranks (one GPU each) and the results all-gathered
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
     n_scales = int(sys.argv[2]) if len(sys.argv) > 2 else 256
@@ -82,22 +90,29 @@ def main():
     unit_tgt = np.repeat(np.arange(n_scales, dtype=np.int32), n_starts)
     U = len(unit_src)
     d_src, d_tgt = _lib.to_device(sources), _lib.to_device(targets)
-    opt = GeneralizedICP() if which == "gicp" else FastGlobalOptimizer(feature_mode="fixed")
+    inner = GeneralizedICP() if which == "gicp" else FastGlobalOptimizer(feature_mode="fixed")
     if which == "gicp":
-        opt.profile = True
+        inner.profile = True
+    opt = ShardedOptimizer(inner) if world > 1 else inner
     torch.cuda.synchronize()
     times = []
     for rep in range(2):
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         res = opt.optimize_batch(d_src, d_tgt, unit_src, unit_tgt, rigid_base=src)
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
     wall = min(times)
-    out = dict(optimizer=which, n_points=n, scales=n_scales, starts=n_starts, units=U, wall_s=wall,
+    if world > 1:
+        tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        wall = float(tw[0])
+    out = dict(optimizer=which, n_gpus=world, n_points=n, scales=n_scales, starts=n_starts, units=U, wall_s=wall,
                registrations_per_s=U / wall, rmse_min=float(res.rmse[res.status == 0].min()) if (res.status == 0).any() else None,
                failed_units=int((res.status != 0).sum()), mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
-    if which == "gicp":
+    if which == "gicp" and world == 1:
         p = res.profile
         out.update(mean_iterations=float(res.iterations.mean()), round_kernel_ms=p[1], pairs_visited=p[2],
                    visited_fraction=p[2] / max(p[7] * float(n) * n, 1), exact_fallback_fraction=p[4] / max(p[7] * n, 1))
@@ -128,7 +143,11 @@ def main():
                                                   rmse_eval=float(st[1]), rmse_reported=float(res.rmse[u]), rel=float(rel_rmse)))
         ok = ok and mism == 0 and rel_rmse < 1e-9
     out["ok"] = bool(ok)
-    print(json.dumps(out))
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
