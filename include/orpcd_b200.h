@@ -154,8 +154,9 @@ int orpcd_apply_rigid_batch(const double *d_points, int n, const double *d_rot,
 
 /* ------------------------------------------------------------------------
  * Batched Generalized-ICP: n_units independent inner registrations
- * (one per multi-start x scale candidate) advanced together, one launch
- * sequence per Gauss-Newton iteration for all of them.
+ * (one per multi-start x scale candidate) advanced together, one kernel
+ * launch per Gauss-Newton iteration for all of them (update, chunk-culled
+ * FP32 1-NN sweep with certified float64 re-rank, Jacobian sums, 6x6 solve).
  * Replaces registration_generalized_icp(source, target, max_dist, I,
  * TransformationEstimationForGeneralizedICP(), ICPConvergenceCriteria(
  * max_iteration)) at Optimizer/generalizedICP.py:59-70, called once per
@@ -170,26 +171,29 @@ typedef struct {
     int n_src_sets;
     int n_tgt_sets;
     int max_iterations;   /* ICPConvergenceCriteria.max_iteration  */
-    int target_splits;    /* 0 = choose automatically              */
+    int target_splits;    /* dense sweeps only: splits of the target table, 0 = automatic */
     int poll_interval;    /* >0: every that many iterations the call waits on
                              the stream and stops early once every unit is done */
-    int profile;          /* !=0: time every sweep launch with CUDA events on the
-                             stream and synchronise at the end (fills h_profile) */
+    int profile;          /* !=0: time every round kernel (dense modes: sweep) launch with
+                             CUDA events on the stream and synchronise at the end
+                             (fills h_profile) */
     int cov_mode;         /* 0: d_*_cov hold 3x3 covariances, 6 doubles per point, and
                                 (Cs+Ct)^-1/2 comes from a Jacobi eigen-solve;
                              1: d_*_cov hold the unit AXIS a of each GICP plane
                                 covariance C = I - (1-eps) a a^T (3 doubles per point,
-                                d_gicp_axis of orpcd_normals_cov) and the whitening
-                                matrix is evaluated in closed form               */
+                                d_gicp_axis of orpcd_normals_cov) and (Cs+Ct)^-1 is
+                                evaluated in closed form                          */
     double max_correspondence_distance;
     double relative_fitness; /* 1e-6 in the reference's call       */
     double relative_rmse;    /* 1e-6                               */
     double gicp_epsilon;     /* eps of diag(eps,1,1); used by cov_mode 1 (Open3D: 1e-3) */
-    int sweep_q;             /* tuning: queries per thread in the 1-NN sweep (4|8), 0 = auto */
-    int sweep_tj;            /* tuning: targets per inner step (2|4|8), 0 = auto            */
-    int sweep_smem_pad;      /* tuning: unused dynamic smem bytes (caps blocks per SM), 0    */
-    int sweep_mode;          /* tuning: 1 = all packed FFMA2, 2 = FFMA2 + scalar FFMA,
-                                3 = all scalar FFMA, 0 = auto                              */
+    int sweep_q;             /* tuning (modes 1..4): queries per thread (4|8), 0 = auto       */
+    int sweep_tj;            /* tuning (modes 1..4): targets per inner step (2|4|8), 0 = auto */
+    int sweep_smem_pad;      /* tuning (modes 1..3): unused dynamic smem bytes, 0             */
+    int sweep_mode;          /* 0 = default: one fused kernel per round, chunk-culled sweep;
+                                4 = culled sweep with separate update / resolve / fix /
+                                reduce kernels; 1..3 = dense (brute-force) sweep + separate
+                                kernels: 1 all packed FFMA2, 2 FFMA2 + scalar FFMA, 3 scalar */
 } orpcd_gicp_params;
 
 size_t orpcd_gicp_batch_workspace_bytes(const orpcd_gicp_params *p);
@@ -201,9 +205,10 @@ size_t orpcd_gicp_batch_workspace_bytes(const orpcd_gicp_params *p);
  * d_out_status[n_units]     0 = ok, 1 = no correspondence (inlier_rmse == 0:
  *                           the reference raises ValueError, generalizedICP.py:77-81),
  * d_trace (may be NULL) [n_units][max_iterations+1][2] (fitness, rmse) per Evaluate,
- * h_profile (HOST, may be NULL) [8]: {kernels launched, ms inside the 1-NN sweep
- *   kernel*, (query,target) pairs swept*, rounds issued, queries sent to the exact
- *   work list*, target splits, sweep launches with work*, unit-rounds*};
+ * h_profile (HOST, may be NULL) [8]: {kernels launched, ms inside the round kernel
+ *   (dense modes: the 1-NN sweep kernel)*, (query,target) pairs evaluated*, rounds
+ *   issued, queries that needed the exact float64 search*, target splits, launches
+ *   with work*, unit-rounds*};
  *   entries marked * are filled only when p->profile != 0.                    */
 int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_points,
                      const double *d_src_cov, const double *d_tgt_points,
