@@ -6,26 +6,31 @@
 // from Optimizer/generalizedICP.py:59-70 (once per start, Aligner/Aligner.py:188-190).
 // Algorithm: SURVEY.md Appendix A.4-A.5.
 //
-// Per iteration (all units in each launch):
+// Default path: ONE launch per Gauss-Newton round for all units, gicp_round_kernel (see its header comment):
+// every warp owns a patch of 64 Hilbert-consecutive source points and runs the pending rigid update, the
+// chunk-culled FP32 1-NN sweep (packed fma.rn.f32x2 on |p|^2 - 2 q.p, FMNMX3 minima per 8-target sub-chunk),
+// the FP32 certificate with the float64 re-rank, the exact float64 search for what the certificate leaves open,
+// and the Mahalanobis residual / Jacobian sums; the last warp of a unit adds the per-patch partials in patch
+// order, tests convergence, solves the 6x6 system (LDLT) and composes the transform.
+//
+// The same arithmetic as separate kernels (sweep_mode 1..4, kept for the dense brute-force sweeps and A/B runs):
 //   update_kernel     applies the pending rigid update to the stored float64 source
 //                     points and covariances (or covariance axes) and writes the
 //                     centred FP32 copy the sweep reads.
-//   nn_sweep_kernel   FP32 filter over all (query, target) pairs on the FMA pipe:
-//                     packed FFMA2 (fma.rn.f32x2) on the expanded form
-//                     |p|^2 - 2 q.p, FMNMX3 running minima per 32-target chunk,
-//                     per query (best chunk min, best chunk, second-best chunk min).
+//   nn_sweep_kernel / nn_sweep_cull_kernel
+//                     FP32 filter on the FMA pipe: per query (best chunk min, best chunk,
+//                     second-best chunk min), over all targets or over the chunks a patch
+//                     cannot exclude.
 //   nn_resolve_kernel proves with an FP32 error bound that the best chunk holds the
 //                     exact nearest neighbour, then a warp-wide ballot over that
 //                     chunk finds the single target inside the certified margin
 //                     and its float64 distance is taken in Open3D's operation
 //                     order; anything ambiguous at FP32 resolution goes to a work
 //                     list.
-//   nn_fix_kernel     exact float64 scan, one warp per listed query.
-//   reduce_kernel     Mahalanobis residual/Jacobian per correspondence, warp
-//                     shuffle + block reduction of the 21+6 J^T J / J^T r terms,
-//                     squared error and count; the last block of a unit sums the
-//                     block partials in index order, tests convergence, solves the
-//                     6x6 system (LDLT) and composes the transform.
+//   nn_fix_kernel     exact float64 search, one warp per listed query.
+//   reduce_kernel     residual / Jacobian sums per correspondence, block partials, the
+//                     last block of a unit sums them in index order, tests convergence,
+//                     solves the 6x6 system and composes the transform.
 #include <stdio.h>
 #include <stdlib.h>
 
