@@ -744,6 +744,7 @@ __device__ void fgr_ldlt_solve6(double *A, const double *b, double *x)
 __global__ void __launch_bounds__(FG_THREADS) fgr_gnc_kernel(FgrCtx c)
 {
     __shared__ double sh_part[FG_THREADS / 32][28];
+    __shared__ double sh_tot[28];
     __shared__ double sh_delta[12];
     const int u = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const FgrUnit fu = c.unit[u];
@@ -798,13 +799,15 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_gnc_kernel(FgrCtx c)
                 for (int k = 0; k < 27; ++k) sh_part[wid][k] = acc[k];
             }
             __syncthreads();
+            if (tid < 27) {   // 27 threads add the warps' partials (same order as one thread would)
+                double s = 0.0;
+                for (int w = 0; w < FG_THREADS / 32; ++w) s += sh_part[w][tid];
+                sh_tot[tid] = s;
+            }
+            __syncthreads();
             if (tid == 0) {
                 double tot[27];
-                for (int k = 0; k < 27; ++k) {
-                    double s = 0.0;
-                    for (int w = 0; w < FG_THREADS / 32; ++w) s += sh_part[w][k];
-                    tot[k] = s;
-                }
+                for (int k = 0; k < 27; ++k) tot[k] = sh_tot[k];
                 double A[36], x[6];
                 int k = 0;
                 for (int a = 0; a < 6; ++a)

@@ -423,6 +423,7 @@ __global__ void sor_mask_kernel(const double *__restrict__ avg, int n, double *_
 // scaled cloud with factor = min(s)^2.
 // ---------------------------------------------------------------------------
 constexpr int RR_BLOCK = 128;
+constexpr int RR_STEP = 8;     // candidates gathered per step
 
 __global__ void __launch_bounds__(RR_BLOCK)
 knn_rerank_kernel(const int *__restrict__ cand, const double *__restrict__ bound, int kc,
@@ -440,21 +441,21 @@ knn_rerank_kernel(const int *__restrict__ cand, const double *__restrict__ bound
     const double qx = pts[(size_t)i * 3], qy = pts[(size_t)i * 3 + 1], qz = pts[(size_t)i * 3 + 2];
     const int *row = cand + (size_t)i * kc;
     int cnt = 0;
-    // four candidates per step: their indices and coordinates are fetched together (the gathers are what this
+    // RR_STEP candidates per step: their indices and coordinates are fetched together (the gathers are what this
     // kernel waits for), then inserted one after the other in list order
-    for (int s0 = 0; s0 < kc; s0 += 4) {
-        int jj[4];
-        double cx[4], cy[4], cz[4];
+    for (int s0 = 0; s0 < kc; s0 += RR_STEP) {
+        int jj[RR_STEP];
+        double cx[RR_STEP], cy[RR_STEP], cz[RR_STEP];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) jj[r] = s0 + r < kc ? row[s0 + r] : -1;
+        for (int r = 0; r < RR_STEP; ++r) jj[r] = s0 + r < kc ? row[s0 + r] : -1;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < RR_STEP; ++r) {
             const int jr = jj[r] < 0 ? 0 : jj[r];
             cx[r] = pts[(size_t)jr * 3]; cy[r] = pts[(size_t)jr * 3 + 1]; cz[r] = pts[(size_t)jr * 3 + 2];
         }
         bool stop = false;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < RR_STEP; ++r) {
         const int j = jj[r];
         if (j < 0) stop = true;
         if (stop) continue;
