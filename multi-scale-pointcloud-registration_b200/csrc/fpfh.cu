@@ -111,9 +111,6 @@ fpfh_kernel(int n, const int *__restrict__ nn_idx, const double *__restrict__ nn
     const int *idx = nn_idx + row * list_k;
     const double *d2 = nn_d2 + row * list_k;
     const double *sp = spfh + (size_t)b * n * FP_DIM;
-    double acc[FP_DIM];
-#pragma unroll
-    for (int j = 0; j < FP_DIM; ++j) acc[j] = 0.0;
     int cnt = 0;
     for (; cnt < knn; ++cnt) {
         if (idx[cnt] < 0) break;
@@ -121,33 +118,39 @@ fpfh_kernel(int n, const int *__restrict__ nn_idx, const double *__restrict__ nn
     }
     double *o = fpfh + row * FP_DIM;
     if (cnt > 1) {
-        double sum[3] = {0.0, 0.0, 0.0};
-        for (int k = 1; k < cnt; ++k) {
-            const double dist = d2[k];
-            if (dist == 0.0) continue;
-            const double *s = sp + (size_t)idx[k] * FP_DIM;
-            // 33 correctly rounded quotients s[j] / dist from ONE division: with y = RN(1 / dist), q = s y,
-            // r = s - q dist (exact in an FMA), q' = q + r y is RN(s / dist) (Markstein) unless dist's significand
-            // is all ones -- that case takes the plain division.  Histogram values and distances are far from
-            // the overflow / subnormal ranges.
-            const double y = 1.0 / dist;
-            const bool plain = (__double2hiint(dist) & 0x000fffff) == 0x000fffff && (unsigned)__double2loint(dist) == 0xffffffffu;
-#pragma unroll
-            for (int j = 0; j < FP_DIM; ++j) {
-                const double sj = s[j];
-                const double q = __dmul_rn(sj, y);
-                double val = fma(fma(-q, dist, sj), y, q);
-                if (plain) val = sj / dist;
-                sum[j / 11] += val;
-                acc[j] += val;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            if (sum[j] != 0.0) sum[j] = 100.0 / sum[j];
         const double *self = sp + (size_t)i * FP_DIM;
+        // one pass per histogram (the three are independent, each with its own normaliser): 11 running sums in
+        // registers instead of 33 double the resident warps of a kernel that waits on the gathers of the rows
+#pragma unroll 1
+        for (int h = 0; h < 3; ++h) {
+            double acc[11];
 #pragma unroll
-        for (int j = 0; j < FP_DIM; ++j) o[j] = acc[j] * sum[j / 11] + self[j];
+            for (int j = 0; j < 11; ++j) acc[j] = 0.0;
+            double sum = 0.0;
+            for (int k = 1; k < cnt; ++k) {
+                const double dist = d2[k];
+                if (dist == 0.0) continue;
+                const double *s = sp + (size_t)idx[k] * FP_DIM + h * 11;
+                // 11 correctly rounded quotients s[j] / dist from ONE division: with y = RN(1 / dist), q = s y,
+                // r = s - q dist (exact in an FMA), q' = q + r y is RN(s / dist) (Markstein) unless dist's
+                // significand is all ones -- that case takes the plain division.  Histogram values and distances
+                // are far from the overflow / subnormal ranges.
+                const double y = 1.0 / dist;
+                const bool plain = (__double2hiint(dist) & 0x000fffff) == 0x000fffff && (unsigned)__double2loint(dist) == 0xffffffffu;
+#pragma unroll
+                for (int j = 0; j < 11; ++j) {
+                    const double sj = s[j];
+                    const double q = __dmul_rn(sj, y);
+                    double val = fma(fma(-q, dist, sj), y, q);
+                    if (plain) val = sj / dist;
+                    sum += val;
+                    acc[j] += val;
+                }
+            }
+            if (sum != 0.0) sum = 100.0 / sum;
+#pragma unroll
+            for (int j = 0; j < 11; ++j) o[h * 11 + j] = acc[j] * sum + self[h * 11 + j];
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < FP_DIM; ++j) o[j] = 0.0;
