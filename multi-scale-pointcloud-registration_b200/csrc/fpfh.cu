@@ -100,7 +100,7 @@ spfh_kernel(const double *__restrict__ points, const double *__restrict__ normal
 }
 
 // FPFH: own SPFH + the 1/d2-weighted, per-histogram renormalised SPFH of the neighbours.
-__global__ void __launch_bounds__(FP_THREADS)
+__global__ void __launch_bounds__(FP_THREADS, 8)
 fpfh_kernel(int n, const int *__restrict__ nn_idx, const double *__restrict__ nn_d2, int list_k, int knn,
             double radius2, const double *__restrict__ spfh, double *__restrict__ fpfh)
 {
