@@ -39,7 +39,7 @@ typedef void *orpcd_stream_t; /* cudaStream_t */
 #define ORPCD_ERR_WORKSPACE (-2) /* workspace too small / misaligned      */
 #define ORPCD_ERR_CUDA (-3)      /* a CUDA runtime call or launch failed  */
 
-#define ORPCD_MAX_KNN 64
+#define ORPCD_MAX_KNN 512
 
 /* Library / build identification. */
 int orpcd_version(void);
@@ -331,6 +331,14 @@ typedef struct {
     double tuple_scale;
     double max_correspondence_distance;
 } orpcd_fgr_params;
+
+/* Keys of the per-unit tuple-test streams: key[u] = tuple_key(seed, source cloud, target cloud) of
+ * or_pcd_b200/Optimizer/fastGlobalOptimizer.py (hash of the seed, the cloud sizes and the bit patterns of
+ * each cloud's first and last point).  Stands in for Open3D's unseeded global std::mt19937
+ * (FastGlobalRegistration.cpp AdvancedMatching; Optimizer/fastGlobalOptimizer.py:166-174). */
+int orpcd_fgr_tuple_keys(const double *d_src_points, int n_src, const double *d_tgt_points, int n_tgt,
+                         const int *d_unit_src, const int *d_unit_tgt, int n_units,
+                         unsigned long long seed, unsigned long long *d_keys, orpcd_stream_t stream);
 
 size_t orpcd_fgr_batch_workspace_bytes(const orpcd_fgr_params *p);
 int orpcd_fgr_batch(const orpcd_fgr_params *p, const double *d_src_points,

@@ -180,3 +180,77 @@ __device__ __forceinline__ double det_cos(double x)
     const double yt = (t - y) - pi_lo;
     return -det_kcos(y, yt);
 }
+
+// atan / atan2: bit-identical twins of det_atan / det_atan2 in oracle/orpcd_oracle.c (fdlibm's s_atan.c /
+// e_atan2.c restated).  Feeds the floor() that bins FPFH's f0 angle (Feature.cpp ComputePairFeatures).
+__device__ __forceinline__ double det_atan(double x)
+{
+    const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01, aT2 = 1.42857142725034663711e-01,
+                 aT3 = -1.11111104054623557880e-01, aT4 = 9.09088713343650656196e-02, aT5 = -7.69187620504482999495e-02,
+                 aT6 = 6.66107313738753120669e-02, aT7 = -5.83357013379057348645e-02, aT8 = 4.97687799461593236017e-02,
+                 aT9 = -3.65315727442169155270e-02, aT10 = 1.62858201153657823623e-02;
+    const unsigned hx = (unsigned)__double2hiint(x), ix = hx & 0x7fffffffu;
+    double hi = 0.0, lo = 0.0;
+    bool reduced = true;
+    if (ix >= 0x44100000u) {                        // |x| >= 2^66 (or NaN)
+        if (x != x) return x + x;
+        const double r = 1.57079632679489655800e+00 + 6.12323399573676603587e-17;
+        return (hx >> 31) ? -1.57079632679489655800e+00 - 6.12323399573676603587e-17 : r;
+    }
+    if (ix < 0x3fdc0000u) {                         // |x| < 0.4375
+        if (ix < 0x3e200000u) return x;             // |x| < 2^-29
+        reduced = false;
+    } else {
+        x = fabs(x);
+        if (ix < 0x3ff30000u) {
+            if (ix < 0x3fe60000u) {
+                hi = 4.63647609000806093515e-01; lo = 2.26987774529616870924e-17;
+                x = (2.0 * x - 1.0) / (2.0 + x);
+            } else {
+                hi = 7.85398163397448278999e-01; lo = 3.06161699786838301793e-17;
+                x = (x - 1.0) / (x + 1.0);
+            }
+        } else {
+            if (ix < 0x40038000u) {
+                hi = 9.82793723247329054082e-01; lo = 1.39033110312309984516e-17;
+                x = (x - 1.5) / (1.0 + 1.5 * x);
+            } else {
+                hi = 1.57079632679489655800e+00; lo = 6.12323399573676603587e-17;
+                x = -1.0 / x;
+            }
+        }
+    }
+    const double z = x * x;
+    const double w = z * z;
+    const double s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
+    const double s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
+    if (!reduced) return x - x * (s1 + s2);
+    const double r = hi - ((x * (s1 + s2) - lo) - x);
+    return (hx >> 31) ? -r : r;
+}
+
+__device__ __forceinline__ double det_atan2(double y, double x)
+{
+    const double pi_o_2 = 1.5707963267948965580e+00, pi = 3.1415926535897931160e+00, pi_lo = 1.2246467991473531772e-16;
+    if (x != x || y != y) return x + y;
+    if (x == 1.0) return det_atan(y);
+    const unsigned hx = (unsigned)__double2hiint(x), hy = (unsigned)__double2hiint(y);
+    const int m = (int)((hy >> 31) & 1u) | (int)((hx >> 30) & 2u);
+    if (y == 0.0) return m < 2 ? y : (m == 2 ? pi : -pi);
+    if (x == 0.0) return (hy >> 31) ? -pi_o_2 : pi_o_2;
+    const int ix = (int)(hx & 0x7fffffffu), iy = (int)(hy & 0x7fffffffu);
+    if (ix >= 0x7ff00000 || iy >= 0x7ff00000) {
+        if (iy >= 0x7ff00000 && ix < 0x7ff00000) return (hy >> 31) ? -pi_o_2 : pi_o_2;
+        if (ix >= 0x7ff00000 && iy < 0x7ff00000) return m == 0 ? 0.0 : (m == 1 ? -0.0 : (m == 2 ? pi : -pi));
+        return m == 0 ? 0.5 * pi_o_2 : (m == 1 ? -0.5 * pi_o_2 : (m == 2 ? 1.5 * pi_o_2 : -1.5 * pi_o_2));
+    }
+    const int k = (iy - ix) >> 20;
+    double z;
+    if (k > 60) z = pi_o_2 + 0.5 * pi_lo;
+    else if ((hx >> 31) && k < -60) z = 0.0;
+    else z = det_atan(fabs(y / x));
+    if (m == 0) return z;
+    if (m == 1) return -z;
+    if (m == 2) return pi - (z - pi_lo);
+    return (z - pi_lo) - pi;
+}

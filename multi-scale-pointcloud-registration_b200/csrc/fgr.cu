@@ -960,6 +960,45 @@ ORPCD_API int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q
     return ORPCD_OK;
 }
 
+namespace {
+
+// tuple_key(seed, source, target) of Optimizer/fastGlobalOptimizer.py: a hash of the seed, the two cloud sizes and
+// the bit patterns of the first and last point of each cloud (one thread per unit).
+__global__ void fgr_tuple_keys_kernel(const double *__restrict__ src, const double *__restrict__ tgt, int n_src,
+                                      int n_tgt, const int *__restrict__ unit_src, const int *__restrict__ unit_tgt,
+                                      int n_units, unsigned long long seed, unsigned long long *__restrict__ keys)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const double *s = src + (size_t)unit_src[u] * n_src * 3, *t = tgt + (size_t)unit_tgt[u] * n_tgt * 3;
+    unsigned long long h = seed * 0x9E3779B97F4A7C15ull + 0x243F6A8885A308D3ull;
+    auto mix = [&](unsigned long long w) {
+        h = (h ^ w) * 0xBF58476D1CE4E5B9ull;
+        h ^= h >> 31;
+    };
+    mix((unsigned long long)n_src);
+    mix((unsigned long long)n_tgt);
+    const double *ends[4] = {s, s + (size_t)(n_src - 1) * 3, t, t + (size_t)(n_tgt - 1) * 3};
+    for (int e = 0; e < 4; ++e)
+        for (int k = 0; k < 3; ++k) mix((unsigned long long)__double_as_longlong(ends[e][k]));
+    keys[u] = h;
+}
+
+}  // namespace
+
+ORPCD_API int orpcd_fgr_tuple_keys(const double *d_src_points, int n_src, const double *d_tgt_points, int n_tgt,
+                                   const int *d_unit_src, const int *d_unit_tgt, int n_units,
+                                   unsigned long long seed, unsigned long long *d_keys, orpcd_stream_t stream)
+{
+    if (!d_src_points || !d_tgt_points || !d_unit_src || !d_unit_tgt || !d_keys || n_units <= 0 || n_src <= 0 ||
+        n_tgt <= 0)
+        return ORPCD_ERR_INVALID;
+    fgr_tuple_keys_kernel<<<(n_units + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        d_src_points, d_tgt_points, n_src, n_tgt, d_unit_src, d_unit_tgt, n_units, seed, d_keys);
+    ORPCD_CHECK_LAUNCH();
+    return ORPCD_OK;
+}
+
 ORPCD_API size_t orpcd_fgr_batch_workspace_bytes(const orpcd_fgr_params *p)
 {
     FgrLayout L;

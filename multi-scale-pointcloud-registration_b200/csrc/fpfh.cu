@@ -8,9 +8,9 @@
 // Both passes run over neighbour lists computed elsewhere (orpcd_knn_exact /
 // orpcd_knn_rerank: exact float64, sorted by (distance, index)); the Hybrid search is
 // the k-NN list truncated at d2 < radius^2.  One thread per point; every sum is taken in
-// neighbour order like the CPU code; the one discontinuous libm call (the acos comparison that
-// picks the pair's source point) uses the deterministic det_acos shared with the oracle, so the
-// only remaining difference is the device atan2 within an ulp of a histogram-bin edge.
+// neighbour order like the CPU code; the libm calls that feed discontinuous decisions (the acos
+// comparison that picks the pair's source point, the atan2 whose result is binned by floor()) use the
+// deterministic det_acos / det_atan2 shared with the oracle: SPFH and FPFH are bit-identical to it.
 #include "common.cuh"
 
 namespace {
@@ -55,7 +55,7 @@ __device__ __forceinline__ bool pair_features(const double *p1, const double *n1
     const double wx = ay * vz - az * vy, wy = az * vx - ax * vz, wz = ax * vy - ay * vx;
     f2 = g2;
     f1 = vx * bx + vy * by + vz * bz;
-    f0 = atan2(wx * bx + wy * by + wz * bz, ax * bx + ay * by + az * bz);
+    f0 = det_atan2(wx * bx + wy * by + wz * bz, ax * bx + ay * by + az * bz);
     return true;
 }
 

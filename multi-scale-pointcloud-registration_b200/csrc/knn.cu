@@ -13,8 +13,10 @@
 
 namespace {
 
-constexpr int KNN_BLOCK = 128;  // queries per block (one per thread)
 constexpr int KNN_TILE = 512;   // points staged per shared-memory tile
+// queries per block (one per thread): the k-best sets take k * 12 bytes of shared memory per query, so the block
+// shrinks as k grows (k <= 128: 128 queries, k <= 256: 64, k <= ORPCD_MAX_KNN = 512: 32)
+__host__ __device__ constexpr int knn_block_for(int k) { return k <= 128 ? 128 : (k <= 256 ? 64 : 32); }
 
 // One thread per query; its k best (d2, idx) pairs live in shared memory, slot-major so
 // a warp's accesses to one slot are conflict free.  The set is kept UNSORTED with the
@@ -23,6 +25,7 @@ constexpr int KNN_TILE = 512;   // points staged per shared-memory tile
 // lane inserting makes the whole warp wait).  Points are visited in ascending index order
 // and replace only on a strict '<', so the kept set is the k smallest under (d2, idx)
 // lexicographic order; it is sorted once at the end.
+template <int KNN_BLOCK>
 __global__ void __launch_bounds__(KNN_BLOCK)
 knn_f64_kernel(const double *__restrict__ points, int n, long long points_stride,
                const double *__restrict__ queries, int m, long long queries_stride, int k,
@@ -172,7 +175,8 @@ knn_merge_kernel(const int *__restrict__ part_idx, const double *__restrict__ pa
 // are strict with slack, so a skipped chunk holds no point that could enter a list -- not even on an exact
 // tie -- and the lists equal the brute-force result under the (d2, original index) order.
 // ----------------------------------------------------------------------------
-constexpr int KC_WARPS = 4;
+// warps per block: 4 for k <= 128, 2 for k <= 256, 1 up to ORPCD_MAX_KNN (the lists take k * 384 bytes per warp)
+__host__ __device__ constexpr int kc_warps_for(int k) { return k <= 128 ? 4 : (k <= 256 ? 2 : 1); }
 
 // sorted copy of the cloud + chunk spheres.  grid (chunks, batch), 32 threads.
 __global__ void __launch_bounds__(32)
@@ -202,6 +206,7 @@ knn_cull_prep_kernel(const double *__restrict__ points, int n, const int *__rest
     if (lane == 0) spheres[(size_t)b * (n_pad / 32) + ch] = make_double4(cx, cy, cz, r * (1.0 + 1e-12) + 1e-300);
 }
 
+template <int KC_WARPS>
 __global__ void __launch_bounds__(KC_WARPS * 32)
 knn_cull_kernel(const double *__restrict__ sorted, const double4 *__restrict__ spheres, const int *__restrict__ perm,
                 int n, int n_pad, int k, int *__restrict__ out_idx, double *__restrict__ out_d2)
@@ -346,7 +351,42 @@ constexpr int KNN_CULL_MIN_N = 2048;   // below this the brute-force kernel is a
 
 size_t knn_smem_bytes(int k)
 {
-    return (size_t)3 * KNN_TILE * sizeof(double) + (size_t)k * KNN_BLOCK * (sizeof(double) + sizeof(int));
+    return (size_t)3 * KNN_TILE * sizeof(double) + (size_t)k * knn_block_for(k) * (sizeof(double) + sizeof(int));
+}
+
+template <int B>
+int launch_knn_f64(dim3 grid, size_t smem, cudaStream_t st, const double *points, int n, long long points_stride,
+                   const double *queries, int m, long long queries_stride, int k, int split_len, int *out_idx,
+                   double *out_d2)
+{
+    if (cudaFuncSetAttribute(knn_f64_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return ORPCD_ERR_CUDA;
+    knn_f64_kernel<B><<<grid, B, smem, st>>>(points, n, points_stride, queries, m, queries_stride, k, split_len, out_idx,
+                                            out_d2);
+    return cudaGetLastError() == cudaSuccess ? ORPCD_OK : ORPCD_ERR_CUDA;
+}
+
+int launch_knn_f64_any(int gy, int gz, size_t smem, cudaStream_t st, const double *points, int n,
+                       long long points_stride, const double *queries, int m, long long queries_stride, int k,
+                       int split_len, int *out_idx, double *out_d2)
+{
+    const int B = knn_block_for(k);
+    const dim3 grid((m + B - 1) / B, gy, gz);
+    if (B == 128) return launch_knn_f64<128>(grid, smem, st, points, n, points_stride, queries, m, queries_stride, k, split_len, out_idx, out_d2);
+    if (B == 64) return launch_knn_f64<64>(grid, smem, st, points, n, points_stride, queries, m, queries_stride, k, split_len, out_idx, out_d2);
+    return launch_knn_f64<32>(grid, smem, st, points, n, points_stride, queries, m, queries_stride, k, split_len, out_idx, out_d2);
+}
+
+template <int W>
+int launch_knn_cull(int n_chunks, int batch, cudaStream_t st, const double *sorted, const double4 *sph, const int *perm,
+                    int n, int n_pad, int k, int *out_idx, double *out_d2)
+{
+    const size_t sm = (size_t)W * k * 32 * (sizeof(double) + sizeof(int));
+    if (cudaFuncSetAttribute(knn_cull_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+        return ORPCD_ERR_CUDA;
+    knn_cull_kernel<W><<<dim3((n_chunks + W - 1) / W, batch), W * 32, sm, st>>>(sorted, sph, perm, n, n_pad, k, out_idx,
+                                                                              out_d2);
+    return cudaGetLastError() == cudaSuccess ? ORPCD_OK : ORPCD_ERR_CUDA;
 }
 
 // avg_i = sum_j sqrt(d2_ij) / cnt_i  in ascending-distance order (A.2)
@@ -583,9 +623,6 @@ int orpcd_launch_knn(const double *d_points, int n, long long points_stride, con
         return ORPCD_ERR_INVALID;
     if (m == 0 || batch == 0) return ORPCD_OK;
     const size_t smem = knn_smem_bytes(k);
-    if (cudaFuncSetAttribute(knn_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess)
-        return ORPCD_ERR_CUDA;
     const bool have_scratch = d_scratch && scratch_bytes >= orpcd_knn_scratch_bytes(n, m, batch, k) &&
                               !((uintptr_t)d_scratch & 255);
     if (have_scratch && d_queries == d_points && m == n && queries_stride == points_stride && n >= KNN_CULL_MIN_N &&
@@ -601,30 +638,22 @@ int orpcd_launch_knn(const double *d_points, int n, long long points_stride, con
             return ORPCD_ERR_CUDA;
         const int n_chunks = L.n_pad / 32;
         knn_cull_prep_kernel<<<dim3(n_chunks, batch), 32, 0, st>>>(d_points, n, perm, L.n_pad, sorted, sph);
-        const size_t sm = (size_t)KC_WARPS * k * 32 * (sizeof(double) + sizeof(int));
-        if (cudaFuncSetAttribute(knn_cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
-            return ORPCD_ERR_CUDA;
-        knn_cull_kernel<<<dim3((n_chunks + KC_WARPS - 1) / KC_WARPS, batch), KC_WARPS * 32, sm, st>>>(
-            sorted, sph, perm, n, L.n_pad, k, d_idx, d_d2);
-        ORPCD_CHECK_LAUNCH();
-        return ORPCD_OK;
+        const int W = kc_warps_for(k);
+        return W == 4 ? launch_knn_cull<4>(n_chunks, batch, st, sorted, sph, perm, n, L.n_pad, k, d_idx, d_d2)
+                      : (W == 2 ? launch_knn_cull<2>(n_chunks, batch, st, sorted, sph, perm, n, L.n_pad, k, d_idx, d_d2)
+                                : launch_knn_cull<1>(n_chunks, batch, st, sorted, sph, perm, n, L.n_pad, k, d_idx, d_d2));
     }
     int splits = orpcd_knn_splits(n, m, batch);
     if (!d_scratch || scratch_bytes < orpcd_knn_scratch_bytes(n, m, batch, k) || ((uintptr_t)d_scratch & 255)) splits = 1;
-    if (splits <= 1) {
-        dim3 grid((m + KNN_BLOCK - 1) / KNN_BLOCK, batch, 1);
-        knn_f64_kernel<<<grid, KNN_BLOCK, smem, st>>>(d_points, n, points_stride, d_queries, m, queries_stride, k,
-                                                      n > 0 ? n : 1, d_idx, d_d2);
-        ORPCD_CHECK_LAUNCH();
-        return ORPCD_OK;
-    }
+    if (splits <= 1)
+        return launch_knn_f64_any(batch, 1, smem, st, d_points, n, points_stride, d_queries, m, queries_stride, k,
+                                  n > 0 ? n : 1, d_idx, d_d2);
     const size_t e = (size_t)m * batch * splits * k;
     double *pd = (double *)d_scratch;
     int *pi = (int *)((unsigned char *)d_scratch + orpcd_align_up(e * sizeof(double), 256));
-    dim3 grid((m + KNN_BLOCK - 1) / KNN_BLOCK, batch, splits);
-    knn_f64_kernel<<<grid, KNN_BLOCK, smem, st>>>(d_points, n, points_stride, d_queries, m, queries_stride, k,
-                                                  (n + splits - 1) / splits, pi, pd);
-    ORPCD_CHECK_LAUNCH();
+    if (launch_knn_f64_any(batch, splits, smem, st, d_points, n, points_stride, d_queries, m, queries_stride, k,
+                           (n + splits - 1) / splits, pi, pd) != ORPCD_OK)
+        return ORPCD_ERR_CUDA;
     const long long nq = (long long)m * batch;
     knn_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(pi, pd, nq, splits, k, d_idx, d_d2);
     ORPCD_CHECK_LAUNCH();
@@ -707,7 +736,7 @@ ORPCD_API int orpcd_knn_rerank(const int *d_cand_idx, const double *d_cand_bound
                                size_t workspace_bytes, orpcd_stream_t stream)
 {
     if (!d_cand_idx || !d_cand_bound || !d_points || !d_factor || !d_idx || !d_d2 || n <= 0 || batch <= 0 ||
-        k < 1 || k > ORPCD_MAX_KNN || kc < k || (long long)n * batch > 0x7fffffffLL)
+        k < 1 || k > 64 || kc < k || (long long)n * batch > 0x7fffffffLL)   /* lists: k * 1536 bytes of shared memory */
         return ORPCD_ERR_INVALID;
     if (!d_workspace || workspace_bytes < orpcd_knn_rerank_workspace_bytes(n, batch) || ((uintptr_t)d_workspace & 255))
         return ORPCD_ERR_WORKSPACE;

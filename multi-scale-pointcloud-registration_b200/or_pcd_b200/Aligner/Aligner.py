@@ -84,6 +84,7 @@ class Aligner:
         self.n_units_evaluated = 0         # inner registrations actually run (speculation included)
         self.device_starts = True          # build the start clouds on the GPU when the optimizer allows it
         self._d_source, self._d_source_key = None, None
+        self._d_target, self._d_target_key = None, None
         self._device_starts_verified = False
 
     # ------------------------------------------------------------------ starts
@@ -210,10 +211,23 @@ class Aligner:
         rotation, metric = self.multistart_registration(source, target * new_scale_factors)
         return new_scale_factors, rotation, metric
 
+    def _scaled_targets(self, target: np.ndarray, scales: np.ndarray):
+        """``target * scales[c]`` for every poll candidate (reference: Aligner.py:221-222).  One rounded float64
+        multiply per coordinate either way; on the device (orpcd_apply_scale_batch) when the optimizer takes CUDA
+        tensors, so a sweep uploads 144 bytes of scale factors instead of six scaled clouds."""
+        if not self._device_starts():
+            return np.stack([target * s for s in scales], axis=0)
+        from .. import _lib, ops
+
+        if self._d_target_key is not target:
+            self._d_target, self._d_target_key = _lib.to_device(np.asarray(target, dtype=np.float64)), target
+        return ops.apply_scale_batch(self._d_target, _lib.to_device(np.concatenate(scales, axis=0)))
+
     def _poll_sweep(self, source, target, scale, delta):
-        """All six poll candidates of one sweep in a single batch, then the reference's
-        sequential accept logic replayed over the results.  Returns
-        (accepted_index or None, step, transform, metric_of_last_evaluated)."""
+        """All six poll candidates of one sweep in a single batch (6 x attempts units).  Returns
+        (steps, starts, states, res): the six scale steps in poll order, the starts drawn for each, the
+        ``np.random`` state after each candidate's draws, and the optimizer's BatchResult; ``align`` replays the
+        reference's sequential accept logic over them."""
         steps = []
         for axis in range(3):
             e = np.zeros(3)
@@ -226,7 +240,7 @@ class Aligner:
             states.append(np.random.get_state())
         A = self._attempts
         sources = self._start_clouds(source, starts)
-        targets = np.stack([target * (scale + st) for st in steps], axis=0)   # Aligner.py:221-222
+        targets = self._scaled_targets(target, [scale + st for st in steps])
         unit_src = np.arange(6 * A, dtype=np.int32)
         unit_tgt = np.repeat(np.arange(6, dtype=np.int32), A)
         res = self._optimizer.optimize_batch(sources, targets, unit_src, unit_tgt, **self._batch_kwargs(source))

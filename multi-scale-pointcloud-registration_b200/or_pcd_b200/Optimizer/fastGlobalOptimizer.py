@@ -182,14 +182,8 @@ class FastGlobalOptimizer(IOptimizer):
             ji, _, st2, _ = ops.feature_match(pf_t, pf_s, ut, us, mode=self.match_mode)
             scans = st1 + st2
 
-        # tuple-test keys from the first / last point of each unit's clouds
-        ends_s = d_src[:, [0, -1], :].cpu().numpy()
-        ends_t = d_tgt[:, [0, -1], :].cpu().numpy()
-        ns, nt = d_src.shape[1], d_tgt.shape[1]
-        keys = np.empty(U, dtype=np.uint64)
-        for u in range(U):
-            keys[u] = _tuple_key_from_ends(self.tuple_seed, ns, nt, ends_s[unit_src[u]], ends_t[unit_tgt[u]])
-        d_keys = t.as_tensor(keys.view(np.int64)).to("cuda")
+        # tuple-test keys (tuple_key of every unit's two clouds), hashed on the device
+        d_keys = ops.fgr_tuple_keys(d_src, d_tgt, us, ut, self.tuple_seed)
 
         T, info = ops.fgr_batch(d_src, d_tgt, us, ut, ij, ji, d_keys, self._division_factor, self._tuple_scale,
                                 self._maximum_correspondence_distance, self._iteration_number, self._decrease_mu,
@@ -202,8 +196,11 @@ class FastGlobalOptimizer(IOptimizer):
         self.last_exact_scans = int(scans[0].item()) if hasattr(scans, "cpu") else int(scans)
         self.last_rescored_chunks = int(scans[1].item()) if hasattr(scans, "cpu") else 0
         Th[:, :3, :3] = np.transpose(Th[:, :3, :3], (0, 2, 1)).copy()       # fastGlobalOptimizer.py:176-178
+        # the reference fails iff the final correspondence set is EMPTY (fastGlobalOptimizer.py:181-188); an exact
+        # alignment with rmse == 0 and correspondences is a success (unlike GICP's rmse == 0 rule)
+        status = (stats[:, 3] == 0).astype(np.int32)
         return BatchResult(Th, stats[:, 1].copy(), stats[:, 0].copy(), self.last_info[:, 1].astype(np.int64),
-                           status.cpu().numpy(), [])
+                           status, [])
 
     def __repr__(self):
         return f"""{self.__class__.__name__}
@@ -219,12 +216,3 @@ class FastGlobalOptimizer(IOptimizer):
         """
 
 
-def _tuple_key_from_ends(seed, ns, nt, ends_s, ends_t) -> int:
-    h = (int(seed) * 0x9E3779B97F4A7C15 + 0x243F6A8885A308D3) & _M64
-    words = [ns, nt]
-    for c in (ends_s[0], ends_s[1], ends_t[0], ends_t[1]):
-        words.extend(int(v) for v in np.ascontiguousarray(c, dtype=np.float64).view(np.uint64))
-    for w in words:
-        h = ((h ^ (w & _M64)) * 0xBF58476D1CE4E5B9) & _M64
-        h ^= h >> 31
-    return h

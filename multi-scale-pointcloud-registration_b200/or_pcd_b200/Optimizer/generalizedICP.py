@@ -92,6 +92,31 @@ class GeneralizedICP(IOptimizer):
         return BatchResult(T, stats[:, 1].copy(), stats[:, 0].copy(), stats[:, 2].astype(np.int64), status,
                            d_res.profile)
 
+    def optimize_batch_records(self, sources, targets, unit_src: Sequence[int], unit_tgt: Sequence[int],
+                               poll_interval: int = 0, rigid_base: Optional[np.ndarray] = None):
+        """``optimize_batch`` with the results left on the device as one (U, 20) float64 record per unit --
+        rmse, fitness, iterations, status, the 16 entries of the transform with its rotation block transposed
+        (generalizedICP.py:72-74) -- the layout ShardedOptimizer all-gathers between the GPUs."""
+        t = _lib.torch()
+        d_src = sources if hasattr(sources, "is_cuda") else _lib.to_device(np.asarray(sources))
+        d_tgt = targets if hasattr(targets, "is_cuda") else _lib.to_device(np.asarray(targets))
+        us = t.as_tensor(np.asarray(unit_src, dtype=np.int32)).to("cuda")
+        ut = t.as_tensor(np.asarray(unit_tgt, dtype=np.int32)).to("cuda")
+        src_cov, tgt_cov = self.covariances(d_src, d_tgt, rigid_base)
+        r = self.optimize_batch_device(d_src, d_tgt, us, ut, poll_interval=poll_interval, src_cov=src_cov,
+                                       tgt_cov=tgt_cov)
+        self.last_profile = r.profile
+        U = us.shape[0]
+        T = r.T.clone()
+        T[:, :3, :3] = r.T[:, :3, :3].transpose(1, 2)
+        rec = t.empty((U, 20), dtype=t.float64, device="cuda")
+        rec[:, 0] = r.stats[:, 1]
+        rec[:, 1] = r.stats[:, 0]
+        rec[:, 2] = r.stats[:, 2]
+        rec[:, 3] = r.status.to(t.float64)
+        rec[:, 4:] = T.reshape(U, 16)
+        return rec
+
     RERANK_KC = 48   # candidates kept per point of the base cloud (k = 20 are needed)
     accepts_device_sources = True   # the Aligner may hand over start clouds built on the GPU (CUDA tensors)
 

@@ -3,16 +3,23 @@
 The units of a poll round (scale candidate x random start) are independent inner
 registrations, so they shard with no data-path collective: every rank (one process
 per GPU, ``torch.distributed``) derives the same unit list from the same numpy
-stream, runs the units ``u = rank (mod world)`` on its own GPU and contributes one
-fixed-size record per unit -- {rmse, fitness, iterations, status, T[16]} = 20
-float64 = 160 bytes -- to a single all-gather (NCCL over NVLink on the GPU box,
-gloo in the CPU tests).  Every rank then holds the full result and replays the
-Aligner's accept logic identically; no decision broadcast is needed.
+stream, runs one block of it on its own GPU and contributes one fixed-size record
+per unit -- {rmse, fitness, iterations, status, T[16]} = 20 float64 = 160 bytes --
+to a single all-gather (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+Every rank then holds the full result and replays the Aligner's accept logic
+identically; no decision broadcast is needed.
+
+Blocks follow the TARGET sets: the units are ordered by target set (stable) and cut
+into ``world`` contiguous runs of equal weight, so a rank prepares (k-NN graph,
+covariances, Hilbert order, chunk spheres) only the few target sets its own units
+touch -- with round-robin dealing every rank would repeat that work for every set.
+With an optimizer that offers ``optimize_batch_records`` (GeneralizedICP) the records
+are packed on the device and go GPU -> all-gather -> one D2H copy of the result.
 
 The reference has no counterpart (single process; Aligner/Aligner.py:164-204 runs
 the starts one after another)."""
 import inspect
-from typing import Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -21,10 +28,33 @@ from .iOptimizer import BatchResult, IOptimizer
 RECORD_F64 = 20   # rmse, fitness, iterations, status, 16 transform entries
 
 
-def unit_shard(n_units: int, rank: int, world: int) -> np.ndarray:
-    """Indices of the units rank ``rank`` runs: round-robin, so every rank gets the same
-    mix of scale candidates (units are ordered candidate-major) and of easy/hard starts."""
-    return np.arange(rank, n_units, world, dtype=np.int64)
+def shard_plan(unit_tgt: Sequence[int], world: int, weights: Optional[Sequence[float]] = None) -> List[np.ndarray]:
+    """Unit indices of every rank.  Units are ordered by target set (stable: ties keep the caller's order) and
+    the ordered list is cut into ``world`` contiguous runs of (nearly) equal total weight -- equal counts when
+    ``weights`` is None -- so each rank touches at most ``ceil(sets / world) + 1`` target sets."""
+    unit_tgt = np.asarray(unit_tgt)
+    n = len(unit_tgt)
+    order = np.argsort(unit_tgt, kind="stable").astype(np.int64)
+    if weights is None:
+        cuts = [(n * r) // world for r in range(world + 1)]
+    else:
+        w = np.asarray(weights, dtype=np.float64)[order]
+        if (w < 0).any() or not np.isfinite(w).all():
+            raise ValueError("shard weights must be finite and non-negative")
+        c = np.concatenate([[0.0], np.cumsum(w)])
+        total = c[-1]
+        if total <= 0:
+            cuts = [(n * r) // world for r in range(world + 1)]
+        else:   # unit i goes to the rank whose weight interval holds the midpoint of its own
+            mid = 0.5 * (c[:-1] + c[1:]) / total * world
+            owner = np.minimum(mid.astype(np.int64), world - 1)
+            cuts = [int(np.searchsorted(owner, r, side="left")) for r in range(world)] + [n]
+    return [order[cuts[r]:cuts[r + 1]] for r in range(world)]
+
+
+def unit_shard(unit_tgt: Sequence[int], rank: int, world: int, weights=None) -> np.ndarray:
+    """Indices of the units rank ``rank`` runs (see shard_plan)."""
+    return shard_plan(unit_tgt, world, weights)[rank]
 
 
 def pack_records(res: BatchResult, n_slots: int) -> np.ndarray:
@@ -40,17 +70,17 @@ def pack_records(res: BatchResult, n_slots: int) -> np.ndarray:
     return rec
 
 
-def unpack_records(all_rec: np.ndarray, n_units: int, world: int) -> BatchResult:
-    """Inverse of the round-robin shard: all_rec is (world, n_slots, 20)."""
+def unpack_records(all_rec: np.ndarray, plan: List[np.ndarray]) -> BatchResult:
+    """Inverse of the shard: all_rec is (world, n_slots, 20), ``plan`` the shard_plan every rank derived."""
+    n_units = int(sum(len(p) for p in plan))
     T = np.empty((n_units, 4, 4), dtype=np.float64)
     rmse = np.empty(n_units, dtype=np.float64)
     fit = np.empty(n_units, dtype=np.float64)
     iters = np.empty(n_units, dtype=np.int64)
     status = np.empty(n_units, dtype=np.int32)
-    for r in range(world):
-        mine = unit_shard(n_units, r, world)
+    for r, mine in enumerate(plan):
         rec = all_rec[r, : len(mine)]
-        if (rec[:, 3] < 0).any():
+        if (rec[:, 3] < 0).any() or np.isnan(rec[:, 3]).any():
             raise RuntimeError(f"rank {r} contributed fewer records than its shard holds")
         rmse[mine] = rec[:, 0]
         fit[mine] = rec[:, 1]
@@ -62,7 +92,11 @@ def unpack_records(all_rec: np.ndarray, n_units: int, world: int) -> BatchResult
 
 class ShardedOptimizer(IOptimizer):
     """Wraps a batched optimizer; ``optimize_batch`` runs this rank's share of the units and
-    all-gathers the records.  With no process group (or world size 1) it is a pass-through."""
+    all-gathers the records.  With no process group (or world size 1) it is a pass-through.
+
+    ``unit_weights`` (optional, set per call through ``optimize_batch(..., unit_weights=w)``): a difficulty proxy per
+    unit -- e.g. the iteration counts of the same candidates in the previous poll sweep -- used to cut blocks of
+    equal expected work instead of equal unit counts."""
 
     def __init__(self, inner: IOptimizer, group=None):
         if not hasattr(inner, "optimize_batch"):
@@ -73,6 +107,8 @@ class ShardedOptimizer(IOptimizer):
         # start clouds built on the GPU by the Aligner (CUDA tensors) are passed through when the inner optimizer takes them
         self.accepts_device_sources = bool(getattr(inner, "accepts_device_sources", False))
         self.last_local_units = 0
+        self.last_local_target_sets = 0
+        self.last_timing = {}     # {"compute_ms", "gather_ms"} of the last sharded call (CUDA events / perf_counter)
 
     def _dist(self):
         import torch.distributed as dist
@@ -85,42 +121,72 @@ class ShardedOptimizer(IOptimizer):
         return self._inner.optimize(source, target, **kwargs)
 
     def optimize_batch(self, sources, targets, unit_src: Sequence[int], unit_tgt: Sequence[int],
-                       rigid_base: Optional[np.ndarray] = None, **kwargs) -> BatchResult:
+                       rigid_base: Optional[np.ndarray] = None, unit_weights=None, **kwargs) -> BatchResult:
         dist, rank, world = self._dist()
         if self._takes_rigid_base:
             kwargs["rigid_base"] = rigid_base
         if world == 1:
             res = self._inner.optimize_batch(sources, targets, unit_src, unit_tgt, **kwargs)
             self.last_local_units = len(res.rmse)
+            self.last_local_target_sets = len(np.unique(np.asarray(unit_tgt)))
             return res
+        import time
+
         import torch
 
         unit_src = np.asarray(unit_src)
         unit_tgt = np.asarray(unit_tgt)
-        n_units = len(unit_src)
-        mine = unit_shard(n_units, rank, world)
-        # only the source / target sets this rank's units touch travel to its GPU
+        plan = shard_plan(unit_tgt, world, unit_weights)
+        mine = plan[rank]
+        n_slots = max(len(p) for p in plan)
+        backend = dist.get_backend(self._group)
+        on_gpu = backend == "nccl"
+        dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+        # only the source / target sets this rank's units touch travel to (or stay on) its GPU
         src_sets, local_src = np.unique(unit_src[mine], return_inverse=True)
         tgt_sets, local_tgt = np.unique(unit_tgt[mine], return_inverse=True)
-        n_slots = (n_units + world - 1) // world
-        if len(mine):
-            def pick(sets, idx):
-                if hasattr(sets, "is_cuda"):
-                    return sets.index_select(0, torch.as_tensor(idx, dtype=torch.int64, device=sets.device))
-                return np.asarray(sets)[idx]
+        self.last_local_units, self.last_local_target_sets = len(mine), len(tgt_sets)
 
-            res = self._inner.optimize_batch(pick(sources, src_sets), pick(targets, tgt_sets),
-                                             local_src.astype(np.int32), local_tgt.astype(np.int32), **kwargs)
-            rec = pack_records(res, n_slots)
+        def pick(sets, idx):
+            if hasattr(sets, "is_cuda"):
+                if len(idx) == sets.shape[0]:
+                    return sets
+                return sets.index_select(0, torch.as_tensor(idx, dtype=torch.int64, device=sets.device))
+            return np.asarray(sets)[idx]
+
+        t0 = time.perf_counter()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if on_gpu else None
+        if ev:
+            ev[0].record()
+        rec_t = None
+        if len(mine):
+            args = (pick(sources, src_sets), pick(targets, tgt_sets), local_src.astype(np.int32), local_tgt.astype(np.int32))
+            records = getattr(self._inner, "optimize_batch_records", None) if on_gpu else None
+            if records is not None:      # records packed on the device: nothing comes back to the host before the gather
+                rec_local = records(*args, **kwargs)
+                rec_t = torch.full((n_slots, RECORD_F64), float("nan"), dtype=torch.float64, device=dev)
+                rec_t[:, 3] = -1.0
+                rec_t[: len(mine)] = rec_local
+            else:
+                rec = pack_records(self._inner.optimize_batch(*args, **kwargs), n_slots)
         else:
             rec = pack_records(BatchResult(np.empty((0, 4, 4)), *(np.empty(0),) * 4, []), n_slots)
-        self.last_local_units = len(mine)
-        backend = dist.get_backend(self._group)
-        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-        mine_t = torch.from_numpy(rec).to(dev)
+        if rec_t is None:
+            rec_t = torch.from_numpy(rec).to(dev)
+        t1 = time.perf_counter()
+        if ev:
+            ev[1].record()
         out = torch.empty((world * n_slots, RECORD_F64), dtype=torch.float64, device=dev)   # rank-major concat
-        dist.all_gather_into_tensor(out, mine_t, group=self._group)
-        return unpack_records(out.cpu().numpy().reshape(world, n_slots, RECORD_F64), n_units, world)
+        dist.all_gather_into_tensor(out, rec_t, group=self._group)
+        if ev:
+            ev[2].record()
+        host = out.cpu().numpy().reshape(world, n_slots, RECORD_F64)    # the one D2H copy (synchronises)
+        t2 = time.perf_counter()
+        if ev:
+            self.last_timing = {"compute_ms": ev[0].elapsed_time(ev[1]), "gather_ms": ev[1].elapsed_time(ev[2])}
+        else:
+            self.last_timing = {"compute_ms": 1e3 * (t1 - t0), "gather_ms": 1e3 * (t2 - t1)}
+        return unpack_records(host, plan)
 
     def raise_failure(self):
         raise_failure = getattr(self._inner, "raise_failure", None)

@@ -21,7 +21,9 @@ class SOR(IProcessBlock):
             # Open3D logs an error and returns an empty selection for illegal arguments
             raise ValueError("SOR: nb_neighbours must be >= 1 and std_ratio > 0")
         if self._nb_neighbours > _lib.MAX_KNN:
-            raise ValueError(f"SOR: nb_neighbours > {_lib.MAX_KNN} is not supported by the CUDA kNN kernel")
+            # the reference accepts any value (sor.py:24-37); the CUDA k-NN keeps its k-best sets in shared memory,
+            # which bounds k at ORPCD_MAX_KNN = 512 (8x the reference's default of 64)
+            raise ValueError(f"SOR: nb_neighbours > {_lib.MAX_KNN} exceeds the shared-memory k-NN lists of the CUDA kernel")
         d_cloud = _lib.to_device(cloud)
         mask, avg, stats = ops.sor_mask(d_cloud, self._nb_neighbours, float(self._std_ratio))
         self.last_mask = mask.cpu().numpy().astype(bool)

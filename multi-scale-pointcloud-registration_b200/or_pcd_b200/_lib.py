@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ORPCD_B200_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "liborpcd_b200.so")
 
 ORPCD_OK = 0
-MAX_KNN = 64
+MAX_KNN = 512
 
 _lib = None
 
@@ -142,6 +142,8 @@ def lib():
     L.orpcd_fgr_batch_workspace_bytes.argtypes = [C.POINTER(FgrParams)]
     L.orpcd_fgr_batch.restype = ip
     L.orpcd_fgr_batch.argtypes = [C.POINTER(FgrParams), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp, vp]
+    L.orpcd_fgr_tuple_keys.restype = ip
+    L.orpcd_fgr_tuple_keys.argtypes = [vp, ip, vp, ip, vp, vp, ip, C.c_ulonglong, vp, vp]
     L.orpcd_ffma_burn.restype = ip
     L.orpcd_ffma_burn.argtypes = [ip, ip, vp, vp]
     L.orpcd_ffma2_burn.restype = ip

@@ -2,15 +2,14 @@
 (reference: or_pcd/data/__init__.py:5-19 uses pkg_resources + o3d.io.read_point_cloud).
 
 The Stanford Armadillo range scans the reference ships as big-endian PLY files are
-kept here as one compressed ``.npz`` of their float32 vertex arrays
-(``tests/golden/armadillo_scans.npz``); Open3D's reader widens to float64, so do we."""
+kept here, inside the package, as one compressed ``.npz`` of their float32 vertex arrays
+(``armadillo_scans.npz`` next to this file); Open3D's reader widens to float64, so do we."""
 import os
 import struct
 
 import numpy as np
 
-_NPZ = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "..", "tests", "golden",
-                    "armadillo_scans.npz")
+_NPZ = os.path.join(os.path.dirname(os.path.abspath(__file__)), "armadillo_scans.npz")
 
 _PLY_TYPES = {"char": "i1", "uchar": "u1", "short": "i2", "ushort": "u2", "int": "i4", "uint": "u4",
               "float": "f4", "double": "f8", "int8": "i1", "uint8": "u1", "int16": "i2", "uint16": "u2",
@@ -22,12 +21,13 @@ def sample_cloud_names():
         return sorted(z.files)
 
 
-def load_sample_cloud(cloud_name: str) -> np.ndarray:
-    """(N,3) float64 vertices of one of the bundled scans, e.g. ``ArmadilloBack_330``."""
+def load_sample_cloud(name: str = "ArmadilloBack_180") -> np.ndarray:
+    """(N,3) float64 vertices of one of the bundled scans (reference signature: data/__init__.py:5,
+    ``load_sample_cloud(name="ArmadilloBack_180")``; it returns an Open3D cloud there, the vertex array here)."""
     with np.load(_NPZ) as z:
-        if cloud_name not in z.files:
-            raise FileNotFoundError(f"unknown sample cloud {cloud_name!r}; have {sorted(z.files)}")
-        return z[cloud_name].astype(np.float64)
+        if name not in z.files:
+            raise FileNotFoundError(f"unknown sample cloud {name!r}; have {sorted(z.files)}")
+        return z[name].astype(np.float64)
 
 
 def load_cloud(path: str) -> np.ndarray:
@@ -35,8 +35,16 @@ def load_cloud(path: str) -> np.ndarray:
     (main.py:55-71): ``.npz`` archives with a ``points`` array (first three columns), anything else
     is read as PLY (``o3d.io.read_point_cloud`` in the reference)."""
     if path.lower().endswith(".npz"):
-        with np.load(path, allow_pickle=True) as z:
-            return np.ascontiguousarray(np.array(z["points"])[:, :3], dtype=np.float64)
+        with np.load(path, allow_pickle=False) as z:   # a numeric array needs no pickle; object arrays are refused
+            if "points" not in z.files:
+                raise ValueError(f"{path}: no 'points' array in the archive")
+            try:
+                pts = z["points"]
+            except ValueError as e:
+                raise ValueError(f"{path}: 'points' must be a plain numeric array (object arrays are not loaded)") from e
+            if pts.ndim != 2 or pts.shape[1] < 3 or not np.issubdtype(pts.dtype, np.number):
+                raise ValueError(f"{path}: 'points' must be a numeric (N, >=3) array, got {pts.dtype} {pts.shape}")
+            return np.ascontiguousarray(pts[:, :3], dtype=np.float64)
     return read_ply_vertices(path)
 
 

@@ -420,6 +420,20 @@ def fgr_batch(src_points, tgt_points, unit_src, unit_tgt, ij, ji, keys, division
     return T, info
 
 
+def fgr_tuple_keys(src_points, tgt_points, unit_src, unit_tgt, seed: int):
+    """Per-unit keys (int64 bit patterns of the uint64 keys) of the tuple-test streams, computed on the device."""
+    t = _t()
+    src_points, tgt_points = _f64(src_points), _f64(tgt_points)
+    U = unit_src.shape[0]
+    keys = t.empty(U, dtype=t.int64, device="cuda")
+    check(_lib.lib().orpcd_fgr_tuple_keys(src_points.data_ptr(), src_points.shape[1], tgt_points.data_ptr(),
+                                          tgt_points.shape[1], unit_src.data_ptr(), unit_tgt.data_ptr(), U,
+                                          int(seed) & ((1 << 64) - 1), keys.data_ptr(), _lib.stream_ptr()),
+          "orpcd_fgr_tuple_keys")
+    launch_counter["kernels"] += 1
+    return keys
+
+
 def gicp_sweep_only(params: GicpParams, ws) -> None:
     check(_lib.lib().orpcd_gicp_sweep_only(C.byref(params), ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
           "orpcd_gicp_sweep_only")

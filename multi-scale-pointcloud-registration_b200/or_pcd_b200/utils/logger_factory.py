@@ -1,6 +1,8 @@
 """Logging helper with the reference's ``LoggerFactory.get_logger`` signature
-(or_pcd/utils/logger_factory.py:19-100).  One stdout handler per logger name
-(the reference adds a handler per call and duplicates lines); a file handler
+(or_pcd/utils/logger_factory.py:19-100).  One stream handler per logger name
+(the reference adds a handler per call and duplicates lines), on **stderr** so that
+programs printing machine-readable results on stdout (bench.py's JSON line) stay clean --
+set ``OR_PCD_B200_LOG_STDOUT=1`` for the reference's stdout handler; a file handler
 only when ``log_on_file`` is set AND ``OR_PCD_B200_LOG_DIR`` names a directory,
 so constructing a block has no file-system side effects by default."""
 import logging
@@ -15,7 +17,7 @@ class LoggerFactory:
     def get_logger(log_name: str, log_on_file: bool = False, level: int = logging.WARNING) -> logging.Logger:
         logger = logging.getLogger("or_pcd_b200." + log_name)
         if not logger.handlers:
-            h = logging.StreamHandler(sys.stdout)
+            h = logging.StreamHandler(sys.stdout if os.environ.get("OR_PCD_B200_LOG_STDOUT") == "1" else sys.stderr)
             h.setFormatter(logging.Formatter(_FORMAT))
             logger.addHandler(h)
             logger.setLevel(level)

@@ -564,8 +564,9 @@ class Aligner:
 # --------------------------------------------------------------------------
 def load_scan(name: str) -> np.ndarray:
     """Armadillo range scans (reference data/*.ply vertices, float32 -> float64 as
-    Open3D's PLY reader does), stored as tests/golden/armadillo_scans.npz."""
-    p = os.path.join(os.path.dirname(_HERE), "tests", "golden", "armadillo_scans.npz")
+    Open3D's PLY reader does), stored as multi-scale-pointcloud-registration_b200/or_pcd_b200/data/armadillo_scans.npz (a data file; no product code is imported)."""
+    p = os.path.join(os.path.dirname(_HERE), "multi-scale-pointcloud-registration_b200", "or_pcd_b200", "data",
+                     "armadillo_scans.npz")
     with np.load(p) as z:
         return z[name].astype(np.float64)
 

@@ -443,8 +443,87 @@ static double det_cos(double x)
     return -det_kcos(y, yt);
 }
 
+/* atan (Sun fdlibm s_atan.c restated: argument reduction to |x| < 7/16 around 0.5, 1, 1.5, inf;
+ * odd polynomial split into two Horner chains), < 1 ulp */
+static double det_atan(double x)
+{
+    const double atanhi[4] = {4.63647609000806093515e-01, 7.85398163397448278999e-01, 9.82793723247329054082e-01,
+                              1.57079632679489655800e+00};
+    const double atanlo[4] = {2.26987774529616870924e-17, 3.06161699786838301793e-17, 1.39033110312309984516e-17,
+                              6.12323399573676603587e-17};
+    const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01, aT2 = 1.42857142725034663711e-01,
+                 aT3 = -1.11111104054623557880e-01, aT4 = 9.09088713343650656196e-02, aT5 = -7.69187620504482999495e-02,
+                 aT6 = 6.66107313738753120669e-02, aT7 = -5.83357013379057348645e-02, aT8 = 4.97687799461593236017e-02,
+                 aT9 = -3.65315727442169155270e-02, aT10 = 1.62858201153657823623e-02;
+    const uint32_t hx = dbl_high(x), ix = hx & 0x7fffffffu;
+    int id;
+    if (ix >= 0x44100000u) {                        /* |x| >= 2^66 (or NaN) */
+        if (x != x) return x + x;
+        return (hx >> 31) ? -atanhi[3] - atanlo[3] : atanhi[3] + atanlo[3];
+    }
+    if (ix < 0x3fdc0000u) {                         /* |x| < 0.4375 */
+        if (ix < 0x3e200000u) return x;             /* |x| < 2^-29 */
+        id = -1;
+    } else {
+        x = fabs(x);
+        if (ix < 0x3ff30000u) {                     /* |x| < 1.1875 */
+            if (ix < 0x3fe60000u) { id = 0; x = (2.0 * x - 1.0) / (2.0 + x); }
+            else { id = 1; x = (x - 1.0) / (x + 1.0); }
+        } else {
+            if (ix < 0x40038000u) { id = 2; x = (x - 1.5) / (1.0 + 1.5 * x); }
+            else { id = 3; x = -1.0 / x; }
+        }
+    }
+    const double z = x * x;
+    const double w = z * z;
+    const double s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
+    const double s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
+    if (id < 0) return x - x * (s1 + s2);
+    const double r = atanhi[id] - ((x * (s1 + s2) - atanlo[id]) - x);
+    return (hx >> 31) ? -r : r;
+}
+
+/* atan2 (fdlibm e_atan2.c restated; finite arguments, signed zeros as in C).  Open3D's
+ * ComputePairFeatures bins floor(11 (atan2(..) + pi) / (2 pi)): a discontinuous consumer. */
+static double det_atan2(double y, double x)
+{
+    const double pi_o_2 = 1.5707963267948965580e+00, pi = 3.1415926535897931160e+00, pi_lo = 1.2246467991473531772e-16;
+    if (x != x || y != y) return x + y;
+    if (x == 1.0) return det_atan(y);
+    const uint32_t hx = dbl_high(x), hy = dbl_high(y);
+    const int m = (int)((hy >> 31) & 1u) | (int)((hx >> 30) & 2u);       /* 2 * sign(x) + sign(y) */
+    if (y == 0.0) {
+        switch (m) {
+        case 0: case 1: return y;
+        case 2: return pi;
+        default: return -pi;
+        }
+    }
+    if (x == 0.0) return (hy >> 31) ? -pi_o_2 : pi_o_2;
+    const int ix = (int)(hx & 0x7fffffffu), iy = (int)(hy & 0x7fffffffu);
+    if (ix >= 0x7ff00000 || iy >= 0x7ff00000) {                          /* infinities: libm semantics not needed here */
+        if (iy >= 0x7ff00000 && ix < 0x7ff00000) return (hy >> 31) ? -pi_o_2 : pi_o_2;
+        if (ix >= 0x7ff00000 && iy < 0x7ff00000) {
+            switch (m) { case 0: return 0.0; case 1: return -0.0; case 2: return pi; default: return -pi; }
+        }
+        switch (m) { case 0: return 0.5 * pi_o_2; case 1: return -0.5 * pi_o_2; case 2: return 1.5 * pi_o_2; default: return -1.5 * pi_o_2; }
+    }
+    const int k = (iy - ix) >> 20;
+    double z;
+    if (k > 60) z = pi_o_2 + 0.5 * pi_lo;
+    else if ((hx >> 31) && k < -60) z = 0.0;
+    else z = det_atan(fabs(y / x));
+    switch (m) {
+    case 0: return z;
+    case 1: return -z;
+    case 2: return pi - (z - pi_lo);
+    default: return (z - pi_lo) - pi;
+    }
+}
+
 ORACLE_API double oracle_det_acos(double x) { return det_acos(x); }
 ORACLE_API double oracle_det_cos(double x) { return det_cos(x); }
+ORACLE_API double oracle_det_atan2(double y, double x) { return det_atan2(y, x); }
 
 /* ------------------------------------------------------------------------ */
 /* Covariance + FastEigen3x3 normal (EstimateNormals.cpp)     */
@@ -1125,7 +1204,7 @@ static void pair_features(const double *p1, const double *n1, const double *p2, 
     f[3] = len;
     f[2] = f2;
     f[1] = dot3(v, b);
-    f[0] = atan2(dot3(w, b), dot3(a, b));
+    f[0] = det_atan2(dot3(w, b), dot3(a, b));
 }
 
 static inline int hist_bin(double x)

@@ -47,7 +47,7 @@ def test_argument_validation_needs_no_gpu():
     need = L.orpcd_gicp_batch_workspace_bytes(ctypes.byref(p))
     assert 50e6 < need < 2e9                         # sized for HBM, not for smem
     assert L.orpcd_knn_exact(None, 10, 30, None, 10, 30, 1, 0, None, None, None, 0, None) < 0      # k = 0
-    assert L.orpcd_knn_exact(None, 10, 30, None, 10, 30, 1, 65, None, None, None, 0, None) < 0     # k > ORPCD_MAX_KNN
+    assert L.orpcd_knn_exact(None, 10, 30, None, 10, 30, 1, 513, None, None, None, 0, None) < 0     # k > ORPCD_MAX_KNN
 
 
 def test_product_path_refuses_to_run_without_cuda():

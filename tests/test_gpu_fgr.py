@@ -34,20 +34,15 @@ def test_fpfh_matches_oracle(oracle, armadillo_pair):
         idx, d2 = ops.knn_exact(d, d, 20)
         out, sp = ops.fpfh(d, _dev(nrm[None]), idx, d2, 20, 0.1, want_spfh=True)
         out, sp = out[0].cpu().numpy(), sp[0].cpu().numpy()
-        # same arithmetic on both sides except atan2 (device libm) within an ulp of a bin edge:
-        # at most one point in thousands may land in a neighbouring bin
-        assert (np.abs(sp - ref_sp).max(1) > 1e-9).sum() <= 1
-        assert (np.abs(out - ref).max(1) > 1e-9).sum() <= 25
-        # everything else is bit-identical (the device forms its 33 quotients per neighbour from one division)
-        assert (out != ref).any(1).sum() == (np.abs(out - ref).max(1) > 1e-9).sum()
-        assert np.allclose(sp.sum(1), ref_sp.sum(1), atol=1e-9)             # three histograms of 100 each
+        # same arithmetic on both sides, det_acos / det_atan2 included: SPFH and FPFH are bit-identical
+        # (the device forms its 33 quotients per neighbour from one division, correctly rounded)
+        assert np.array_equal(sp, ref_sp)
+        assert np.array_equal(out, ref)
         # device normals (bit-identical to the oracle's) through the plugin class
         from or_pcd_b200.Optimizer import FastGlobalOptimizer
 
         fs, _ = FastGlobalOptimizer().get_fpfh_features(cloud, cloud)
-        assert (np.abs(fs - ref).max(1) > 1e-9).sum() <= 25
-        print("fpfh rows differing from the oracle:", (np.abs(out - ref).max(1) > 1e-9).sum(),
-              (np.abs(fs - ref).max(1) > 1e-9).sum())
+        assert np.array_equal(fs, ref)
 
 
 @pytest.mark.parametrize("mode", [0, 1])

@@ -93,6 +93,27 @@ def test_sor_mask_bit_exact(oracle, scan):
     assert int(st[3]) == int(om.sum())
 
 
+@pytest.mark.parametrize("k", [65, 100, 200, 300, 512])
+def test_sor_and_knn_beyond_64_neighbours(oracle, k):
+    """The reference accepts any nb_neighbours (Preprocessor/Outliers/sor.py:24-37); the CUDA lists go to 512."""
+    from or_pcd_b200 import ops
+    from or_pcd_b200.Preprocessor import SOR
+
+    rng = np.random.default_rng(k)
+    cloud = oracle.RadiusScaler().process(oracle.synthetic_cloud(2600 if k < 300 else 1500, rng))
+    cloud[100:110] = cloud[200:210]                       # duplicates: exact ties
+    mask, avg, stats = ops.sor_mask(_dev(cloud), k, 2.0)
+    om, oavg, ostats = oracle.sor(cloud, k, 2.0)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), om) and np.array_equal(avg.cpu().numpy(), oavg)
+    assert np.array_equal(SOR(nb_neighbours=k).process(cloud), cloud[om])
+    q = cloud[:333] + 1e-3
+    idx, d2 = ops.knn_exact(_dev(cloud), _dev(q), k)      # foreign queries: the brute-force kernel
+    oi, od = oracle.knn(cloud, q, k)
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(d2.cpu().numpy(), od)
+    with pytest.raises(ValueError):
+        SOR(nb_neighbours=513).process(cloud)
+
+
 def test_normals_and_gicp_covariances(oracle, armadillo_pair):
     from or_pcd_b200 import ops
 

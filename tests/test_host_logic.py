@@ -185,3 +185,12 @@ def test_cloud_io_ply_and_npz(tmp_path):
         assert np.array_equal(read_ply_vertices(ref), load_sample_cloud("ArmadilloBack_330"))
     with pytest.raises(FileNotFoundError):
         load_sample_cloud("nope")
+    # the reference's signature: load_sample_cloud(name="ArmadilloBack_180") (data/__init__.py:5)
+    assert load_sample_cloud().shape == (20535, 3) and np.array_equal(load_sample_cloud(name="ArmadilloBack_180"), load_sample_cloud())
+    # object arrays are never unpickled (an untrusted .npz must not execute code)
+    np.savez(tmp_path / "evil.npz", points=np.array([{"a": 1}, None], dtype=object))
+    with pytest.raises(ValueError):
+        load_cloud(str(tmp_path / "evil.npz"))
+    np.savez(tmp_path / "nopoints.npz", other=v)
+    with pytest.raises(ValueError):
+        load_cloud(str(tmp_path / "nopoints.npz"))

@@ -211,6 +211,23 @@ def test_det_acos_cos_within_one_ulp_of_libm(oracle):
     assert np.abs(c - np.cos(ys)).max() <= 1.2e-16
 
 
+def test_det_atan2_within_an_ulp_of_libm(oracle):
+    """det_atan2 (fdlibm restated) against numpy's arctan2: all four quadrants, axes, signed zeros, tiny and huge ratios."""
+    import ctypes as C
+
+    L = oracle.lib()
+    L.oracle_det_atan2.restype = C.c_double; L.oracle_det_atan2.argtypes = [C.c_double, C.c_double]
+    rng = np.random.default_rng(1)
+    ys = np.concatenate([rng.uniform(-1, 1, 30000), rng.uniform(-1, 1, 3000) * 10.0 ** rng.uniform(-300, 0, 3000),
+                         [0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 0.0, 1.0, -1.0, 1e-200, 1e200, 0.4375, 0.6875, 1.1875, 2.4375]])
+    xs = np.concatenate([rng.uniform(-1, 1, 30000), rng.uniform(-1, 1, 3000) * 10.0 ** rng.uniform(-300, 0, 3000),
+                         [1.0, 1.0, -1.0, -1.0, 0.0, 0.0, 0.0, 1.0, -1.0, 1e200, 1e-200, 1.0, 1.0, 1.0, 1.0]])
+    a = np.array([L.oracle_det_atan2(float(y), float(x)) for y, x in zip(ys, xs)])
+    ref = np.arctan2(ys, xs)
+    assert (np.abs(a - ref) <= 1.0 * np.spacing(np.abs(ref)) + 5e-324).all()
+    assert np.array_equal(np.signbit(a), np.signbit(ref))
+
+
 def test_fpfh_structure(oracle):
     rng = np.random.default_rng(6)
     pts = oracle.RadiusScaler().process(oracle.synthetic_cloud(1500, rng))

@@ -1,5 +1,5 @@
 """N>1 path on CPU: two processes over the gloo backend shard the units of a poll round
-round-robin, all-gather the 160-byte records, and every rank replays the same decisions
+in contiguous target-set blocks, all-gather the 160-byte records, and every rank replays the same decisions
 (SURVEY.md 8(e)).  The inner optimizer is the deterministic fake (no GPU)."""
 import os
 import socket
@@ -81,32 +81,51 @@ def test_two_rank_gloo_sharding_matches_single_process(tmp_path):
     for k in range(world):
         assert np.array_equal(r[k]["T"], truth.transforms) and np.array_equal(r[k]["rmse"], truth.rmse)
         assert np.array_equal(r[k]["status"], truth.status) and np.array_equal(r[k]["iters"], truth.iterations)
-        assert int(r[k]["calls"]) == len(unit_shard(7, k, world))           # each rank ran only its share
+        assert int(r[k]["calls"]) == len(unit_shard(ut, k, world))          # each rank ran only its share
         assert np.array_equal(r[k]["aT"], T) and float(r[k]["am"]) == m
         assert np.array_equal(r[k]["ascale"], scale) and np.array_equal(r[k]["aerr"], np.array(errors))
         assert np.array_equal(r[k]["rng"], np.random.get_state()[1])        # every rank replays the same stream
         assert int(r[k]["local_units"]) == 15                               # 6 candidates x 5 starts / 2 ranks
 
 
-def test_unit_shard_is_a_partition():
-    from or_pcd_b200.Optimizer.shardedOptimizer import pack_records, unit_shard, unpack_records
+def test_shard_plan_is_a_partition_in_target_blocks():
+    from or_pcd_b200.Optimizer.shardedOptimizer import pack_records, shard_plan, unit_shard, unpack_records
     from or_pcd_b200.Optimizer.iOptimizer import BatchResult
 
-    for n, w in ((180, 8), (7, 2), (3, 4), (1024, 8)):
-        parts = [unit_shard(n, r, w) for r in range(w)]
-        assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(n))
-        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
-    # records survive the round trip, ragged last rank included
-    rng = np.random.default_rng(0)
+    rng = np.random.default_rng(1)
+    cases = [(np.repeat(np.arange(6), 30), 8), (np.array([0, 0, 0, 1, 1, 1, 1]), 2), (np.array([0, 1, 0]), 4),
+             (np.repeat(np.arange(32), 32), 8), (rng.integers(0, 5, 97), 3), (np.tile(np.arange(32), 32), 4)]
+    for ut, w in cases:
+        plan = shard_plan(ut, w)
+        assert np.array_equal(np.sort(np.concatenate(plan)), np.arange(len(ut)))          # a partition
+        assert max(len(p) for p in plan) - min(len(p) for p in plan) <= 1                   # equal counts
+        n_sets = len(np.unique(ut))
+        for r in range(w):                                                                  # few target sets per rank
+            assert len(np.unique(ut[plan[r]])) <= -(-n_sets // w) + 1
+            assert np.array_equal(plan[r], unit_shard(ut, r, w))
+        ordered = ut[np.concatenate(plan)]
+        assert (np.diff(ordered) >= 0).all()                                                # contiguous in target order
+    # weights: blocks of equal expected work instead of equal counts
+    ut = np.repeat(np.arange(4), 8)
+    wts = np.where(ut < 2, 3.0, 1.0)           # the first two target sets are three times as hard
+    plan = shard_plan(ut, 2, wts)
+    assert np.array_equal(np.sort(np.concatenate(plan)), np.arange(32))
+    loads = [wts[p].sum() for p in plan]
+    assert abs(loads[0] - loads[1]) <= 3.0 and len(plan[0]) < len(plan[1])
+    with pytest.raises(ValueError):
+        shard_plan(ut, 2, -wts)
+    # records survive the round trip, ragged shards included
     n, w = 7, 2
+    ut = np.array([0, 0, 0, 1, 1, 1, 1])
+    plan = shard_plan(ut, w)
     full = BatchResult(rng.standard_normal((n, 4, 4)), rng.random(n), rng.random(n), np.arange(n), np.arange(n) % 2, [])
-    slots = (n + w - 1) // w
-    recs = np.stack([pack_records(BatchResult(*(np.asarray(f)[unit_shard(n, r, w)] for f in full[:5]), []), slots)
+    slots = max(len(p) for p in plan)
+    recs = np.stack([pack_records(BatchResult(*(np.asarray(f)[plan[r]] for f in full[:5]), []), slots)
                      for r in range(w)])
-    back = unpack_records(recs, n, w)
+    back = unpack_records(recs, plan)
     for a, b in zip(full[:5], back[:5]):
         assert np.array_equal(np.asarray(a), np.asarray(b))
     bad = recs.copy()
-    bad[1, 2, 3] = -1.0                                # rank 1 left one of its three slots unfilled
+    bad[0, 2, 3] = -1.0                                # rank 0 left one of its three slots unfilled
     with pytest.raises(RuntimeError):
-        unpack_records(bad, n, w)
+        unpack_records(bad, plan)

@@ -75,6 +75,7 @@ def main():
     n_scales = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     n_starts = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     which = sys.argv[4] if len(sys.argv) > 4 else "gicp"
+    reps = int(sys.argv[5]) if len(sys.argv) > 5 else 2
     rng = np.random.default_rng(1234)
     src, tgt, true_scale = make_pair(n, rng)
     scales = latin_hypercube(n_scales, np.random.default_rng(7)) if n_scales > 1 else np.ones((1, 3))
@@ -96,7 +97,7 @@ def main():
     opt = ShardedOptimizer(inner) if world > 1 else inner
     torch.cuda.synchronize()
     times = []
-    for rep in range(2):
+    for rep in range(reps):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
