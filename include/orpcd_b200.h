@@ -172,11 +172,13 @@ typedef struct {
     int n_tgt_sets;
     int max_iterations;   /* ICPConvergenceCriteria.max_iteration  */
     int target_splits;    /* dense sweeps only: splits of the target table, 0 = automatic */
-    int poll_interval;    /* >0: every that many iterations the call waits on
-                             the stream and stops early once every unit is done */
-    int profile;          /* !=0: time every round kernel (dense modes: sweep) launch with
-                             CUDA events on the stream and synchronise at the end
-                             (fills h_profile) */
+    int poll_interval;    /* launch-per-round modes (sweep_mode != 0) only: >0: every that many
+                             iterations the call waits on the stream and stops early once every
+                             unit is done.  The default persistent kernel ends by itself. */
+    int profile;          /* !=0 (diagnostic): CUDA events around the dominant kernel (persistent
+                             kernel; launch-per-round modes: every round / sweep launch) on the
+                             stream; the call then synchronises and reads the device counters
+                             back (fills the * entries of h_profile) */
     int cov_mode;         /* 0: d_*_cov hold 3x3 covariances, 6 doubles per point, and
                                 (Cs+Ct)^-1/2 comes from a Jacobi eigen-solve;
                              1: d_*_cov hold the unit AXIS a of each GICP plane
@@ -190,7 +192,12 @@ typedef struct {
     int sweep_q;             /* tuning (modes 1..4): queries per thread (4|8), 0 = auto       */
     int sweep_tj;            /* tuning (modes 1..4): targets per inner step (2|4|8), 0 = auto */
     int sweep_smem_pad;      /* tuning (modes 1..3): unused dynamic smem bytes, 0             */
-    int sweep_mode;          /* 0 = default: one fused kernel per round, chunk-culled sweep;
+    int sweep_mode;          /* 0 = default: ONE persistent launch for all rounds of all units --
+                                warps take (unit, patch) items from a work queue, each item is a
+                                fused round (update, chunk-culled sweep, certificate, exact
+                                re-rank, Jacobian sums), the warp closing a unit's round solves
+                                and enqueues the unit's next round;
+                                5 = the same fused round, one launch per round (lock step);
                                 4 = culled sweep with separate update / resolve / fix /
                                 reduce kernels; 1..3 = dense (brute-force) sweep + separate
                                 kernels: 1 all packed FFMA2, 2 FFMA2 + scalar FFMA, 3 scalar */
@@ -207,7 +214,7 @@ size_t orpcd_gicp_batch_workspace_bytes(const orpcd_gicp_params *p);
  * d_trace (may be NULL) [n_units][max_iterations+1][2] (fitness, rmse) per Evaluate,
  * h_profile (HOST, may be NULL) [8]: {kernels launched, ms inside the round kernel
  *   (dense modes: the 1-NN sweep kernel)*, (query,target) pairs evaluated*, rounds
- *   issued, queries that needed the exact float64 search*, target splits, launches
+ *   issued (persistent kernel: rounds that ran*), queries that needed the exact float64 search*, target splits, launches
  *   with work*, unit-rounds*};
  *   entries marked * are filled only when p->profile != 0.                    */
 int orpcd_gicp_batch(const orpcd_gicp_params *p, const double *d_src_points,

@@ -106,7 +106,13 @@ struct Ctx {
     const double *tgt_cov;   // [tgt_sets][n_tgt][cov_stride]
     double *out_T, *out_stats, *trace;
     int *out_status;
+    // work queue of the persistent round kernel: ring of (unit * n_patches + patch + 1), 0 = empty slot
+    unsigned *q_slots;
+    unsigned *q_ctrl;    // [0] head (tickets handed out), [32] tail (items published), [64] all-units-done flag
+    unsigned q_mask;     // ring capacity - 1 (capacity = power of two >= n_units * n_patches)
+    int n_patches;       // patches (warps' work items) per unit and round
 };
+constexpr int Q_HEAD = 0, Q_TAIL = 32, Q_DONE = 64;
 
 // ----------------------------------------------------------------------------
 // small PTX helpers
@@ -1156,8 +1162,9 @@ __device__ __forceinline__ void accumulate_pair(const Ctx &c, double (&acc)[32],
 
 // End of a round for one unit, run by a single thread on the unit's 29 totals: Open3D's stopping rule, the
 // 6x6 solve (or Umeyama), T <- U T, results for finished units.
+// Returns true when the unit goes on to another round.
 template <int EST>
-__device__ void finish_round(const Ctx &c, UnitState &st, int u, double *tot, int round)
+__device__ bool finish_round(const Ctx &c, UnitState &st, int u, double *tot, int round)
 {
     const double n = tot[28];
     if (EST == 1) {   // accumulate_pair<1> sums twice J^T J / J^T r without the identity block
@@ -1182,8 +1189,11 @@ __device__ void finish_round(const Ctx &c, UnitState &st, int u, double *tot, in
         double *os = c.out_stats + (size_t)u * 4;
         os[0] = fitness; os[1] = rmse; os[2] = (double)st.iters; os[3] = n;
         c.out_status[u] = st.status;
-        atomicAdd(c.done_count, 1);
-        return;
+        if (atomicAdd(c.done_count, 1) == c.n_units - 1) {   // last unit of the batch: release the persistent workers
+            __threadfence();
+            atomicExch(c.q_ctrl + Q_DONE, 1u);
+        }
+        return false;
     }
     double Um[12];
     if (EST == 3) {
@@ -1216,6 +1226,7 @@ __device__ void finish_round(const Ctx &c, UnitState &st, int u, double *tot, in
     for (int k = 0; k < 12; ++k) st.U[k] = Um[k];
     st.has_update = 1;
     st.iters = round + 1;
+    return true;
 }
 
 template <int COV_MODE>
@@ -1308,14 +1319,18 @@ __device__ __forceinline__ double warp_transpose_sum32(double (&v)[32], int lane
     return v[0];
 }
 
-template <int Q, int EST>
+// PERSIST: the caller is the persistent kernel -- one launch for all rounds, so data another SM wrote in an earlier
+// round of the same launch (unit state, moving points / axes, correspondences) is read with ld.global.cg (L2, the
+// coherence point; an L1 line could be stale), and the warp that closes a unit's round puts the patches of its next
+// round on the work queue.
+template <int Q, int EST, bool PERSIST>
 __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, int wi, int round,
                                            float4 (*ring)[NN_CH], unsigned short *vl)
 {
     const int lane = threadIdx.x & 31;
     const int wbase = wi * (32 * Q);
     if (wbase >= c.n_src) return;
-    const int tgt_set = st.tgt_set;
+    const int tgt_set = st.tgt_set;   // immutable after init_units_kernel
     if (wi == 0 && lane == 0) atomicAdd(&c.round_active[round], 1);
     const TgtMeta tm = c.tgt_meta[tgt_set];
     const double *tpts = c.tgt_pts + (size_t)tgt_set * c.n_tgt * 3;
@@ -1325,10 +1340,10 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     // ---- 1. pending update, d_ub, centred FP32 copy
     float4 qv[Q];
     {
-        const bool has_update = st.has_update != 0;
+        const bool has_update = __ldcg(&st.has_update) != 0;
         double U[12];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) U[k] = st.U[k];
+        for (int k = 0; k < 12; ++k) U[k] = __ldcg(&st.U[k]);
 #pragma unroll
         for (int k = 0; k < Q; ++k) {
             const int i = wbase + k * 32 + lane;
@@ -1336,16 +1351,19 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
             if (i < c.n_src) {
                 const size_t oi = (size_t)u * c.n_src + i;
                 double *p = c.cur_pts + oi * 3;
-                double x = p[0], y = p[1], z = p[2];
+                double x = __ldcg(p), y = __ldcg(p + 1), z = __ldcg(p + 2);
                 if (has_update) {
                     transform_point(U, x, y, z);
                     p[0] = x; p[1] = y; p[2] = z;
                     if (EST == 0) {
                         double *cp = c.cur_cov + oi * 6;
-                        store_sym3(cp, rotate_sym3(U, load_sym3(cp)));
+                        Sym3 C;
+                        C.xx = __ldcg(cp); C.xy = __ldcg(cp + 1); C.xz = __ldcg(cp + 2);
+                        C.yy = __ldcg(cp + 3); C.yz = __ldcg(cp + 4); C.zz = __ldcg(cp + 5);
+                        store_sym3(cp, rotate_sym3(U, C));
                     } else if (EST == 1) {
                         double *ap = c.cur_cov + oi * 3;
-                        const double ax = ap[0], ay = ap[1], az = ap[2];
+                        const double ax = __ldcg(ap), ay = __ldcg(ap + 1), az = __ldcg(ap + 2);
                         ap[0] = U[0] * ax + U[1] * ay + U[2] * az;
                         ap[1] = U[4] * ax + U[5] * ay + U[6] * az;
                         ap[2] = U[8] * ax + U[9] * ay + U[10] * az;
@@ -1353,7 +1371,7 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
                 }
                 float dub = c.dcap;
                 if (round >= 1) {
-                    const int j = c.corr[oi];
+                    const int j = __ldcg(c.corr + oi);
                     if (j >= 0) {
                         const double *tp = tpts + (size_t)j * 3;
                         const double dx = x - tp[0], dy = y - tp[1], dz = z - tp[2];
@@ -1429,7 +1447,8 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
             const float qfz = __shfl_sync(0xffffffffu, qv[k].z, l);
             double best;
             int bj;
-            exact_search_warp(c, tgt_set, p[0], p[1], p[2], qfx, qfy, qfz, __shfl_sync(0xffffffffu, c1[k], l) >> 2, best, bj);
+            exact_search_warp(c, tgt_set, __ldcg(p), __ldcg(p + 1), __ldcg(p + 2), qfx, qfy, qfz,
+                              __shfl_sync(0xffffffffu, c1[k], l) >> 2, best, bj);
             if (lane == l) { tj[k] = bj == 0x7fffffff ? -1 : bj; fd2[k] = best; }
         }
     }
@@ -1448,13 +1467,19 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
             if (j >= 0) {
                 const double *ps = c.cur_pts + oi * 3;
                 const double *pt = tpts + (size_t)j * 3;
-                const double sx = ps[0], sy = ps[1], sz = ps[2], tx = pt[0], ty = pt[1], tz = pt[2];
+                const double sx = __ldcg(ps), sy = __ldcg(ps + 1), sz = __ldcg(ps + 2), tx = pt[0], ty = pt[1], tz = pt[2];
                 const double d2 = fd2[k] >= 0.0 ? fd2[k] : sqdist3_rn(sx, sy, sz, tx, ty, tz);
-                if (d2 < c.r2)
-                    accumulate_pair<EST>(c, acc, sx, sy, sz, tx, ty, tz, c.cur_cov + oi * CST,
+                if (d2 < c.r2) {
+                    double cs[CST];   // the moving source's covariance data: written this round, read through L2
+                    if (EST <= 1) {
+#pragma unroll
+                        for (int e = 0; e < CST; ++e) cs[e] = __ldcg(c.cur_cov + oi * CST + e);
+                    }
+                    accumulate_pair<EST>(c, acc, sx, sy, sz, tx, ty, tz, cs,
                                          c.tgt_cov + ((size_t)tgt_set * c.n_tgt + j) * CST, d2);
-                else
+                } else {
                     j = -1;
+                }
             }
             c.corr[oi] = j;
         }
@@ -1483,9 +1508,26 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     double *tot = reinterpret_cast<double *>(vl);   // the visit list is free now
     tot[lane] = (s0 + s1) + (s2 + s3);
     __syncwarp();
-    if (lane != 0) return;
-    c.red_counter[u] = 0;
-    finish_round<EST>(c, st, u, tot, round);
+    int go_on = 0;
+    if (lane == 0) {
+        c.red_counter[u] = 0;
+        go_on = finish_round<EST>(c, st, u, tot, round) ? 1 : 0;
+        __threadfence();   // the unit's new state is visible before its next round is published
+    }
+    if (!PERSIST) return;
+    go_on = __shfl_sync(0xffffffffu, go_on, 0);
+    if (!go_on) return;
+    // publish the patches of the unit's next round: n_patches consecutive tickets of the ring
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(c.q_ctrl + Q_TAIL, (unsigned)c.n_patches);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int k = lane; k < c.n_patches; k += 32) {
+        unsigned *slot = c.q_slots + ((base + (unsigned)k) & c.q_mask);
+        const unsigned item = (unsigned)(u * c.n_patches + k) + 1u;
+        // the ring holds at most one round per unit, so a slot still occupied belongs to a consumer that has taken
+        // its ticket and is about to clear it
+        while (atomicCAS(slot, 0u, item) != 0u) __nanosleep(32);
+    }
 }
 
 // 64 source points per warp (Q = 2): the smaller the patch, the tighter its sphere and the fewer chunks it
@@ -1510,7 +1552,58 @@ __global__ void __launch_bounds__(ROUND_W * 32, ROUND_MIN_BLOCKS) gicp_round_ker
     const int u = blockIdx.z, warp = threadIdx.x >> 5;
     UnitState &st = c.state[u];
     if (st.done) return;
-    round_body<ROUND_Q, EST>(c, st, u, blockIdx.x * ROUND_W + warp, round, ring[warp], vlist[warp]);
+    round_body<ROUND_Q, EST, false>(c, st, u, blockIdx.x * ROUND_W + warp, round, ring[warp], vlist[warp]);
+}
+
+// The whole registration of every unit in ONE launch (the default path).  The grid is sized to what is resident at
+// once; every warp is a worker that takes (unit, patch) items from a ring in global memory -- a ticket from the head
+// counter, then the slot the ticket names -- and runs round_body on them.  Units advance independently: the warp that
+// closes a unit's round (finish_round: stopping rule, 6x6 solve, T <- U T) publishes the patches of that unit's next
+// round, so there is no lock step between units, no launch per round and no partly filled last wave: late in a batch
+// the workers simply find the stragglers' patches in the ring.  The warp that finishes the last unit raises the done
+// flag, which is what idle workers poll while they wait on an empty slot.
+template <int EST>
+__global__ void __launch_bounds__(ROUND_W * 32, ROUND_MIN_BLOCKS) gicp_persistent_kernel(Ctx c)
+{
+    __shared__ __align__(16) float4 ring[ROUND_W][CULL_RING][NN_CH];
+    __shared__ __align__(16) unsigned short vlist[ROUND_W][CULL_LIST];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        unsigned item = 0u;
+        if (lane == 0) {
+            const unsigned t = atomicAdd(c.q_ctrl + Q_HEAD, 1u);
+            unsigned *slot = c.q_slots + (t & c.q_mask);
+            for (;;) {
+                if (*reinterpret_cast<volatile unsigned *>(slot) != 0u) {
+                    item = atomicExch(slot, 0u);      // claim; 0 if the previous owner of this slot took it first
+                    if (item != 0u) break;
+                }
+                if (*reinterpret_cast<volatile unsigned *>(c.q_ctrl + Q_DONE) != 0u) break;
+                __nanosleep(64);
+            }
+        }
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item == 0u) return;                       // every unit is done
+        __threadfence();                              // what the publisher wrote before the item is visible from here on
+        const int u = (int)((item - 1u) / (unsigned)c.n_patches), wi = (int)((item - 1u) % (unsigned)c.n_patches);
+        UnitState &st = c.state[u];
+        round_body<ROUND_Q, EST, true>(c, st, u, wi, __ldcg(&st.iters), ring[warp], vlist[warp]);
+        __syncwarp();
+    }
+}
+
+// ring <- the patches of round 0 of every unit, unit-major (units of one target set are neighbours: the first
+// workers share target chunks in L2 / L1)
+__global__ void queue_init_kernel(Ctx c)
+{
+    const unsigned cap = c.q_mask + 1u, n_items = (unsigned)c.n_units * (unsigned)c.n_patches;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x)
+        c.q_slots[i] = i < n_items ? i + 1u : 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        c.q_ctrl[Q_HEAD] = 0u;
+        c.q_ctrl[Q_TAIL] = n_items;
+        c.q_ctrl[Q_DONE] = 0u;
+    }
 }
 
 // correspondences of unit u in the caller's source order (the unit arrays are spatially sorted)
@@ -1528,10 +1621,13 @@ __global__ void __launch_bounds__(256) unpermute_corr_kernel(Ctx c, int *__restr
 struct Layout {
     size_t off_state, off_pts, off_cov, off_qf, off_corr, off_d2, off_m1, off_c1, off_m2, off_tgt4, off_meta,
         off_partial, off_counter, off_worklist, off_wcount, off_ract, off_done, off_visit, off_sperm, off_tperm,
-        off_sph, off_ssph, off_sort, off_bbox, total;
+        off_sph, off_ssph, off_sort, off_bbox, off_qslots, off_qctrl, total;
     int nt_pad, n_chunks, splits, chunks_per_split, red_blocks, q_tiles, nn_q, nn_tj, cov_stride, smem_pad, nn_mode;
     int cull;
     int fused;       // one gicp_round_kernel launch per round instead of update / sweep / resolve / fix / reduce
+    int persistent;  // ... and all rounds in one launch of gicp_persistent_kernel (the default)
+    int n_patches;   // work items per unit and round of the fused kernels
+    unsigned q_cap;  // work-queue ring capacity (power of two)
     int red_grid;    // blocks per unit of reduce_kernel (red_blocks is the partial-sum stride, >= patches per unit)
 };
 
@@ -1550,9 +1646,10 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     L.smem_pad = p->sweep_smem_pad > 0 && p->sweep_smem_pad <= 190000 ? p->sweep_smem_pad : 0;
     L.nn_tj = (p->sweep_tj == 2 || p->sweep_tj == 4 || p->sweep_tj == 8) ? p->sweep_tj : 4;
     L.nn_mode = (p->sweep_mode >= 1 && p->sweep_mode <= 3) ? p->sweep_mode - 1 : 0;
-    L.cull = !(p->sweep_mode >= 1 && p->sweep_mode <= 3);   // 0 (auto), 4: culled sweep; 1..3: dense variants
+    L.cull = !(p->sweep_mode >= 1 && p->sweep_mode <= 3);   // 0 (auto), 4, 5: culled sweep; 1..3: dense variants
     if (L.cull && !(p->sweep_q == 4 || p->sweep_q == 8)) L.nn_q = 4;   // smaller patches cull better
     L.fused = L.cull && p->sweep_mode != 4;  // 4: culled sweep with the five separate kernels
+    L.persistent = L.fused && p->sweep_mode != 5;   // 5: fused rounds, one launch per round (A/B runs)
     L.q_tiles = (p->n_src + NN_THREADS * L.nn_q - 1) / (NN_THREADS * L.nn_q);
     int s = p->target_splits;
     if (s <= 0) {
@@ -1572,6 +1669,14 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     L.red_grid = (p->n_src + RED_THREADS * RED_PER_THREAD - 1) / (RED_THREADS * RED_PER_THREAD);
     const int patches = (p->n_src + 32 * ROUND_Q - 1) / (32 * ROUND_Q);   // fused rounds: one partial per patch
     L.red_blocks = L.red_grid > patches ? L.red_grid : patches;
+    L.n_patches = patches;
+    {
+        const unsigned long long items = (unsigned long long)p->n_units * (unsigned long long)patches;
+        if (items >= 0x7fffffffull) return false;
+        unsigned cap = 1024;
+        while ((unsigned long long)cap < items) cap <<= 1;
+        L.q_cap = cap;
+    }
     if (L.fused) { L.chunks_per_split = L.n_chunks; L.splits = 1; }
     const size_t U = p->n_units, ns = p->n_src;
     size_t o = 0;
@@ -1601,6 +1706,8 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     const size_t sort_s = (size_t)p->n_src_sets * sort_pad(p->n_src), sort_t = (size_t)p->n_tgt_sets * sort_pad(p->n_tgt);
     L.off_sort = take((sort_s > sort_t ? sort_s : sort_t) * sizeof(unsigned long long));
     L.off_bbox = take((size_t)(p->n_src_sets > p->n_tgt_sets ? p->n_src_sets : p->n_tgt_sets) * 6 * sizeof(double));
+    L.off_qslots = take((size_t)L.q_cap * sizeof(unsigned));
+    L.off_qctrl = take(128 * sizeof(unsigned));
     L.total = o;
     return true;
 }
@@ -1640,6 +1747,10 @@ void fill_ctx(const orpcd_gicp_params *p, const Layout &L, void *ws, Ctx &c)
     c.n_super = (L.n_chunks + 31) / 32;
     c.sortbuf = (unsigned long long *)(w + L.off_sort);
     c.bbox = (double *)(w + L.off_bbox);
+    c.q_slots = (unsigned *)(w + L.off_qslots);
+    c.q_ctrl = (unsigned *)(w + L.off_qctrl);
+    c.q_mask = L.q_cap - 1u;
+    c.n_patches = L.n_patches;
     c.dcap = (float)(p->max_correspondence_distance * (1.0 + 1e-5)) * (1.f + 1e-6f) + 1e-30f;
     c.tgt_pts = nullptr; c.tgt_cov = nullptr; c.out_T = nullptr; c.out_stats = nullptr; c.trace = nullptr;
     c.out_status = nullptr;
@@ -1698,6 +1809,39 @@ void launch_round_e(const Ctx &c, int n_units, int round, cudaStream_t st)
     gicp_round_kernel<EST><<<g, ROUND_W * 32, 0, st>>>(c, round);
 }
 
+// all rounds of all units in one launch: grid = what is resident at once, capped at the round-0 work
+template <int EST>
+int launch_persistent_e(const Ctx &c, cudaStream_t st)
+{
+    static int blocks_per_sm = 0, n_sm = 0;   // per template instance; one device per process (one process per GPU)
+    if (blocks_per_sm == 0) {
+        int dev = 0, b = 0, sm = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+        if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, gicp_persistent_kernel<EST>, ROUND_W * 32, 0) != cudaSuccess)
+            return -1;
+        if (b < 1 || sm < 1) return -1;
+        n_sm = sm;
+        blocks_per_sm = b;
+    }
+    const long long items = (long long)c.n_units * c.n_patches;
+    long long blocks = (long long)n_sm * blocks_per_sm;        // every block is resident: workers may spin on the ring
+    const long long need = (items + ROUND_W - 1) / ROUND_W;
+    if (blocks > need) blocks = need;
+    queue_init_kernel<<<(unsigned)((c.q_mask + 1u + 255u) / 256u > 1184u ? 1184u : (c.q_mask + 1u + 255u) / 256u), 256, 0, st>>>(c);
+    gicp_persistent_kernel<EST><<<(unsigned)blocks, ROUND_W * 32, 0, st>>>(c);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_persistent(const Ctx &c, int est, cudaStream_t st)
+{
+    if (est == 0) return launch_persistent_e<0>(c, st);
+    if (est == 1) return launch_persistent_e<1>(c, st);
+    if (est == 2) return launch_persistent_e<2>(c, st);
+    if (est == 3) return launch_persistent_e<3>(c, st);
+    return launch_persistent_e<4>(c, st);
+}
+
 // one fused round; est: 0 / 1 Generalized-ICP, 2 evaluation, 3 point-to-point, 4 point-to-plane
 void launch_round(const Ctx &c, int est, int n_units, int round, cudaStream_t st)
 {
@@ -1745,6 +1889,30 @@ ORPCD_API size_t orpcd_gicp_batch_workspace_bytes(const orpcd_gicp_params *p)
 
 namespace {
 
+// profiling-mode resources, released on every return path
+struct ProfEvents {
+    cudaEvent_t *ev = nullptr;
+    int n = 0;
+    bool init(int count)
+    {
+        ev = (cudaEvent_t *)malloc(sizeof(cudaEvent_t) * (size_t)count);
+        if (!ev) return false;
+        for (n = 0; n < count; ++n)
+            if (cudaEventCreate(&ev[n]) != cudaSuccess) return false;
+        return true;
+    }
+    ~ProfEvents()
+    {
+        for (int k = 0; k < n; ++k) cudaEventDestroy(ev[k]);
+        free(ev);
+    }
+};
+struct HostBuf {
+    void *p = nullptr;
+    bool alloc(size_t bytes) { p = malloc(bytes); return p != nullptr; }
+    ~HostBuf() { free(p); }
+};
+
 // est_mode: 0 / 1 = Generalized-ICP (covariances / plane axes), 3 = point-to-point, 4 = point-to-plane
 // (d_tgt_cov = target normals).  d_init_T: optional initial transforms [n_units][16].
 int run_registration(const orpcd_gicp_params *p, int est_mode, const double *d_src_points,
@@ -1774,44 +1942,49 @@ int run_registration(const orpcd_gicp_params *p, int est_mode, const double *d_s
     const dim3 g_res((p->n_src + 127) / 128, p->n_units);
     const dim3 g_red(L.red_grid, p->n_units);
     const int fix_blocks = 148 * 4;
-    // profiling mode: CUDA events around every sweep launch on the caller's stream
+    // profiling mode (a diagnostic: it synchronises the stream and reads counters back before returning): CUDA
+    // events around every launch of the dominant kernel, on the caller's stream.  Everything it owns is released
+    // on every return path.
     const bool prof = p->profile != 0 && h_profile != nullptr;
     const int n_rounds_max = p->max_iterations + 1;
-    cudaEvent_t *ev = nullptr;
-    if (prof) {
-        ev = (cudaEvent_t *)malloc(sizeof(cudaEvent_t) * 2 * n_rounds_max);
-        if (!ev) return ORPCD_ERR_INVALID;
-        for (int k = 0; k < 2 * n_rounds_max; ++k)
-            if (cudaEventCreate(&ev[k]) != cudaSuccess) return ORPCD_ERR_CUDA;
-    }
+    ProfEvents pe;
+    if (prof && !pe.init(L.persistent ? 2 : 2 * n_rounds_max)) return ORPCD_ERR_CUDA;
     int rounds = 0;
-    for (int round = 0; round <= p->max_iterations; ++round) {
-        if (L.fused) {
-            if (prof) cudaEventRecord(ev[2 * round], st);
-            launch_round(c, est_mode, p->n_units, round, st);
-            if (prof) cudaEventRecord(ev[2 * round + 1], st);
-            launches += 1;
-        } else {
-            update_kernel<<<g_upd, 256, 0, st>>>(c, round);
-            if (prof) cudaEventRecord(ev[2 * round], st);
-            launch_sweep(c, L, p->n_units, round, st);
-            if (prof) cudaEventRecord(ev[2 * round + 1], st);
-            nn_resolve_kernel<<<g_res, 128, 0, st>>>(c, round);
-            nn_fix_kernel<<<fix_blocks, 128, 0, st>>>(c, round);
-            if (est_mode == 0) reduce_kernel<0><<<g_red, RED_THREADS, 0, st>>>(c, round);
-            else if (est_mode == 1) reduce_kernel<1><<<g_red, RED_THREADS, 0, st>>>(c, round);
-            else if (est_mode == 3) reduce_kernel<3><<<g_red, RED_THREADS, 0, st>>>(c, round);
-            else reduce_kernel<4><<<g_red, RED_THREADS, 0, st>>>(c, round);
-            launches += 5;
-        }
-        ORPCD_CHECK_LAUNCH();
-        rounds = round + 1;
-        if (p->poll_interval > 0 && round < p->max_iterations && (round + 1) % p->poll_interval == 0) {
-            int done = 0;
-            if (cudaMemcpyAsync(&done, c.done_count, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess)
-                return ORPCD_ERR_CUDA;
-            if (cudaStreamSynchronize(st) != cudaSuccess) return ORPCD_ERR_CUDA;
-            if (done >= p->n_units) break;
+    if (L.persistent) {
+        if (prof) cudaEventRecord(pe.ev[0], st);
+        if (launch_persistent(c, est_mode, st) != 0) return ORPCD_ERR_CUDA;
+        if (prof) cudaEventRecord(pe.ev[1], st);
+        launches += 2;                       // queue_init_kernel + gicp_persistent_kernel
+        rounds = n_rounds_max;               // upper bound; profiling mode replaces it by the rounds that ran
+    } else {
+        for (int round = 0; round <= p->max_iterations; ++round) {
+            if (L.fused) {
+                if (prof) cudaEventRecord(pe.ev[2 * round], st);
+                launch_round(c, est_mode, p->n_units, round, st);
+                if (prof) cudaEventRecord(pe.ev[2 * round + 1], st);
+                launches += 1;
+            } else {
+                update_kernel<<<g_upd, 256, 0, st>>>(c, round);
+                if (prof) cudaEventRecord(pe.ev[2 * round], st);
+                launch_sweep(c, L, p->n_units, round, st);
+                if (prof) cudaEventRecord(pe.ev[2 * round + 1], st);
+                nn_resolve_kernel<<<g_res, 128, 0, st>>>(c, round);
+                nn_fix_kernel<<<fix_blocks, 128, 0, st>>>(c, round);
+                if (est_mode == 0) reduce_kernel<0><<<g_red, RED_THREADS, 0, st>>>(c, round);
+                else if (est_mode == 1) reduce_kernel<1><<<g_red, RED_THREADS, 0, st>>>(c, round);
+                else if (est_mode == 3) reduce_kernel<3><<<g_red, RED_THREADS, 0, st>>>(c, round);
+                else reduce_kernel<4><<<g_red, RED_THREADS, 0, st>>>(c, round);
+                launches += 5;
+            }
+            ORPCD_CHECK_LAUNCH();
+            rounds = round + 1;
+            if (p->poll_interval > 0 && round < p->max_iterations && (round + 1) % p->poll_interval == 0) {
+                int done = 0;
+                if (cudaMemcpyAsync(&done, c.done_count, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                    return ORPCD_ERR_CUDA;
+                if (cudaStreamSynchronize(st) != cudaSuccess) return ORPCD_ERR_CUDA;
+                if (done >= p->n_units) break;
+            }
         }
     }
     if (h_profile) {
@@ -1821,49 +1994,49 @@ int run_registration(const orpcd_gicp_params *p, int est_mode, const double *d_s
         h_profile[5] = (double)L.splits;
     }
     if (prof) {
-        if (cudaStreamSynchronize(st) != cudaSuccess) return ORPCD_ERR_CUDA;
-        double sweep_ms = 0.0;
-        float *round_ms = (float *)malloc(sizeof(float) * n_rounds_max);
-        if (!round_ms) return ORPCD_ERR_INVALID;
-        for (int r = 0; r < rounds; ++r) {
+        const int nr = p->max_iterations + 2;
+        HostBuf hb;
+        if (!hb.alloc((sizeof(int) * 2 + sizeof(unsigned long long)) * (size_t)nr)) return ORPCD_ERR_INVALID;
+        unsigned long long *hv = (unsigned long long *)hb.p;
+        int *h_active = (int *)(hv + nr), *h_fixed = h_active + nr;
+        if (cudaMemcpyAsync(hv, c.visit_count, sizeof(unsigned long long) * nr, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(h_active, c.round_active, sizeof(int) * nr, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(h_fixed, c.worklist_count, sizeof(int) * nr, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            return ORPCD_ERR_CUDA;
+        double kernel_ms = 0.0, unit_rounds = 0.0, fixed = 0.0, visited = 0.0;
+        int launches_with_work = 0, rounds_run = 0;
+        for (int r = 0; r < n_rounds_max; ++r) {
+            if (h_active[r] <= 0) continue;
+            rounds_run = r + 1;
+            unit_rounds += h_active[r];
+            fixed += h_fixed[r];
+            visited += (double)hv[r];
+            if (!L.persistent && r < rounds) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, pe.ev[2 * r], pe.ev[2 * r + 1]);
+                kernel_ms += ms;
+                ++launches_with_work;
+            }
+        }
+        if (L.persistent) {
             float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev[2 * r], ev[2 * r + 1]);
-            round_ms[r] = ms;
-            sweep_ms += ms;
+            cudaEventElapsedTime(&ms, pe.ev[0], pe.ev[1]);   // includes the ring set-up kernel (microseconds)
+            kernel_ms = ms;
+            launches_with_work = 1;
+            rounds = rounds_run;
+            h_profile[3] = (double)rounds;
         }
-        for (int k = 0; k < 2 * n_rounds_max; ++k) cudaEventDestroy(ev[k]);
-        free(ev);
-        int *h = (int *)malloc(sizeof(int) * 2 * (p->max_iterations + 2));
-        if (!h) return ORPCD_ERR_INVALID;
-        cudaMemcpy(h, c.round_active, sizeof(int) * (p->max_iterations + 2), cudaMemcpyDeviceToHost);
-        cudaMemcpy(h + p->max_iterations + 2, c.worklist_count, sizeof(int) * (p->max_iterations + 2),
-                   cudaMemcpyDeviceToHost);
-        double unit_rounds = 0.0, fixed = 0.0;
-        int sweep_launches = 0;
-        for (int r = 0; r < rounds; ++r) {
-            unit_rounds += h[r];
-            fixed += h[p->max_iterations + 2 + r];
-            if (h[r] > 0) ++sweep_launches;
-        }
-        unsigned long long *hv = (unsigned long long *)malloc(sizeof(unsigned long long) * (p->max_iterations + 2));
-        if (!hv) return ORPCD_ERR_INVALID;
-        cudaMemcpy(hv, c.visit_count, sizeof(unsigned long long) * (p->max_iterations + 2), cudaMemcpyDeviceToHost);
-        double visited = 0.0;
-        for (int r = 0; r < rounds; ++r) visited += (double)hv[r];
         if (getenv("ORPCD_DEBUG_ROUNDS")) {
             for (int r = 0; r < rounds; ++r)
-                fprintf(stderr, "round %3d active %4d visited %.3f sweep_us %.1f worklist %d\n", r, h[r],
-                        h[r] > 0 ? (double)hv[r] / ((double)h[r] * p->n_src * p->n_tgt) : 0.0, round_ms[r] * 1e3,
-                        h[p->max_iterations + 2 + r]);
+                fprintf(stderr, "round %3d active %4d visited %.3f worklist %d\n", r, h_active[r],
+                        h_active[r] > 0 ? (double)hv[r] / ((double)h_active[r] * p->n_src * p->n_tgt) : 0.0, h_fixed[r]);
         }
-        free(hv);
-        free(h);
-        free(round_ms);
-        h_profile[1] = sweep_ms;                                        // total time inside the sweep kernel
-        h_profile[2] = visited;                                         // (query, target) pairs the sweep evaluated
-        h_profile[4] = fixed;                                           // queries sent to the exact work list
-        h_profile[6] = (double)sweep_launches;                          // sweep launches that had work
-        h_profile[7] = unit_rounds;                                     // brute force would be unit_rounds*n_src*n_tgt pairs
+        h_profile[1] = kernel_ms;                       // total time inside the dominant kernel (round / sweep)
+        h_profile[2] = visited;                         // (query, target) pairs the sweep evaluated
+        h_profile[4] = fixed;                           // queries sent to the exact float64 search
+        h_profile[6] = (double)launches_with_work;      // launches of the dominant kernel that had work
+        h_profile[7] = unit_rounds;                     // brute force would be unit_rounds * n_src * n_tgt pairs
     }
     return ORPCD_OK;
 }
@@ -1924,7 +2097,9 @@ ORPCD_API int orpcd_evaluate_batch(const orpcd_gicp_params *p_in, const double *
     if ((size_t)q.n_units * 16 > (size_t)q.n_units * q.n_src * 3) return ORPCD_ERR_INVALID;
     if (prepare_batch(c, L, &q, d_src_points, nullptr, d_unit_src, d_unit_tgt, d_T, st, nullptr) != 0)
         return ORPCD_ERR_CUDA;
-    if (L.fused) {
+    if (L.persistent) {
+        if (launch_persistent(c, 2, st) != 0) return ORPCD_ERR_CUDA;
+    } else if (L.fused) {
         launch_round(c, 2, q.n_units, 0, st);
     } else {
         update_kernel<<<dim3((q.n_src + 255) / 256, q.n_units), 256, 0, st>>>(c, 0);

@@ -46,7 +46,7 @@ class GeneralizedICP(IOptimizer):
         # generic 3x3 covariance path with a Jacobi eigen-solve per correspondence
         self.analytic_whitening = True
         self.profile = False          # set True to collect sweep timings in BatchResult.profile
-        self.sweep_mode = 0           # tuning: 0 = fused culled rounds, 4 = culled sweep + separate kernels, 1..3 = dense sweeps
+        self.sweep_mode = 0           # tuning: 0 = persistent work-queue kernel, 5 = one fused launch per round, 4 = culled sweep + separate kernels, 1..3 = dense sweeps
         self.sweep_q = 0              # tuning: queries per thread (4 | 8), 0 = auto
         self.target_splits = 0        # tuning: target splits per sweep, 0 = auto
         self.sweep_tj = 0             # tuning: dense sweep targets per step; culled sweep warps per block (2->1, 4->2, 8->4)

@@ -280,7 +280,7 @@ def icp_batch(src_points, tgt_points, unit_src, unit_tgt, init_transforms=None, 
                             init_transforms.data_ptr() if init_transforms is not None else None, ws.data_ptr(),
                             ws.numel(), T.data_ptr(), stats.data_ptr(), status.data_ptr(), _lib.stream_ptr()),
           "orpcd_icp_batch")
-    launch_counter["kernels"] += 5 * (int(max_iterations) + 1)
+    launch_counter["kernels"] += 9   # Hilbert sort + set-up kernels, ring set-up, one persistent launch for all rounds
     return T, stats, status
 
 

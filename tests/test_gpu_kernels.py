@@ -271,9 +271,11 @@ def test_optimize_batch_rigid_base_same_result(oracle, armadillo_pair):
 
 
 def test_fused_round_kernel_agrees_with_the_unfused_and_dense_paths(oracle, armadillo_pair):
-    """Three implementations of the same round -- one fused kernel (default), culled sweep + separate kernels
-    (sweep_mode 4), dense sweep + separate kernels (sweep_mode 1) -- find the same correspondences, so they differ
-    only by the order of the float64 sums: same iteration counts, rmse and transforms to 1e-9."""
+    """Four implementations of the same rounds -- the persistent work-queue kernel (default: all rounds in one launch),
+    one fused kernel launch per round (sweep_mode 5), culled sweep + separate kernels (sweep_mode 4), dense sweep +
+    separate kernels (sweep_mode 1) -- find the same correspondences, so they differ only by the order of the float64
+    sums: same iteration counts, rmse and transforms to 1e-9.  The persistent kernel and the launch-per-round kernel
+    share every instruction of the round and sum in the same (patch) order: bit-identical."""
     from or_pcd_b200.Optimizer import GeneralizedICP
 
     s, t, _ = armadillo_pair
@@ -283,10 +285,11 @@ def test_fused_round_kernel_agrees_with_the_unfused_and_dense_paths(oracle, arma
     targets = np.stack([t, t * np.array([1.0, 1.15, 1.0])])
     us, ut = [0, 1, 2, 3, 0, 1], [0, 0, 0, 0, 1, 1]
     res = []
-    for mode in (0, 4, 1):
+    for mode in (0, 5, 4, 1):
         opt = GeneralizedICP()
         opt.sweep_mode = mode
         res.append(opt.optimize_batch(sources, targets, us, ut))
+    assert np.array_equal(res[0].rmse, res[1].rmse) and np.array_equal(res[0].transforms, res[1].transforms)
     for other in res[1:]:
         assert np.array_equal(res[0].iterations, other.iterations)
         assert np.allclose(res[0].rmse, other.rmse, rtol=1e-9, atol=0)
