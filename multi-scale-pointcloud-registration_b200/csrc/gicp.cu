@@ -51,6 +51,12 @@ constexpr int RED_VALS = 29;                     // 21 JTJ + 6 JTr + sum d2 + co
 constexpr int RED_STRIDE = 32;
 constexpr int RED_PER_THREAD = 4;                // correspondences accumulated per thread before the shuffles
 constexpr float F32_EPS = 5.9604644775390625e-8f;  // 2^-24, unit roundoff
+#ifndef ORPCD_SPIN_NS
+#define ORPCD_SPIN_NS 500          // back-off of a worker waiting on an empty ring slot (a patch takes tens of microseconds)
+#endif
+#ifndef ORPCD_PLANE_MMA
+#define ORPCD_PLANE_MMA 1          // EST 1: Jacobian sums on the float64 tensor cores (0: per-lane accumulators + butterfly)
+#endif
 
 struct UnitState {
     double T[16];       // accumulated transform (row-major 4x4, column convention)
@@ -87,7 +93,7 @@ struct Ctx {
     float *part_m2;
     float4 *tgt4;        // [tgt_sets][nt_pad]  (-2x, -2y, -2z, |p|^2), centred
     TgtMeta *tgt_meta;   // [tgt_sets]
-    double *red_partial; // [units][red_blocks][RED_STRIDE]
+    double *red_partial; // [units][red_blocks][RED_STRIDE_MMA] (the unfused reduce_kernel uses the first RED_STRIDE of each row... see its indexing)
     unsigned *red_counter;  // [units]
     int *worklist;       // [units*n_src]
     int *worklist_count; // [max_iter+2]
@@ -517,6 +523,18 @@ __global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c, int round)
 // warps per block (template parameter W): warps are independent workers, 2 by default
 constexpr int CULL_RING = 4;       // chunk buffers per warp (512 B each), filled by cp.async
 constexpr int CULL_LIST = 1024;    // visit-list capacity per pass (chunk ids)
+constexpr int RED_STRIDE_MMA = 128;   // doubles per patch partial of the tensor-core Jacobian sums (two 8x8 tiles)
+
+// a worker warp's private shared memory in the fused round kernels: the chunk ring and the visit list of the sweep,
+// then (the sweep is over by then) the 96 x 8 float64 records of the Jacobian sums, then the unit totals
+struct __align__(16) WarpSmem {
+    float4 ring[CULL_RING][NN_CH];      // 2 KB
+    unsigned short vl[CULL_LIST];       // 2 KB
+};
+static_assert(sizeof(WarpSmem) == 4096, "WarpSmem holds 64 records of 8 doubles");
+// (shared memory is kept small on purpose: it comes out of the same 256 KB as the L1 cache, and the target tables,
+// chunk spheres and permutations of the sweep live on L1 hits -- 6 KB per warp with the large carve-out measured
+// 14.9 ms per 180-unit batch against 12.8 ms with 4 KB)
 
 // The sweep of one warp over its patch.  qv[k] = (centred FP32 query, d_ub) of query k*32+lane of the patch
 // (lanes past the end of the cloud carry a copy of another query of the same patch); chunks [cb, ce) of the
@@ -1177,17 +1195,22 @@ __device__ bool finish_round(const Ctx &c, UnitState &st, int u, double *tot, in
         double *tr = c.trace + ((size_t)u * (c.max_iter + 1) + round) * 2;
         tr[0] = fitness; tr[1] = rmse;
     }
-    const bool converged = round >= 1 && fabs(st.fitness - fitness) < c.rel_fit && fabs(st.rmse - rmse) < c.rel_rmse;
+    // the unit's state was written by whichever warp closed its previous round, possibly on another SM of the same
+    // (persistent) launch: read it through L2
+    const bool converged = round >= 1 && fabs(__ldcg(&st.fitness) - fitness) < c.rel_fit &&
+                           fabs(__ldcg(&st.rmse) - rmse) < c.rel_rmse;
     st.fitness = fitness;
     st.rmse = rmse;
     st.n_corr = (int)n;
+    double Told[16];
+    for (int k = 0; k < 16; ++k) Told[k] = __ldcg(&st.T[k]);
     if (converged || round >= c.max_iter) {
         st.done = 1;
         st.has_update = 0;
         st.status = (rmse == 0.0) ? 1 : 0;
-        for (int k = 0; k < 16; ++k) c.out_T[(size_t)u * 16 + k] = st.T[k];
+        for (int k = 0; k < 16; ++k) c.out_T[(size_t)u * 16 + k] = Told[k];
         double *os = c.out_stats + (size_t)u * 4;
-        os[0] = fitness; os[1] = rmse; os[2] = (double)st.iters; os[3] = n;
+        os[0] = fitness; os[1] = rmse; os[2] = (double)__ldcg(&st.iters); os[3] = n;
         c.out_status[u] = st.status;
         if (atomicAdd(c.done_count, 1) == c.n_units - 1) {   // last unit of the batch: release the persistent workers
             __threadfence();
@@ -1219,9 +1242,9 @@ __device__ bool finish_round(const Ctx &c, UnitState &st, int u, double *tot, in
     double Tn[16];
     for (int r = 0; r < 3; ++r)
         for (int cc = 0; cc < 4; ++cc)
-            Tn[r * 4 + cc] = Um[r * 4] * st.T[cc] + Um[r * 4 + 1] * st.T[4 + cc] + Um[r * 4 + 2] * st.T[8 + cc] +
-                             Um[r * 4 + 3] * st.T[12 + cc];
-    Tn[12] = st.T[12]; Tn[13] = st.T[13]; Tn[14] = st.T[14]; Tn[15] = st.T[15];
+            Tn[r * 4 + cc] = Um[r * 4] * Told[cc] + Um[r * 4 + 1] * Told[4 + cc] + Um[r * 4 + 2] * Told[8 + cc] +
+                             Um[r * 4 + 3] * Told[12 + cc];
+    Tn[12] = Told[12]; Tn[13] = Told[13]; Tn[14] = Told[14]; Tn[15] = Told[15];
     for (int k = 0; k < 16; ++k) st.T[k] = Tn[k];
     for (int k = 0; k < 12; ++k) st.U[k] = Um[k];
     st.has_update = 1;
@@ -1319,18 +1342,66 @@ __device__ __forceinline__ double warp_transpose_sum32(double (&v)[32], int lane
     return v[0];
 }
 
+// D += A (8x4) B (4x8) in float64 on the tensor cores: lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4) + {0,1}]
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// record v (8 doubles: six vector entries, the residual projection, the weight) of the warp's record buffer.  The
+// four 16-byte pieces of a record are stored at piece index (q ^ ((v >> 1) & 3)): eight lanes writing the same piece
+// of eight consecutive records then hit eight different bank groups, and the reads of a tensor-core step (four
+// consecutive records, all 32 doubles) stay conflict free.
+__device__ __forceinline__ void store_record(double *rec, int v, double x0, double x1, double x2, double x3, double x4,
+                                             double x5, double x6, double x7)
+{
+    double2 *r = reinterpret_cast<double2 *>(rec + v * 8);
+    const int sw = (v >> 1) & 3;
+    r[0 ^ sw] = make_double2(x0, x1);
+    r[1 ^ sw] = make_double2(x2, x3);
+    r[2 ^ sw] = make_double2(x4, x5);
+    r[3 ^ sw] = make_double2(x6, x7);
+}
+
+// The 29 sums finish_round works on, from the totals of the two 8x8 tiles of the tensor-core path (EST 1):
+//   EF = sum_pairs  g+ (e|re)(e|re)^T + g- (f|rf)(f|rf)^T   (rows / cols 0..5 = J^T J part, col 6 = J^T r part),
+//   S  = sum_pairs  z z^T,  z = (sx, sy, sz, 1, dx, dy, dz),
+// t[63] (the unused EF(7,7) slot) carries sum d2.  Same "twice the sums, identity block left out" convention as
+// accumulate_pair<1>.
+__device__ void plane_tiles_to_sums(const double *t, double *o)
+{
+    int k = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) o[k++] = t[a * 8 + b];
+    for (int a = 0; a < 6; ++a) o[21 + a] = t[a * 8 + 6];
+    const double *S = t + 64;
+    const double Sxx = S[0], Sxy = S[1], Sxz = S[2], Syy = S[9], Syz = S[10], Szz = S[18];
+    const double sx = S[3], sy = S[11], sz = S[19];
+    o[0] += Syy + Szz; o[1] -= Sxy; o[2] -= Sxz; o[6] += Sxx + Szz; o[7] -= Syz; o[11] += Sxx + Syy;
+    o[4] -= sz; o[5] += sy; o[8] += sz; o[10] -= sx; o[12] -= sy; o[13] += sx;
+    o[21] += S[8 + 6] - S[16 + 5];      // sum (sy dz - sz dy)
+    o[22] += S[16 + 4] - S[6];          // sum (sz dx - sx dz)
+    o[23] += S[5] - S[8 + 4];           // sum (sx dy - sy dx)
+    o[24] += S[24 + 4]; o[25] += S[24 + 5]; o[26] += S[24 + 6];
+    o[27] = t[63];
+    o[28] = S[24 + 3];
+    for (k = 29; k < 32; ++k) o[k] = 0.0;
+}
+
 // PERSIST: the caller is the persistent kernel -- one launch for all rounds, so data another SM wrote in an earlier
 // round of the same launch (unit state, moving points / axes, correspondences) is read with ld.global.cg (L2, the
 // coherence point; an L1 line could be stale), and the warp that closes a unit's round puts the patches of its next
 // round on the work queue.
 template <int Q, int EST, bool PERSIST>
-__device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, int wi, int round,
-                                           float4 (*ring)[NN_CH], unsigned short *vl)
+__device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, int wi, int round, WarpSmem &wsm)
 {
+    float4 (*ring)[NN_CH] = wsm.ring;
+    unsigned short *vl = wsm.vl;
     const int lane = threadIdx.x & 31;
     const int wbase = wi * (32 * Q);
     if (wbase >= c.n_src) return;
-    const int tgt_set = st.tgt_set;   // immutable after init_units_kernel
+    const int tgt_set = __ldcg(&st.tgt_set);   // (immutable after init_units_kernel; .cg keeps the state's lines out of L1)
     if (wi == 0 && lane == 0) atomicAdd(&c.round_active[round], 1);
     const TgtMeta tm = c.tgt_meta[tgt_set];
     const double *tpts = c.tgt_pts + (size_t)tgt_set * c.n_tgt * 3;
@@ -1455,39 +1526,128 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     if (lane == 0 && n_fix) atomicAdd(&c.worklist_count[round], n_fix);
 
     // ---- 5. sums over this warp's correspondences
-    double acc[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < Q; ++k) {
-        const int i = wbase + k * 32 + lane;
-        if (i < c.n_src) {
-            const size_t oi = (size_t)u * c.n_src + i;
-            int j = tj[k];
-            if (j >= 0) {
-                const double *ps = c.cur_pts + oi * 3;
-                const double *pt = tpts + (size_t)j * 3;
-                const double sx = __ldcg(ps), sy = __ldcg(ps + 1), sz = __ldcg(ps + 2), tx = pt[0], ty = pt[1], tz = pt[2];
-                const double d2 = fd2[k] >= 0.0 ? fd2[k] : sqdist3_rn(sx, sy, sz, tx, ty, tz);
-                if (d2 < c.r2) {
-                    double cs[CST];   // the moving source's covariance data: written this round, read through L2
-                    if (EST <= 1) {
-#pragma unroll
-                        for (int e = 0; e < CST; ++e) cs[e] = __ldcg(c.cur_cov + oi * CST + e);
-                    }
-                    accumulate_pair<EST>(c, acc, sx, sy, sz, tx, ty, tz, cs,
-                                         c.tgt_cov + ((size_t)tgt_set * c.n_tgt + j) * CST, d2);
-                } else {
-                    j = -1;
-                }
-            }
-            c.corr[oi] = j;
-        }
-    }
-    const double mine = warp_transpose_sum32(acc, lane);
     const int n_warps = (c.n_src + 32 * Q - 1) / (32 * Q);
-    double *part = c.red_partial + (size_t)u * c.red_blocks * RED_STRIDE;
-    __stcg(part + (size_t)wi * RED_STRIDE + lane, mine);
+    double *tot = reinterpret_cast<double *>(&wsm);   // the sweep's ring and visit list are free now
+    if constexpr (EST == 1 && ORPCD_PLANE_MMA) {
+        // Plane-to-plane Generalized-ICP on the float64 tensor cores.  Per correspondence three weighted 8-vectors
+        //   (e | p.d ; 2g+)   (f | m.d ; 2g-)   (sx, sy, sz, 1, dx, dy, dz ; 1)
+        // go through the warp's record buffer (see accumulate_pair<1> for e, f, g+-); sum_v w v v^T over the 32 pairs
+        // of a sub-round is 24 mma.m8n8k4.f64 steps (A = w v, B = v: lane l reads entry l/4 of record 4 s + l%4):
+        // 16 on the (e, f) records into one 8x8 tile, then 8 on the (s, d) records into a second one -- 27 + 16
+        // needed sums for 4 registers of accumulators.
+        double *rec = reinterpret_cast<double *>(&wsm);
+        double ef0 = 0.0, ef1 = 0.0, sd0 = 0.0, sd1 = 0.0, d2sum = 0.0;
+        const int jv = lane & 3, cc = lane >> 2;
+        // offsets (in doubles) of this lane's entry and of the weight inside record 4 s + jv, for even / odd s
+        const int sw_e = jv >> 1, sw_o = 2 + (jv >> 1);
+        const int x_e = jv * 8 + ((((cc >> 1) ^ sw_e) << 1) | (cc & 1)), w_e = jv * 8 + (((3 ^ sw_e) << 1) | 1);
+        const int x_o = jv * 8 + ((((cc >> 1) ^ sw_o) << 1) | (cc & 1)), w_o = jv * 8 + (((3 ^ sw_o) << 1) | 1);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+            const int i = wbase + k * 32 + lane;
+            bool have = false;
+            double sx = 0, sy = 0, sz = 0, dx = 0, dy = 0, dz = 0;
+            if (i < c.n_src) {
+                const size_t oi = (size_t)u * c.n_src + i;
+                int j = tj[k];
+                if (j >= 0) {
+                    const double *ps = c.cur_pts + oi * 3;
+                    const double *pt = tpts + (size_t)j * 3;
+                    sx = __ldcg(ps); sy = __ldcg(ps + 1); sz = __ldcg(ps + 2);
+                    const double tx = pt[0], ty = pt[1], tz = pt[2];
+                    const double d2 = fd2[k] >= 0.0 ? fd2[k] : sqdist3_rn(sx, sy, sz, tx, ty, tz);
+                    if (d2 < c.r2) {
+                        have = true;
+                        d2sum += d2;
+                        dx = sx - tx; dy = sy - ty; dz = sz - tz;
+                        const double *as = c.cur_cov + oi * 3;   // moving source axis: written this round, read through L2
+                        const double *bt = c.tgt_cov + ((size_t)tgt_set * c.n_tgt + j) * 3;
+                        const double ax = __ldcg(as), ay = __ldcg(as + 1), az = __ldcg(as + 2);
+                        const double bx = bt[0], by = bt[1], bz = bt[2];
+                        const double dot = fma(ax, bx, fma(ay, by, az * bz));
+                        const double sg = dot >= 0 ? 1.0 : -1.0;
+                        const double ac = fmin(fabs(dot), 1.0);
+                        const double lp = fma(-c.kappa, 1.0 + ac, 2.0), lm = fma(-c.kappa, 1.0 - ac, 2.0);
+                        const double inv = (0.5 * c.kappa) / (lp * lm);
+                        {
+                            const double px = fma(sg, bx, ax), py = fma(sg, by, ay), pz = fma(sg, bz, az);
+                            store_record(rec, lane, fma(sy, pz, -(sz * py)), fma(sz, px, -(sx * pz)), fma(sx, py, -(sy * px)),
+                                         px, py, pz, fma(px, dx, fma(py, dy, pz * dz)), inv * lm);       // weight 2 g+
+                        }
+                        {
+                            const double mx = fma(-sg, bx, ax), my = fma(-sg, by, ay), mz = fma(-sg, bz, az);
+                            store_record(rec, 32 + lane, fma(sy, mz, -(sz * my)), fma(sz, mx, -(sx * mz)),
+                                         fma(sx, my, -(sy * mx)), mx, my, mz, fma(mx, dx, fma(my, dy, mz * dz)),
+                                         inv * lp);                                                      // weight 2 g-
+                        }
+                    } else {
+                        j = -1;
+                    }
+                }
+                c.corr[oi] = j;
+            }
+            if (!have) {
+                store_record(rec, lane, 0, 0, 0, 0, 0, 0, 0, 0);
+                store_record(rec, 32 + lane, 0, 0, 0, 0, 0, 0, 0, 0);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int sstep = 0; sstep < 16; ++sstep) {
+                const double *r4 = rec + sstep * 32;
+                const double x = r4[(sstep & 1) ? x_o : x_e], w = r4[(sstep & 1) ? w_o : w_e];
+                dmma884(ef0, ef1, w * x, x);
+            }
+            __syncwarp();
+            // the (s, d) records of the same 32 pairs reuse the first half of the buffer
+            if (have) store_record(rec, lane, sx, sy, sz, 1.0, dx, dy, dz, 1.0);
+            else store_record(rec, lane, 0, 0, 0, 0, 0, 0, 0, 0);
+            __syncwarp();
+#pragma unroll
+            for (int sstep = 0; sstep < 8; ++sstep) {
+                const double *r4 = rec + sstep * 32;
+                const double x = r4[(sstep & 1) ? x_o : x_e], w = r4[(sstep & 1) ? w_o : w_e];
+                dmma884(sd0, sd1, w * x, x);
+            }
+            __syncwarp();
+        }
+        d2sum = warp_sum(d2sum);
+        if (lane == 31) ef1 = d2sum;      // EF(7,7) is not a needed sum: its slot carries sum d2
+        double *part = c.red_partial + ((size_t)u * c.red_blocks + wi) * RED_STRIDE_MMA;
+        __stcg(reinterpret_cast<double2 *>(part) + lane, make_double2(ef0, ef1));
+        __stcg(reinterpret_cast<double2 *>(part + 64) + lane, make_double2(sd0, sd1));
+    } else {
+        double acc[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+            const int i = wbase + k * 32 + lane;
+            if (i < c.n_src) {
+                const size_t oi = (size_t)u * c.n_src + i;
+                int j = tj[k];
+                if (j >= 0) {
+                    const double *ps = c.cur_pts + oi * 3;
+                    const double *pt = tpts + (size_t)j * 3;
+                    const double sx = __ldcg(ps), sy = __ldcg(ps + 1), sz = __ldcg(ps + 2), tx = pt[0], ty = pt[1], tz = pt[2];
+                    const double d2 = fd2[k] >= 0.0 ? fd2[k] : sqdist3_rn(sx, sy, sz, tx, ty, tz);
+                    if (d2 < c.r2) {
+                        double cs[CST];   // the moving source's covariance data: written this round, read through L2
+                        if (EST <= 1) {
+#pragma unroll
+                            for (int e = 0; e < CST; ++e) cs[e] = __ldcg(c.cur_cov + oi * CST + e);
+                        }
+                        accumulate_pair<EST>(c, acc, sx, sy, sz, tx, ty, tz, cs,
+                                             c.tgt_cov + ((size_t)tgt_set * c.n_tgt + j) * CST, d2);
+                    } else {
+                        j = -1;
+                    }
+                }
+                c.corr[oi] = j;
+            }
+        }
+        const double mine = warp_transpose_sum32(acc, lane);
+        __stcg(c.red_partial + ((size_t)u * c.red_blocks + wi) * RED_STRIDE_MMA + lane, mine);
+    }
     __threadfence();
     __syncwarp();
     int last = 0;
@@ -1495,18 +1655,31 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
     __threadfence();
-    // totals in warp order, four interleaved chains (fixed order)
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int b = 0;
-    for (; b + 3 < n_warps; b += 4) {
-        s0 += __ldcg(part + (size_t)b * RED_STRIDE + lane);
-        s1 += __ldcg(part + (size_t)(b + 1) * RED_STRIDE + lane);
-        s2 += __ldcg(part + (size_t)(b + 2) * RED_STRIDE + lane);
-        s3 += __ldcg(part + (size_t)(b + 3) * RED_STRIDE + lane);
+    // unit totals: the patch partials added in patch order (a fixed order: run-to-run deterministic)
+    const double *part_u = c.red_partial + (size_t)u * c.red_blocks * RED_STRIDE_MMA;
+    if constexpr (EST == 1 && ORPCD_PLANE_MMA) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int b = 0; b < n_warps; ++b) {
+            const double2 *pp = reinterpret_cast<const double2 *>(part_u + (size_t)b * RED_STRIDE_MMA) + lane * 2;
+            const double2 v0 = __ldcg(pp), v1 = __ldcg(pp + 1);
+            a0 += v0.x; a1 += v0.y; a2 += v1.x; a3 += v1.y;
+        }
+        double *t128 = tot + 32;
+        t128[lane * 4] = a0; t128[lane * 4 + 1] = a1; t128[lane * 4 + 2] = a2; t128[lane * 4 + 3] = a3;
+        __syncwarp();
+        if (lane == 0) plane_tiles_to_sums(t128, tot);
+    } else {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int b = 0;
+        for (; b + 3 < n_warps; b += 4) {
+            s0 += __ldcg(part_u + (size_t)b * RED_STRIDE_MMA + lane);
+            s1 += __ldcg(part_u + (size_t)(b + 1) * RED_STRIDE_MMA + lane);
+            s2 += __ldcg(part_u + (size_t)(b + 2) * RED_STRIDE_MMA + lane);
+            s3 += __ldcg(part_u + (size_t)(b + 3) * RED_STRIDE_MMA + lane);
+        }
+        for (; b < n_warps; ++b) s0 += __ldcg(part_u + (size_t)b * RED_STRIDE_MMA + lane);
+        tot[lane] = (s0 + s1) + (s2 + s3);
     }
-    for (; b < n_warps; ++b) s0 += __ldcg(part + (size_t)b * RED_STRIDE + lane);
-    double *tot = reinterpret_cast<double *>(vl);   // the visit list is free now
-    tot[lane] = (s0 + s1) + (s2 + s3);
     __syncwarp();
     int go_on = 0;
     if (lane == 0) {
@@ -1537,6 +1710,16 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
 #ifndef ROUND_MIN_BLOCKS
 #define ROUND_MIN_BLOCKS 6
 #endif
+#ifndef ROUND_MIN_BLOCKS_PLANE
+// EST 1 (tensor-core Jacobian sums).  Measured on the 180-unit bench batch, persistent kernel, ms per batch:
+// 8 blocks (64 registers, 436 B spills) 14.9, 7 (72) 13.2, 6 (80) 12.0, 5 (96 registers, 136 B spills) 11.7,
+// 4 (128) 11.7 -- the kernel is bound by the shared-memory / L1 data pipe (58 % of peak over the whole launch, the
+// target-chunk LDS.128 broadcasts of the sweep) and by its L1 hit rate, not by resident warps: spill traffic and
+// a smaller L1 carve-out cost more than extra warps hide.
+#define ROUND_MIN_BLOCKS_PLANE 5
+#endif
+#define ROUND_BLOCKS(EST) ((EST) == 1 ? ROUND_MIN_BLOCKS_PLANE : ROUND_MIN_BLOCKS)
+
 #ifndef ROUND_W
 #define ROUND_W 4            // warps per block (independent workers)
 #endif
@@ -1545,14 +1728,13 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
 #endif
 
 template <int EST>
-__global__ void __launch_bounds__(ROUND_W * 32, ROUND_MIN_BLOCKS) gicp_round_kernel(Ctx c, int round)
+__global__ void __launch_bounds__(ROUND_W * 32, ROUND_BLOCKS(EST)) gicp_round_kernel(Ctx c, int round)
 {
-    __shared__ __align__(16) float4 ring[ROUND_W][CULL_RING][NN_CH];     // 2 KB per warp
-    __shared__ __align__(16) unsigned short vlist[ROUND_W][CULL_LIST];   // 2 KB per warp; reused for the unit totals
+    __shared__ WarpSmem wsm[ROUND_W];     // 4 KB per warp
     const int u = blockIdx.z, warp = threadIdx.x >> 5;
     UnitState &st = c.state[u];
     if (st.done) return;
-    round_body<ROUND_Q, EST, false>(c, st, u, blockIdx.x * ROUND_W + warp, round, ring[warp], vlist[warp]);
+    round_body<ROUND_Q, EST, false>(c, st, u, blockIdx.x * ROUND_W + warp, round, wsm[warp]);
 }
 
 // The whole registration of every unit in ONE launch (the default path).  The grid is sized to what is resident at
@@ -1563,10 +1745,9 @@ __global__ void __launch_bounds__(ROUND_W * 32, ROUND_MIN_BLOCKS) gicp_round_ker
 // the workers simply find the stragglers' patches in the ring.  The warp that finishes the last unit raises the done
 // flag, which is what idle workers poll while they wait on an empty slot.
 template <int EST>
-__global__ void __launch_bounds__(ROUND_W * 32, ROUND_MIN_BLOCKS) gicp_persistent_kernel(Ctx c)
+__global__ void __launch_bounds__(ROUND_W * 32, ROUND_BLOCKS(EST)) gicp_persistent_kernel(Ctx c)
 {
-    __shared__ __align__(16) float4 ring[ROUND_W][CULL_RING][NN_CH];
-    __shared__ __align__(16) unsigned short vlist[ROUND_W][CULL_LIST];
+    __shared__ WarpSmem wsm[ROUND_W];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (;;) {
         unsigned item = 0u;
@@ -1579,7 +1760,7 @@ __global__ void __launch_bounds__(ROUND_W * 32, ROUND_MIN_BLOCKS) gicp_persisten
                     if (item != 0u) break;
                 }
                 if (*reinterpret_cast<volatile unsigned *>(c.q_ctrl + Q_DONE) != 0u) break;
-                __nanosleep(64);
+                __nanosleep(ORPCD_SPIN_NS);      // an idle worker must not take issue slots from the busy warps of its SM
             }
         }
         item = __shfl_sync(0xffffffffu, item, 0);
@@ -1587,7 +1768,7 @@ __global__ void __launch_bounds__(ROUND_W * 32, ROUND_MIN_BLOCKS) gicp_persisten
         __threadfence();                              // what the publisher wrote before the item is visible from here on
         const int u = (int)((item - 1u) / (unsigned)c.n_patches), wi = (int)((item - 1u) % (unsigned)c.n_patches);
         UnitState &st = c.state[u];
-        round_body<ROUND_Q, EST, true>(c, st, u, wi, __ldcg(&st.iters), ring[warp], vlist[warp]);
+        round_body<ROUND_Q, EST, true>(c, st, u, wi, __ldcg(&st.iters), wsm[warp]);
         __syncwarp();
     }
 }
@@ -1692,7 +1873,7 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     L.off_m2 = take(U * L.splits * ns * sizeof(float));
     L.off_tgt4 = take((size_t)p->n_tgt_sets * L.nt_pad * sizeof(float4));
     L.off_meta = take((size_t)p->n_tgt_sets * sizeof(TgtMeta));
-    L.off_partial = take(U * L.red_blocks * RED_STRIDE * sizeof(double));
+    L.off_partial = take(U * L.red_blocks * RED_STRIDE_MMA * sizeof(double));
     L.off_counter = take(U * sizeof(unsigned));
     L.off_worklist = take(U * ns * sizeof(int));
     L.off_wcount = take((size_t)(p->max_iterations + 2) * sizeof(int));
