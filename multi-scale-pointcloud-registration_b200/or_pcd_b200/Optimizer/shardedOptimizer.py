@@ -109,6 +109,7 @@ class ShardedOptimizer(IOptimizer):
         self.last_local_units = 0
         self.last_local_target_sets = 0
         self.last_timing = {}     # {"compute_ms", "gather_ms"} of the last sharded call (CUDA events / perf_counter)
+        self.last_iterations = None   # iterations per unit of the last call: a difficulty proxy for the next one
 
     def _dist(self):
         import torch.distributed as dist
@@ -129,6 +130,7 @@ class ShardedOptimizer(IOptimizer):
             res = self._inner.optimize_batch(sources, targets, unit_src, unit_tgt, **kwargs)
             self.last_local_units = len(res.rmse)
             self.last_local_target_sets = len(np.unique(np.asarray(unit_tgt)))
+            self.last_iterations = res.iterations
             return res
         import time
 
@@ -148,9 +150,13 @@ class ShardedOptimizer(IOptimizer):
         self.last_local_units, self.last_local_target_sets = len(mine), len(tgt_sets)
 
         def pick(sets, idx):
+            if len(idx) == sets.shape[0]:
+                return sets
+            if len(idx) and int(idx[-1]) - int(idx[0]) + 1 == len(idx):
+                # a contiguous run (the usual case: blocks follow the unit order): a view, so a pinned host array
+                # stays pinned for its H2D copy and a CUDA tensor is not copied at all
+                return sets[int(idx[0]):int(idx[-1]) + 1]
             if hasattr(sets, "is_cuda"):
-                if len(idx) == sets.shape[0]:
-                    return sets
                 return sets.index_select(0, torch.as_tensor(idx, dtype=torch.int64, device=sets.device))
             return np.asarray(sets)[idx]
 
@@ -186,7 +192,9 @@ class ShardedOptimizer(IOptimizer):
             self.last_timing = {"compute_ms": ev[0].elapsed_time(ev[1]), "gather_ms": ev[1].elapsed_time(ev[2])}
         else:
             self.last_timing = {"compute_ms": 1e3 * (t1 - t0), "gather_ms": 1e3 * (t2 - t1)}
-        return unpack_records(host, plan)
+        res = unpack_records(host, plan)
+        self.last_iterations = res.iterations
+        return res
 
     def raise_failure(self):
         raise_failure = getattr(self._inner, "raise_failure", None)

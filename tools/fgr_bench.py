@@ -21,7 +21,7 @@ def main():
 
     mode = sys.argv[1] if len(sys.argv) > 1 else "fixed"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-    src, sources, targets, unit_src, unit_tgt = bench.make_workload(0)
+    src, sources, targets, unit_src, unit_tgt = bench.make_workload(1)
     opt = FastGlobalOptimizer(feature_mode=mode)
     for rep in range(reps):
         k0 = ops.launch_counter["kernels"]
