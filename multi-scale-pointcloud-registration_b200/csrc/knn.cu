@@ -329,9 +329,152 @@ knn_cull_kernel(const double *__restrict__ sorted, const double4 *__restrict__ s
     }
 }
 
+// ----------------------------------------------------------------------------
+// Self k-NN, one WARP per query (k <= 64): the form that fills the GPU at 5000 points.  knn_cull_kernel above gives a
+// warp 32 queries and a serial insertion per lane -- 157 warps per 5000-point cloud, 7.7 % achieved occupancy, more
+// than half of its instructions in the rescans for the worst list member.  Here the 32 lanes score the 32 points of a
+// chunk at once against ONE query; points that beat the current bound tau = (d2, index) of the k-th best are appended
+// to a buffer in shared memory with a ballot / popc prefix; when the buffer cannot take another chunk it is sorted
+// (bitonic, one compare-exchange per lane and step) and cut back to its k best, which tightens tau.  Chunks are
+// visited own chunk first, then along the Hilbert curve until k points are in hand, then the rest of the cloud under
+// two-level bounding-sphere culling against tau (strict tests with slack: a skipped chunk holds no point that could
+// enter the list, not even on an exact tie).  Same (d2, original index) order as every other k-NN here: bit-exact.
+// ----------------------------------------------------------------------------
+constexpr int WQ_WARPS = 8;
+
+// one sphere around each group of 32 chunk spheres.  grid (n_super, batch), 32 threads.
+__global__ void __launch_bounds__(32)
+knn_super_sphere_kernel(const double4 *__restrict__ spheres, int n_chunks, int n_super, double4 *__restrict__ super)
+{
+    const int b = blockIdx.y, g = blockIdx.x, lane = threadIdx.x;
+    const int ch = g * 32 + lane;
+    const bool valid = ch < n_chunks;
+    const double4 t = valid ? spheres[(size_t)b * n_chunks + ch] : make_double4(0, 0, 0, 0);
+    double lo[3] = {valid ? t.x - t.w : CUDART_INF, valid ? t.y - t.w : CUDART_INF, valid ? t.z - t.w : CUDART_INF};
+    double hi[3] = {valid ? t.x + t.w : -CUDART_INF, valid ? t.y + t.w : -CUDART_INF, valid ? t.z + t.w : -CUDART_INF};
+    for (int k = 0; k < 3; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    const double cx = 0.5 * (lo[0] + hi[0]), cy = 0.5 * (lo[1] + hi[1]), cz = 0.5 * (lo[2] + hi[2]);
+    double r = valid ? sqrt((t.x - cx) * (t.x - cx) + (t.y - cy) * (t.y - cy) + (t.z - cz) * (t.z - cz)) + t.w : 0.0;
+    for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+    if (lane == 0) super[(size_t)b * n_super + g] = make_double4(cx, cy, cz, r * (1.0 + 1e-12) + 1e-300);
+}
+
+// C = buffer capacity per query (64 for k <= 32, 128 for k <= 64)
+template <int C>
+__global__ void __launch_bounds__(WQ_WARPS * 32)
+knn_wq_kernel(const double *__restrict__ sorted, const double4 *__restrict__ spheres, const double4 *__restrict__ super,
+              const int *__restrict__ perm, int n, int n_pad, int n_super, int k, int *__restrict__ out_idx,
+              double *__restrict__ out_d2)
+{
+    __shared__ double bd_s[WQ_WARPS][C];
+    __shared__ int bi_s[WQ_WARPS][C];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, n_chunks = n_pad / 32;
+    const int qpos = blockIdx.x * WQ_WARPS + warp;         // the query's position in Hilbert order
+    if (qpos >= n_pad) return;
+    const int *pm = perm + (size_t)b * n_pad;
+    const int qorig = pm[qpos];
+    if (qorig < 0) return;                                  // padding
+    const double *pts = sorted + (size_t)b * n_pad * 3;
+    const double4 *sph = spheres + (size_t)b * n_chunks;
+    const double4 *ssph = super + (size_t)b * n_super;
+    double *bd = bd_s[warp];
+    int *bi = bi_s[warp];
+    const double qx = pts[(size_t)qpos * 3], qy = pts[(size_t)qpos * 3 + 1], qz = pts[(size_t)qpos * 3 + 2];
+    int cnt = 0;
+    double tau_d = CUDART_INF;      // the k-th best so far (inf until k points are in hand)
+    int tau_i = 0x7fffffff;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // buffer -> its k best under (d2, index), sorted; tau tightened
+    auto compact = [&]() {
+        for (int e = cnt + lane; e < C; e += 32) { bd[e] = CUDART_INF; bi[e] = 0x7fffffff; }
+        __syncwarp();
+        for (int kk = 2; kk <= C; kk <<= 1)
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+#pragma unroll
+                for (int t = lane; t < C / 2; t += 32) {
+                    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;   // partners at distance j
+                    const bool up = (lo & kk) == 0;
+                    const double dl = bd[lo], dh = bd[hi];
+                    const int il = bi[lo], ih = bi[hi];
+                    const bool gt = dl > dh || (dl == dh && il > ih);
+                    if (gt == up) { bd[lo] = dh; bd[hi] = dl; bi[lo] = ih; bi[hi] = il; }
+                }
+                __syncwarp();
+            }
+        cnt = min(cnt, k);
+        if (cnt >= k) { tau_d = bd[k - 1]; tau_i = bi[k - 1]; }
+    };
+    // the 32 points of chunk ch against the query; the ones that beat tau are appended
+    auto scan = [&](int ch) {
+        if (cnt + 32 > C) compact();
+        const int id = pm[ch * 32 + lane];
+        const double *cp = pts + ((size_t)ch * 32 + lane) * 3;
+        const double d = sqdist3_rn(qx, qy, qz, cp[0], cp[1], cp[2]);
+        const bool keep = id >= 0 && (d < tau_d || (d == tau_d && id < tau_i));
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = cnt + __popc(bal & lt_mask);
+            bd[pos] = d;
+            bi[pos] = id;
+        }
+        cnt += __popc(bal);
+        __syncwarp();
+    };
+
+    // 1) own chunk and its neighbours along the curve until k points are in hand (or the cloud is exhausted)
+    const int c0 = qpos >> 5;
+    int lo = c0, hi = c0;
+    scan(c0);
+    while ((hi - lo + 1) * 32 < k + 32 && (lo > 0 || hi < n_chunks - 1)) {
+        if (hi < n_chunks - 1) scan(++hi);
+        if (lo > 0) scan(--lo);
+    }
+    compact();
+    // 2) every other chunk, culled on two levels against the ball of the k-th best
+    auto far = [&](const double4 &sc) {      // true: the sphere holds no point that could enter the list
+        const double dx = sc.x - qx, dy = sc.y - qy, dz = sc.z - qz;
+        const double lb = sqrt(dx * dx + dy * dy + dz * dz) - sc.w;
+        return cnt >= k && lb > 0.0 && lb * lb * (1.0 - 1e-9) > tau_d;
+    };
+    for (int g0 = 0; g0 < n_super; g0 += 32) {
+        bool gneed = false;
+        if (g0 + lane < n_super) gneed = !far(ssph[g0 + lane]);
+        unsigned gbal = __ballot_sync(0xffffffffu, gneed);
+        while (gbal) {
+            const int gl = __ffs(gbal) - 1;
+            gbal &= gbal - 1;
+            const int ch = (g0 + gl) * 32 + lane;
+            bool need = false;
+            if (ch < n_chunks && (ch < lo || ch > hi)) need = !far(sph[ch]);
+            unsigned bal = __ballot_sync(0xffffffffu, need);
+            while (bal) {
+                const int l = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const int cc = (g0 + gl) * 32 + l;
+                // tau may have tightened since the lane-parallel test: one more look before the 32 loads
+                const double4 sc = sph[cc];
+                if (!far(sc)) scan(cc);
+            }
+        }
+    }
+    compact();
+    int *oi = out_idx + ((size_t)b * n + qorig) * k;
+    double *od = out_d2 + ((size_t)b * n + qorig) * k;
+    for (int s2 = lane; s2 < k; s2 += 32) {
+        oi[s2] = s2 < cnt ? bi[s2] : -1;
+        od[s2] = s2 < cnt ? bd[s2] : CUDART_INF;
+    }
+}
+
 struct CullLayout {
-    size_t off_perm, off_sorted, off_sph, off_keys, off_bbox, total;
-    int n_pad;
+    size_t off_perm, off_sorted, off_sph, off_super, off_keys, off_bbox, total;
+    int n_pad, n_super;
 };
 CullLayout knn_cull_layout(int n, int batch)
 {
@@ -342,6 +485,8 @@ CullLayout knn_cull_layout(int n, int batch)
     L.off_perm = take((size_t)batch * L.n_pad * sizeof(int));
     L.off_sorted = take((size_t)batch * L.n_pad * 3 * sizeof(double));
     L.off_sph = take((size_t)batch * (L.n_pad / 32) * sizeof(double4));
+    L.n_super = (L.n_pad / 32 + 31) / 32;
+    L.off_super = take((size_t)batch * L.n_super * sizeof(double4));
     L.off_keys = take((size_t)batch * sort_pad(n) * sizeof(unsigned long long));
     L.off_bbox = take((size_t)batch * 6 * sizeof(double));
     L.total = o;
@@ -638,6 +783,17 @@ int orpcd_launch_knn(const double *d_points, int n, long long points_stride, con
             return ORPCD_ERR_CUDA;
         const int n_chunks = L.n_pad / 32;
         knn_cull_prep_kernel<<<dim3(n_chunks, batch), 32, 0, st>>>(d_points, n, perm, L.n_pad, sorted, sph);
+        if (k <= 64) {      // one warp per query
+            double4 *ssph = (double4 *)(w + L.off_super);
+            knn_super_sphere_kernel<<<dim3(L.n_super, batch), 32, 0, st>>>(sph, n_chunks, L.n_super, ssph);
+            const dim3 grid((L.n_pad + WQ_WARPS - 1) / WQ_WARPS, batch);
+            if (k <= 32)
+                knn_wq_kernel<64><<<grid, WQ_WARPS * 32, 0, st>>>(sorted, sph, ssph, perm, n, L.n_pad, L.n_super, k, d_idx, d_d2);
+            else
+                knn_wq_kernel<128><<<grid, WQ_WARPS * 32, 0, st>>>(sorted, sph, ssph, perm, n, L.n_pad, L.n_super, k, d_idx, d_d2);
+            ORPCD_CHECK_LAUNCH();
+            return ORPCD_OK;
+        }
         const int W = kc_warps_for(k);
         return W == 4 ? launch_knn_cull<4>(n_chunks, batch, st, sorted, sph, perm, n, L.n_pad, k, d_idx, d_d2)
                       : (W == 2 ? launch_knn_cull<2>(n_chunks, batch, st, sorted, sph, perm, n, L.n_pad, k, d_idx, d_d2)
