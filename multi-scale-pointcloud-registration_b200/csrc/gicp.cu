@@ -1408,17 +1408,25 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     const float4 *tg = c.tgt4 + (size_t)tgt_set * c.nt_pad;
     constexpr int CST = EST == 0 ? 6 : 3;
 
+    // The two queries of a lane (k = 0, 1) go through phases 1, 3, 4 and 5 in ROLLED loops: the state of the query
+    // in hand lives in the "a" variables, the other one's in "b", and they trade places at the end of each pass.
+    // Unrolled, the straight-line code of a round was 38 KB per warp with 24 warps per SM in different phases: ncu
+    // showed the SM's instruction cache at 87 % hits and the GPC-level instruction cache at 79 % of its request
+    // peak over the whole launch -- the kernel was bound by instruction fetch, not by any execution pipe.
+    static_assert(Q == 2, "round_body rolls its per-query phases over exactly two queries per lane");
+#define ORPCD_SWAP(T, x, y) { const T t__ = x; x = y; y = t__; }
+
     // ---- 1. pending update, d_ub, centred FP32 copy
-    float4 qv[Q];
+    float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
     {
         const bool has_update = __ldcg(&st.has_update) != 0;
         double U[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) U[k] = __ldcg(&st.U[k]);
-#pragma unroll
-        for (int k = 0; k < Q; ++k) {
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
             const int i = wbase + k * 32 + lane;
-            qv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < c.n_src) {
                 const size_t oi = (size_t)u * c.n_src + i;
                 double *p = c.cur_pts + oi * 3;
@@ -1449,46 +1457,53 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
                         dub = fminf(dub, __double2float_ru(sqrt(dx * dx + dy * dy + dz * dz)) * (1.f + 1e-6f));
                     }
                 }
-                qv[k] = make_float4((float)(x - tm.cx), (float)(y - tm.cy), (float)(z - tm.cz), dub);
+                r = make_float4((float)(x - tm.cx), (float)(y - tm.cy), (float)(z - tm.cz), dub);
             }
+            qa = qb;
+            qb = r;        // after the two passes: qa = query 0, qb = query 1
         }
         // lanes past the end of the cloud carry the patch's first query (always a real one)
-        const float fx = __shfl_sync(0xffffffffu, qv[0].x, 0), fy = __shfl_sync(0xffffffffu, qv[0].y, 0);
-        const float fz = __shfl_sync(0xffffffffu, qv[0].z, 0), fw = __shfl_sync(0xffffffffu, qv[0].w, 0);
-#pragma unroll
-        for (int k = 0; k < Q; ++k)
-            if (wbase + k * 32 + lane >= c.n_src) qv[k] = make_float4(fx, fy, fz, fw);
+        const float fx = __shfl_sync(0xffffffffu, qa.x, 0), fy = __shfl_sync(0xffffffffu, qa.y, 0);
+        const float fz = __shfl_sync(0xffffffffu, qa.z, 0), fw = __shfl_sync(0xffffffffu, qa.w, 0);
+        if (wbase + lane >= c.n_src) qa = make_float4(fx, fy, fz, fw);
+        if (wbase + 32 + lane >= c.n_src) qb = make_float4(fx, fy, fz, fw);
     }
 
     // ---- 2. sweep
-    float m1[Q], m2[Q];
-    int c1[Q];
-    const int visited = cull_sweep_core<Q, true>(c, tg, c.chunk_sph + (size_t)tgt_set * c.n_chunks,
-                                           c.super_sph + (size_t)tgt_set * c.n_super, c.n_super, (float)tm.rmax, 0,
-                                           c.n_chunks, qv, ring, vl, m1, c1, m2);
-    if (lane == 0)
-        atomicAdd(c.visit_count + round, (unsigned long long)visited * NN_CH * min(32 * Q, c.n_src - wbase));
+    float m1a, m1b, m2a, m2b;
+    int c1a, c1b;
+    {
+        const float4 qv[Q] = {qa, qb};
+        float m1[Q], m2[Q];
+        int c1[Q];
+        const int visited = cull_sweep_core<Q, true>(c, tg, c.chunk_sph + (size_t)tgt_set * c.n_chunks,
+                                                     c.super_sph + (size_t)tgt_set * c.n_super, c.n_super, (float)tm.rmax, 0,
+                                                     c.n_chunks, qv, ring, vl, m1, c1, m2);
+        if (lane == 0)
+            atomicAdd(c.visit_count + round, (unsigned long long)visited * NN_CH * min(32 * Q, c.n_src - wbase));
+        m1a = m1[0]; m1b = m1[1]; m2a = m2[0]; m2b = m2[1]; c1a = c1[0]; c1b = c1[1];
+    }
 
     // ---- 3. certificate (nn_resolve_kernel's bound), then each lane scans the best 8-target sub-chunk of its own queries:
     //         the FP32 values are recomputed with the sweep's FMA chain (bit-identical), and the chunk decides
     //         the query iff exactly one target lies within the certified margin of the minimum
-    int tj[Q];          // matched target (original index); -1 none within the cut-off; -2 exact search needed
+    int tja = -1, tjb = -1;   // matched target (original index); -1 none within the cut-off; -2 exact search needed
     const int *tperm = c.tperm + (size_t)tgt_set * c.nt_pad;
-#pragma unroll
-    for (int k = 0; k < Q; ++k) {
-        const float fx = qv[k].x, fy = qv[k].y, fz = qv[k].z;
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        const float fx = qa.x, fy = qa.y, fz = qa.z;
         const double qn = (double)fx * fx + (double)fy * fy + (double)fz * fz;
         const double qnorm = sqrt(qn);
         const double rho_max = qnorm + tm.rmax;
         const double e_glob = (double)F32_EPS * 6.0 * rho_max * rho_max * 1.001;
-        const double d_ub = sqrt(fmax((double)m1[k] + qn, 0.0) + e_glob) * (1.0 + 1e-6);
+        const double d_ub = sqrt(fmax((double)m1a + qn, 0.0) + e_glob) * (1.0 + 1e-6);
         const double rho = 2.0 * qnorm + d_ub + 4.0 * (double)F32_EPS * rho_max;
         const double margin = 2.02 * (double)F32_EPS * (4.0 * rho * rho + 2.0 * d_ub * rho) * 1.001 + 1e-300;
-        const double lim = (double)m1[k] + margin;
-        const bool none = !(m1[k] < CUDART_INF_F);        // no chunk visited: nothing within the cut-off
-        const bool cross = !((double)m2[k] > lim);        // another chunk may hold the true neighbour
+        const double lim = (double)m1a + margin;
+        const bool none = !(m1a < CUDART_INF_F);          // no chunk visited: nothing within the cut-off
+        const bool cross = !((double)m2a > lim);          // another chunk may hold the true neighbour
         const float thr = __double2float_ru(lim);
-        const float4 *tc = tg + (size_t)c1[k] * 8;   // c1 = 8-target sub-chunk (cull_sweep_core<Q, true>)
+        const float4 *tc = tg + (size_t)c1a * 8;   // c1 = 8-target sub-chunk (cull_sweep_core<Q, true>)
         int cnt = 0, first = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -1498,30 +1513,33 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
             first = (in && cnt == 0) ? j : first;
             cnt += in ? 1 : 0;
         }
-        tj[k] = none ? -1 : ((cross || cnt != 1) ? -2 : tperm[(size_t)c1[k] * 8 + first]);
-        if (wbase + k * 32 + lane >= c.n_src) tj[k] = -1;
+        int t = none ? -1 : ((cross || cnt != 1) ? -2 : tperm[(size_t)c1a * 8 + first]);
+        if (wbase + k * 32 + lane >= c.n_src) t = -1;
+        tja = tjb;
+        tjb = t;           // after the two passes: tja = query 0, tjb = query 1
+        ORPCD_SWAP(float4, qa, qb) ORPCD_SWAP(float, m1a, m1b) ORPCD_SWAP(float, m2a, m2b) ORPCD_SWAP(int, c1a, c1b)
     }
 
     // ---- 4. exact search for what the FP32 filter could not decide
-    double fd2[Q];
+    double fda = -1.0, fdb = -1.0;
     int n_fix = 0;
-#pragma unroll
-    for (int k = 0; k < Q; ++k) {
-        fd2[k] = -1.0;
-        unsigned fb = __ballot_sync(0xffffffffu, tj[k] == -2);
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        unsigned fb = __ballot_sync(0xffffffffu, tja == -2);
         n_fix += __popc(fb);
         while (fb) {
             const int l = __ffs(fb) - 1;
             fb &= fb - 1;
             const double *p = c.cur_pts + ((size_t)u * c.n_src + wbase + k * 32 + l) * 3;
-            const float qfx = __shfl_sync(0xffffffffu, qv[k].x, l), qfy = __shfl_sync(0xffffffffu, qv[k].y, l);
-            const float qfz = __shfl_sync(0xffffffffu, qv[k].z, l);
+            const float qfx = __shfl_sync(0xffffffffu, qa.x, l), qfy = __shfl_sync(0xffffffffu, qa.y, l);
+            const float qfz = __shfl_sync(0xffffffffu, qa.z, l);
             double best;
             int bj;
             exact_search_warp(c, tgt_set, __ldcg(p), __ldcg(p + 1), __ldcg(p + 2), qfx, qfy, qfz,
-                              __shfl_sync(0xffffffffu, c1[k], l) >> 2, best, bj);
-            if (lane == l) { tj[k] = bj == 0x7fffffff ? -1 : bj; fd2[k] = best; }
+                              __shfl_sync(0xffffffffu, c1a, l) >> 2, best, bj);
+            if (lane == l) { tja = bj == 0x7fffffff ? -1 : bj; fda = best; }
         }
+        ORPCD_SWAP(int, tja, tjb) ORPCD_SWAP(double, fda, fdb) ORPCD_SWAP(float4, qa, qb) ORPCD_SWAP(int, c1a, c1b)
     }
     if (lane == 0 && n_fix) atomicAdd(&c.worklist_count[round], n_fix);
 
@@ -1532,7 +1550,7 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
         // Plane-to-plane Generalized-ICP on the float64 tensor cores.  Per correspondence three weighted 8-vectors
         //   (e | p.d ; 2g+)   (f | m.d ; 2g-)   (sx, sy, sz, 1, dx, dy, dz ; 1)
         // go through the warp's record buffer (see accumulate_pair<1> for e, f, g+-); sum_v w v v^T over the 32 pairs
-        // of a sub-round is 24 mma.m8n8k4.f64 steps (A = w v, B = v: lane l reads entry l/4 of record 4 s + l%4):
+        // of a pass is 24 mma.m8n8k4.f64 steps (A = w v, B = v: lane l reads entry l/4 of record 4 s + l%4):
         // 16 on the (e, f) records into one 8x8 tile, then 8 on the (s, d) records into a second one -- 27 + 16
         // needed sums for 4 registers of accumulators.
         double *rec = reinterpret_cast<double *>(&wsm);
@@ -1542,20 +1560,20 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
         const int sw_e = jv >> 1, sw_o = 2 + (jv >> 1);
         const int x_e = jv * 8 + ((((cc >> 1) ^ sw_e) << 1) | (cc & 1)), w_e = jv * 8 + (((3 ^ sw_e) << 1) | 1);
         const int x_o = jv * 8 + ((((cc >> 1) ^ sw_o) << 1) | (cc & 1)), w_o = jv * 8 + (((3 ^ sw_o) << 1) | 1);
-#pragma unroll
-        for (int k = 0; k < Q; ++k) {
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
             const int i = wbase + k * 32 + lane;
             bool have = false;
             double sx = 0, sy = 0, sz = 0, dx = 0, dy = 0, dz = 0;
             if (i < c.n_src) {
                 const size_t oi = (size_t)u * c.n_src + i;
-                int j = tj[k];
+                int j = tja;
                 if (j >= 0) {
                     const double *ps = c.cur_pts + oi * 3;
                     const double *pt = tpts + (size_t)j * 3;
                     sx = __ldcg(ps); sy = __ldcg(ps + 1); sz = __ldcg(ps + 2);
                     const double tx = pt[0], ty = pt[1], tz = pt[2];
-                    const double d2 = fd2[k] >= 0.0 ? fd2[k] : sqdist3_rn(sx, sy, sz, tx, ty, tz);
+                    const double d2 = fda >= 0.0 ? fda : sqdist3_rn(sx, sy, sz, tx, ty, tz);
                     if (d2 < c.r2) {
                         have = true;
                         d2sum += d2;
@@ -1591,7 +1609,7 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
                 store_record(rec, 32 + lane, 0, 0, 0, 0, 0, 0, 0, 0);
             }
             __syncwarp();
-#pragma unroll
+#pragma unroll 2
             for (int sstep = 0; sstep < 16; ++sstep) {
                 const double *r4 = rec + sstep * 32;
                 const double x = r4[(sstep & 1) ? x_o : x_e], w = r4[(sstep & 1) ? w_o : w_e];
@@ -1602,13 +1620,14 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
             if (have) store_record(rec, lane, sx, sy, sz, 1.0, dx, dy, dz, 1.0);
             else store_record(rec, lane, 0, 0, 0, 0, 0, 0, 0, 0);
             __syncwarp();
-#pragma unroll
+#pragma unroll 2
             for (int sstep = 0; sstep < 8; ++sstep) {
                 const double *r4 = rec + sstep * 32;
                 const double x = r4[(sstep & 1) ? x_o : x_e], w = r4[(sstep & 1) ? w_o : w_e];
                 dmma884(sd0, sd1, w * x, x);
             }
             __syncwarp();
+            ORPCD_SWAP(int, tja, tjb) ORPCD_SWAP(double, fda, fdb)
         }
         d2sum = warp_sum(d2sum);
         if (lane == 31) ef1 = d2sum;      // EF(7,7) is not a needed sum: its slot carries sum d2
@@ -1619,17 +1638,17 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
         double acc[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) acc[k] = 0.0;
-#pragma unroll
-        for (int k = 0; k < Q; ++k) {
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
             const int i = wbase + k * 32 + lane;
             if (i < c.n_src) {
                 const size_t oi = (size_t)u * c.n_src + i;
-                int j = tj[k];
+                int j = tja;
                 if (j >= 0) {
                     const double *ps = c.cur_pts + oi * 3;
                     const double *pt = tpts + (size_t)j * 3;
                     const double sx = __ldcg(ps), sy = __ldcg(ps + 1), sz = __ldcg(ps + 2), tx = pt[0], ty = pt[1], tz = pt[2];
-                    const double d2 = fd2[k] >= 0.0 ? fd2[k] : sqdist3_rn(sx, sy, sz, tx, ty, tz);
+                    const double d2 = fda >= 0.0 ? fda : sqdist3_rn(sx, sy, sz, tx, ty, tz);
                     if (d2 < c.r2) {
                         double cs[CST];   // the moving source's covariance data: written this round, read through L2
                         if (EST <= 1) {
@@ -1644,10 +1663,12 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
                 }
                 c.corr[oi] = j;
             }
+            ORPCD_SWAP(int, tja, tjb) ORPCD_SWAP(double, fda, fdb)
         }
         const double mine = warp_transpose_sum32(acc, lane);
         __stcg(c.red_partial + ((size_t)u * c.red_blocks + wi) * RED_STRIDE_MMA + lane, mine);
     }
+#undef ORPCD_SWAP
     __threadfence();
     __syncwarp();
     int last = 0;
