@@ -1252,6 +1252,159 @@ __device__ bool finish_round(const Ctx &c, UnitState &st, int u, double *tot, in
     return true;
 }
 
+// ----------------------------------------------------------------------------
+// The same end of a round run by a whole WARP (the fused kernels): in a persistent launch the closing of a unit's
+// round sits on the unit's critical path -- round r+1 cannot start before it -- and the single-thread version spends
+// ~19 us in the 6x6 LDLT alone (36-entry arrays in local memory, every access a dependent L1 round trip), a third of
+// a straggler's per-round latency.  Here the matrix lives in shared memory, the pivot search is a shuffle arg-max, the
+// 15 updates of a step run on 15 lanes, the three sincos on three lanes and the rows of T <- U T on twelve.  Every
+// entry sees exactly the operations of ldlt_solve6 / finish_round in the same order: bit-identical results.
+// sm: >= 96 doubles of the warp's shared memory that do not overlap tot[0..31].
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void ldlt_solve6_warp(double *A, const double *b, double *x, int *sperm, int lane)
+{
+    int perm_mine = lane;                                    // lanes 0..5: perm[lane]
+    const int pi_ = 1 + lane / 5, pj_ = 1 + lane % 5;        // lanes 0..24: the pair (i, j) of the trailing update
+    for (int k = 0; k < 6; ++k) {
+        double v = (lane >= k && lane < 6) ? fabs(A[lane * 6 + lane]) : -1.0;
+        int idx = lane;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {                    // arg-max over lanes 0..7, lowest index on ties
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        const int piv = __shfl_sync(0xffffffffu, idx, 0);
+        if (piv != k) {
+            if (lane < 6) { const double t = A[k * 6 + lane]; A[k * 6 + lane] = A[piv * 6 + lane]; A[piv * 6 + lane] = t; }
+            __syncwarp();
+            if (lane < 6) { const double t = A[lane * 6 + k]; A[lane * 6 + k] = A[lane * 6 + piv]; A[lane * 6 + piv] = t; }
+            __syncwarp();
+            const int pk = __shfl_sync(0xffffffffu, perm_mine, k), pp = __shfl_sync(0xffffffffu, perm_mine, piv);
+            if (lane == k) perm_mine = pp;
+            else if (lane == piv) perm_mine = pk;
+        }
+        const double d = A[k * 6 + k];
+        if (d == 0.0) continue;                              // (uniform)
+        const bool act = lane < 25 && pj_ > k && pj_ <= pi_;     // k < j <= i < 6
+        const bool colw = lane > k && lane < 6;                  // lane i writes L[i][k]
+        double nv = 0.0, li = 0.0;
+        if (act) {
+            const double l = A[pi_ * 6 + k] / d;
+            nv = A[pi_ * 6 + pj_] - l * A[pj_ * 6 + k];
+        }
+        if (colw) li = A[lane * 6 + k] / d;
+        __syncwarp();                                        // column k is read before it is overwritten
+        if (act) { A[pi_ * 6 + pj_] = nv; A[pj_ * 6 + pi_] = nv; }
+        if (colw) A[lane * 6 + k] = li;
+        __syncwarp();
+    }
+    if (lane < 6) sperm[lane] = perm_mine;
+    __syncwarp();
+    if (lane == 0) {
+        double y[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) y[i] = b[sperm[i]];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < i; ++j) y[i] -= A[i * 6 + j] * y[j];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) y[i] = A[i * 6 + i] != 0.0 ? y[i] / A[i * 6 + i] : 0.0;
+#pragma unroll
+        for (int i = 5; i >= 0; --i)
+#pragma unroll
+            for (int j = i + 1; j < 6; ++j) y[i] -= A[j * 6 + i] * y[j];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[sperm[i]] = y[i];
+    }
+    __syncwarp();
+}
+
+template <int EST>
+__device__ __forceinline__ bool finish_round_warp(const Ctx &c, UnitState &st, int u, double *tot, double *sm, int round,
+                                                  int lane)
+{
+    double *A = sm, *nb = sm + 36, *x = sm + 42, *Um = sm + 48, *sc = sm + 60, *Told = sm + 66;   // 36+6+6+12+6+16
+    int *sperm = reinterpret_cast<int *>(sm + 82);
+    int what = 0;        // 0: the unit is done; 1: solve the 6x6 system; 2: Um is ready (Umeyama / identity)
+    if (lane < 16) Told[lane] = __ldcg(&st.T[lane]);
+    __syncwarp();
+    if (lane == 0) {
+        const double n = tot[28];
+        if (EST == 1) {   // accumulate_pair<1> sums twice J^T J / J^T r without the identity block
+            tot[15] += n; tot[18] += n; tot[20] += n;
+            for (int k = 0; k < 27; ++k) tot[k] *= 0.5;
+        }
+        double fitness = 0.0, rmse = 0.0;
+        if (n > 0) { fitness = n / (double)c.n_src; rmse = sqrt(tot[27] / n); }
+        if (c.trace) {
+            double *tr = c.trace + ((size_t)u * (c.max_iter + 1) + round) * 2;
+            tr[0] = fitness; tr[1] = rmse;
+        }
+        const bool converged = round >= 1 && fabs(__ldcg(&st.fitness) - fitness) < c.rel_fit &&
+                               fabs(__ldcg(&st.rmse) - rmse) < c.rel_rmse;
+        st.fitness = fitness;
+        st.rmse = rmse;
+        st.n_corr = (int)n;
+        if (converged || round >= c.max_iter) {
+            st.done = 1;
+            st.has_update = 0;
+            st.status = (rmse == 0.0) ? 1 : 0;
+            for (int k = 0; k < 16; ++k) c.out_T[(size_t)u * 16 + k] = Told[k];
+            double *os = c.out_stats + (size_t)u * 4;
+            os[0] = fitness; os[1] = rmse; os[2] = (double)__ldcg(&st.iters); os[3] = n;
+            c.out_status[u] = st.status;
+            if (atomicAdd(c.done_count, 1) == c.n_units - 1) {   // last unit of the batch: release the persistent workers
+                __threadfence();
+                atomicExch(c.q_ctrl + Q_DONE, 1u);
+            }
+            what = 0;
+        } else if (EST == 3) {
+            double U3[12];
+            umeyama_from_sums(tot, n, U3);
+            for (int k = 0; k < 12; ++k) Um[k] = U3[k];
+            what = 2;
+        } else if (n > 0) {
+            int k = 0;
+            for (int a = 0; a < 6; ++a)
+                for (int b = a; b < 6; ++b) { A[a * 6 + b] = tot[k]; A[b * 6 + a] = tot[k]; ++k; }
+            for (int a = 0; a < 6; ++a) nb[a] = -tot[21 + a];
+            what = 1;
+        } else {
+            for (int k = 0; k < 12; ++k) Um[k] = (k % 5 == 0) ? 1.0 : 0.0;
+            what = 2;
+        }
+    }
+    what = __shfl_sync(0xffffffffu, what, 0);
+    if (what == 0) return false;
+    __syncwarp();
+    if (what == 1) {
+        ldlt_solve6_warp(A, nb, x, sperm, lane);
+        if (lane < 3) sincos(x[lane], &sc[lane], &sc[3 + lane]);       // sin alpha, beta, gamma | cos alpha, beta, gamma
+        __syncwarp();
+        if (lane == 0) {
+            const double sa = sc[0], sb = sc[1], sg = sc[2], ca = sc[3], cb = sc[4], cg = sc[5];
+            Um[0] = cg * cb; Um[1] = cg * sb * sa - sg * ca; Um[2] = cg * sb * ca + sg * sa; Um[3] = x[3];
+            Um[4] = sg * cb; Um[5] = sg * sb * sa + cg * ca; Um[6] = sg * sb * ca - cg * sa; Um[7] = x[4];
+            Um[8] = -sb;     Um[9] = cb * sa;                Um[10] = cb * ca;               Um[11] = x[5];
+        }
+    }
+    __syncwarp();
+    // T = U * T (twelve lanes, one entry each), the pending update for the points, the unit's round counter
+    if (lane < 12) {
+        const int r = lane >> 2, cc = lane & 3;
+        st.T[lane] = Um[r * 4] * Told[cc] + Um[r * 4 + 1] * Told[4 + cc] + Um[r * 4 + 2] * Told[8 + cc] +
+                     Um[r * 4 + 3] * Told[12 + cc];
+        st.U[lane] = Um[lane];
+    }
+    if (lane == 0) {
+        st.has_update = 1;
+        st.iters = round + 1;
+    }
+    return true;
+}
+
 template <int COV_MODE>
 __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
 {
@@ -1680,7 +1833,8 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     const double *part_u = c.red_partial + (size_t)u * c.red_blocks * RED_STRIDE_MMA;
     if constexpr (EST == 1 && ORPCD_PLANE_MMA) {
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        for (int b = 0; b < n_warps; ++b) {
+#pragma unroll 8
+        for (int b = 0; b < n_warps; ++b) {      // (unrolled: the loads of eight partials are in flight together)
             const double2 *pp = reinterpret_cast<const double2 *>(part_u + (size_t)b * RED_STRIDE_MMA) + lane * 2;
             const double2 v0 = __ldcg(pp), v1 = __ldcg(pp + 1);
             a0 += v0.x; a1 += v0.y; a2 += v1.x; a3 += v1.y;
@@ -1702,14 +1856,11 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
         tot[lane] = (s0 + s1) + (s2 + s3);
     }
     __syncwarp();
-    int go_on = 0;
-    if (lane == 0) {
-        c.red_counter[u] = 0;
-        go_on = finish_round<EST>(c, st, u, tot, round) ? 1 : 0;
-        __threadfence();   // the unit's new state is visible before its next round is published
-    }
+    if (lane == 0) c.red_counter[u] = 0;
+    const bool go_on = finish_round_warp<EST>(c, st, u, tot, tot + 160, round, lane);
+    __threadfence();       // the unit's new state is visible before its next round is published
+    __syncwarp();
     if (!PERSIST) return;
-    go_on = __shfl_sync(0xffffffffu, go_on, 0);
     if (!go_on) return;
     // publish the patches of the unit's next round: n_patches consecutive tickets of the ring
     unsigned base = 0;
