@@ -410,9 +410,11 @@ def strong_scaling(opt, world, barrier):
     unit_tgt = np.repeat(np.arange(n_scales, dtype=np.int32), n_starts)
     inner = opt._inner
     best, weights, walls = None, None, []
-    for rep in range(2):
-        # rep 0 cuts blocks of equal unit counts; rep 1 cuts blocks of equal expected work, with the iteration counts
-        # of rep 0 as the difficulty proxy -- what the Aligner has from the previous poll sweep of the same candidates
+    opt.time_feedback = True       # 200k-point units: correct the iteration proxy by the measured rank times
+    for rep in range(3 if world > 1 else 2):
+        # rep 0 cuts blocks of equal unit counts; rep 1 cuts blocks of equal expected work: ShardedOptimizer weighs every
+        # unit by the mean iteration count of its target set (scale candidate) in the previous call of the same layout
+        # -- what the Aligner has from the previous poll sweep; rep 2 corrects that proxy by the measured rank times
         inner._base_key = None
         barrier()
         t0 = time.perf_counter()
@@ -420,14 +422,21 @@ def strong_scaling(opt, world, barrier):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         walls.append(dt)
-        weights = np.asarray(res.iterations, dtype=np.float64) + 4.0
+        weights = None      # (ShardedOptimizer weighs by the per-target-set mean iterations of the previous call itself)
         best = dt if best is None else min(best, dt)
-    tw = torch.tensor([best], dtype=torch.float64, device="cuda")
+    tw = torch.tensor([best, opt.last_timing.get("compute_ms", 0.0) * 1e-3], dtype=torch.float64, device="cuda")
+    per_rank_compute = None
     if world > 1:
         import torch.distributed as dist
 
-        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-    wall = float(tw[0])
+        allr = torch.empty((world, 2), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, tw)
+        allr = allr.cpu().numpy()
+        wall = float(allr[:, 0].max())
+        per_rank_compute = [float(x) for x in allr[:, 1]]      # of the last (weighted) repetition
+    else:
+        wall = float(tw[0])
+    opt.time_feedback = False
     del d_src, d_tgt
     inner._ws = None
     torch.cuda.empty_cache()
@@ -436,8 +445,8 @@ def strong_scaling(opt, world, barrier):
             "units": 1024, "wall_s": wall, "value": 1024 / wall, "unit": "registrations/s", "scaling": "strong",
             "failed_units": int((res.status != 0).sum()), "local_units": opt.last_local_units,
             "local_target_sets": opt.last_local_target_sets, "mean_iterations": float(np.mean(res.iterations)),
-            "wall_s_equal_counts_then_weighted": walls,
-            "sharding": "contiguous target-set blocks; second repetition weighted by the first one's iteration counts"}
+            "wall_s_per_repetition": walls, "per_rank_compute_s_weighted": per_rank_compute,
+            "sharding": "contiguous target-set blocks; repetition 0 equal counts, 1 weighted by per-target-set mean iterations of the previous call, 2 corrected by measured rank times"}
 
 
 def single_gpu_extras(inner, src, sources, targets, unit_src, unit_tgt, d_src, d_tgt, ms_per_step):

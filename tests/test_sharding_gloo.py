@@ -85,7 +85,8 @@ def test_two_rank_gloo_sharding_matches_single_process(tmp_path):
         assert np.array_equal(r[k]["aT"], T) and float(r[k]["am"]) == m
         assert np.array_equal(r[k]["ascale"], scale) and np.array_equal(r[k]["aerr"], np.array(errors))
         assert np.array_equal(r[k]["rng"], np.random.get_state()[1])        # every rank replays the same stream
-        assert int(r[k]["local_units"]) == 15                               # 6 candidates x 5 starts / 2 ranks
+        assert 1 <= int(r[k]["local_units"]) <= 29                          # 6 candidates x 5 starts over 2 ranks, blocks weighted
+    assert sum(int(r[k]["local_units"]) for k in range(world)) == 30       # by the previous sweep's iterations per candidate
 
 
 def test_shard_plan_is_a_partition_in_target_blocks():
@@ -114,6 +115,10 @@ def test_shard_plan_is_a_partition_in_target_blocks():
     assert abs(loads[0] - loads[1]) <= 3.0 and len(plan[0]) < len(plan[1])
     with pytest.raises(ValueError):
         shard_plan(ut, 2, -wts)
+    # the automatic weights of consecutive calls: per-target-set mean iterations of the previous call
+    from or_pcd_b200.Optimizer.shardedOptimizer import target_set_weights
+    w = target_set_weights(np.array([0, 0, 1, 1]), [10, 20, 50, 70])
+    assert np.array_equal(w, [19.0, 19.0, 64.0, 64.0])
     # records survive the round trip, ragged shards included
     n, w = 7, 2
     ut = np.array([0, 0, 0, 1, 1, 1, 1])
