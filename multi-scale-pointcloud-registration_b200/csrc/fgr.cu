@@ -702,43 +702,6 @@ __global__ void __launch_bounds__(FG_WIDE) fgr_tuple_kernel(FgrCtx c)
     }
 }
 
-// x = A.ldlt().solve(b), 6x6 symmetric (possibly negative definite), diagonal pivoting.
-__device__ void fgr_ldlt_solve6(double *A, const double *b, double *x)
-{
-    int perm[6];
-    for (int i = 0; i < 6; ++i) perm[i] = i;
-    for (int k = 0; k < 6; ++k) {
-        int piv = k;
-        double best = fabs(A[k * 6 + k]);
-        for (int i = k + 1; i < 6; ++i)
-            if (fabs(A[i * 6 + i]) > best) { best = fabs(A[i * 6 + i]); piv = i; }
-        if (piv != k) {
-            for (int j = 0; j < 6; ++j) { const double t = A[k * 6 + j]; A[k * 6 + j] = A[piv * 6 + j]; A[piv * 6 + j] = t; }
-            for (int j = 0; j < 6; ++j) { const double t = A[j * 6 + k]; A[j * 6 + k] = A[j * 6 + piv]; A[j * 6 + piv] = t; }
-            const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
-        }
-        const double d = A[k * 6 + k];
-        if (d == 0.0) continue;
-        double col[6];
-        for (int i = k + 1; i < 6; ++i) col[i] = A[i * 6 + k];
-        for (int i = k + 1; i < 6; ++i) {
-            const double l = col[i] / d;
-            for (int j = k + 1; j <= i; ++j) A[i * 6 + j] -= l * col[j];
-            A[i * 6 + k] = l;
-        }
-        for (int i = k + 1; i < 6; ++i)
-            for (int j = i + 1; j < 6; ++j) A[i * 6 + j] = A[j * 6 + i];
-    }
-    double y[6];
-    for (int i = 0; i < 6; ++i) y[i] = b[perm[i]];
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < i; ++j) y[i] -= A[i * 6 + j] * y[j];
-    for (int i = 0; i < 6; ++i) y[i] = A[i * 6 + i] != 0.0 ? y[i] / A[i * 6 + i] : 0.0;
-    for (int i = 5; i >= 0; --i)
-        for (int j = i + 1; j < 6; ++j) y[i] -= A[j * 6 + i] * y[j];
-    for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
-}
-
 // OptimizePairwiseRegistration (graduated non-convexity, Geman-McClure weights) and
 // GetTransformationOriginalScale(...).inverse(), one block per unit.
 __global__ void __launch_bounds__(FG_THREADS) fgr_gnc_kernel(FgrCtx c)
@@ -746,6 +709,8 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_gnc_kernel(FgrCtx c)
     __shared__ double sh_part[FG_THREADS / 32][28];
     __shared__ double sh_tot[28];
     __shared__ double sh_delta[12];
+    __shared__ double sh_A[36], sh_x[6], sh_sc[6];
+    __shared__ int sh_perm[6];
     const int u = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const FgrUnit fu = c.unit[u];
     const int ncorr = fu.n_pairs;
@@ -805,21 +770,23 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_gnc_kernel(FgrCtx c)
                 sh_tot[tid] = s;
             }
             __syncthreads();
-            if (tid == 0) {
-                double tot[27];
-                for (int k = 0; k < 27; ++k) tot[k] = sh_tot[k];
-                double A[36], x[6];
-                int k = 0;
-                for (int a = 0; a < 6; ++a)
-                    for (int b = a; b < 6; ++b) { A[a * 6 + b] = -tot[k]; A[b * 6 + a] = -tot[k]; ++k; }
-                fgr_ldlt_solve6(A, tot + 21, x);
-                double sa, ca, sb, cb, sg, cg;
-                sincos(x[0], &sa, &ca);
-                sincos(x[1], &sb, &cb);
-                sincos(x[2], &sg, &cg);
-                sh_delta[0] = cg * cb; sh_delta[1] = cg * sb * sa - sg * ca; sh_delta[2] = cg * sb * ca + sg * sa; sh_delta[3] = x[3];
-                sh_delta[4] = sg * cb; sh_delta[5] = sg * sb * sa + cg * ca; sh_delta[6] = sg * sb * ca - cg * sa; sh_delta[7] = x[4];
-                sh_delta[8] = -sb;     sh_delta[9] = cb * sa;                sh_delta[10] = cb * ca;               sh_delta[11] = x[5];
+            if (wid == 0) {      // warp 0 solves (-J^T J) x = J^T r cooperatively (ldlt_solve6_warp, common.cuh)
+                if (lane == 0) {
+                    int k = 0;
+                    for (int a = 0; a < 6; ++a)
+                        for (int b = a; b < 6; ++b) { sh_A[a * 6 + b] = -sh_tot[k]; sh_A[b * 6 + a] = -sh_tot[k]; ++k; }
+                }
+                __syncwarp();
+                ldlt_solve6_warp(sh_A, sh_tot + 21, sh_x, sh_perm, lane);
+                if (lane < 3) sincos(sh_x[lane], &sh_sc[lane], &sh_sc[3 + lane]);
+                __syncwarp();
+                if (lane == 0) {
+                    const double sa = sh_sc[0], sb = sh_sc[1], sg = sh_sc[2], ca = sh_sc[3], cb = sh_sc[4], cg = sh_sc[5];
+                    const double *x = sh_x;
+                    sh_delta[0] = cg * cb; sh_delta[1] = cg * sb * sa - sg * ca; sh_delta[2] = cg * sb * ca + sg * sa; sh_delta[3] = x[3];
+                    sh_delta[4] = sg * cb; sh_delta[5] = sg * sb * sa + cg * ca; sh_delta[6] = sg * sb * ca - cg * sa; sh_delta[7] = x[4];
+                    sh_delta[8] = -sb;     sh_delta[9] = cb * sa;                sh_delta[10] = cb * ca;               sh_delta[11] = x[5];
+                }
             }
             __syncthreads();
             double D[12];

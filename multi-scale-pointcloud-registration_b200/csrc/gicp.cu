@@ -1261,66 +1261,6 @@ __device__ bool finish_round(const Ctx &c, UnitState &st, int u, double *tot, in
 // entry sees exactly the operations of ldlt_solve6 / finish_round in the same order: bit-identical results.
 // sm: >= 96 doubles of the warp's shared memory that do not overlap tot[0..31].
 // ----------------------------------------------------------------------------
-__device__ __forceinline__ void ldlt_solve6_warp(double *A, const double *b, double *x, int *sperm, int lane)
-{
-    int perm_mine = lane;                                    // lanes 0..5: perm[lane]
-    const int pi_ = 1 + lane / 5, pj_ = 1 + lane % 5;        // lanes 0..24: the pair (i, j) of the trailing update
-    for (int k = 0; k < 6; ++k) {
-        double v = (lane >= k && lane < 6) ? fabs(A[lane * 6 + lane]) : -1.0;
-        int idx = lane;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {                    // arg-max over lanes 0..7, lowest index on ties
-            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-        }
-        const int piv = __shfl_sync(0xffffffffu, idx, 0);
-        if (piv != k) {
-            if (lane < 6) { const double t = A[k * 6 + lane]; A[k * 6 + lane] = A[piv * 6 + lane]; A[piv * 6 + lane] = t; }
-            __syncwarp();
-            if (lane < 6) { const double t = A[lane * 6 + k]; A[lane * 6 + k] = A[lane * 6 + piv]; A[lane * 6 + piv] = t; }
-            __syncwarp();
-            const int pk = __shfl_sync(0xffffffffu, perm_mine, k), pp = __shfl_sync(0xffffffffu, perm_mine, piv);
-            if (lane == k) perm_mine = pp;
-            else if (lane == piv) perm_mine = pk;
-        }
-        const double d = A[k * 6 + k];
-        if (d == 0.0) continue;                              // (uniform)
-        const bool act = lane < 25 && pj_ > k && pj_ <= pi_;     // k < j <= i < 6
-        const bool colw = lane > k && lane < 6;                  // lane i writes L[i][k]
-        double nv = 0.0, li = 0.0;
-        if (act) {
-            const double l = A[pi_ * 6 + k] / d;
-            nv = A[pi_ * 6 + pj_] - l * A[pj_ * 6 + k];
-        }
-        if (colw) li = A[lane * 6 + k] / d;
-        __syncwarp();                                        // column k is read before it is overwritten
-        if (act) { A[pi_ * 6 + pj_] = nv; A[pj_ * 6 + pi_] = nv; }
-        if (colw) A[lane * 6 + k] = li;
-        __syncwarp();
-    }
-    if (lane < 6) sperm[lane] = perm_mine;
-    __syncwarp();
-    if (lane == 0) {
-        double y[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) y[i] = b[sperm[i]];
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int j = 0; j < i; ++j) y[i] -= A[i * 6 + j] * y[j];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) y[i] = A[i * 6 + i] != 0.0 ? y[i] / A[i * 6 + i] : 0.0;
-#pragma unroll
-        for (int i = 5; i >= 0; --i)
-#pragma unroll
-            for (int j = i + 1; j < 6; ++j) y[i] -= A[j * 6 + i] * y[j];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) x[sperm[i]] = y[i];
-    }
-    __syncwarp();
-}
-
 template <int EST>
 __device__ __forceinline__ bool finish_round_warp(const Ctx &c, UnitState &st, int u, double *tot, double *sm, int round,
                                                   int lane)
