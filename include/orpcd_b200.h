@@ -201,6 +201,9 @@ typedef struct {
                                 4 = culled sweep with separate update / resolve / fix /
                                 reduce kernels; 1..3 = dense (brute-force) sweep + separate
                                 kernels: 1 all packed FFMA2, 2 FFMA2 + scalar FFMA, 3 scalar */
+    int src_rigid_copies;    /* != 0: every source set is a rigid image of ONE cloud with the same point
+                                order (the Aligner's random starts, Aligner/Aligner.py:179-185): the spatial
+                                (Hilbert) order of set 0 is reused for all of them instead of sorting each */
 } orpcd_gicp_params;
 
 size_t orpcd_gicp_batch_workspace_bytes(const orpcd_gicp_params *p);

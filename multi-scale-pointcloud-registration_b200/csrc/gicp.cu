@@ -221,6 +221,13 @@ __global__ void init_units_kernel(Ctx c, const int *__restrict__ unit_src, const
     }
 }
 
+// perm of set 0 copied to sets 1.. (src_rigid_copies).  grid (ceil(n/256), sets - 1)
+__global__ void __launch_bounds__(256) replicate_perm_kernel(int *__restrict__ perm, int n)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) perm[(size_t)(blockIdx.y + 1) * n + i] = perm[i];
+}
+
 // one block per target set: bounding-box centre, then centred float4 table.
 __global__ void __launch_bounds__(1024) prep_targets_kernel(Ctx c)
 {
@@ -2150,7 +2157,11 @@ int prepare_batch(const Ctx &c, const Layout &L, const orpcd_gicp_params *p, con
                   const double *d_src_cov, const int *d_unit_src, const int *d_unit_tgt, const double *d_init_T,
                   cudaStream_t st, int *launches)
 {
-    if (spatial_perm(d_src_points, p->n_src, p->n_src_sets, p->n_src, c.bbox, c.sortbuf, c.sperm, st) != 0) return -1;
+    // rigid copies of one cloud keep its spatial coherence under the same point order: one sort serves them all
+    const int sort_sets = p->src_rigid_copies ? 1 : p->n_src_sets;
+    if (spatial_perm(d_src_points, p->n_src, sort_sets, p->n_src, c.bbox, c.sortbuf, c.sperm, st) != 0) return -1;
+    if (sort_sets < p->n_src_sets)
+        replicate_perm_kernel<<<dim3((p->n_src + 255) / 256, p->n_src_sets - 1), 256, 0, st>>>(c.sperm, p->n_src);
     if (spatial_perm(c.tgt_pts, p->n_tgt, p->n_tgt_sets, L.nt_pad, c.bbox, c.sortbuf, c.tperm, st) != 0) return -1;
     const int gx = (p->n_src + 255) / 256;
     init_units_kernel<<<dim3(gx > 64 ? 64 : gx, p->n_units), 256, 0, st>>>(c, d_unit_src, d_unit_tgt, d_src_points,

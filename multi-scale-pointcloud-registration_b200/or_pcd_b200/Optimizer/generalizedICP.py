@@ -83,7 +83,7 @@ class GeneralizedICP(IOptimizer):
         ut = t.as_tensor(np.asarray(unit_tgt, dtype=np.int32)).to("cuda")
         src_cov, tgt_cov = self.covariances(d_src, d_tgt, rigid_base)
         d_res = self.optimize_batch_device(d_src, d_tgt, us, ut, poll_interval=poll_interval, src_cov=src_cov,
-                                           tgt_cov=tgt_cov)
+                                           tgt_cov=tgt_cov, rigid_copies=rigid_base is not None)
         T = d_res.T.cpu().numpy()
         stats = d_res.stats.cpu().numpy()
         status = d_res.status.cpu().numpy()
@@ -104,7 +104,7 @@ class GeneralizedICP(IOptimizer):
         ut = t.as_tensor(np.asarray(unit_tgt, dtype=np.int32)).to("cuda")
         src_cov, tgt_cov = self.covariances(d_src, d_tgt, rigid_base)
         r = self.optimize_batch_device(d_src, d_tgt, us, ut, poll_interval=poll_interval, src_cov=src_cov,
-                                       tgt_cov=tgt_cov)
+                                       tgt_cov=tgt_cov, rigid_copies=rigid_base is not None)
         self.last_profile = r.profile
         U = us.shape[0]
         T = r.T.clone()
@@ -160,7 +160,7 @@ class GeneralizedICP(IOptimizer):
                                         want_gicp_axis=ax)["gicp_axis" if ax else "gicp_cov"]
 
     def optimize_batch_device(self, d_src, d_tgt, unit_src, unit_tgt, poll_interval: int = 0, want_trace=False,
-                              src_cov=None, tgt_cov=None):
+                              src_cov=None, tgt_cov=None, rigid_copies: bool = False):
         """Device-resident variant: CUDA tensors in, ``ops.GicpBatchResult`` (CUDA tensors) out."""
         ax = self.analytic_whitening
         key = "gicp_axis" if ax else "gicp_cov"
@@ -176,7 +176,8 @@ class GeneralizedICP(IOptimizer):
                              relative_rmse=ICP_RELATIVE_RMSE, poll_interval=poll_interval, profile=self.profile,
                              want_trace=want_trace, ws=self._ws, gicp_epsilon=GICP_EPSILON,
                              sweep_mode=self.sweep_mode, sweep_q=self.sweep_q, target_splits=self.target_splits,
-                             sweep_tj=self.sweep_tj, sweep_smem_pad=self.sweep_smem_pad)
+                             sweep_tj=self.sweep_tj, sweep_smem_pad=self.sweep_smem_pad,
+                             src_rigid_copies=rigid_copies)
         self._ws = res.workspace
         return res
 

@@ -43,6 +43,7 @@ class GicpParams(C.Structure):
         ("sweep_tj", C.c_int),
         ("sweep_smem_pad", C.c_int),
         ("sweep_mode", C.c_int),
+        ("src_rigid_copies", C.c_int),
     ]
 
 

@@ -266,8 +266,11 @@ def test_optimize_batch_rigid_base_same_result(oracle, armadillo_pair):
     opt = GeneralizedICP()
     a = opt.optimize_batch(srcs, t[None], [0, 1, 2, 3], [0, 0, 0, 0])
     b = opt.optimize_batch(srcs, t[None], [0, 1, 2, 3], [0, 0, 0, 0], rigid_base=s)
-    assert np.array_equal(a.transforms, b.transforms) and np.array_equal(a.rmse, b.rmse)
+    # the neighbour lists re-ranked from the base cloud equal the searched ones (so do the covariances, bit for bit);
+    # with rigid_base the source copies also share the base cloud's spatial order, so their 64-point patches hold other
+    # points and the float64 Jacobian sums are taken in another order: same iterations, results equal to rounding
     assert np.array_equal(a.iterations, b.iterations)
+    assert np.allclose(a.rmse, b.rmse, rtol=1e-9, atol=0) and np.allclose(a.transforms, b.transforms, rtol=0, atol=1e-9)
 
 
 def test_fused_round_kernel_agrees_with_the_unfused_and_dense_paths(oracle, armadillo_pair):
