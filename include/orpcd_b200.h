@@ -375,7 +375,10 @@ int orpcd_farthest_point_sample(const double *d_points, int n, int first_index, 
  * (ix, iy, iz) order of the voxel index, so parity is as a set / after sorting.
  * d_out_points [n][3] (first *d_out_count rows valid), d_out_first_index (may be
  * NULL) [n] lowest point index of each voxel, d_out_count int32[1]: number of
- * voxels, or -1 when the grid is too fine for a 64-bit (cell, index) word.
+ * voxels; -1 when Open3D itself would fail ("voxel_size is too small": voxel_size * INT_MAX
+ * < extent); -2 when the grid is too fine for THIS implementation's 64-bit (dense cell id,
+ * point index) sort word -- dim_x dim_y dim_z must stay below 2^(63 - ceil(log2 n)); Open3D hashes
+ * the occupied cells and has no such limit.
  * ---------------------------------------------------------------------- */
 size_t orpcd_voxel_downsample_workspace_bytes(int n);
 int orpcd_voxel_downsample(const double *d_points, int n, double voxel_size, void *d_workspace,

@@ -108,7 +108,13 @@ __global__ void voxel_grid_kernel(const double *__restrict__ bbox, int n, double
         g->dim[k] = (long long)top + 1;
         cells *= (double)g->dim[k];
     }
-    g->error = !(cells < ldexp(1.0, 63 - bits)) ? 1 : 0;
+    // error 1: Open3D's own condition ("voxel_size is too small": voxel_size * INT_MAX < extent);
+    // error 2: a limit of THIS implementation -- the dense linear cell id and the point index share one 64-bit sort
+    // word, so dim_x * dim_y * dim_z must stay below 2^(63 - idx_bits) (Open3D hashes the occupied cells and has
+    // no such limit; a cloud of extent 100 with a 1e-4 voxel would hit it)
+    bool o3d_small = false;
+    for (int k = 0; k < 3; ++k) o3d_small = o3d_small || (voxel_size * 2147483647.0 < bbox[3 + k] - bbox[k]);
+    g->error = o3d_small ? 1 : (!(cells < ldexp(1.0, 63 - bits)) ? 2 : 0);
     g->n_voxels = 0;
 }
 
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(1024) voxel_average_kernel(const double *__res
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (g->error) {
-        if (tid == 0) g->n_voxels = -1;
+        if (tid == 0) g->n_voxels = -g->error;     // -1: Open3D's "voxel_size is too small"; -2: sort-word limit
         return;
     }
     const int shift = g->idx_bits;

@@ -245,8 +245,13 @@ def voxel_downsample(points, voxel_size: float, ws=None):
                                    first.data_ptr(), count.data_ptr(), _lib.stream_ptr()), "orpcd_voxel_downsample")
     launch_counter["kernels"] += 8
     n = int(count.item())
-    if n < 0:
+    if n == -1:
         raise _lib.OrpcdError("voxel_size is too small.")    # Open3D: "[VoxelDownSample] voxel_size is too small."
+    if n < 0:
+        # not an Open3D error: a limit of this implementation (dense cell id and point index share a 64-bit sort word)
+        raise _lib.OrpcdError("orpcd_voxel_downsample: the voxel grid has too many cells for the 64-bit sort key "
+                              "(dim_x * dim_y * dim_z * n_points must stay below 2^63); scale the cloud (RadiusScaler) "
+                              "or use a larger voxel_size.  Open3D itself would accept this input.")
     return out[:n], first[:n], ws
 
 

@@ -65,3 +65,19 @@ def test_voxel_downsampler_search_matches_golden(oracle, gold, name):
     assert np.allclose(out.sum(0), gold[f"voxel_{name}_sum"], rtol=1e-13)
     with pytest.raises(ValueError):
         VoxelDownsampler(0)
+
+
+def test_voxel_grid_limits_are_told_apart():
+    """Open3D's own failure (voxel_size * INT_MAX < extent) and this implementation's sort-word limit raise different
+    messages: the second is not an Open3D error."""
+    from or_pcd_b200 import _lib, ops
+
+    rng = np.random.default_rng(0)
+    cloud = rng.uniform(-50, 50, (4000, 3))
+    with pytest.raises(_lib.OrpcdError, match="voxel_size is too small"):
+        ops.voxel_downsample(_lib.to_device(cloud), 1e-9)
+    with pytest.raises(_lib.OrpcdError, match="64-bit sort key"):
+        ops.voxel_downsample(_lib.to_device(cloud), 1e-4)
+    out, first, _ = ops.voxel_downsample(_lib.to_device(cloud), 5.0)
+    assert 0 < out.shape[0] <= 4000
+
