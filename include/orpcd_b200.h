@@ -204,6 +204,11 @@ typedef struct {
     int src_rigid_copies;    /* != 0: every source set is a rigid image of ONE cloud with the same point
                                 order (the Aligner's random starts, Aligner/Aligner.py:179-185): the spatial
                                 (Hilbert) order of set 0 is reused for all of them instead of sorting each */
+    int half_patch_from_round; /* fused rounds: a unit's work items are 64-point patches below this round and
+                                32-point patches from it on (shorter per-round latency for the stragglers of a
+                                batch); 0 = default (round 32 for clouds of at most 16384 points, never for larger
+                                ones), < 0 = never.  Depends on the round index and the cloud size only: results are
+                                deterministic and independent of the other units of the batch */
 } orpcd_gicp_params;
 
 size_t orpcd_gicp_batch_workspace_bytes(const orpcd_gicp_params *p);

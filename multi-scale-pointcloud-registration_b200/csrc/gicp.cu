@@ -51,6 +51,9 @@ constexpr int RED_VALS = 29;                     // 21 JTJ + 6 JTr + sum d2 + co
 constexpr int RED_STRIDE = 32;
 constexpr int RED_PER_THREAD = 4;                // correspondences accumulated per thread before the shuffles
 constexpr float F32_EPS = 5.9604644775390625e-8f;  // 2^-24, unit roundoff
+#ifndef ORPCD_HALF_FROM_ROUND
+#define ORPCD_HALF_FROM_ROUND 32   // fused rounds: 32-point patches from this round on (see round_body)
+#endif
 #ifndef ORPCD_SPIN_NS
 #define ORPCD_SPIN_NS 500          // back-off of a worker waiting on an empty ring slot (a patch takes tens of microseconds)
 #endif
@@ -94,7 +97,8 @@ struct Ctx {
     float4 *tgt4;        // [tgt_sets][nt_pad]  (-2x, -2y, -2z, |p|^2), centred
     TgtMeta *tgt_meta;   // [tgt_sets]
     double *red_partial; // [units][red_blocks][RED_STRIDE_MMA] (the unfused reduce_kernel uses the first RED_STRIDE of each row... see its indexing)
-    unsigned *red_counter;  // [units]
+    unsigned *red_counter;  // [units][red_groups + 1]: [0] groups closed in the unit's round, [1 + g] arrivals in group g
+    int red_groups;         // counter stride - 1 (>= groups of the finest patch size)
     int *worklist;       // [units*n_src]
     int *worklist_count; // [max_iter+2]
     int *done_count;     // [1]
@@ -115,8 +119,11 @@ struct Ctx {
     // work queue of the persistent round kernel: ring of (unit * n_patches + patch + 1), 0 = empty slot
     unsigned *q_slots;
     unsigned *q_ctrl;    // [0] head (tickets handed out), [32] tail (items published), [64] all-units-done flag
+    unsigned long long *q_stats;   // ORPCD_QUEUE_STATS: [0] start time; [64..127] idle ns per 250 us bucket; [128..191] items per bucket
     unsigned q_mask;     // ring capacity - 1 (capacity = power of two >= n_units * n_patches)
-    int n_patches;       // patches (warps' work items) per unit and round
+    int n_patches;       // 64-point patches (warps' work items) per unit and round
+    int n_patches2;      // 32-point patches per unit and round (rounds >= half_from_round); also the item stride of a unit
+    int half_from_round; // from this round on a unit's work items are 32-point patches (see round_body)
 };
 constexpr int Q_HEAD = 0, Q_TAIL = 32, Q_DONE = 64;
 
@@ -202,7 +209,7 @@ __global__ void init_units_kernel(Ctx c, const int *__restrict__ unit_src, const
         for (int k = 0; k < 12; ++k) s.U[k] = s.T[k];
         s.fitness = 0; s.rmse = 0; s.iters = 0; s.done = 0; s.has_update = init_T ? 1 : 0; s.n_corr = 0;
         s.src_set = ss; s.tgt_set = unit_tgt[u]; s.status = 0; s.pad = 0;
-        c.red_counter[u] = 0;
+        for (int k = 0; k <= c.red_groups; ++k) c.red_counter[(size_t)u * (c.red_groups + 1) + k] = 0;
         if (u == 0) {
             *c.done_count = 0;
             for (int k = 0; k < c.max_iter + 2; ++k) { c.worklist_count[k] = 0; c.round_active[k] = 0; c.visit_count[k] = 0ull; }
@@ -550,7 +557,11 @@ static_assert(sizeof(WarpSmem) == 4096, "WarpSmem holds 64 records of 8 doubles"
 // SUB = false: (m1, c1, m2) fold per 32-target chunk, c1 = chunk id.  SUB = true: fold per 8-target sub-chunk,
 // c1 = chunk * 4 + sub-chunk, m2 = second-best sub-chunk minimum (the certificate works at either granularity; the
 // finer one leaves the caller 8 candidates to re-score instead of 32).
-template <int Q, bool SUB>
+// HALF (32-point patches, Q = 2): both half-warps hold the SAME pair of queries per lane (32 queries per warp) and
+// split the 32 targets of a chunk by parity -- lane l takes targets 2 i + (l >> 4) -- so a warp spends half the FMA
+// work per chunk on half the queries; each half folds the 8-target sub-chunks it sees, id = chunk * 4 + parity * 2 +
+// (first | second 16 targets), and the caller merges the two halves' (m1, c1, m2).
+template <int Q, bool SUB, bool HALF = false>
 __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__restrict__ tg, const float4 *__restrict__ sph,
                                                const float4 *__restrict__ ssph, int n_super, float rmax_tgt, int cb,
                                                int ce, const float4 (&qv)[Q],
@@ -558,7 +569,9 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                                                float (&m2)[Q])
 {
     constexpr int TJ = 4;
+    static_assert(!HALF || (Q == 2 && SUB), "the half-warp split is written for one query pair per lane and sub-chunk folds");
     const int lane = threadIdx.x & 31;
+    const int par = HALF ? (lane >> 4) : 0;      // which targets of a chunk this half-warp takes
     uint64_t qx[Q / 2], qy[Q / 2], qz[Q / 2];
     float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     float D = 0.f, rw = 0.f, pcx, pcy, pcz;
@@ -682,10 +695,10 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
 #pragma unroll
             for (int q = 0; q < Q; ++q) mc[q] = CUDART_INF_F;
 #pragma unroll
-            for (int j = 0; j < NN_CH; j += TJ) {
+            for (int j = 0; j < (HALF ? NN_CH / 2 : NN_CH); j += TJ) {
                 float4 t[TJ];
 #pragma unroll
-                for (int r = 0; r < TJ; ++r) t[r] = tc[j + r];
+                for (int r = 0; r < TJ; ++r) t[r] = HALF ? tc[(j + r) * 2 + par] : tc[j + r];
 #pragma unroll
                 for (int h = 0; h < Q / 2; ++h) {
                     uint64_t a[TJ];
@@ -705,7 +718,7 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                     }
                 }
                 if (SUB && ((j + TJ) & 7) == 0) {   // end of an 8-target sub-chunk
-                    const int id = chunk * 4 + (j >> 3);
+                    const int id = HALF ? chunk * 4 + par * 2 + (j >> 3) : chunk * 4 + (j >> 3);
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
                         m2[q] = fminf(m2[q], fmaxf(m1[q], mc[q]));
@@ -1277,9 +1290,10 @@ __device__ __forceinline__ bool finish_round_warp(const Ctx &c, UnitState &st, i
     int what = 0;        // 0: the unit is done; 1: solve the 6x6 system; 2: Um is ready (Umeyama / identity)
     if (lane < 16) Told[lane] = __ldcg(&st.T[lane]);
     __syncwarp();
+    constexpr bool ASSEMBLED = EST == 1 && ORPCD_PLANE_MMA;    // plane_tiles_to_system halved the sums and wrote A, nb
     if (lane == 0) {
         const double n = tot[28];
-        if (EST == 1) {   // accumulate_pair<1> sums twice J^T J / J^T r without the identity block
+        if (EST == 1 && !ASSEMBLED) {   // accumulate_pair<1> sums twice J^T J / J^T r without the identity block
             tot[15] += n; tot[18] += n; tot[20] += n;
             for (int k = 0; k < 27; ++k) tot[k] *= 0.5;
         }
@@ -1313,10 +1327,12 @@ __device__ __forceinline__ bool finish_round_warp(const Ctx &c, UnitState &st, i
             for (int k = 0; k < 12; ++k) Um[k] = U3[k];
             what = 2;
         } else if (n > 0) {
-            int k = 0;
-            for (int a = 0; a < 6; ++a)
-                for (int b = a; b < 6; ++b) { A[a * 6 + b] = tot[k]; A[b * 6 + a] = tot[k]; ++k; }
-            for (int a = 0; a < 6; ++a) nb[a] = -tot[21 + a];
+            if (!ASSEMBLED) {
+                int k = 0;
+                for (int a = 0; a < 6; ++a)
+                    for (int b = a; b < 6; ++b) { A[a * 6 + b] = tot[k]; A[b * 6 + a] = tot[k]; ++k; }
+                for (int a = 0; a < 6; ++a) nb[a] = -tot[21 + a];
+            }
             what = 1;
         } else {
             for (int k = 0; k < 12; ++k) Um[k] = (k % 5 == 0) ? 1.0 : 0.0;
@@ -1396,7 +1412,7 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const unsigned prev = atomicAdd(&c.red_counter[u], 1u);
+        const unsigned prev = atomicAdd(&c.red_counter[(size_t)u * (c.red_groups + 1)], 1u);
         is_last = (prev == (unsigned)gridDim.x - 1u);
     }
     __syncthreads();
@@ -1410,7 +1426,7 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(Ctx c, int round)
     }
     __syncthreads();
     if (tid != 0) return;
-    c.red_counter[u] = 0;
+    c.red_counter[(size_t)u * (c.red_groups + 1)] = 0;
     finish_round<COV_MODE>(c, st, u, tot, round);
 }
 
@@ -1464,42 +1480,98 @@ __device__ __forceinline__ void store_record(double *rec, int v, double x0, doub
     r[3 ^ sw] = make_double2(x6, x7);
 }
 
-// The 29 sums finish_round works on, from the totals of the two 8x8 tiles of the tensor-core path (EST 1):
+// The totals of the two 8x8 tiles of the tensor-core path (EST 1) are
 //   EF = sum_pairs  g+ (e|re)(e|re)^T + g- (f|rf)(f|rf)^T   (rows / cols 0..5 = J^T J part, col 6 = J^T r part),
 //   S  = sum_pairs  z z^T,  z = (sx, sy, sz, 1, dx, dy, dz),
-// t[63] (the unused EF(7,7) slot) carries sum d2.  Same "twice the sums, identity block left out" convention as
-// accumulate_pair<1>.
-__device__ void plane_tiles_to_sums(const double *t, double *o)
+// t[63] (the unused EF(7,7) slot) carries sum d2; "twice the sums, identity block left out" as in accumulate_pair<1>.
+// Their assembly by a whole warp, one entry per lane, straight into the system finish_round_warp solves: lane k
+// (k < 29) computes sum k (the 21 + 6 + 2 sums of accumulate_pair), lanes 0..26 also the halved entry ("twice the sums, identity block
+// left out": + n on the translation diagonal, x 0.5) and write it to the 6x6 matrix A (both triangles) or to the
+// right-hand side nb = -J^T r.  sm = the buffer of finish_round_warp (A at 0, nb at 36).
+__device__ __forceinline__ void plane_tiles_to_system(const double *t, double *o, double *sm, int lane)
 {
-    int k = 0;
-    for (int a = 0; a < 6; ++a)
-        for (int b = a; b < 6; ++b) o[k++] = t[a * 8 + b];
-    for (int a = 0; a < 6; ++a) o[21 + a] = t[a * 8 + 6];
     const double *S = t + 64;
-    const double Sxx = S[0], Sxy = S[1], Sxz = S[2], Syy = S[9], Syz = S[10], Szz = S[18];
-    const double sx = S[3], sy = S[11], sz = S[19];
-    o[0] += Syy + Szz; o[1] -= Sxy; o[2] -= Sxz; o[6] += Sxx + Szz; o[7] -= Syz; o[11] += Sxx + Syy;
-    o[4] -= sz; o[5] += sy; o[8] += sz; o[10] -= sx; o[12] -= sy; o[13] += sx;
-    o[21] += S[8 + 6] - S[16 + 5];      // sum (sy dz - sz dy)
-    o[22] += S[16 + 4] - S[6];          // sum (sz dx - sx dz)
-    o[23] += S[5] - S[8 + 4];           // sum (sx dy - sy dx)
-    o[24] += S[24 + 4]; o[25] += S[24 + 5]; o[26] += S[24 + 6];
-    o[27] = t[63];
-    o[28] = S[24 + 3];
-    for (k = 29; k < 32; ++k) o[k] = 0.0;
+    const int k = lane;
+    double v = 0.0;
+    int a = 0, b = 0;
+    if (k < 21) {
+        // (a, b) of upper-triangle entry k, row-major
+        int r = k;
+        a = 0;
+        while (r >= 6 - a) { r -= 6 - a; ++a; }
+        b = a + r;
+        v = t[a * 8 + b];
+        const double Sxx = S[0], Sxy = S[1], Sxz = S[2], Syy = S[9], Syz = S[10], Szz = S[18];
+        const double sx = S[3], sy = S[11], sz = S[19];
+        switch (k) {
+        case 0: v += Syy + Szz; break;
+        case 1: v -= Sxy; break;
+        case 2: v -= Sxz; break;
+        case 4: v -= sz; break;
+        case 5: v += sy; break;
+        case 6: v += Sxx + Szz; break;
+        case 7: v -= Syz; break;
+        case 8: v += sz; break;
+        case 10: v -= sx; break;
+        case 11: v += Sxx + Syy; break;
+        case 12: v -= sy; break;
+        case 13: v += sx; break;
+        default: break;
+        }
+    } else if (k < 27) {
+        a = k - 21;
+        v = t[a * 8 + 6];
+        switch (a) {
+        case 0: v += S[8 + 6] - S[16 + 5]; break;     // sum (sy dz - sz dy)
+        case 1: v += S[16 + 4] - S[6]; break;         // sum (sz dx - sx dz)
+        case 2: v += S[5] - S[8 + 4]; break;          // sum (sx dy - sy dx)
+        default: v += S[24 + 4 + (a - 3)]; break;     // sum d
+        }
+    } else if (k == 27) {
+        v = t[63];
+    } else if (k == 28) {
+        v = S[24 + 3];
+    }
+    const double n = S[24 + 3];
+    if (k < 27) {
+        if (k == 15 || k == 18 || k == 20) v += n;
+        v *= 0.5;
+    }
+    o[k] = v;                       // the sums as finish_round_warp's lane 0 reads them (already halved)
+    if (k < 21) { sm[a * 6 + b] = v; sm[b * 6 + a] = v; }
+    else if (k < 27) sm[36 + a] = -v;
+}
+
+// items per group of the two-level totals: the multiple of 8 next to sqrt(items), so that both levels read about
+// the same number of partials (8 for up to 64 items, 16 up to 256, ..., 56 for the 3125 patches of a 200k-point cloud)
+__host__ __device__ inline int red_group_size(int n_items)
+{
+    int g = 8;
+    while (g * g < n_items) g += 8;
+    return g;
 }
 
 // PERSIST: the caller is the persistent kernel -- one launch for all rounds, so data another SM wrote in an earlier
 // round of the same launch (unit state, moving points / axes, correspondences) is read with ld.global.cg (L2, the
 // coherence point; an L1 line could be stale), and the warp that closes a unit's round puts the patches of its next
 // round on the work queue.
+//
+// Patch size.  Rounds below c.half_from_round work on 64-point patches (two queries per lane); from that round on a
+// unit's items are 32-point patches (one query per lane, `half`): a unit cannot overlap its own rounds, so late in a
+// batch -- when the units that run to the iteration cap are all that is left and workers wait on an empty ring -- the
+// time is set by the latency of a unit's round, and a 32-point patch has half the sweep per warp and one pass
+// through the per-query phases instead of two.  (Smaller patches cost more list building per query, which is why
+// the loaded first rounds keep 64.)  The switch depends on the round index only, so results are deterministic and
+// independent of which other units share the batch.
 template <int Q, int EST, bool PERSIST>
 __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, int wi, int round, WarpSmem &wsm)
 {
     float4 (*ring)[NN_CH] = wsm.ring;
     unsigned short *vl = wsm.vl;
     const int lane = threadIdx.x & 31;
-    const int wbase = wi * (32 * Q);
+    const bool half = round >= c.half_from_round;
+    const int nk = half ? 1 : 2;                    // queries per lane
+    const int wbase = wi * (half ? 32 : 64);
     if (wbase >= c.n_src) return;
     const int tgt_set = __ldcg(&st.tgt_set);   // (immutable after init_units_kernel; .cg keeps the state's lines out of L1)
     if (wi == 0 && lane == 0) atomicAdd(&c.round_active[round], 1);
@@ -1524,7 +1596,7 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
 #pragma unroll
         for (int k = 0; k < 12; ++k) U[k] = __ldcg(&st.U[k]);
 #pragma unroll 1
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < nk; ++k) {
             const int i = wbase + k * 32 + lane;
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < c.n_src) {
@@ -1559,20 +1631,20 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
                 }
                 r = make_float4((float)(x - tm.cx), (float)(y - tm.cy), (float)(z - tm.cz), dub);
             }
-            qa = qb;
-            qb = r;        // after the two passes: qa = query 0, qb = query 1
+            if (k == 0) qa = r;
+            else qb = r;
         }
         // lanes past the end of the cloud carry the patch's first query (always a real one)
         const float fx = __shfl_sync(0xffffffffu, qa.x, 0), fy = __shfl_sync(0xffffffffu, qa.y, 0);
         const float fz = __shfl_sync(0xffffffffu, qa.z, 0), fw = __shfl_sync(0xffffffffu, qa.w, 0);
         if (wbase + lane >= c.n_src) qa = make_float4(fx, fy, fz, fw);
-        if (wbase + 32 + lane >= c.n_src) qb = make_float4(fx, fy, fz, fw);
+        if (half || wbase + 32 + lane >= c.n_src) qb = make_float4(fx, fy, fz, fw);
     }
 
     // ---- 2. sweep
     float m1a, m1b, m2a, m2b;
     int c1a, c1b;
-    {
+    if (!half) {
         const float4 qv[Q] = {qa, qb};
         float m1[Q], m2[Q];
         int c1[Q];
@@ -1580,8 +1652,39 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
                                                      c.super_sph + (size_t)tgt_set * c.n_super, c.n_super, (float)tm.rmax, 0,
                                                      c.n_chunks, qv, ring, vl, m1, c1, m2);
         if (lane == 0)
-            atomicAdd(c.visit_count + round, (unsigned long long)visited * NN_CH * min(32 * Q, c.n_src - wbase));
+            atomicAdd(c.visit_count + round, (unsigned long long)visited * NN_CH * min(64, c.n_src - wbase));
         m1a = m1[0]; m1b = m1[1]; m2a = m2[0]; m2b = m2[1]; c1a = c1[0]; c1b = c1[1];
+    } else {
+        // both half-warps take the pair (query l & 15, query (l & 15) + 16) and one parity of every chunk's targets
+        float4 qv[Q];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int from = (lane & 15) + 16 * e;
+            qv[e].x = __shfl_sync(0xffffffffu, qa.x, from); qv[e].y = __shfl_sync(0xffffffffu, qa.y, from);
+            qv[e].z = __shfl_sync(0xffffffffu, qa.z, from); qv[e].w = __shfl_sync(0xffffffffu, qa.w, from);
+        }
+        float m1[Q], m2[Q];
+        int c1[Q];
+        const int visited = cull_sweep_core<Q, true, true>(c, tg, c.chunk_sph + (size_t)tgt_set * c.n_chunks,
+                                                           c.super_sph + (size_t)tgt_set * c.n_super, c.n_super,
+                                                           (float)tm.rmax, 0, c.n_chunks, qv, ring, vl, m1, c1, m2);
+        if (lane == 0)
+            atomicAdd(c.visit_count + round, (unsigned long long)visited * NN_CH * min(32, c.n_src - wbase));
+        // merge the two halves (each saw the targets of one parity); on an exact tie both keep parity 0's sub-chunk --
+        // the certificate then sees m2 == m1 and sends the query to the exact search
+        const int par = lane >> 4;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float om1 = __shfl_xor_sync(0xffffffffu, m1[e], 16), om2 = __shfl_xor_sync(0xffffffffu, m2[e], 16);
+            const int oc1 = __shfl_xor_sync(0xffffffffu, c1[e], 16);
+            const bool take = om1 < m1[e] || (om1 == m1[e] && par == 1);
+            m2[e] = fminf(fminf(m2[e], om2), fmaxf(m1[e], om1));
+            c1[e] = take ? oc1 : c1[e];
+            m1[e] = fminf(m1[e], om1);
+        }
+        // lane l's own query is element l >> 4 of its pair
+        m1a = par ? m1[1] : m1[0]; m2a = par ? m2[1] : m2[0]; c1a = par ? c1[1] : c1[0];
+        m1b = CUDART_INF_F; m2b = CUDART_INF_F; c1b = 0;
     }
 
     // ---- 3. certificate (nn_resolve_kernel's bound), then each lane scans the best 8-target sub-chunk of its own queries:
@@ -1590,7 +1693,7 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     int tja = -1, tjb = -1;   // matched target (original index); -1 none within the cut-off; -2 exact search needed
     const int *tperm = c.tperm + (size_t)tgt_set * c.nt_pad;
 #pragma unroll 1
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < nk; ++k) {
         const float fx = qa.x, fy = qa.y, fz = qa.z;
         const double qn = (double)fx * fx + (double)fy * fy + (double)fz * fz;
         const double qnorm = sqrt(qn);
@@ -1603,28 +1706,34 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
         const bool none = !(m1a < CUDART_INF_F);          // no chunk visited: nothing within the cut-off
         const bool cross = !((double)m2a > lim);          // another chunk may hold the true neighbour
         const float thr = __double2float_ru(lim);
-        const float4 *tc = tg + (size_t)c1a * 8;   // c1 = 8-target sub-chunk (cull_sweep_core<Q, true>)
+        // c1 = 8-target sub-chunk: 8 consecutive targets, or (32-point patches) 8 targets of one parity, stride 2
+        const size_t sub_base = half ? (size_t)(c1a >> 2) * 32 + (size_t)(c1a & 1) * 16 + (size_t)((c1a >> 1) & 1)
+                                     : (size_t)c1a * 8;
+        const int sub_stride = half ? 2 : 1;
+        const float4 *tc = tg + sub_base;
         int cnt = 0, first = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 t = __ldg(tc + j);
+            const float4 t = __ldg(tc + j * sub_stride);
             const float sv = __fmaf_rn(fx, t.x, __fmaf_rn(fy, t.y, __fmaf_rn(fz, t.z, t.w)));
             const bool in = sv <= thr;
             first = (in && cnt == 0) ? j : first;
             cnt += in ? 1 : 0;
         }
-        int t = none ? -1 : ((cross || cnt != 1) ? -2 : tperm[(size_t)c1a * 8 + first]);
+        int t = none ? -1 : ((cross || cnt != 1) ? -2 : tperm[sub_base + (size_t)first * sub_stride]);
         if (wbase + k * 32 + lane >= c.n_src) t = -1;
-        tja = tjb;
-        tjb = t;           // after the two passes: tja = query 0, tjb = query 1
-        ORPCD_SWAP(float4, qa, qb) ORPCD_SWAP(float, m1a, m1b) ORPCD_SWAP(float, m2a, m2b) ORPCD_SWAP(int, c1a, c1b)
+        tja = t;
+        if (nk == 2) {     // trade places: after the two passes the "a" set is query 0 again
+            ORPCD_SWAP(float4, qa, qb) ORPCD_SWAP(float, m1a, m1b) ORPCD_SWAP(float, m2a, m2b) ORPCD_SWAP(int, c1a, c1b)
+            ORPCD_SWAP(int, tja, tjb)
+        }
     }
 
     // ---- 4. exact search for what the FP32 filter could not decide
     double fda = -1.0, fdb = -1.0;
     int n_fix = 0;
 #pragma unroll 1
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < nk; ++k) {
         unsigned fb = __ballot_sync(0xffffffffu, tja == -2);
         n_fix += __popc(fb);
         while (fb) {
@@ -1639,12 +1748,14 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
                               __shfl_sync(0xffffffffu, c1a, l) >> 2, best, bj);
             if (lane == l) { tja = bj == 0x7fffffff ? -1 : bj; fda = best; }
         }
-        ORPCD_SWAP(int, tja, tjb) ORPCD_SWAP(double, fda, fdb) ORPCD_SWAP(float4, qa, qb) ORPCD_SWAP(int, c1a, c1b)
+        if (nk == 2) {
+            ORPCD_SWAP(int, tja, tjb) ORPCD_SWAP(double, fda, fdb) ORPCD_SWAP(float4, qa, qb) ORPCD_SWAP(int, c1a, c1b)
+        }
     }
     if (lane == 0 && n_fix) atomicAdd(&c.worklist_count[round], n_fix);
 
     // ---- 5. sums over this warp's correspondences
-    const int n_warps = (c.n_src + 32 * Q - 1) / (32 * Q);
+    const int n_warps = half ? c.n_patches2 : c.n_patches;     // work items of this unit's round
     double *tot = reinterpret_cast<double *>(&wsm);   // the sweep's ring and visit list are free now
     if constexpr (EST == 1 && ORPCD_PLANE_MMA) {
         // Plane-to-plane Generalized-ICP on the float64 tensor cores.  Per correspondence three weighted 8-vectors
@@ -1661,7 +1772,7 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
         const int x_e = jv * 8 + ((((cc >> 1) ^ sw_e) << 1) | (cc & 1)), w_e = jv * 8 + (((3 ^ sw_e) << 1) | 1);
         const int x_o = jv * 8 + ((((cc >> 1) ^ sw_o) << 1) | (cc & 1)), w_o = jv * 8 + (((3 ^ sw_o) << 1) | 1);
 #pragma unroll 1
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < nk; ++k) {
             const int i = wbase + k * 32 + lane;
             bool have = false;
             double sx = 0, sy = 0, sz = 0, dx = 0, dy = 0, dz = 0;
@@ -1727,7 +1838,7 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
                 dmma884(sd0, sd1, w * x, x);
             }
             __syncwarp();
-            ORPCD_SWAP(int, tja, tjb) ORPCD_SWAP(double, fda, fdb)
+            if (nk == 2) { ORPCD_SWAP(int, tja, tjb) ORPCD_SWAP(double, fda, fdb) }
         }
         d2sum = warp_sum(d2sum);
         if (lane == 31) ef1 = d2sum;      // EF(7,7) is not a needed sum: its slot carries sum d2
@@ -1739,7 +1850,7 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
 #pragma unroll
         for (int k = 0; k < 32; ++k) acc[k] = 0.0;
 #pragma unroll 1
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < nk; ++k) {
             const int i = wbase + k * 32 + lane;
             if (i < c.n_src) {
                 const size_t oi = (size_t)u * c.n_src + i;
@@ -1763,63 +1874,151 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
                 }
                 c.corr[oi] = j;
             }
-            ORPCD_SWAP(int, tja, tjb) ORPCD_SWAP(double, fda, fdb)
+            if (nk == 2) { ORPCD_SWAP(int, tja, tjb) ORPCD_SWAP(double, fda, fdb) }
         }
         const double mine = warp_transpose_sum32(acc, lane);
         __stcg(c.red_partial + ((size_t)u * c.red_blocks + wi) * RED_STRIDE_MMA + lane, mine);
     }
 #undef ORPCD_SWAP
+    // Two-level, fixed-order totals.  The items of a round are grouped (red_group_size: 16 for the 79 / 157 patches
+    // of a 5000-point cloud); the last warp to arrive in a group adds the group's partials in item order into a group
+    // partial, and the last group to close adds the group partials in group order.  The warp that closes the round
+    // therefore waits for two or three batches of loads instead of ten (a single warp reading 79 x 1 KB took ~10 us,
+    // a sixth of a straggler's round); the order of the additions is fixed: results stay run-to-run deterministic.
+    constexpr bool MMA = EST == 1 && ORPCD_PLANE_MMA;
+    const int gsz = red_group_size(n_warps);
+    const int n_groups = (n_warps + gsz - 1) / gsz;
+    const int grp = wi / gsz;
+    unsigned *cnt = c.red_counter + (size_t)u * (c.red_groups + 1);
+    double *part_u = c.red_partial + (size_t)u * c.red_blocks * RED_STRIDE_MMA;
+    double *gpart_u = part_u + (size_t)c.n_patches2 * RED_STRIDE_MMA;  // group partials follow the item partials
     __threadfence();
     __syncwarp();
     int last = 0;
-    if (lane == 0) last = atomicAdd(&c.red_counter[u], 1u) == (unsigned)n_warps - 1u;
+    if (lane == 0) last = atomicAdd(cnt + 1 + grp, 1u) == (unsigned)min(gsz, n_warps - grp * gsz) - 1u;
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
     __threadfence();
-    // unit totals: the patch partials added in patch order (a fixed order: run-to-run deterministic)
-    const double *part_u = c.red_partial + (size_t)u * c.red_blocks * RED_STRIDE_MMA;
-    if constexpr (EST == 1 && ORPCD_PLANE_MMA) {
+    {
+        const int b0 = grp * gsz, b1 = min(n_warps, b0 + gsz);
+        double *gp = gpart_u + (size_t)grp * RED_STRIDE_MMA;
+        if constexpr (MMA) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 8
+            for (int b = b0; b < b1; ++b) {
+                const double2 *pp = reinterpret_cast<const double2 *>(part_u + (size_t)b * RED_STRIDE_MMA) + lane * 2;
+                const double2 v0 = __ldcg(pp), v1 = __ldcg(pp + 1);
+                a0 += v0.x; a1 += v0.y; a2 += v1.x; a3 += v1.y;
+            }
+            __stcg(reinterpret_cast<double2 *>(gp) + lane * 2, make_double2(a0, a1));
+            __stcg(reinterpret_cast<double2 *>(gp) + lane * 2 + 1, make_double2(a2, a3));
+        } else {
+            double a0 = 0.0;
+#pragma unroll 8
+            for (int b = b0; b < b1; ++b) a0 += __ldcg(part_u + (size_t)b * RED_STRIDE_MMA + lane);
+            __stcg(gp + lane, a0);
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    last = 0;
+    if (lane == 0) {
+        cnt[1 + grp] = 0u;                                   // ready for the unit's next round
+        last = atomicAdd(cnt, 1u) == (unsigned)n_groups - 1u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+#ifdef ORPCD_QUEUE_STATS
+    unsigned long long tc0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tc0));
+#endif
+    __threadfence();
+#ifdef ORPCD_QUEUE_STATS
+    {   // span of this unit's round: from its publication (stamp kept in the unused work list) to its last arrival
+        unsigned long long *pub = reinterpret_cast<unsigned long long *>(c.worklist) + u;
+        const unsigned long long t0 = *reinterpret_cast<volatile unsigned long long *>(c.q_stats);
+        const unsigned long long tpub = __ldcg(pub);
+        if (lane == 0 && tpub != 0ull) {
+            const unsigned b = (unsigned)min((unsigned long long)63, (tc0 - t0) / 250000ull);
+            atomicAdd(c.q_stats + 448 + b, tc0 - tpub);
+        }
+    }
+#endif
+    // unit totals: the group partials added in group order
+    if constexpr (MMA) {
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll 8
-        for (int b = 0; b < n_warps; ++b) {      // (unrolled: the loads of eight partials are in flight together)
-            const double2 *pp = reinterpret_cast<const double2 *>(part_u + (size_t)b * RED_STRIDE_MMA) + lane * 2;
+        for (int b = 0; b < n_groups; ++b) {
+            const double2 *pp = reinterpret_cast<const double2 *>(gpart_u + (size_t)b * RED_STRIDE_MMA) + lane * 2;
             const double2 v0 = __ldcg(pp), v1 = __ldcg(pp + 1);
             a0 += v0.x; a1 += v0.y; a2 += v1.x; a3 += v1.y;
         }
         double *t128 = tot + 32;
         t128[lane * 4] = a0; t128[lane * 4 + 1] = a1; t128[lane * 4 + 2] = a2; t128[lane * 4 + 3] = a3;
         __syncwarp();
-        if (lane == 0) plane_tiles_to_sums(t128, tot);
+        plane_tiles_to_system(t128, tot, tot + 160, lane);   // the 29 sums AND the halved 6x6 system, one entry per lane
     } else {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int b = 0;
-        for (; b + 3 < n_warps; b += 4) {
-            s0 += __ldcg(part_u + (size_t)b * RED_STRIDE_MMA + lane);
-            s1 += __ldcg(part_u + (size_t)(b + 1) * RED_STRIDE_MMA + lane);
-            s2 += __ldcg(part_u + (size_t)(b + 2) * RED_STRIDE_MMA + lane);
-            s3 += __ldcg(part_u + (size_t)(b + 3) * RED_STRIDE_MMA + lane);
-        }
-        for (; b < n_warps; ++b) s0 += __ldcg(part_u + (size_t)b * RED_STRIDE_MMA + lane);
-        tot[lane] = (s0 + s1) + (s2 + s3);
+        double s0 = 0.0;
+        for (int b = 0; b < n_groups; ++b) s0 += __ldcg(gpart_u + (size_t)b * RED_STRIDE_MMA + lane);
+        tot[lane] = s0;
     }
     __syncwarp();
-    if (lane == 0) c.red_counter[u] = 0;
+#ifdef ORPCD_QUEUE_STATS
+    unsigned long long tc_tot;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tc_tot));
+#endif
+    if (lane == 0) cnt[0] = 0u;
     const bool go_on = finish_round_warp<EST>(c, st, u, tot, tot + 160, round, lane);
+#ifdef ORPCD_QUEUE_STATS
+    unsigned long long tc_fin;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tc_fin));
+    if (lane == 0) {
+        const unsigned long long t0 = *reinterpret_cast<volatile unsigned long long *>(c.q_stats);
+        const unsigned b = (unsigned)min((unsigned long long)63, (tc_fin - t0) / 250000ull);
+        atomicAdd(c.q_stats + 512 + b, tc_tot - tc0);      // totals
+        atomicAdd(c.q_stats + 576 + b, tc_fin - tc_tot);   // stopping rule, solve, T
+    }
+#endif
     __threadfence();       // the unit's new state is visible before its next round is published
     __syncwarp();
     if (!PERSIST) return;
     if (!go_on) return;
-    // publish the patches of the unit's next round: n_patches consecutive tickets of the ring
+    // publish the work items of the unit's next round: consecutive tickets of the ring
+    const int n_next = (round + 1 >= c.half_from_round) ? c.n_patches2 : c.n_patches;
     unsigned base = 0;
-    if (lane == 0) base = atomicAdd(c.q_ctrl + Q_TAIL, (unsigned)c.n_patches);
+    if (lane == 0) base = atomicAdd(c.q_ctrl + Q_TAIL, (unsigned)n_next);
     base = __shfl_sync(0xffffffffu, base, 0);
-    for (int k = lane; k < c.n_patches; k += 32) {
-        unsigned *slot = c.q_slots + ((base + (unsigned)k) & c.q_mask);
-        const unsigned item = (unsigned)(u * c.n_patches + k) + 1u;
-        // the ring holds at most one round per unit, so a slot still occupied belongs to a consumer that has taken
-        // its ticket and is about to clear it
-        while (atomicCAS(slot, 0u, item) != 0u) __nanosleep(32);
+    // the ring holds at most one round per unit, so a slot still occupied belongs to a consumer that has taken its
+    // ticket and is about to clear it.  Four compare-and-swaps per lane are issued together (their round trips
+    // overlap); the rare occupied slot is retried afterwards.
+    for (int k0 = lane; k0 < n_next; k0 += 128) {
+        unsigned old[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0 + 32 * e;
+            old[e] = k < n_next ? atomicCAS(c.q_slots + ((base + (unsigned)k) & c.q_mask), 0u,
+                                            (unsigned)(u * c.n_patches2 + k) + 1u) : 0u;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0 + 32 * e;
+            if (old[e] != 0u)
+                while (atomicCAS(c.q_slots + ((base + (unsigned)k) & c.q_mask), 0u, (unsigned)(u * c.n_patches2 + k) + 1u) != 0u)
+                    __nanosleep(32);
+        }
     }
+#ifdef ORPCD_QUEUE_STATS
+    __syncwarp();
+    if (lane == 0) {
+        unsigned long long tc1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tc1));
+        reinterpret_cast<unsigned long long *>(c.worklist)[u] = tc1;     // publication stamp of the next round
+        const unsigned long long t0 = *reinterpret_cast<volatile unsigned long long *>(c.q_stats);
+        const unsigned b = (unsigned)min((unsigned long long)63, (tc1 - t0) / 250000ull);
+        atomicAdd(c.q_stats + 320 + b, tc1 - tc0);              // closing ns (totals, solve, publish)
+        atomicAdd(c.q_stats + 384 + b, 1ull);                   // closings
+    }
+#endif
 }
 
 // 64 source points per warp (Q = 2): the smaller the patch, the tighter its sphere and the fewer chunks it
@@ -1871,6 +2070,11 @@ __global__ void __launch_bounds__(ROUND_W * 32, ROUND_BLOCKS(EST)) gicp_persiste
     for (;;) {
         unsigned item = 0u;
         if (lane == 0) {
+#ifdef ORPCD_QUEUE_STATS
+            unsigned long long tw0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw0));
+            if (c.q_stats[0] == 0ull) atomicCAS(c.q_stats, 0ull, tw0);
+#endif
             const unsigned t = atomicAdd(c.q_ctrl + Q_HEAD, 1u);
             unsigned *slot = c.q_slots + (t & c.q_mask);
             for (;;) {
@@ -1881,14 +2085,36 @@ __global__ void __launch_bounds__(ROUND_W * 32, ROUND_BLOCKS(EST)) gicp_persiste
                 if (*reinterpret_cast<volatile unsigned *>(c.q_ctrl + Q_DONE) != 0u) break;
                 __nanosleep(ORPCD_SPIN_NS);      // an idle worker must not take issue slots from the busy warps of its SM
             }
+#ifdef ORPCD_QUEUE_STATS
+            unsigned long long tw1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw1));
+            const unsigned long long t0 = *reinterpret_cast<volatile unsigned long long *>(c.q_stats);
+            const unsigned b = (unsigned)min((unsigned long long)63, (tw1 - t0) / 250000ull);
+            atomicAdd(c.q_stats + 64 + b, tw1 - tw0);
+            if (item) atomicAdd(c.q_stats + 128 + b, 1ull);
+#endif
         }
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item == 0u) return;                       // every unit is done
         __threadfence();                              // what the publisher wrote before the item is visible from here on
-        const int u = (int)((item - 1u) / (unsigned)c.n_patches), wi = (int)((item - 1u) % (unsigned)c.n_patches);
+        const int u = (int)((item - 1u) / (unsigned)c.n_patches2), wi = (int)((item - 1u) % (unsigned)c.n_patches2);
         UnitState &st = c.state[u];
+#ifdef ORPCD_QUEUE_STATS
+        unsigned long long tp0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp0));
+#endif
         round_body<ROUND_Q, EST, true>(c, st, u, wi, __ldcg(&st.iters), wsm[warp]);
         __syncwarp();
+#ifdef ORPCD_QUEUE_STATS
+        if (lane == 0) {
+            unsigned long long tp1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp1));
+            const unsigned long long t0 = *reinterpret_cast<volatile unsigned long long *>(c.q_stats);
+            const unsigned b = (unsigned)min((unsigned long long)63, (tp1 - t0) / 250000ull);
+            atomicAdd(c.q_stats + 192 + b, tp1 - tp0);          // busy ns (patch incl. a closing if this warp did one)
+            atomicMax(c.q_stats + 256 + b, tp1 - tp0);          // longest item
+        }
+#endif
     }
 }
 
@@ -1896,14 +2122,20 @@ __global__ void __launch_bounds__(ROUND_W * 32, ROUND_BLOCKS(EST)) gicp_persiste
 // workers share target chunks in L2 / L1)
 __global__ void queue_init_kernel(Ctx c)
 {
-    const unsigned cap = c.q_mask + 1u, n_items = (unsigned)c.n_units * (unsigned)c.n_patches;
+    const unsigned per_unit = (unsigned)(0 >= c.half_from_round ? c.n_patches2 : c.n_patches);   // items of round 0
+    const unsigned cap = c.q_mask + 1u, n_items = (unsigned)c.n_units * per_unit;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x)
-        c.q_slots[i] = i < n_items ? i + 1u : 0u;
+        c.q_slots[i] = i < n_items ? (i / per_unit) * (unsigned)c.n_patches2 + (i % per_unit) + 1u : 0u;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         c.q_ctrl[Q_HEAD] = 0u;
         c.q_ctrl[Q_TAIL] = n_items;
         c.q_ctrl[Q_DONE] = 0u;
     }
+#ifdef ORPCD_QUEUE_STATS
+    if (blockIdx.x == 0) for (int k = threadIdx.x; k < 640; k += blockDim.x) c.q_stats[k] = 0ull;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)c.n_units; i += gridDim.x * blockDim.x)
+        reinterpret_cast<unsigned long long *>(c.worklist)[i] = 0ull;
+#endif
 }
 
 // correspondences of unit u in the caller's source order (the unit arrays are spatially sorted)
@@ -1921,12 +2153,14 @@ __global__ void __launch_bounds__(256) unpermute_corr_kernel(Ctx c, int *__restr
 struct Layout {
     size_t off_state, off_pts, off_cov, off_qf, off_corr, off_d2, off_m1, off_c1, off_m2, off_tgt4, off_meta,
         off_partial, off_counter, off_worklist, off_wcount, off_ract, off_done, off_visit, off_sperm, off_tperm,
-        off_sph, off_ssph, off_sort, off_bbox, off_qslots, off_qctrl, total;
+        off_sph, off_ssph, off_sort, off_bbox, off_qslots, off_qctrl, off_qstats, total;
     int nt_pad, n_chunks, splits, chunks_per_split, red_blocks, q_tiles, nn_q, nn_tj, cov_stride, smem_pad, nn_mode;
     int cull;
     int fused;       // one gicp_round_kernel launch per round instead of update / sweep / resolve / fix / reduce
     int persistent;  // ... and all rounds in one launch of gicp_persistent_kernel (the default)
-    int n_patches;   // work items per unit and round of the fused kernels
+    int n_patches;   // work items per unit and round of the fused kernels (64-point patches)
+    int n_patches2;  // ... of their late rounds (32-point patches)
+    int red_groups;  // groups of the two-level totals
     unsigned q_cap;  // work-queue ring capacity (power of two)
     int red_grid;    // blocks per unit of reduce_kernel (red_blocks is the partial-sum stride, >= patches per unit)
 };
@@ -1968,10 +2202,17 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     L.splits = (L.n_chunks + L.chunks_per_split - 1) / L.chunks_per_split;
     L.red_grid = (p->n_src + RED_THREADS * RED_PER_THREAD - 1) / (RED_THREADS * RED_PER_THREAD);
     const int patches = (p->n_src + 32 * ROUND_Q - 1) / (32 * ROUND_Q);   // fused rounds: one partial per patch
-    L.red_blocks = L.red_grid > patches ? L.red_grid : patches;
-    L.n_patches = patches;
+    const int patches2 = (p->n_src + 31) / 32;                            // ... or per 32-point patch (late rounds)
     {
-        const unsigned long long items = (unsigned long long)p->n_units * (unsigned long long)patches;
+        const int g1 = (patches + red_group_size(patches) - 1) / red_group_size(patches);
+        const int g2 = (patches2 + red_group_size(patches2) - 1) / red_group_size(patches2);
+        L.red_groups = g1 > g2 ? g1 : g2;
+    }
+    L.red_blocks = (L.red_grid > patches2 ? L.red_grid : patches2) + L.red_groups;   // item partials, then group partials
+    L.n_patches = patches;
+    L.n_patches2 = patches2;
+    {
+        const unsigned long long items = (unsigned long long)p->n_units * (unsigned long long)patches2;
         if (items >= 0x7fffffffull) return false;
         unsigned cap = 1024;
         while ((unsigned long long)cap < items) cap <<= 1;
@@ -1993,7 +2234,7 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     L.off_tgt4 = take((size_t)p->n_tgt_sets * L.nt_pad * sizeof(float4));
     L.off_meta = take((size_t)p->n_tgt_sets * sizeof(TgtMeta));
     L.off_partial = take(U * L.red_blocks * RED_STRIDE_MMA * sizeof(double));
-    L.off_counter = take(U * sizeof(unsigned));
+    L.off_counter = take(U * (size_t)(L.red_groups + 1) * sizeof(unsigned));
     L.off_worklist = take(U * ns * sizeof(int));
     L.off_wcount = take((size_t)(p->max_iterations + 2) * sizeof(int));
     L.off_ract = take((size_t)(p->max_iterations + 2) * sizeof(int));
@@ -2008,6 +2249,7 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     L.off_bbox = take((size_t)(p->n_src_sets > p->n_tgt_sets ? p->n_src_sets : p->n_tgt_sets) * 6 * sizeof(double));
     L.off_qslots = take((size_t)L.q_cap * sizeof(unsigned));
     L.off_qctrl = take(128 * sizeof(unsigned));
+    L.off_qstats = take(10 * 64 * sizeof(unsigned long long));
     L.total = o;
     return true;
 }
@@ -2049,8 +2291,15 @@ void fill_ctx(const orpcd_gicp_params *p, const Layout &L, void *ws, Ctx &c)
     c.bbox = (double *)(w + L.off_bbox);
     c.q_slots = (unsigned *)(w + L.off_qslots);
     c.q_ctrl = (unsigned *)(w + L.off_qctrl);
+    c.q_stats = (unsigned long long *)(w + L.off_qstats);
     c.q_mask = L.q_cap - 1u;
     c.n_patches = L.n_patches;
+    c.n_patches2 = L.n_patches2;
+    c.red_groups = L.red_groups;
+    // default: 32-point patches from round 32 on for clouds of at most 16384 points (a unit-round of a larger cloud
+    // has hundreds of patches and fills the GPU by itself: measured +8 % time at 200k points with the switch on)
+    c.half_from_round = p->half_patch_from_round > 0 ? p->half_patch_from_round
+                        : ((p->half_patch_from_round < 0 || p->n_src > 16384) ? 0x7fffffff : ORPCD_HALF_FROM_ROUND);
     c.dcap = (float)(p->max_correspondence_distance * (1.0 + 1e-5)) * (1.f + 1e-6f) + 1e-30f;
     c.tgt_pts = nullptr; c.tgt_cov = nullptr; c.out_T = nullptr; c.out_stats = nullptr; c.trace = nullptr;
     c.out_status = nullptr;
@@ -2105,7 +2354,8 @@ void launch_sweep(const Ctx &c, const Layout &L, int n_units, int round, cudaStr
 template <int EST>
 void launch_round_e(const Ctx &c, int n_units, int round, cudaStream_t st)
 {
-    const dim3 g((c.n_src + ROUND_W * 32 * ROUND_Q - 1) / (ROUND_W * 32 * ROUND_Q), 1, n_units);
+    const int items = round >= c.half_from_round ? c.n_patches2 : c.n_patches;
+    const dim3 g((items + ROUND_W - 1) / ROUND_W, 1, n_units);
     gicp_round_kernel<EST><<<g, ROUND_W * 32, 0, st>>>(c, round);
 }
 
@@ -2124,7 +2374,7 @@ int launch_persistent_e(const Ctx &c, cudaStream_t st)
         n_sm = sm;
         blocks_per_sm = b;
     }
-    const long long items = (long long)c.n_units * c.n_patches;
+    const long long items = (long long)c.n_units * (0 >= c.half_from_round ? c.n_patches2 : c.n_patches);
     long long blocks = (long long)n_sm * blocks_per_sm;        // every block is resident: workers may spin on the ring
     const long long need = (items + ROUND_W - 1) / ROUND_W;
     if (blocks > need) blocks = need;
@@ -2331,6 +2581,22 @@ int run_registration(const orpcd_gicp_params *p, int est_mode, const double *d_s
             rounds = rounds_run;
             h_profile[3] = (double)rounds;
         }
+#ifdef ORPCD_QUEUE_STATS
+        {
+            unsigned long long hq[640];
+            cudaMemcpy(hq, c.q_stats, sizeof(hq), cudaMemcpyDeviceToHost);
+            for (int b = 0; b < 64; ++b)
+                if (hq[128 + b] || hq[64 + b])
+                    fprintf(stderr, "t %5.2f ms  items %7llu  idle %5.1f %%  item mean %6.1f us max %6.1f us  closings %5llu mean %5.1f us\n",
+                            b * 0.25, hq[128 + b], 100.0 * hq[64 + b] * 1e-6 / (0.25 * 148 * 20),
+                            hq[128 + b] ? hq[192 + b] * 1e-3 / hq[128 + b] : 0.0, hq[256 + b] * 1e-3, hq[384 + b],
+                            hq[384 + b] ? hq[320 + b] * 1e-3 / hq[384 + b] : 0.0),
+                    fprintf(stderr, "            round span mean %6.1f us   closing: totals %5.1f us, solve %5.1f us, publish %5.1f us\n",
+                            hq[384 + b] ? hq[448 + b] * 1e-3 / hq[384 + b] : 0.0, hq[384 + b] ? hq[512 + b] * 1e-3 / hq[384 + b] : 0.0,
+                            hq[384 + b] ? hq[576 + b] * 1e-3 / hq[384 + b] : 0.0,
+                            hq[384 + b] ? (hq[320 + b] - hq[512 + b] - hq[576 + b]) * 1e-3 / hq[384 + b] : 0.0);
+        }
+#endif
         if (getenv("ORPCD_DEBUG_ROUNDS")) {
             for (int r = 0; r < rounds; ++r)
                 fprintf(stderr, "round %3d active %4d visited %.3f worklist %d\n", r, h_active[r],

@@ -51,6 +51,7 @@ class GeneralizedICP(IOptimizer):
         self.target_splits = 0        # tuning: target splits per sweep, 0 = auto
         self.sweep_tj = 0             # tuning: dense sweep targets per step; culled sweep warps per block (2->1, 4->2, 8->4)
         self.sweep_smem_pad = 0       # tuning: dense sweep occupancy pad; negative -(n+1): small patches below n
+        self.half_patch_from_round = int(__import__("os").environ.get("ORPCD_HALF_FROM_ROUND", "0"))   # tuning: 0 = default
         self.last_profile = None
 
     # ------------------------------------------------------------------ reference API
@@ -177,7 +178,7 @@ class GeneralizedICP(IOptimizer):
                              want_trace=want_trace, ws=self._ws, gicp_epsilon=GICP_EPSILON,
                              sweep_mode=self.sweep_mode, sweep_q=self.sweep_q, target_splits=self.target_splits,
                              sweep_tj=self.sweep_tj, sweep_smem_pad=self.sweep_smem_pad,
-                             src_rigid_copies=rigid_copies)
+                             src_rigid_copies=rigid_copies, half_patch_from_round=self.half_patch_from_round)
         self._ws = res.workspace
         return res
 

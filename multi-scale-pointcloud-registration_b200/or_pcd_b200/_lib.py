@@ -44,6 +44,7 @@ class GicpParams(C.Structure):
         ("sweep_smem_pad", C.c_int),
         ("sweep_mode", C.c_int),
         ("src_rigid_copies", C.c_int),
+        ("half_patch_from_round", C.c_int),
     ]
 
 

@@ -174,7 +174,7 @@ class GicpBatchResult:
 def gicp_batch(src_points, src_cov6, tgt_points, tgt_cov6, unit_src, unit_tgt, max_correspondence_distance=0.5,
                max_iterations=100, relative_fitness=1e-6, relative_rmse=1e-6, target_splits=0, poll_interval=0,
                profile=False, want_trace=False, ws=None, gicp_epsilon=1e-3, sweep_q=0, sweep_tj=0, sweep_smem_pad=0, sweep_mode=0,
-               src_rigid_copies=False) -> GicpBatchResult:
+               src_rigid_copies=False, half_patch_from_round=0) -> GicpBatchResult:
     """Batched GICP.  src_points [S,Ns,3], tgt_points [C,Nt,3], unit_* int32 [U]; the covariance
     inputs are either [.,N,6] covariance matrices (generic path) or [.,N,3] plane axes (closed-form
     whitening, ``cov_mode`` 1 of the C ABI) -- the last dimension selects the mode."""
@@ -190,7 +190,7 @@ def gicp_batch(src_points, src_cov6, tgt_points, tgt_cov6, unit_src, unit_tgt, m
     prm = GicpParams(U, Ns, Nt, S, Cn, int(max_iterations), int(target_splits), int(poll_interval), int(bool(profile)),
                      cov_mode, float(max_correspondence_distance), float(relative_fitness), float(relative_rmse),
                      float(gicp_epsilon), int(sweep_q), int(sweep_tj), int(sweep_smem_pad), int(sweep_mode),
-                     int(bool(src_rigid_copies)))
+                     int(bool(src_rigid_copies)), int(half_patch_from_round))
     L = _lib.lib()
     need = L.orpcd_gicp_batch_workspace_bytes(C.byref(prm))
     if need == 0:
@@ -266,7 +266,7 @@ def icp_batch(src_points, tgt_points, unit_src, unit_tgt, init_transforms=None, 
     Cn, Nt, _ = tgt_points.shape
     U = unit_src.shape[0]
     prm = GicpParams(U, Ns, Nt, S, Cn, int(max_iterations), 0, int(poll_interval), 0, 1,
-                     float(max_correspondence_distance), float(relative_fitness), float(relative_rmse), 1e-3, 0, 0, 0, 0, 0)
+                     float(max_correspondence_distance), float(relative_fitness), float(relative_rmse), 1e-3, 0, 0, 0, 0, 0, 0)
     L = _lib.lib()
     need = L.orpcd_gicp_batch_workspace_bytes(C.byref(prm))
     if need == 0:
@@ -299,7 +299,7 @@ def evaluate_batch(src_points, tgt_points, unit_src, unit_tgt, transforms=None, 
     S, Ns, _ = src_points.shape
     Cn, Nt, _ = tgt_points.shape
     U = unit_src.shape[0]
-    prm = GicpParams(U, Ns, Nt, S, Cn, 0, 0, 0, 0, 1, float(max_correspondence_distance), 1e-6, 1e-6, 1e-3, 0, 0, 0, 0, 0)
+    prm = GicpParams(U, Ns, Nt, S, Cn, 0, 0, 0, 0, 1, float(max_correspondence_distance), 1e-6, 1e-6, 1e-3, 0, 0, 0, 0, 0, 0)
     L = _lib.lib()
     need = L.orpcd_gicp_batch_workspace_bytes(C.byref(prm))
     if need == 0:
