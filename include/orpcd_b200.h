@@ -90,7 +90,16 @@ size_t orpcd_knn_rerank_workspace_bytes(int n, int batch);
 int orpcd_knn_rerank(const int *d_cand_idx, const double *d_cand_bound, int kc,
                      const double *d_points, int n, long long points_stride, int batch,
                      const double *d_factor, int k, int *d_idx, double *d_d2, void *d_workspace,
-                     size_t workspace_bytes, orpcd_stream_t stream);
+                     size_t workspace_bytes, const int *d_order, const double *d_cand_d2,
+                     orpcd_stream_t stream);
+/* d_order (may be NULL) [n]: order in which the points are processed, e.g. the base cloud's spatial order
+ * (orpcd_spatial_order): neighbouring threads then gather the same candidates and most gathers hit L1.
+ * d_cand_d2 (may be NULL) [n][kc]: the base distances of the candidates (ascending, as orpcd_knn_exact returned
+ * them): the scan of a point stops once the next candidate's lower bound factor x base d2 exceeds the k-th moved
+ * distance.  Neither changes the results. */
+size_t orpcd_spatial_order_workspace_bytes(int n);
+int orpcd_spatial_order(const double *d_points, int n, void *d_workspace, size_t workspace_bytes,
+                        int *d_order, orpcd_stream_t stream);   /* d_order[pos] = index of the point at Hilbert position pos */
 
 /* ------------------------------------------------------------------------
  * Statistical outlier removal mask.
@@ -130,7 +139,7 @@ int orpcd_normals_cov_from_knn(const double *d_points, int n, long long points_s
                                int knn, const int *d_knn_idx, const double *d_knn_d2, double radius,
                                double gicp_eps, double *d_normals, double *d_cov6,
                                double *d_gicp_cov6, double *d_gicp_axis, int *d_nn_idx,
-                               orpcd_stream_t stream);
+                               const int *d_order /* may be NULL, see orpcd_knn_rerank */, orpcd_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * target * (sx, sy, sz) for a batch of scale candidates

@@ -167,11 +167,12 @@ normals_cov_kernel(const double *__restrict__ points, int n, long long points_st
                    const int *__restrict__ nn_idx, const double *__restrict__ nn_d2, int knn,
                    double radius2, double gicp_eps, double *__restrict__ normals,
                    double *__restrict__ cov6, double *__restrict__ gicp_cov6,
-                   double *__restrict__ gicp_axis, int *__restrict__ nn_out)
+                   double *__restrict__ gicp_axis, int *__restrict__ nn_out, const int *__restrict__ order)
 {
     const int b = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int i = order ? order[t] : t;     // spatial processing order: neighbouring threads gather the same points (L1)
     const double *pts = points + (size_t)b * points_stride;
     const size_t row = ((size_t)b * n + i);
     const int *idx = nn_idx + row * knn;
@@ -259,7 +260,7 @@ ORPCD_API int orpcd_normals_cov(const double *d_points, int n, long long points_
     dim3 grid((n + 127) / 128, batch);
     normals_cov_kernel<<<grid, 128, 0, st>>>(d_points, n, points_stride, idx, d2, knn,
                                              radius > 0 ? radius * radius : 0.0, gicp_eps, d_normals,
-                                             d_cov6, d_gicp_cov6, d_gicp_axis, d_nn_idx);
+                                             d_cov6, d_gicp_cov6, d_gicp_axis, d_nn_idx, nullptr);
     ORPCD_CHECK_LAUNCH();
     return ORPCD_OK;
 }
@@ -268,14 +269,14 @@ ORPCD_API int orpcd_normals_cov_from_knn(const double *d_points, int n, long lon
                                          int knn, const int *d_knn_idx, const double *d_knn_d2, double radius,
                                          double gicp_eps, double *d_normals, double *d_cov6,
                                          double *d_gicp_cov6, double *d_gicp_axis, int *d_nn_idx,
-                                         orpcd_stream_t stream)
+                                         const int *d_order, orpcd_stream_t stream)
 {
     if (!d_points || !d_knn_idx || !d_knn_d2 || n <= 0 || batch <= 0 || knn < 1) return ORPCD_ERR_INVALID;
     if ((d_gicp_cov6 || d_gicp_axis) && !(gicp_eps > 0)) return ORPCD_ERR_INVALID;
     dim3 grid((n + 127) / 128, batch);
     normals_cov_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_points, n, points_stride, d_knn_idx, d_knn_d2, knn,
                                                                radius > 0 ? radius * radius : 0.0, gicp_eps,
-                                                               d_normals, d_cov6, d_gicp_cov6, d_gicp_axis, d_nn_idx);
+                                                               d_normals, d_cov6, d_gicp_cov6, d_gicp_axis, d_nn_idx, d_order);
     ORPCD_CHECK_LAUNCH();
     return ORPCD_OK;
 }

@@ -614,21 +614,31 @@ __global__ void __launch_bounds__(RR_BLOCK)
 knn_rerank_kernel(const int *__restrict__ cand, const double *__restrict__ bound, int kc,
                   const double *__restrict__ points, int n, long long stride,
                   const double *__restrict__ factor, int k, int *__restrict__ out_idx,
-                  double *__restrict__ out_d2, int *__restrict__ worklist, int *__restrict__ wcount)
+                  double *__restrict__ out_d2, int *__restrict__ worklist, int *__restrict__ wcount,
+                  const int *__restrict__ order, const double *__restrict__ cand_d2)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *ld = reinterpret_cast<double *>(smem_raw);                  // [k][RR_BLOCK]
     int *li = reinterpret_cast<int *>(ld + (size_t)k * RR_BLOCK);       // [k][RR_BLOCK]
     const int b = blockIdx.y, tid = threadIdx.x;
-    const int i = blockIdx.x * RR_BLOCK + tid;
-    if (i >= n) return;
+    const int t = blockIdx.x * RR_BLOCK + tid;
+    if (t >= n) return;
+    // processing order: with the base cloud's spatial (Hilbert) order the threads of a block handle neighbouring
+    // points, whose candidate lists overlap -- most of the 48 random 24-byte gathers per point then hit L1
+    const int i = order ? order[t] : t;
     const double *pts = points + (size_t)b * stride;
     const double qx = pts[(size_t)i * 3], qy = pts[(size_t)i * 3 + 1], qz = pts[(size_t)i * 3 + 2];
     const int *row = cand + (size_t)i * kc;
+    const double *row_d2 = cand_d2 ? cand_d2 + (size_t)i * kc : nullptr;
+    const double flo = factor[b];
     int cnt = 0;
     // RR_STEP candidates per step: their indices and coordinates are fetched together (the gathers are what this
     // kernel waits for), then inserted one after the other in list order
     for (int s0 = 0; s0 < kc; s0 += RR_STEP) {
+        // the candidates are in ascending order of their BASE distance and a moved distance is at least factor x the
+        // base one: once k are in hand and the next candidate's bound already exceeds the k-th moved distance, no later
+        // candidate can enter the list (strictly: a tie goes on scanning).  Rigid copies stop after ~k + 8 of the 48.
+        if (row_d2 && cnt == k && flo * row_d2[s0] > ld[(size_t)(k - 1) * RR_BLOCK + tid]) break;
         int jj[RR_STEP];
         double cx[RR_STEP], cy[RR_STEP], cz[RR_STEP];
 #pragma unroll
@@ -886,10 +896,29 @@ ORPCD_API int orpcd_knn_candidate_bound(const int *d_cand_idx, const double *d_c
     return ORPCD_OK;
 }
 
+ORPCD_API size_t orpcd_spatial_order_workspace_bytes(int n)
+{
+    if (n <= 0) return 0;
+    return orpcd_align_up((size_t)sort_pad(n) * sizeof(unsigned long long), 256) + 256;
+}
+
+ORPCD_API int orpcd_spatial_order(const double *d_points, int n, void *d_workspace, size_t workspace_bytes,
+                                  int *d_order, orpcd_stream_t stream)
+{
+    if (!d_points || !d_order || n <= 0) return ORPCD_ERR_INVALID;
+    if (!d_workspace || workspace_bytes < orpcd_spatial_order_workspace_bytes(n) || ((uintptr_t)d_workspace & 255))
+        return ORPCD_ERR_WORKSPACE;
+    unsigned char *w = (unsigned char *)d_workspace;
+    double *bbox = (double *)w;                                     // 6 doubles
+    unsigned long long *keys = (unsigned long long *)(w + 256);
+    return spatial_perm(d_points, n, 1, n, bbox, keys, d_order, (cudaStream_t)stream) == 0 ? ORPCD_OK : ORPCD_ERR_CUDA;
+}
+
 ORPCD_API int orpcd_knn_rerank(const int *d_cand_idx, const double *d_cand_bound, int kc,
                                const double *d_points, int n, long long points_stride, int batch,
                                const double *d_factor, int k, int *d_idx, double *d_d2, void *d_workspace,
-                               size_t workspace_bytes, orpcd_stream_t stream)
+                               size_t workspace_bytes, const int *d_order, const double *d_cand_d2,
+                               orpcd_stream_t stream)
 {
     if (!d_cand_idx || !d_cand_bound || !d_points || !d_factor || !d_idx || !d_d2 || n <= 0 || batch <= 0 ||
         k < 1 || k > 64 || kc < k || (long long)n * batch > 0x7fffffffLL)   /* lists: k * 1536 bytes of shared memory */
@@ -905,7 +934,7 @@ ORPCD_API int orpcd_knn_rerank(const int *d_cand_idx, const double *d_cand_bound
         return ORPCD_ERR_CUDA;
     dim3 grid((n + RR_BLOCK - 1) / RR_BLOCK, batch);
     knn_rerank_kernel<<<grid, RR_BLOCK, smem, st>>>(d_cand_idx, d_cand_bound, kc, d_points, n, points_stride, d_factor,
-                                                    k, d_idx, d_d2, worklist, wcount);
+                                                    k, d_idx, d_d2, worklist, wcount, d_order, d_cand_d2);
     ORPCD_CHECK_LAUNCH();
     knn_rerank_fix_kernel<<<148 * 2, 128, 0, st>>>(d_points, n, points_stride, k, d_idx, d_d2, worklist, wcount);
     ORPCD_CHECK_LAUNCH();

@@ -112,9 +112,9 @@ class FastGlobalOptimizer(IOptimizer):
             if key != self._base_key:
                 self._base_lists = ops.knn_candidates(_lib.to_device(base), self.RERANK_KC)
                 self._base_key = key
-            cand, bound = self._base_lists
+            cand, bound, order = self._base_lists
             factor = t.full((d_clouds.shape[0],), 1.0 - 1e-9, dtype=t.float64, device="cuda")
-            idx, d2, _ = ops.knn_rerank(cand, bound, d_clouds, factor, k)
+            idx, d2, _ = ops.knn_rerank(cand, bound, d_clouds, factor, k, order=order)
             return idx, d2
         return ops.knn_exact(d_clouds, d_clouds, k)
 

@@ -152,13 +152,13 @@ class GeneralizedICP(IOptimizer):
         if key != self._base_key:
             self._base_lists = ops.knn_candidates(_lib.to_device(base), self.RERANK_KC)
             self._base_key = key
-        cand, bound = self._base_lists
+        cand, bound, order = self._base_lists
         factor = t.full((d_src.shape[0],), 1.0 - 1e-9, dtype=t.float64, device="cuda")
-        idx, d2, n_fixed = ops.knn_rerank(cand, bound, d_src, factor, GICP_COVARIANCE_KNN)
+        idx, d2, n_fixed = ops.knn_rerank(cand, bound, d_src, factor, GICP_COVARIANCE_KNN, order=order)
         self.last_rerank_fixed = n_fixed
         ax = self.analytic_whitening
         return ops.normals_cov_from_knn(d_src, idx, d2, gicp_eps=GICP_EPSILON, want_gicp_cov=not ax,
-                                        want_gicp_axis=ax)["gicp_axis" if ax else "gicp_cov"]
+                                        want_gicp_axis=ax, order=order[0])["gicp_axis" if ax else "gicp_cov"]
 
     def optimize_batch_device(self, d_src, d_tgt, unit_src, unit_tgt, poll_interval: int = 0, want_trace=False,
                               src_cov=None, tgt_cov=None, rigid_copies: bool = False):

@@ -96,9 +96,13 @@ def lib():
     L.orpcd_knn_rerank_workspace_bytes.restype = sz
     L.orpcd_knn_rerank_workspace_bytes.argtypes = [ip, ip]
     L.orpcd_knn_rerank.restype = ip
-    L.orpcd_knn_rerank.argtypes = [vp, vp, ip, vp, ip, ll, ip, vp, ip, vp, vp, vp, sz, vp]
+    L.orpcd_knn_rerank.argtypes = [vp, vp, ip, vp, ip, ll, ip, vp, ip, vp, vp, vp, sz, vp, vp, vp]
+    L.orpcd_spatial_order_workspace_bytes.restype = sz
+    L.orpcd_spatial_order_workspace_bytes.argtypes = [ip]
+    L.orpcd_spatial_order.restype = ip
+    L.orpcd_spatial_order.argtypes = [vp, ip, vp, sz, vp, vp]
     L.orpcd_normals_cov_from_knn.restype = ip
-    L.orpcd_normals_cov_from_knn.argtypes = [vp, ip, ll, ip, ip, vp, vp, dp, dp, vp, vp, vp, vp, vp, vp]
+    L.orpcd_normals_cov_from_knn.argtypes = [vp, ip, ll, ip, ip, vp, vp, dp, dp, vp, vp, vp, vp, vp, vp, vp]
     L.orpcd_sor_workspace_bytes.restype = sz
     L.orpcd_sor_workspace_bytes.argtypes = [ip, ip]
     L.orpcd_sor_mask.restype = ip

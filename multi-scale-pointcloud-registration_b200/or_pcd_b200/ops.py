@@ -45,8 +45,23 @@ def knn_exact(points, queries, k: int):
     return (idx[0], d2[0]) if squeeze else (idx, d2)
 
 
+def spatial_order(points):
+    """int32 [N]: index of the point at each position of the cloud's Hilbert order."""
+    t = _t()
+    points = _f64(points)
+    N = points.shape[0]
+    L = _lib.lib()
+    ws = _lib.workspace(L.orpcd_spatial_order_workspace_bytes(N))
+    order = t.empty(N, dtype=t.int32, device="cuda")
+    check(L.orpcd_spatial_order(points.data_ptr(), N, ws.data_ptr(), ws.numel(), order.data_ptr(), _lib.stream_ptr()),
+          "orpcd_spatial_order")
+    launch_counter["kernels"] += 7
+    return order
+
+
 def knn_candidates(base_points, kc: int):
-    """Neighbour lists of a base cloud for later re-ranking: (cand_idx int32 [N,kc], bound float64 [N])."""
+    """Neighbour lists of a base cloud for later re-ranking: (cand_idx int32 [N,kc], bound float64 [N],
+    (order int32 [N] = the cloud's spatial processing order, cand_d2 float64 [N,kc] = the candidates' base distances))."""
     t = _t()
     base_points = _f64(base_points)
     N = base_points.shape[0]
@@ -55,12 +70,15 @@ def knn_candidates(base_points, kc: int):
     check(_lib.lib().orpcd_knn_candidate_bound(idx.data_ptr(), d2.data_ptr(), N, kc, bound.data_ptr(),
                                                _lib.stream_ptr()), "orpcd_knn_candidate_bound")
     launch_counter["kernels"] += 1
-    return idx, bound
+    return idx, bound, (spatial_order(base_points), d2)
 
 
-def knn_rerank(cand_idx, bound, moved_points, factor, k: int):
+def knn_rerank(cand_idx, bound, moved_points, factor, k: int, order=None):
     """Exact kNN of moved copies [B,N,3] of the base cloud from its candidate lists.
-    factor: float64 [B] lower bound of moved_d2/base_d2.  Returns (idx [B,N,k], d2 [B,N,k])."""
+    factor: float64 [B] lower bound of moved_d2/base_d2.  order: optional (processing order, candidate base distances)
+    as returned by knn_candidates (L1 locality of the gathers; early end of a point's scan) -- the results do not depend
+    on it.  Returns (idx [B,N,k], d2 [B,N,k], device count of points that took the exact fallback)."""
+    order, cand_d2 = order if order is not None else (None, None)
     t = _t()
     moved_points, factor = _f64(moved_points), _f64(factor)
     B, N, _ = moved_points.shape
@@ -71,14 +89,15 @@ def knn_rerank(cand_idx, bound, moved_points, factor, k: int):
     d2 = t.empty((B, N, k), dtype=t.float64, device="cuda")
     check(L.orpcd_knn_rerank(cand_idx.data_ptr(), bound.data_ptr(), kc, moved_points.data_ptr(), N, N * 3, B,
                              factor.data_ptr(), k, idx.data_ptr(), d2.data_ptr(), ws.data_ptr(), ws.numel(),
-                             _lib.stream_ptr()), "orpcd_knn_rerank")
+                             order.data_ptr() if order is not None else None,
+                             cand_d2.data_ptr() if cand_d2 is not None else None, _lib.stream_ptr()), "orpcd_knn_rerank")
     launch_counter["kernels"] += 2
     n_fixed = ws[:4].view(t.int32)   # device scalar: points that needed the exact fallback
     return idx, d2, n_fixed
 
 
 def normals_cov_from_knn(points, nn_idx, nn_d2, radius: float = 0.0, gicp_eps: float = 1e-3, want_normals=False,
-                         want_cov=False, want_gicp_cov=True, want_gicp_axis=False) -> Dict[str, object]:
+                         want_cov=False, want_gicp_cov=True, want_gicp_axis=False, order=None) -> Dict[str, object]:
     """As normals_cov, from neighbour lists [B,N,k] computed elsewhere."""
     t = _t()
     points = _f64(points)
@@ -91,7 +110,8 @@ def normals_cov_from_knn(points, nn_idx, nn_d2, radius: float = 0.0, gicp_eps: f
     p = lambda x: x.data_ptr() if x is not None else None
     check(_lib.lib().orpcd_normals_cov_from_knn(points.data_ptr(), N, N * 3, B, knn, nn_idx.data_ptr(),
                                                 nn_d2.data_ptr(), float(radius), float(gicp_eps), p(nrm), p(cov),
-                                                p(gc), p(ax), None, _lib.stream_ptr()), "orpcd_normals_cov_from_knn")
+                                                p(gc), p(ax), None, order.data_ptr() if order is not None else None,
+                                                _lib.stream_ptr()), "orpcd_normals_cov_from_knn")
     launch_counter["kernels"] += 1
     out = {}
     for k_, v in (("normal", nrm), ("cov", cov), ("gicp_cov", gc), ("gicp_axis", ax)):

@@ -246,9 +246,14 @@ def test_knn_rerank_equals_exact_knn(oracle, armadillo_pair):
     moved.append(s * scale)
     moved = np.stack(moved)
     t_ = _lib.torch()
-    cand, bound = ops.knn_candidates(_dev(s), 48)
-    for factors, expect_all_fixed in (([1 - 1e-9] * 3 + [0.81 * (1 - 1e-9)], False), ([0.0] * 4, True)):
-        idx, d2, n_fixed = ops.knn_rerank(cand, bound, _dev(moved), _dev(np.array(factors)), 20)
+    cand, bound, order = ops.knn_candidates(_dev(s), 48)
+    assert np.array_equal(np.sort(order[0].cpu().numpy()), np.arange(s.shape[0]))       # a permutation of the cloud
+    for factors, expect_all_fixed, use_order in (([1 - 1e-9] * 3 + [0.81 * (1 - 1e-9)], False, True),
+                                                 ([1 - 1e-9] * 3 + [0.81 * (1 - 1e-9)], False, False),
+                                                 ([0.0] * 4, True, True)):
+        # the processing order (the base cloud's Hilbert order: L1 locality of the gathers) never changes the result
+        idx, d2, n_fixed = ops.knn_rerank(cand, bound, _dev(moved), _dev(np.array(factors)), 20,
+                                          order=order if use_order else None)
         for b in range(moved.shape[0]):
             oi, od = oracle.knn(moved[b], moved[b], 20)
             assert np.array_equal(idx[b].cpu().numpy(), oi), b
