@@ -64,6 +64,15 @@ __device__ __forceinline__ float tf32_rna(float x)
 }
 
 // grid (tiles, sets), 128 threads: thread r packs row r of the tile.
+// chunks recorded per query row by the tensor-core filter (smallest 32-column chunk minima, ascending, with their ids;
+// one more minimum is kept as the bound for everything not recorded).  With 3, 1.4 % of the FPFH rows exhausted their
+// chunks without a certificate, and their exact scans of the whole set (1.3 MB each) were 60 % of
+// feat_resolve_kernel's traffic.  Measured on the 180-unit FGR batch (ms per batch / rows needing the exact scan):
+// 3: 19.4 / 25759, 4: 19.1 / 14524, 5: 18.7 / 9014, 6: 18.0 / 6008, 8: 18.0 / 3013, 10: 17.4 / 1703, 12: 17.9 / 1009.
+#ifndef FM_TOP
+#define FM_TOP 8
+#endif
+
 __global__ void __launch_bounds__(FM_ROWS)
 feat_pack_kernel(const double *__restrict__ feat, int n, int tiles, const double *__restrict__ center,
                  unsigned char *__restrict__ packed, float *__restrict__ set_maxnorm)
@@ -249,8 +258,12 @@ feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const
     const uint32_t tmem_base = *tmem_slot;
 
     // the FM_TOP smallest chunk minima (ascending, with chunk ids) and the next one as the bound for the rest
-    float m1 = CUDART_INF_F, m2 = CUDART_INF_F, m3 = CUDART_INF_F, m4 = CUDART_INF_F;
-    int c1 = 0, c2 = 0, c3 = 0;
+    float mm[FM_TOP + 1];
+    int cc[FM_TOP];
+#pragma unroll
+    for (int k = 0; k <= FM_TOP; ++k) mm[k] = CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < FM_TOP; ++k) cc[k] = 0;
     const int row = (qt0 + atile) * FM_ROWS + quarter * 32 + (tid & 31);
     const bool have_tile = warp < FM_EPI_WARPS && atile < n_at;
 
@@ -332,12 +345,12 @@ feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const
                     }
                     float x = fminf(ma, mb);
                     int cx = e * 4 + ch;
-                    if (x < m3) {   // sorted insertion; strict compares keep the lowest chunk id first among equals
-                        if (x < m1) { const float tt = m1; m1 = x; x = tt; const int tc = c1; c1 = cx; cx = tc; }
-                        if (x < m2) { const float tt = m2; m2 = x; x = tt; const int tc = c2; c2 = cx; cx = tc; }
-                        if (x < m3) { const float tt = m3; m3 = x; x = tt; c3 = cx; }
+                    if (x < mm[FM_TOP - 1]) {   // sorted insertion; strict compares keep the lowest chunk id first among equals
+#pragma unroll
+                        for (int k = 0; k < FM_TOP; ++k)
+                            if (x < mm[k]) { const float tt = mm[k]; mm[k] = x; x = tt; const int tc = cc[k]; cc[k] = cx; cx = tc; }
                     }
-                    m4 = fminf(m4, x);
+                    mm[FM_TOP] = fminf(mm[FM_TOP], x);
                 }
             }
             // this warp is done with accumulator buffer e&1 and with stage s (the norms)
@@ -348,8 +361,10 @@ feat_match_kernel(const unsigned char *__restrict__ packed_q, int q_tiles, const
     }
     if (have_tile && row < nq) {
         const size_t o = (size_t)pair * nq + row;
-        out_m[o] = m1; out_m[o + out_stride] = m2; out_m[o + 2 * out_stride] = m3; out_m[o + 3 * out_stride] = m4;
-        out_c[o] = c1; out_c[o + out_stride] = c2; out_c[o + 2 * out_stride] = c3;
+#pragma unroll
+        for (int k = 0; k <= FM_TOP; ++k) out_m[o + (size_t)k * out_stride] = mm[k];
+#pragma unroll
+        for (int k = 0; k < FM_TOP; ++k) out_c[o + (size_t)k * out_stride] = cc[k];
     }
     tc_fence_before();
     __syncthreads();
@@ -378,7 +393,6 @@ __device__ __forceinline__ double sqdist33_fm(const double *__restrict__ a, cons
 // above the best exact distance found so far; a row that exhausts the FM_TOP recorded chunks without
 // reaching that certificate gets the exact scan of the whole set.  Ties -> lowest index.
 // stats[0] += rows that needed the exact scan, stats[1] += chunks re-scored.
-constexpr int FM_TOP = 3;
 
 #ifndef FR_MIN_BLOCKS
 #define FR_MIN_BLOCKS 8
@@ -886,7 +900,7 @@ ORPCD_API int orpcd_feature_pack(const double *d_features, int n, int n_sets, co
 ORPCD_API size_t orpcd_feature_match_workspace_bytes(int n_query, int n_pairs)
 {
     if (n_query <= 0 || n_pairs <= 0) return 0;
-    return 7 * orpcd_align_up((size_t)n_query * n_pairs * 4, 256);   // 4 chunk minima + 3 chunk ids per row
+    return (2 * FM_TOP + 1) * orpcd_align_up((size_t)n_query * n_pairs * 4, 256);   // FM_TOP + 1 chunk minima, FM_TOP chunk ids per row
 }
 
 ORPCD_API int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q, int n_query,
@@ -904,8 +918,8 @@ ORPCD_API int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q
         return ORPCD_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t slice = orpcd_align_up((size_t)n_query * n_pairs * 4, 256);
-    float *fm = (float *)d_workspace;                                     // [4][pairs * n_query]
-    int *fc = (int *)((unsigned char *)d_workspace + 4 * slice);          // [3][pairs * n_query]
+    float *fm = (float *)d_workspace;                                                // [FM_TOP + 1][pairs * n_query]
+    int *fc = (int *)((unsigned char *)d_workspace + (size_t)(FM_TOP + 1) * slice);  // [FM_TOP][pairs * n_query]
     const size_t stride = slice / 4;
     const int q_tiles = (n_query + FM_ROWS - 1) / FM_ROWS, db_tiles = (n_db + FM_ROWS - 1) / FM_ROWS;
     if (mode == 0) {
