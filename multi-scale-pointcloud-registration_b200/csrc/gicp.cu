@@ -197,6 +197,42 @@ __device__ __forceinline__ void cp_async_wait()
 // ----------------------------------------------------------------------------
 // set-up kernels
 // ----------------------------------------------------------------------------
+// Release / acquire without wiping the L1.  `__threadfence()` is `fence.sc.gpu`: SASS MEMBAR.SC.GPU + CCTL.IVALL, i.e.
+// every fence INVALIDATES THE SM'S WHOLE L1 -- two per work item with 20 worker warps per SM emptied the L1 (target
+// tables, chunk spheres, permutations: the immutable data the sweep lives on) every microsecond.  The queue only
+// needs (1) a release before the atomic that hands data on -- `atom.release.gpu` is MEMBAR.ALL.GPU + the atomic, no
+// invalidate; `__syncwarp()` before it orders the other lanes' stores ahead of lane 0's release (cumulativity) -- and
+// (2) on the consuming side nothing at all: every load of data that another SM wrote during the launch is a strong
+// L2 load (`__ldcg`, SASS LDG.STRONG.GPU) whose address depends on the value the consuming atomic returned, and the
+// L1 never holds a line of that data.  ORPCD_LIGHT_FENCE=0 restores the fences for A/B runs.
+#ifndef ORPCD_LIGHT_FENCE
+#define ORPCD_LIGHT_FENCE 1
+#endif
+__device__ __forceinline__ unsigned atom_add_release(unsigned *p, unsigned v)
+{
+#if ORPCD_LIGHT_FENCE
+    unsigned r;
+    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+    return r;
+#else
+    return atomicAdd(p, v);
+#endif
+}
+__device__ __forceinline__ void fence_release_side()     // all lanes, before __syncwarp() + atom_add_release by lane 0
+{
+#if !ORPCD_LIGHT_FENCE
+    __threadfence();
+#endif
+}
+__device__ __forceinline__ void fence_acquire_side()     // after the consuming atomic
+{
+#if ORPCD_LIGHT_FENCE
+    asm volatile("" ::: "memory");
+#else
+    __threadfence();
+#endif
+}
+
 __global__ void init_units_kernel(Ctx c, const int *__restrict__ unit_src, const int *__restrict__ unit_tgt,
                                   const double *__restrict__ src_pts, const double *__restrict__ src_cov,
                                   const double *__restrict__ init_T)
@@ -1892,13 +1928,13 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     unsigned *cnt = c.red_counter + (size_t)u * (c.red_groups + 1);
     double *part_u = c.red_partial + (size_t)u * c.red_blocks * RED_STRIDE_MMA;
     double *gpart_u = part_u + (size_t)c.n_patches2 * RED_STRIDE_MMA;  // group partials follow the item partials
-    __threadfence();
+    fence_release_side();
     __syncwarp();
     int last = 0;
-    if (lane == 0) last = atomicAdd(cnt + 1 + grp, 1u) == (unsigned)min(gsz, n_warps - grp * gsz) - 1u;
+    if (lane == 0) last = atom_add_release(cnt + 1 + grp, 1u) == (unsigned)min(gsz, n_warps - grp * gsz) - 1u;
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
-    __threadfence();
+    fence_acquire_side();
     {
         const int b0 = grp * gsz, b1 = min(n_warps, b0 + gsz);
         double *gp = gpart_u + (size_t)grp * RED_STRIDE_MMA;
@@ -1919,12 +1955,12 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
             __stcg(gp + lane, a0);
         }
     }
-    __threadfence();
+    fence_release_side();
     __syncwarp();
     last = 0;
     if (lane == 0) {
         cnt[1 + grp] = 0u;                                   // ready for the unit's next round
-        last = atomicAdd(cnt, 1u) == (unsigned)n_groups - 1u;
+        last = atom_add_release(cnt, 1u) == (unsigned)n_groups - 1u;
     }
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
@@ -1932,7 +1968,7 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     unsigned long long tc0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tc0));
 #endif
-    __threadfence();
+    fence_acquire_side();
 #ifdef ORPCD_QUEUE_STATS
     {   // span of this unit's round: from its publication (stamp kept in the unused work list) to its last arrival
         unsigned long long *pub = reinterpret_cast<unsigned long long *>(c.worklist) + u;
@@ -1979,14 +2015,15 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
         atomicAdd(c.q_stats + 576 + b, tc_fin - tc_tot);   // stopping rule, solve, T
     }
 #endif
-    __threadfence();       // the unit's new state is visible before its next round is published
+    fence_release_side();  // the unit's new state is visible before its next round is published
     __syncwarp();
     if (!PERSIST) return;
     if (!go_on) return;
-    // publish the work items of the unit's next round: consecutive tickets of the ring
+    // publish the work items of the unit's next round: consecutive tickets of the ring.  The ticket atomic is the
+    // release: the slot writes below depend on its result.
     const int n_next = (round + 1 >= c.half_from_round) ? c.n_patches2 : c.n_patches;
     unsigned base = 0;
-    if (lane == 0) base = atomicAdd(c.q_ctrl + Q_TAIL, (unsigned)n_next);
+    if (lane == 0) base = atom_add_release(c.q_ctrl + Q_TAIL, (unsigned)n_next);
     base = __shfl_sync(0xffffffffu, base, 0);
     // the ring holds at most one round per unit, so a slot still occupied belongs to a consumer that has taken its
     // ticket and is about to clear it.  Four compare-and-swaps per lane are issued together (their round trips
@@ -2096,7 +2133,7 @@ __global__ void __launch_bounds__(ROUND_W * 32, ROUND_BLOCKS(EST)) gicp_persiste
         }
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item == 0u) return;                       // every unit is done
-        __threadfence();                              // what the publisher wrote before the item is visible from here on
+        fence_acquire_side();                         // what the publisher wrote before the item is visible from here on
         const int u = (int)((item - 1u) / (unsigned)c.n_patches2), wi = (int)((item - 1u) % (unsigned)c.n_patches2);
         UnitState &st = c.state[u];
 #ifdef ORPCD_QUEUE_STATS
