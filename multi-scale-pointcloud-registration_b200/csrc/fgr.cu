@@ -487,6 +487,7 @@ struct FgrUnit {
     double mean_s[3], mean_t[3];
     double scale;        // scale_global
     int n_init, n_pairs, trials, swapped;
+    int tt_done, tt_cnt;  // tuple test: quota reached or trials exhausted; accepted tuples so far
 };
 
 struct FgrCtx {
@@ -500,6 +501,8 @@ struct FgrCtx {
     FgrUnit *unit;
     int2 *corres_init, *corres;         // [U][cap]
     double *qcur, *pcur;                // [U][cap][3] each
+    unsigned *tt_flags;                 // [U][tt_epoch / 32] accept bits of the tuple-test epoch in hand
+    int tt_epoch;                       // trials of a unit evaluated per epoch (multiple of 1024)
     double *out_T;
     int *out_info;
 };
@@ -542,6 +545,35 @@ __device__ __forceinline__ int block_scan_flag(int flag, int *sh, int &total)
     }
     total = tot;
     return base + within;
+}
+
+// exclusive block scan of small per-thread counts; returns this thread's offset, total in `total`
+__device__ __forceinline__ int block_scan_count(int cnt, int *sh, int &total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    __syncthreads();
+    if (lane == 31) sh[wid] = incl;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        if (w < wid) base += sh[w];
+        tot += sh[w];
+    }
+    total = tot;
+    return base + incl - cnt;
+}
+
+__device__ __forceinline__ void norm_point(const double *p, int i, const double *mean, double scale, double o[3])
+{
+    o[0] = (p[(size_t)i * 3] - mean[0]) / scale;
+    o[1] = (p[(size_t)i * 3 + 1] - mean[1]) / scale;
+    o[2] = (p[(size_t)i * 3 + 2] - mean[2]) / scale;
 }
 
 // NormalizePointCloud (means, global scale) + InitialMatching's cross check, per unit.
@@ -595,6 +627,20 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_prepare_kernel(FgrCtx c)
         if (tid == 0) s_cnt = cnt0 + total;
         __syncthreads();
     }
+    // normalised end points of the cross-checked pairs, once per pair: the tuple test draws ~100 x n_init triples of
+    // them (norm_point in every trial was 18 float64 divisions per trial)
+    {
+        const int n_init = s_cnt;
+        double *pn = c.pcur + (size_t)u * c.cap * 3, *qn = c.qcur + (size_t)u * c.cap * 3;
+        for (int i = tid; i < n_init; i += FG_THREADS) {
+            const int2 pr = out[i];
+            double o[3];
+            norm_point(sp, pr.x, mean[0], scale, o);
+            pn[(size_t)i * 3] = o[0]; pn[(size_t)i * 3 + 1] = o[1]; pn[(size_t)i * 3 + 2] = o[2];
+            norm_point(tp, pr.y, mean[1], scale, o);
+            qn[(size_t)i * 3] = o[0]; qn[(size_t)i * 3 + 1] = o[1]; qn[(size_t)i * 3 + 2] = o[2];
+        }
+    }
     if (tid == 0) {
         FgrUnit &fu = c.unit[u];
         for (int k = 0; k < 3; ++k) { fu.mean_s[k] = mean[0][k]; fu.mean_t[k] = mean[1][k]; }
@@ -602,6 +648,7 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_prepare_kernel(FgrCtx c)
         fu.n_init = s_cnt;
         fu.n_pairs = 0; fu.trials = 0;
         fu.swapped = c.n_tgt > c.n_src ? 1 : 0;
+        fu.tt_done = 0; fu.tt_cnt = 0;
     }
 }
 
@@ -621,98 +668,139 @@ __device__ __forceinline__ void philox4x32_10(unsigned long long counter, unsign
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__device__ __forceinline__ void norm_point(const double *p, int i, const double *mean, double scale, double o[3])
-{
-    o[0] = (p[(size_t)i * 3] - mean[0]) / scale;
-    o[1] = (p[(size_t)i * 3 + 1] - mean[1]) / scale;
-    o[2] = (p[(size_t)i * 3 + 2] - mean[2]) / scale;
-}
-__device__ __forceinline__ double dist3(const double a[3], const double b[3])
+
+// AdvancedMatching's tuple test.  Open3D runs up to 100 x n_init trials one after the other and stops at
+// maximum_tuple_count accepted triples.  Trials are independent given the counter-based stream (trial t draws
+// philox4x32-10(t, key)), so the test is split in two:
+//   fgr_tuple_eval_kernel  evaluates an EPOCH of trials of every unit across the whole GPU (grid: 1024-trial blocks x
+//                          units; one accept bit per trial, a ballot word per warp);
+//   fgr_tuple_pick_kernel  (one block per unit) walks the epoch's accept bits in trial order, re-derives the
+//                          accepted triples and appends them until the quota is reached -- the sequential
+//                          semantics, including the count of trials the sequential loop would have run.
+// Units whose quota is full (or whose trials are exhausted) skip the remaining epochs.  (Round 1 ran one 1024-thread
+// block per unit over all its trials: 2.06 ms per 180-unit batch, two waves of 148 + 32 blocks, 18 float64 divisions
+// and 6 square roots per trial.)
+// The predicate `li * ts < lj && lj < li / ts` on lengths is decided on the SQUARED lengths whenever they are not
+// within 1e-9 (relative) of the boundary -- the roundings of the square roots, the product and the quotient move the
+// exact predicate by a few 1e-16 -- and evaluated literally otherwise: identical decisions, no sqrt or division on
+// the common path.
+constexpr int TT_BLOCK_TRIALS = 1024;
+
+__device__ __forceinline__ double sqlen3(const double *a, const double *b)
 {
     const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
-    return sqrt(x * x + y * y + z * z);
+    return x * x + y * y + z * z;       // dist3's sum before the square root
+}
+// one side of the tuple test: li * ts < lj && lj < li / ts, with Li = li^2, Lj = lj^2 (as dist3 would form them)
+__device__ __forceinline__ bool tuple_edge_ok(double Li, double Lj, double ts, double ts2_hi, double ts2_lo)
+{
+    // li ts < lj  <=>  Li ts^2 < Lj ;  lj < li / ts  <=>  Lj ts^2 < Li   (real arithmetic, all lengths >= 0)
+    const double a_hi = Li * ts2_hi, a_lo = Li * ts2_lo, b_hi = Lj * ts2_hi, b_lo = Lj * ts2_lo;
+    const bool regular = Li > 1e-200 && Lj > 1e-200;   // (zero lengths, denormals and NaNs take the literal test)
+    if (regular && a_hi < Lj && b_hi < Li) return true;        // clear of both boundaries
+    if (regular && (a_lo > Lj || b_lo > Li)) return false;     // clearly violates one
+    const double li = sqrt(Li), lj = sqrt(Lj);      // near a boundary (or not finite): the literal test
+    return (li * ts < lj) && (lj < li / ts);
 }
 
-// AdvancedMatching's tuple test: trials are independent given the counter-based stream, so a block
-// evaluates 256 at a time and keeps the accepted ones in trial order (= the sequential semantics).
-// (1024 threads: the kernel is bound by the latency of one batch of trials, not by throughput)
-constexpr int FG_WIDE = 1024;
-__global__ void __launch_bounds__(FG_WIDE) fgr_tuple_kernel(FgrCtx c)
+__global__ void __launch_bounds__(256) fgr_tuple_eval_kernel(FgrCtx c, long long epoch_base)
 {
-    __shared__ int shi[FG_WIDE / 32];
+    const int u = blockIdx.y, tid = threadIdx.x;
+    const FgrUnit &fu = c.unit[u];
+    if (fu.tt_done) return;
+    const int ncorr = fu.n_init;
+    const long long n_trials = (long long)ncorr * 100;
+    const long long block_base = epoch_base + (long long)blockIdx.x * TT_BLOCK_TRIALS;
+    if (block_base >= n_trials) return;
+    const double *pn = c.pcur + (size_t)u * c.cap * 3;      // normalised source / target point of init pair i
+    const double *qn = c.qcur + (size_t)u * c.cap * 3;
+    const double ts = c.tuple_scale;
+    const double ts2_hi = ts * ts * (1.0 + 1e-9), ts2_lo = ts * ts * (1.0 - 1e-9);
+    const bool swapped = fu.swapped != 0;
+    const unsigned long long key = c.keys[u];
+    unsigned *words = c.tt_flags + (size_t)u * (c.tt_epoch / 32);
+#pragma unroll 2
+    for (int e = 0; e < TT_BLOCK_TRIALS / 256; ++e) {
+        const long long t = block_base + e * 256 + tid;
+        bool flag = false;
+        if (t < n_trials) {
+            uint32_t r[4];
+            philox4x32_10((unsigned long long)t, key, r);
+            const int i0 = (int)(((unsigned long long)r[0] * (unsigned long long)ncorr) >> 32);
+            const int i1 = (int)(((unsigned long long)r[1] * (unsigned long long)ncorr) >> 32);
+            const int i2 = (int)(((unsigned long long)r[2] * (unsigned long long)ncorr) >> 32);
+            const double *a0 = pn + (size_t)i0 * 3, *a1 = pn + (size_t)i1 * 3, *a2 = pn + (size_t)i2 * 3;
+            const double *b0 = qn + (size_t)i0 * 3, *b1 = qn + (size_t)i1 * 3, *b2 = qn + (size_t)i2 * 3;
+            const double A0 = sqlen3(a0, a1), A1 = sqlen3(a1, a2), A2 = sqlen3(a2, a0);
+            const double B0 = sqlen3(b0, b1), B1 = sqlen3(b1, b2), B2 = sqlen3(b2, b0);
+            // fi = the larger cloud: li on the source unless the target is larger (swap)
+            flag = swapped ? (tuple_edge_ok(B0, A0, ts, ts2_hi, ts2_lo) && tuple_edge_ok(B1, A1, ts, ts2_hi, ts2_lo) &&
+                              tuple_edge_ok(B2, A2, ts, ts2_hi, ts2_lo))
+                           : (tuple_edge_ok(A0, B0, ts, ts2_hi, ts2_lo) && tuple_edge_ok(A1, B1, ts, ts2_hi, ts2_lo) &&
+                              tuple_edge_ok(A2, B2, ts, ts2_hi, ts2_lo));
+        }
+        const unsigned w = __ballot_sync(0xffffffffu, flag);
+        if ((tid & 31) == 0) words[(t - epoch_base) >> 5] = w;
+    }
+}
+
+__global__ void __launch_bounds__(FG_THREADS) fgr_tuple_pick_kernel(FgrCtx c, long long epoch_base)
+{
+    __shared__ int shi[FG_THREADS / 32];
     __shared__ int s_cnt;
     const int u = blockIdx.x, tid = threadIdx.x;
     FgrUnit &fu = c.unit[u];
+    if (fu.tt_done) return;
     const int ncorr = fu.n_init;
     const int2 *in = c.corres_init + (size_t)u * c.cap;
     int2 *out = c.corres + (size_t)u * c.cap;
     if (!c.tuple_test) {
-        for (int i = tid; i < ncorr; i += FG_WIDE) out[i] = in[i];
-        if (tid == 0) { fu.n_pairs = ncorr; fu.trials = 0; }
+        for (int i = tid; i < ncorr; i += FG_THREADS) out[i] = in[i];
+        __syncthreads();
+        if (tid == 0) { fu.n_pairs = ncorr; fu.trials = 0; fu.tt_done = 1; }
         return;
     }
-    const double *sp = c.src_pts + (size_t)c.unit_src[u] * c.n_src * 3;
-    const double *tp = c.tgt_pts + (size_t)c.unit_tgt[u] * c.n_tgt * 3;
-    const double ms[3] = {fu.mean_s[0], fu.mean_s[1], fu.mean_s[2]};
-    const double mt[3] = {fu.mean_t[0], fu.mean_t[1], fu.mean_t[2]};
-    const double scale = fu.scale, ts = c.tuple_scale;
-    const bool swapped = fu.swapped != 0;
-    const unsigned long long key = c.keys[u];
     const long long n_trials = (long long)ncorr * 100;
-    if (tid == 0) s_cnt = 0;
+    const long long epoch_end = epoch_base + c.tt_epoch < n_trials ? epoch_base + c.tt_epoch : n_trials;
+    const int n_words = epoch_end > epoch_base ? (int)((epoch_end - epoch_base + 31) >> 5) : 0;
+    const unsigned *words = c.tt_flags + (size_t)u * (c.tt_epoch / 32);
+    const unsigned long long key = c.keys[u];
+    if (tid == 0) s_cnt = fu.tt_cnt;
     __syncthreads();
-    long long done = 0;
-    for (long long base = 0; base < n_trials; base += FG_WIDE) {
-        const long long t = base + tid;
-        int flag = 0;
-        int2 pr[3];
-        if (t < n_trials) {
+    bool full = false;
+    for (int wb = 0; wb < n_words; wb += FG_THREADS) {
+        const int wi = wb + tid;
+        unsigned w = wi < n_words ? words[wi] : 0u;
+        int total;
+        const int off = block_scan_count(__popc(w), shi, total);
+        const int cnt0 = s_cnt;
+        int pos = cnt0 + off;                 // trial order: word-major, then the bits of a word
+        while (w && pos < c.max_tuple) {
+            const int bit = __ffs(w) - 1;
+            w &= w - 1;
+            const long long t = epoch_base + (long long)wi * 32 + bit;
             uint32_t r[4];
             philox4x32_10((unsigned long long)t, key, r);
-            double a[3][3], b[3][3];
+            int2 *o = out + (size_t)pos * 3;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int idx = (int)(((unsigned long long)r[k] * (unsigned long long)ncorr) >> 32);
-                pr[k] = in[idx];
-                norm_point(sp, pr[k].x, ms, scale, a[k]);
-                norm_point(tp, pr[k].y, mt, scale, b[k]);
-            }
-            // fi = the larger cloud: li on the source unless the target is larger (swap)
-            double li0, li1, li2, lj0, lj1, lj2;
-            if (!swapped) {
-                li0 = dist3(a[0], a[1]); li1 = dist3(a[1], a[2]); li2 = dist3(a[2], a[0]);
-                lj0 = dist3(b[0], b[1]); lj1 = dist3(b[1], b[2]); lj2 = dist3(b[2], b[0]);
-            } else {
-                li0 = dist3(b[0], b[1]); li1 = dist3(b[1], b[2]); li2 = dist3(b[2], b[0]);
-                lj0 = dist3(a[0], a[1]); lj1 = dist3(a[1], a[2]); lj2 = dist3(a[2], a[0]);
-            }
-            flag = (li0 * ts < lj0) && (lj0 < li0 / ts) && (li1 * ts < lj1) && (lj1 < li1 / ts) &&
-                   (li2 * ts < lj2) && (lj2 < li2 / ts);
+            for (int k = 0; k < 3; ++k)
+                o[k] = in[(int)(((unsigned long long)r[k] * (unsigned long long)ncorr) >> 32)];
+            // trials the sequential loop would have run: up to and including the one that fills the quota
+            if (pos == c.max_tuple - 1) fu.trials = (int)(t + 1);
+            ++pos;
         }
-        int total;
-        const int off = block_scan_flag(flag, shi, total);
-        const int cnt0 = s_cnt;
-        if (flag && cnt0 + off < c.max_tuple) {
-            int2 *o = out + (size_t)(cnt0 + off) * 3;
-            o[0] = pr[0]; o[1] = pr[1]; o[2] = pr[2];
-        }
-        // trials the sequential loop would have run: up to and including the one that fills the quota
         __syncthreads();
-        if (cnt0 + total >= c.max_tuple) {
-            // position of the accepting trial that reaches max_tuple
-            if (flag && cnt0 + off == c.max_tuple - 1) fu.trials = (int)(t + 1);
-            if (tid == 0) s_cnt = c.max_tuple;
-            __syncthreads();
-            done = -1;
-            break;
-        }
+        if (cnt0 + total >= c.max_tuple) { full = true; break; }
         if (tid == 0) s_cnt = cnt0 + total;
         __syncthreads();
-        done = base + FG_WIDE < n_trials ? base + FG_WIDE : n_trials;
     }
     if (tid == 0) {
-        fu.n_pairs = s_cnt * 3;
-        if (done >= 0) fu.trials = (int)done;
+        if (full) {
+            fu.tt_cnt = c.max_tuple; fu.n_pairs = c.max_tuple * 3; fu.tt_done = 1;
+        } else {
+            fu.tt_cnt = s_cnt;
+            if (epoch_end >= n_trials) { fu.n_pairs = s_cnt * 3; fu.trials = (int)n_trials; fu.tt_done = 1; }
+        }
     }
 }
 
@@ -756,19 +844,25 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_gnc_kernel(FgrCtx c)
                 const double rx = p[0] - qx, ry = p[1] - qy, rz = p[2] - qz;
                 const double temp = par / ((rx * rx + ry * ry + rz * rz) + par);
                 const double s = temp * temp;
-                const double J[3][6] = {{0.0, -qz, qy, -1.0, 0.0, 0.0}, {qz, 0.0, -qx, 0.0, -1.0, 0.0}, {-qy, qx, 0.0, 0.0, 0.0, -1.0}};
-                const double rr[3] = {rx, ry, rz};
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    int k = 0;
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) {
-#pragma unroll
-                        for (int b = a; b < 6; ++b) acc[k++] += J[r][a] * J[r][b] * s;
-                    }
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) acc[21 + a] += J[r][a] * rr[r] * s;
-                }
+                // rows of J: (0, -qz, qy, -1, 0, 0), (qz, 0, -qx, 0, -1, 0), (-qy, qx, 0, 0, 0, -1).  Every entry of
+                // J^T J / J^T r receives `J[r][a] * J[r][b] * s` of rows 0, 1, 2 in that order; a term with a zero
+                // factor is an exact (signed) zero and leaves the sum unchanged, so only the 18 + 9 non-zero terms
+                // are formed -- same values, same order, a third of the float64 instructions (with -fmad=false the
+                // compiler may not drop `0.0 * x` itself: the kernel spent 240 multiplies and adds per pair here).
+                const double nqz = -qz, nqx = -qx, nqy = -qy;
+                // upper-triangle index of (a, b): k(a, b) = a * 6 - a * (a - 1) / 2 + (b - a)
+                // row 0: non-zeros at 1 (-qz), 2 (qy), 3 (-1)
+                acc[6] += nqz * nqz * s;  acc[7] += nqz * qy * s;   acc[8] += nqz * -1.0 * s;
+                acc[11] += qy * qy * s;   acc[12] += qy * -1.0 * s; acc[15] += -1.0 * -1.0 * s;
+                acc[22] += nqz * rx * s;  acc[23] += qy * rx * s;   acc[24] += -1.0 * rx * s;
+                // row 1: non-zeros at 0 (qz), 2 (-qx), 4 (-1)
+                acc[0] += qz * qz * s;    acc[2] += qz * nqx * s;   acc[4] += qz * -1.0 * s;
+                acc[11] += nqx * nqx * s; acc[13] += nqx * -1.0 * s; acc[18] += -1.0 * -1.0 * s;
+                acc[21] += qz * ry * s;   acc[23] += nqx * ry * s;  acc[25] += -1.0 * ry * s;
+                // row 2: non-zeros at 0 (-qy), 1 (qx), 5 (-1)
+                acc[0] += nqy * nqy * s;  acc[1] += nqy * qx * s;   acc[5] += nqy * -1.0 * s;
+                acc[6] += qx * qx * s;    acc[10] += qx * -1.0 * s; acc[20] += -1.0 * -1.0 * s;
+                acc[21] += nqy * rz * s;  acc[22] += qx * rz * s;   acc[26] += -1.0 * rz * s;
             }
 #pragma unroll
             for (int k = 0; k < 27; ++k) acc[k] = warp_sum(acc[k]);
@@ -841,8 +935,8 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_gnc_kernel(FgrCtx c)
 }
 
 struct FgrLayout {
-    size_t off_unit, off_init, off_cor, off_q, off_p, total;
-    int cap;
+    size_t off_unit, off_init, off_cor, off_q, off_p, off_flags, total;
+    int cap, tt_epoch, tt_epochs;
 };
 
 bool fgr_layout(const orpcd_fgr_params *p, FgrLayout &L)
@@ -862,6 +956,14 @@ bool fgr_layout(const orpcd_fgr_params *p, FgrLayout &L)
     L.off_cor = take(U * L.cap * sizeof(int2));
     L.off_q = take(U * L.cap * 3 * sizeof(double));
     L.off_p = take(U * L.cap * 3 * sizeof(double));
+    // tuple-test epochs: at most 100 x n_feat_src trials per unit, an eighth of them per epoch (a unit usually
+    // fills its quota late: 139k of 167k possible trials on the 5000-point bench clouds), 64k .. 1M trials
+    const long long max_trials = 100LL * p->n_feat_src;
+    long long ep = 65536;
+    while (ep * 8 < max_trials && ep < (1LL << 20)) ep *= 2;
+    L.tt_epoch = (int)ep;
+    L.tt_epochs = p->tuple_test ? (int)((max_trials + ep - 1) / ep) : 1;
+    L.off_flags = take(U * (size_t)(ep / 32) * sizeof(unsigned));
     L.total = o;
     return true;
 }
@@ -1015,7 +1117,14 @@ ORPCD_API int orpcd_fgr_batch(const orpcd_fgr_params *p, const double *d_src_poi
     c.pcur = (double *)(w + L.off_p);
     c.out_T = d_out_T; c.out_info = d_out_info;
     fgr_prepare_kernel<<<p->n_units, FG_THREADS, 0, st>>>(c);
-    fgr_tuple_kernel<<<p->n_units, FG_WIDE, 0, st>>>(c);
+    c.tt_flags = (unsigned *)(w + L.off_flags);
+    c.tt_epoch = L.tt_epoch;
+    for (int e = 0; e < L.tt_epochs; ++e) {
+        const long long base = (long long)e * L.tt_epoch;
+        if (p->tuple_test)
+            fgr_tuple_eval_kernel<<<dim3(L.tt_epoch / TT_BLOCK_TRIALS, p->n_units), 256, 0, st>>>(c, base);
+        fgr_tuple_pick_kernel<<<p->n_units, FG_THREADS, 0, st>>>(c, base);
+    }
     fgr_gnc_kernel<<<p->n_units, FG_THREADS, 0, st>>>(c);
     ORPCD_CHECK_LAUNCH();
     return ORPCD_OK;
