@@ -418,11 +418,14 @@ feat_resolve_kernel(const double *__restrict__ feat_q, int nq, const unsigned ch
     qv[lane] = q[lane];
     if (lane == 0) qv[32] = q[32];
     __syncwarp();
-    double qn = 0.0;   // |q - center|^2: what the filter value is offset by
-#pragma unroll
-    for (int k = 0; k < FM_DIM; ++k) {
-        const double qc = center ? qv[k] - center[k] : qv[k];
-        qn += qc * qc;
+    // |q - center|^2: what the filter value is offset by.  One term per lane and a butterfly (it only enters bounds
+    // that carry slack for its rounding; every lane summing all 33 terms was a third of the kernel's instructions).
+    double qn;
+    {
+        const double c0 = center ? qv[lane] - center[lane] : qv[lane];
+        qn = c0 * c0;
+        if (lane == 0) { const double c1 = center ? qv[32] - center[32] : qv[32]; qn += c1 * c1; }
+        for (int s = 16; s > 0; s >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, s);
     }
     const size_t o = (size_t)pair * nq + row;
     // filter error bound (DESIGN.md "feature filter bound"): |v - (d^2 - |q|^2)| <= E,
@@ -430,32 +433,36 @@ feat_resolve_kernel(const double *__restrict__ feat_q, int nq, const unsigned ch
     //   |q|^2 (2^-52 relative) is folded into the last term
     const double dmax = sqrt((double)db_maxnorm[pair_db[pair]]);
     const double E = (ldexp(sqrt(qn) * dmax, -15) + ldexp(dmax * dmax, -23)) * 1.0001 + ldexp(qn + dmax * dmax, -40);
+    // (best, bj): the best exact (distance, index) so far, the same on every lane -- one arg-min butterfly per scored
+    // chunk, which also serves the next certificate test and the result
     double best = CUDART_INF;
     int bj = 0x7fffffff;
     bool certified = false;
     int scored = 0;
     if (!force_exact) {
+        // the recorded minima and chunk ids of this row: lane k holds entry k (one load each instead of one per step)
+        const float my_m = lane <= FM_TOP ? in_m[o + (size_t)lane * in_stride] : 0.f;
+        const int my_c = lane < FM_TOP ? in_c[o + (size_t)lane * in_stride] : 0;
 #pragma unroll 1
         for (int k = 0; k < FM_TOP; ++k) {
             // chunk k holds nothing better than in_m[k] - E; everything not recorded nothing better than in_m[k..]
-            const double lb = (double)in_m[o + (size_t)k * in_stride] - E + qn;
-            double wb = best;
-            for (int s = 16; s > 0; s >>= 1) wb = fmin(wb, __shfl_xor_sync(0xffffffffu, wb, s));
-            if (lb > wb) { certified = true; break; }
-            const int ck = in_c[o + (size_t)k * in_stride];
+            const double lb = (double)__shfl_sync(0xffffffffu, my_m, k) - E + qn;
+            if (lb > best) { certified = true; break; }
+            const int ck = __shfl_sync(0xffffffffu, my_c, k);
             const int j = ck * 32 + lane;
-            if (j < ndb) {
-                const double d = sqdist33_fm(qv, db + (size_t)ck * CH);
-                if (d < best || (d == best && j < bj)) { best = d; bj = j; }
+            double d = CUDART_INF;
+            int dj = 0x7fffffff;
+            if (j < ndb) { d = sqdist33_fm(qv, db + (size_t)ck * CH); dj = j; }
+            if (best < d || (best == d && bj < dj)) { d = best; dj = bj; }     // carry the running best along
+            for (int s = 16; s > 0; s >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, d, s);
+                const int oj = __shfl_xor_sync(0xffffffffu, dj, s);
+                if (od < d || (od == d && oj < dj)) { d = od; dj = oj; }
             }
+            best = d; bj = dj;
             ++scored;
         }
-        if (!certified) {
-            const double lb = (double)in_m[o + (size_t)FM_TOP * in_stride] - E + qn;
-            double wb = best;
-            for (int s = 16; s > 0; s >>= 1) wb = fmin(wb, __shfl_xor_sync(0xffffffffu, wb, s));
-            certified = lb > wb;
-        }
+        if (!certified) certified = (double)__shfl_sync(0xffffffffu, my_m, FM_TOP) - E + qn > best;
     }
     if (!certified) {
         best = CUDART_INF;
@@ -465,11 +472,11 @@ feat_resolve_kernel(const double *__restrict__ feat_q, int nq, const unsigned ch
             if (d < best) { best = d; bj = j; }
         }
         if (lane == 0 && stats) atomicAdd(stats, 1);
-    }
-    for (int s = 16; s > 0; s >>= 1) {
-        const double od = __shfl_xor_sync(0xffffffffu, best, s);
-        const int oj = __shfl_xor_sync(0xffffffffu, bj, s);
-        if (od < best || (od == best && oj < bj)) { best = od; bj = oj; }
+        for (int s = 16; s > 0; s >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, best, s);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, s);
+            if (od < best || (od == best && oj < bj)) { best = od; bj = oj; }
+        }
     }
     if (lane == 0) {
         out_nn[o] = bj == 0x7fffffff ? -1 : bj;
