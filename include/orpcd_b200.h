@@ -288,7 +288,10 @@ int orpcd_evaluate_batch(const orpcd_gicp_params *p, const double *d_src_points,
  * (Optimizer/fastGlobalOptimizer.py:130-143).  Neighbour lists come from
  * orpcd_knn_exact / orpcd_knn_rerank (self query, width list_k >= knn, sorted);
  * radius <= 0 selects the pure k-NN search.  d_spfh is the intermediate SPFH
- * table (same shape as d_fpfh, also an output).
+ * table, also an output: [batch][n][3][12] float64, each of the three 11-bin
+ * histograms followed by a zero (288-byte rows, 32-byte aligned histograms:
+ * the FPFH pass gathers them with 16-byte loads); 32-byte aligned base.
+ * d_fpfh [batch][n][33].
  * ---------------------------------------------------------------------- */
 int orpcd_fpfh(const double *d_points, const double *d_normals, int n, long long points_stride,
                int batch, const int *d_nn_idx, const double *d_nn_d2, int list_k, int knn,
@@ -301,7 +304,7 @@ int orpcd_fpfh(const double *d_points, const double *d_normals, int n, long long
  * the tcgen05 tensor-core filter; orpcd_feature_match then returns, for pair p and
  * every row of query set d_pair_q[p], the exact float64 nearest row of database set
  * d_pair_db[p] (nanoflann summation order, ties -> lowest index).
- * mode 0: tensor-core filter (the three smallest 32-row chunk minima + the fourth as a bound)
+ * mode 0: tensor-core filter (the eight smallest 32-row chunk minima + the ninth as a bound)
  * + certified float64 re-score; mode 1: float64 scan only.
  * Distances are translation invariant, so the filter runs on features centred on
  * d_center[33] (NULL = no centring; e.g. the mean feature of one set from
@@ -310,6 +313,9 @@ int orpcd_fpfh(const double *d_points, const double *d_normals, int n, long long
  * always taken on the original values.
  * d_packed_* : orpcd_feature_pack_bytes(n) bytes per set, 128-byte aligned
  * d_set_maxnorm: [n_sets] float, max |f|^2 of each set (written by the pack)
+ * d_row_mask (may be NULL) [n_pairs][n_query] bytes: rows with a zero are not resolved (d_nn = -1).  FGR's cross
+ * check only reads the reverse table at the images of the forward one (ji[ij[i]] == i), so the reverse match is
+ * asked for those rows only;
  * d_nn [n_pairs][n_query] int32; d_nn_d2 (may be NULL) float64;
  * d_stats (may be NULL) int[2]: rows that needed the exact scan, chunks re-scored;
  * d_debug_v (may be NULL) [n_pairs][n_query][ceil(n_db/128)*128] filter values.
@@ -323,8 +329,8 @@ int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q, int n_qu
                         const double *d_feat_db, const void *d_packed_db,
                         const float *d_db_maxnorm, int n_db, const double *d_center,
                         const int *d_pair_q, const int *d_pair_db, int n_pairs, int mode, void *d_workspace,
-                        size_t workspace_bytes, int *d_nn, double *d_nn_d2, int *d_stats,
-                        float *d_debug_v, orpcd_stream_t stream);
+                        size_t workspace_bytes, const unsigned char *d_row_mask, int *d_nn, double *d_nn_d2,
+                        int *d_stats, float *d_debug_v, orpcd_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Batched Fast Global Registration after feature matching: per unit

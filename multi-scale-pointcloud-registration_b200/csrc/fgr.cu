@@ -402,11 +402,19 @@ feat_resolve_kernel(const double *__restrict__ feat_q, int nq, const unsigned ch
                     int db_tiles, int ndb, const double *__restrict__ center, const int *__restrict__ pair_q, const int *__restrict__ pair_db,
                     const float *__restrict__ db_maxnorm, const float *__restrict__ in_m,
                     const int *__restrict__ in_c, size_t in_stride, int force_exact,
+                    const unsigned char *__restrict__ row_mask,
                     int *__restrict__ out_nn, double *__restrict__ out_d2, int *__restrict__ stats)
 {
     const int pair = blockIdx.y, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= nq) return;
+    if (row_mask && !row_mask[(size_t)pair * nq + row]) {     // the caller does not need this row (see the header)
+        if (lane == 0) {
+            out_nn[(size_t)pair * nq + row] = -1;
+            if (out_d2) out_d2[(size_t)pair * nq + row] = CUDART_INF;
+        }
+        return;
+    }
     const double *q = feat_q + ((size_t)pair_q[pair] * nq + row) * FM_DIM;
     // feature-major float64 chunk blocks of the database set; lane l scores row (chunk * 32 + l)
     const double *db = reinterpret_cast<const double *>(packed_db + (size_t)pair_db[pair] * db_tiles * FM_SET_BYTES_PER_TILE +
@@ -1016,7 +1024,8 @@ ORPCD_API int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q
                                   const double *d_feat_db, const void *d_packed_db, const float *d_db_maxnorm,
                                   int n_db, const double *d_center, const int *d_pair_q, const int *d_pair_db,
                                   int n_pairs, int mode,
-                                  void *d_workspace, size_t workspace_bytes, int *d_nn, double *d_nn_d2,
+                                  void *d_workspace, size_t workspace_bytes, const unsigned char *d_row_mask,
+                                  int *d_nn, double *d_nn_d2,
                                   int *d_stats, float *d_debug_v, orpcd_stream_t stream)
 {
     if (!d_feat_q || !d_packed_q || !d_feat_db || !d_packed_db || !d_db_maxnorm || !d_pair_q || !d_pair_db || !d_nn)
@@ -1045,7 +1054,7 @@ ORPCD_API int orpcd_feature_match(const double *d_feat_q, const void *d_packed_q
                                                                           (const unsigned char *)d_packed_db, db_tiles,
                                                                           n_db, d_center, d_pair_q,
                                                                           d_pair_db, d_db_maxnorm, fm, fc, stride,
-                                                                          mode == 1, d_nn, d_nn_d2, d_stats);
+                                                                          mode == 1, d_row_mask, d_nn, d_nn_d2, d_stats);
     ORPCD_CHECK_LAUNCH();
     return ORPCD_OK;
 }

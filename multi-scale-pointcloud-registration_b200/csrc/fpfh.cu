@@ -17,6 +17,12 @@ namespace {
 
 constexpr int FP_THREADS = 128;
 constexpr int FP_DIM = 33;
+// SPFH rows are stored padded: 3 histograms x 12 doubles (11 bins + a zero), 288 bytes = nine 32-byte sectors, so that
+// the FPFH pass -- one gather of a neighbour's histogram per (neighbour, histogram), bound by the L1's tag rate --
+// reads a histogram as six aligned 16-byte loads (three sectors) instead of eleven 8-byte loads of a row that
+// starts at any multiple of 8.
+constexpr int SP_HIST = 12;
+constexpr int SP_ROW = 3 * SP_HIST;     // 36 doubles
 
 __device__ __forceinline__ int hist_bin(double x)
 {
@@ -94,9 +100,13 @@ spfh_kernel(const double *__restrict__ points, const double *__restrict__ normal
             hist[22 + hist_bin(11 * (f2 + 1.0) * 0.5)][tid] += incr;
         }
     }
-    double *o = spfh + row * FP_DIM;
+    double *o = spfh + row * SP_ROW;
 #pragma unroll
-    for (int j = 0; j < FP_DIM; ++j) o[j] = hist[j][tid];
+    for (int h = 0; h < 3; ++h) {
+#pragma unroll
+        for (int j = 0; j < 11; ++j) o[h * SP_HIST + j] = hist[h * 11 + j][tid];
+        o[h * SP_HIST + 11] = 0.0;
+    }
 }
 
 // FPFH: own SPFH + the 1/d2-weighted, per-histogram renormalised SPFH of the neighbours.
@@ -110,7 +120,7 @@ fpfh_kernel(int n, const int *__restrict__ nn_idx, const double *__restrict__ nn
     const size_t row = (size_t)b * n + i;
     const int *idx = nn_idx + row * list_k;
     const double *d2 = nn_d2 + row * list_k;
-    const double *sp = spfh + (size_t)b * n * FP_DIM;
+    const double *sp = spfh + (size_t)b * n * SP_ROW;
     int cnt = 0;
     for (; cnt < knn; ++cnt) {
         if (idx[cnt] < 0) break;
@@ -118,7 +128,7 @@ fpfh_kernel(int n, const int *__restrict__ nn_idx, const double *__restrict__ nn
     }
     double *o = fpfh + row * FP_DIM;
     if (cnt > 1) {
-        const double *self = sp + (size_t)i * FP_DIM;
+        const double *self = sp + (size_t)i * SP_ROW;
         // one pass per histogram (the three are independent, each with its own normaliser): 11 running sums in
         // registers instead of 33 double the resident warps of a kernel that waits on the gathers of the rows
 #pragma unroll 1
@@ -130,26 +140,42 @@ fpfh_kernel(int n, const int *__restrict__ nn_idx, const double *__restrict__ nn
             for (int k = 1; k < cnt; ++k) {
                 const double dist = d2[k];
                 if (dist == 0.0) continue;
-                const double *s = sp + (size_t)idx[k] * FP_DIM + h * 11;
+                // the neighbour's histogram h: 96 bytes, 32-byte aligned
+                const double2 *s2 = reinterpret_cast<const double2 *>(sp + (size_t)idx[k] * SP_ROW + h * SP_HIST);
+                double s[12];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { const double2 t2 = __ldg(s2 + j); s[2 * j] = t2.x; s[2 * j + 1] = t2.y; }
                 // 11 correctly rounded quotients s[j] / dist from ONE division: with y = RN(1 / dist), q = s y,
                 // r = s - q dist (exact in an FMA), q' = q + r y is RN(s / dist) (Markstein) unless dist's
                 // significand is all ones -- that case takes the plain division.  Histogram values and distances
                 // are far from the overflow / subnormal ranges.
                 const double y = 1.0 / dist;
                 const bool plain = (__double2hiint(dist) & 0x000fffff) == 0x000fffff && (unsigned)__double2loint(dist) == 0xffffffffu;
+                // (the branch sits OUTSIDE the loop over the bins: written as a select per bin, the compiler evaluated
+                // `sj / dist` for every bin, and div.rn.f64 leaves its inline fast path for a ~70-instruction
+                // subroutine whenever the numerator is zero -- most histogram bins are: 63 % of the kernel's
+                // instructions)
+                if (!plain) {
 #pragma unroll
-                for (int j = 0; j < 11; ++j) {
-                    const double sj = s[j];
-                    const double q = __dmul_rn(sj, y);
-                    double val = fma(fma(-q, dist, sj), y, q);
-                    if (plain) val = sj / dist;
-                    sum += val;
-                    acc[j] += val;
+                    for (int j = 0; j < 11; ++j) {
+                        const double sj = s[j];
+                        const double q = __dmul_rn(sj, y);
+                        const double val = fma(fma(-q, dist, sj), y, q);
+                        sum += val;
+                        acc[j] += val;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 11; ++j) {
+                        const double val = s[j] / dist;
+                        sum += val;
+                        acc[j] += val;
+                    }
                 }
             }
             if (sum != 0.0) sum = 100.0 / sum;
 #pragma unroll
-            for (int j = 0; j < 11; ++j) o[h * 11 + j] = acc[j] * sum + self[h * 11 + j];
+            for (int j = 0; j < 11; ++j) o[h * 11 + j] = acc[j] * sum + self[h * SP_HIST + j];
         }
     } else {
 #pragma unroll

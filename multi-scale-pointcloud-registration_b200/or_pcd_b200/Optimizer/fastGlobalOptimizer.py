@@ -179,7 +179,11 @@ class FastGlobalOptimizer(IOptimizer):
             ft, _ = self._fpfh_sets(d_tgt)
             pf_t = ops.feature_pack(ft, center=pf_s.center)
             ij, _, st1, _ = ops.feature_match(pf_s, pf_t, us, ut, mode=self.match_mode)
-            ji, _, st2, _ = ops.feature_match(pf_t, pf_s, ut, us, mode=self.match_mode)
+            # the cross check reads the reverse table only at the images of the forward one (ji[ij[i]] == i):
+            # the other target rows are not resolved
+            needed = t.zeros((U, d_tgt.shape[1]), dtype=t.uint8, device="cuda")
+            needed.scatter_(1, ij.clamp(min=0).long(), 1)
+            ji, _, st2, _ = ops.feature_match(pf_t, pf_s, ut, us, mode=self.match_mode, row_mask=needed)
             scans = st1 + st2
 
         # tuple-test keys (tuple_key of every unit's two clouds), hashed on the device

@@ -143,7 +143,7 @@ def lib():
     L.orpcd_feature_match_workspace_bytes.restype = sz
     L.orpcd_feature_match_workspace_bytes.argtypes = [ip, ip]
     L.orpcd_feature_match.restype = ip
-    L.orpcd_feature_match.argtypes = [vp, vp, ip, vp, vp, vp, ip, vp, vp, vp, ip, ip, vp, sz, vp, vp, vp, vp, vp]
+    L.orpcd_feature_match.argtypes = [vp, vp, ip, vp, vp, vp, ip, vp, vp, vp, ip, ip, vp, sz, vp, vp, vp, vp, vp, vp]
     L.orpcd_fgr_batch_workspace_bytes.restype = sz
     L.orpcd_fgr_batch_workspace_bytes.argtypes = [C.POINTER(FgrParams)]
     L.orpcd_fgr_batch.restype = ip

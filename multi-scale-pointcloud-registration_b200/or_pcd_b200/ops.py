@@ -347,13 +347,13 @@ def fpfh(points, normals, nn_idx, nn_d2, knn: int, radius: float, want_spfh=Fals
     B, N, _ = points.shape
     assert nn_idx.dtype == t.int32 and nn_idx.is_contiguous() and nn_idx.shape[:2] == (B, N)
     list_k = nn_idx.shape[2]
-    spfh = t.empty((B, N, 33), dtype=t.float64, device="cuda")
+    spfh = t.empty((B, N, 3, 12), dtype=t.float64, device="cuda")     # padded rows: 3 histograms x (11 bins + a zero)
     out = t.empty((B, N, 33), dtype=t.float64, device="cuda")
     check(_lib.lib().orpcd_fpfh(points.data_ptr(), normals.data_ptr(), N, N * 3, B, nn_idx.data_ptr(),
                                 nn_d2.data_ptr(), list_k, int(knn), float(radius), spfh.data_ptr(), out.data_ptr(),
                                 _lib.stream_ptr()), "orpcd_fpfh")
     launch_counter["kernels"] += 2
-    return (out, spfh) if want_spfh else out
+    return (out, spfh[..., :11].reshape(B, N, 33)) if want_spfh else out
 
 
 class PackedFeatures:
@@ -391,8 +391,9 @@ def feature_pack(features, center=None) -> PackedFeatures:
 
 
 def feature_match(query: PackedFeatures, db: PackedFeatures, pair_q, pair_db, mode: int = 0, want_d2=False,
-                  want_debug=False):
-    """For pair p: nearest row of db set pair_db[p] for every row of query set pair_q[p].
+                  want_debug=False, row_mask=None):
+    """For pair p: nearest row of db set pair_db[p] for every row of query set pair_q[p]
+    (rows with row_mask[p, row] == 0 are skipped and get -1).
     Returns (nn int32 [P,Nq], d2 | None, device int32[2] = (rows that needed the exact scan, chunks re-scored),
     debug | None)."""
     t = _t()
@@ -401,6 +402,9 @@ def feature_match(query: PackedFeatures, db: PackedFeatures, pair_q, pair_db, mo
     L = _lib.lib()
     if query.center is not db.center:
         raise ValueError("both sides of a feature match must be packed with the same centring vector")
+    if row_mask is not None:
+        assert row_mask.dtype == t.uint8 and row_mask.is_cuda and row_mask.is_contiguous() and \
+            tuple(row_mask.shape) == (P, query.n)
     ws = _lib.workspace(L.orpcd_feature_match_workspace_bytes(query.n, P))
     nn = t.empty((P, query.n), dtype=t.int32, device="cuda")
     d2 = t.empty((P, query.n), dtype=t.float64, device="cuda") if want_d2 else None
@@ -411,7 +415,8 @@ def feature_match(query: PackedFeatures, db: PackedFeatures, pair_q, pair_db, mo
     check(L.orpcd_feature_match(query.features.data_ptr(), query.packed.data_ptr(), query.n, db.features.data_ptr(),
                                 db.packed.data_ptr(), db.maxnorm.data_ptr(), db.n,
                                 db.center.data_ptr() if db.center is not None else None, pair_q.data_ptr(),
-                                pair_db.data_ptr(), P, int(mode), ws.data_ptr(), ws.numel(), nn.data_ptr(),
+                                pair_db.data_ptr(), P, int(mode), ws.data_ptr(), ws.numel(),
+                                row_mask.data_ptr() if row_mask is not None else None, nn.data_ptr(),
                                 d2.data_ptr() if want_d2 else None, stats.data_ptr(),
                                 dbg.data_ptr() if want_debug else None, _lib.stream_ptr()), "orpcd_feature_match")
     launch_counter["kernels"] += 2 if mode == 0 else 1
