@@ -517,6 +517,7 @@ struct FgrCtx {
     int2 *corres_init, *corres;         // [U][cap]
     double *qcur, *pcur;                // [U][cap][3] each
     unsigned *tt_flags;                 // [U][tt_epoch / 32] accept bits of the tuple-test epoch in hand
+    double *tt_pairs;                   // [U][cap][8] (source xyz, target xyz, 0, 0) normalised, of the cross-checked pairs
     int tt_epoch;                       // trials of a unit evaluated per epoch (multiple of 1024)
     double *out_T;
     int *out_info;
@@ -646,14 +647,18 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_prepare_kernel(FgrCtx c)
     // them (norm_point in every trial was 18 float64 divisions per trial)
     {
         const int n_init = s_cnt;
-        double *pn = c.pcur + (size_t)u * c.cap * 3, *qn = c.qcur + (size_t)u * c.cap * 3;
+        // one 64-byte record per pair (two sectors, three 16-byte loads): the trials gather them at random and the
+        // tuple test is bound by the L1's request rate
+        double2 *rec = reinterpret_cast<double2 *>(c.tt_pairs + (size_t)u * c.cap * 8);
         for (int i = tid; i < n_init; i += FG_THREADS) {
             const int2 pr = out[i];
-            double o[3];
-            norm_point(sp, pr.x, mean[0], scale, o);
-            pn[(size_t)i * 3] = o[0]; pn[(size_t)i * 3 + 1] = o[1]; pn[(size_t)i * 3 + 2] = o[2];
-            norm_point(tp, pr.y, mean[1], scale, o);
-            qn[(size_t)i * 3] = o[0]; qn[(size_t)i * 3 + 1] = o[1]; qn[(size_t)i * 3 + 2] = o[2];
+            double a[3], b[3];
+            norm_point(sp, pr.x, mean[0], scale, a);
+            norm_point(tp, pr.y, mean[1], scale, b);
+            rec[(size_t)i * 4] = make_double2(a[0], a[1]);
+            rec[(size_t)i * 4 + 1] = make_double2(a[2], b[0]);
+            rec[(size_t)i * 4 + 2] = make_double2(b[1], b[2]);
+            rec[(size_t)i * 4 + 3] = make_double2(0.0, 0.0);
         }
     }
     if (tid == 0) {
@@ -727,8 +732,7 @@ __global__ void __launch_bounds__(256) fgr_tuple_eval_kernel(FgrCtx c, long long
     const long long n_trials = (long long)ncorr * 100;
     const long long block_base = epoch_base + (long long)blockIdx.x * TT_BLOCK_TRIALS;
     if (block_base >= n_trials) return;
-    const double *pn = c.pcur + (size_t)u * c.cap * 3;      // normalised source / target point of init pair i
-    const double *qn = c.qcur + (size_t)u * c.cap * 3;
+    const double2 *rec = reinterpret_cast<const double2 *>(c.tt_pairs + (size_t)u * c.cap * 8);   // normalised end points of init pair i
     const double ts = c.tuple_scale;
     const double ts2_hi = ts * ts * (1.0 + 1e-9), ts2_lo = ts * ts * (1.0 - 1e-9);
     const bool swapped = fu.swapped != 0;
@@ -744,8 +748,15 @@ __global__ void __launch_bounds__(256) fgr_tuple_eval_kernel(FgrCtx c, long long
             const int i0 = (int)(((unsigned long long)r[0] * (unsigned long long)ncorr) >> 32);
             const int i1 = (int)(((unsigned long long)r[1] * (unsigned long long)ncorr) >> 32);
             const int i2 = (int)(((unsigned long long)r[2] * (unsigned long long)ncorr) >> 32);
-            const double *a0 = pn + (size_t)i0 * 3, *a1 = pn + (size_t)i1 * 3, *a2 = pn + (size_t)i2 * 3;
-            const double *b0 = qn + (size_t)i0 * 3, *b1 = qn + (size_t)i1 * 3, *b2 = qn + (size_t)i2 * 3;
+            double a0[3], a1[3], a2[3], b0[3], b1[3], b2[3];
+            {
+                const double2 u0 = __ldg(rec + (size_t)i0 * 4), u1 = __ldg(rec + (size_t)i0 * 4 + 1), u2 = __ldg(rec + (size_t)i0 * 4 + 2);
+                const double2 v0 = __ldg(rec + (size_t)i1 * 4), v1 = __ldg(rec + (size_t)i1 * 4 + 1), v2 = __ldg(rec + (size_t)i1 * 4 + 2);
+                const double2 w0 = __ldg(rec + (size_t)i2 * 4), w1 = __ldg(rec + (size_t)i2 * 4 + 1), w2 = __ldg(rec + (size_t)i2 * 4 + 2);
+                a0[0] = u0.x; a0[1] = u0.y; a0[2] = u1.x; b0[0] = u1.y; b0[1] = u2.x; b0[2] = u2.y;
+                a1[0] = v0.x; a1[1] = v0.y; a1[2] = v1.x; b1[0] = v1.y; b1[1] = v2.x; b1[2] = v2.y;
+                a2[0] = w0.x; a2[1] = w0.y; a2[2] = w1.x; b2[0] = w1.y; b2[1] = w2.x; b2[2] = w2.y;
+            }
             const double A0 = sqlen3(a0, a1), A1 = sqlen3(a1, a2), A2 = sqlen3(a2, a0);
             const double B0 = sqlen3(b0, b1), B1 = sqlen3(b1, b2), B2 = sqlen3(b2, b0);
             // fi = the larger cloud: li on the source unless the target is larger (swap)
@@ -950,7 +961,7 @@ __global__ void __launch_bounds__(FG_THREADS) fgr_gnc_kernel(FgrCtx c)
 }
 
 struct FgrLayout {
-    size_t off_unit, off_init, off_cor, off_q, off_p, off_flags, total;
+    size_t off_unit, off_init, off_cor, off_q, off_p, off_flags, off_pairs, total;
     int cap, tt_epoch, tt_epochs;
 };
 
@@ -979,6 +990,7 @@ bool fgr_layout(const orpcd_fgr_params *p, FgrLayout &L)
     L.tt_epoch = (int)ep;
     L.tt_epochs = p->tuple_test ? (int)((max_trials + ep - 1) / ep) : 1;
     L.off_flags = take(U * (size_t)(ep / 32) * sizeof(unsigned));
+    L.off_pairs = take(U * L.cap * 8 * sizeof(double));
     L.total = o;
     return true;
 }
@@ -1132,9 +1144,10 @@ ORPCD_API int orpcd_fgr_batch(const orpcd_fgr_params *p, const double *d_src_poi
     c.qcur = (double *)(w + L.off_q);
     c.pcur = (double *)(w + L.off_p);
     c.out_T = d_out_T; c.out_info = d_out_info;
-    fgr_prepare_kernel<<<p->n_units, FG_THREADS, 0, st>>>(c);
     c.tt_flags = (unsigned *)(w + L.off_flags);
+    c.tt_pairs = (double *)(w + L.off_pairs);
     c.tt_epoch = L.tt_epoch;
+    fgr_prepare_kernel<<<p->n_units, FG_THREADS, 0, st>>>(c);
     for (int e = 0; e < L.tt_epochs; ++e) {
         const long long base = (long long)e * L.tt_epoch;
         if (p->tuple_test)
