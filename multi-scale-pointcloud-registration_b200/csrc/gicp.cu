@@ -571,15 +571,6 @@ __global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c, int round)
 // best) certificate over the visited chunks is still a certificate over all targets.
 // ----------------------------------------------------------------------------
 // warps per block (template parameter W): warps are independent workers, 2 by default
-#ifndef ORPCD_LIST_V2
-#define ORPCD_LIST_V2 1
-#endif
-#ifndef ORPCD_PH5_AHEAD
-#define ORPCD_PH5_AHEAD 0
-#endif
-#ifndef ORPCD_PH1_PREFETCH
-#define ORPCD_PH1_PREFETCH 0
-#endif
 constexpr int CULL_RING = 4;       // chunk buffers per warp (512 B each), filled by cp.async
 constexpr int CULL_LIST = 1024;    // visit-list capacity per pass (chunk ids)
 constexpr int RED_STRIDE_MMA = 128;   // doubles per patch partial of the tensor-core Jacobian sums (two 8x8 tiles)
@@ -696,7 +687,6 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                 const float bz = fmaxf(fmaxf(lo[2] - sp.z, sp.z - hi[2]), 0.f);
                 need = !(sqrtf(__fmaf_rn(bx, bx, __fmaf_rn(by, by, bz * bz))) - sp.w > reach_box);
             }
-#if ORPCD_LIST_V2
             const unsigned bal = __ballot_sync(0xffffffffu, need);
             if (bal) {
                 // The exact test of the box survivors.  Their spheres are staged in the (still idle) first ring slot
@@ -739,33 +729,6 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                 nv += __popc(keep);
             }
         }
-#else
-            unsigned bal = __ballot_sync(0xffffffffu, need);
-            while (bal) {
-                const int l = __ffs(bal) - 1;
-                bal &= bal - 1;
-                const float sx = __shfl_sync(0xffffffffu, sp.x, l), sy = __shfl_sync(0xffffffffu, sp.y, l);
-                const float sz = __shfl_sync(0xffffffffu, sp.z, l), sr = __shfl_sync(0xffffffffu, sp.w, l);
-                bool mine = false;
-#pragma unroll
-                for (int h = 0; h < Q / 2; ++h) {
-                    // both queries of the pair at once: |q - s|^2 <= (d_ub(q) + r)^2 (1 + 1e-6), packed FP32
-                    const uint64_t ax = add2_s(qx[h], -sx), ay = add2_s(qy[h], -sy), az = add2_s(qz[h], -sz);
-                    const uint64_t d2 = fma2(ax, ax, fma2(ay, ay, mul2(az, az)));
-                    const uint64_t tt = add2_s(dq2[h], sr);
-                    const uint64_t lim = mul2(mul2(tt, tt), pack_f2(1.f + 1e-6f, 1.f + 1e-6f));
-                    float d0, d1, l0, l1;
-                    unpack_f2(d2, d0, d1);
-                    unpack_f2(lim, l0, l1);
-                    mine |= (d0 <= l0) | (d1 <= l1);
-                }
-                if (__any_sync(0xffffffffu, mine)) {
-                    if (lane == 0) vl[nv] = (unsigned short)(base + l - pass);
-                    ++nv;
-                }
-            }
-        }
-#endif
         __syncwarp();
         visited += nv;
         // 2) stream the listed chunks through the warp's ring (one 16-byte cp.async per lane per chunk)
@@ -1681,86 +1644,6 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     // ---- 1. pending update, d_ub, centred FP32 copy
     float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
     {
-#if ORPCD_PH1_PREFETCH
-        // Every load of this phase whose address does not depend on another load is issued up front, for both queries
-        // of the lane (state, points, axes, previous matches), and the matched targets' points as soon as the matches
-        // are in: two L2 round trips per item instead of two per rolled pass behind the state's (the phase held 12 % of
-        // the kernel's stall samples at 6 % of its instructions, all long-scoreboard).
-        const bool has_update = __ldcg(&st.has_update) != 0;
-        const size_t oa = (size_t)u * c.n_src + wbase + lane;       // the lane's first query; the second is 32 further
-        const bool va = wbase + lane < c.n_src, vb = nk == 2 && wbase + 32 + lane < c.n_src;
-        double pa[3] = {0.0, 0.0, 0.0}, pb[3] = {0.0, 0.0, 0.0}, aa[3] = {0.0, 0.0, 0.0}, ab[3] = {0.0, 0.0, 0.0};
-        int ja = -1, jb = -1;
-        if (va) {
-            if (round >= 1) ja = __ldcg(c.corr + oa);
-#pragma unroll
-            for (int e = 0; e < 3; ++e) pa[e] = __ldcg(c.cur_pts + oa * 3 + e);
-            if (EST == 1) {
-#pragma unroll
-                for (int e = 0; e < 3; ++e) aa[e] = __ldcg(c.cur_cov + oa * 3 + e);
-            }
-        }
-        if (vb) {
-            if (round >= 1) jb = __ldcg(c.corr + oa + 32);
-#pragma unroll
-            for (int e = 0; e < 3; ++e) pb[e] = __ldcg(c.cur_pts + (oa + 32) * 3 + e);
-            if (EST == 1) {
-#pragma unroll
-                for (int e = 0; e < 3; ++e) ab[e] = __ldcg(c.cur_cov + (oa + 32) * 3 + e);
-            }
-        }
-        double U[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) U[k] = __ldcg(&st.U[k]);
-        double ta[3] = {0.0, 0.0, 0.0}, tb[3] = {0.0, 0.0, 0.0};
-        if (ja >= 0) {
-#pragma unroll
-            for (int e = 0; e < 3; ++e) ta[e] = tpts[(size_t)ja * 3 + e];
-        }
-        if (jb >= 0) {
-#pragma unroll
-            for (int e = 0; e < 3; ++e) tb[e] = tpts[(size_t)jb * 3 + e];
-        }
-#pragma unroll 1
-        for (int k = 0; k < nk; ++k) {
-            const int i = wbase + k * 32 + lane;
-            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < c.n_src) {
-                const size_t oi = (size_t)u * c.n_src + i;
-                double *p = c.cur_pts + oi * 3;
-                double x = pa[0], y = pa[1], z = pa[2];
-                if (has_update) {
-                    transform_point(U, x, y, z);
-                    p[0] = x; p[1] = y; p[2] = z;
-                    if (EST == 0) {
-                        double *cp = c.cur_cov + oi * 6;
-                        Sym3 C;
-                        C.xx = __ldcg(cp); C.xy = __ldcg(cp + 1); C.xz = __ldcg(cp + 2);
-                        C.yy = __ldcg(cp + 3); C.yz = __ldcg(cp + 4); C.zz = __ldcg(cp + 5);
-                        store_sym3(cp, rotate_sym3(U, C));
-                    } else if (EST == 1) {
-                        double *ap = c.cur_cov + oi * 3;
-                        const double ax = aa[0], ay = aa[1], az = aa[2];
-                        ap[0] = U[0] * ax + U[1] * ay + U[2] * az;
-                        ap[1] = U[4] * ax + U[5] * ay + U[6] * az;
-                        ap[2] = U[8] * ax + U[9] * ay + U[10] * az;
-                    }
-                }
-                float dub = c.dcap;
-                if (ja >= 0) {
-                    const double dx = x - ta[0], dy = y - ta[1], dz = z - ta[2];
-                    dub = fminf(dub, __double2float_ru(sqrt(dx * dx + dy * dy + dz * dz)) * (1.f + 1e-6f));
-                }
-                r = make_float4((float)(x - tm.cx), (float)(y - tm.cy), (float)(z - tm.cz), dub);
-            }
-            if (k == 0) qa = r;
-            else qb = r;
-            // the second pass works on the lane's second query
-            ja = jb;
-#pragma unroll
-            for (int e = 0; e < 3; ++e) { pa[e] = pb[e]; aa[e] = ab[e]; ta[e] = tb[e]; }
-        }
-#else
         const bool has_update = __ldcg(&st.has_update) != 0;
         double U[12];
 #pragma unroll
@@ -1804,7 +1687,6 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
             if (k == 0) qa = r;
             else qb = r;
         }
-#endif
         // lanes past the end of the cloud carry the patch's first query (always a real one)
         const float fx = __shfl_sync(0xffffffffu, qa.x, 0), fy = __shfl_sync(0xffffffffu, qa.y, 0);
         const float fz = __shfl_sync(0xffffffffu, qa.z, 0), fw = __shfl_sync(0xffffffffu, qa.w, 0);
@@ -1942,89 +1824,6 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
         const int sw_e = jv >> 1, sw_o = 2 + (jv >> 1);
         const int x_e = jv * 8 + ((((cc >> 1) ^ sw_e) << 1) | (cc & 1)), w_e = jv * 8 + (((3 ^ sw_e) << 1) | 1);
         const int x_o = jv * 8 + ((((cc >> 1) ^ sw_o) << 1) | (cc & 1)), w_o = jv * 8 + (((3 ^ sw_o) << 1) | 1);
-#if ORPCD_PH5_AHEAD
-        // The operands of a pass -- source point and axis (L2: written this round), target point and axis (L1 / L2
-        // gathers) -- are loaded ONE PASS AHEAD: those of the lane's second correspondence are in flight while the
-        // tensor-core steps of the first run (the rolled passes otherwise expose two dependent gather latencies each).
-        double nS[3] = {0.0, 0.0, 0.0}, nT[3] = {0.0, 0.0, 0.0}, nA[3] = {0.0, 0.0, 0.0}, nB[3] = {0.0, 0.0, 0.0};
-        auto load_operands = [&](int k, int j) {
-            const int i = wbase + k * 32 + lane;
-            if (i < c.n_src && j >= 0) {
-                const size_t oi = (size_t)u * c.n_src + i;
-                const double *ps = c.cur_pts + oi * 3, *as = c.cur_cov + oi * 3;
-                const double *pt = tpts + (size_t)j * 3, *bt = c.tgt_cov + ((size_t)tgt_set * c.n_tgt + j) * 3;
-#pragma unroll
-                for (int e = 0; e < 3; ++e) { nS[e] = __ldcg(ps + e); nA[e] = __ldcg(as + e); nT[e] = pt[e]; nB[e] = bt[e]; }
-            }
-        };
-        load_operands(0, tja);
-#pragma unroll 1
-        for (int k = 0; k < nk; ++k) {
-            const int i = wbase + k * 32 + lane;
-            bool have = false;
-            double sx = 0, sy = 0, sz = 0, dx = 0, dy = 0, dz = 0;
-            if (i < c.n_src) {
-                const size_t oi = (size_t)u * c.n_src + i;
-                int j = tja;
-                if (j >= 0) {
-                    sx = nS[0]; sy = nS[1]; sz = nS[2];
-                    const double tx = nT[0], ty = nT[1], tz = nT[2];
-                    const double d2 = fda >= 0.0 ? fda : sqdist3_rn(sx, sy, sz, tx, ty, tz);
-                    if (d2 < c.r2) {
-                        have = true;
-                        d2sum += d2;
-                        dx = sx - tx; dy = sy - ty; dz = sz - tz;
-                        const double ax = nA[0], ay = nA[1], az = nA[2];
-                        const double bx = nB[0], by = nB[1], bz = nB[2];
-                        const double dot = fma(ax, bx, fma(ay, by, az * bz));
-                        const double sg = dot >= 0 ? 1.0 : -1.0;
-                        const double ac = fmin(fabs(dot), 1.0);
-                        const double lp = fma(-c.kappa, 1.0 + ac, 2.0), lm = fma(-c.kappa, 1.0 - ac, 2.0);
-                        const double inv = (0.5 * c.kappa) / (lp * lm);
-                        {
-                            const double px = fma(sg, bx, ax), py = fma(sg, by, ay), pz = fma(sg, bz, az);
-                            store_record(rec, lane, fma(sy, pz, -(sz * py)), fma(sz, px, -(sx * pz)), fma(sx, py, -(sy * px)),
-                                         px, py, pz, fma(px, dx, fma(py, dy, pz * dz)), inv * lm);       // weight 2 g+
-                        }
-                        {
-                            const double mx = fma(-sg, bx, ax), my = fma(-sg, by, ay), mz = fma(-sg, bz, az);
-                            store_record(rec, 32 + lane, fma(sy, mz, -(sz * my)), fma(sz, mx, -(sx * mz)),
-                                         fma(sx, my, -(sy * mx)), mx, my, mz, fma(mx, dx, fma(my, dy, mz * dz)),
-                                         inv * lp);                                                      // weight 2 g-
-                        }
-                    } else {
-                        j = -1;
-                    }
-                }
-                c.corr[oi] = j;
-            }
-            if (!have) {
-                store_record(rec, lane, 0, 0, 0, 0, 0, 0, 0, 0);
-                store_record(rec, 32 + lane, 0, 0, 0, 0, 0, 0, 0, 0);
-            }
-            if (k + 1 < nk) load_operands(k + 1, tjb);
-            __syncwarp();
-#pragma unroll 2
-            for (int sstep = 0; sstep < 16; ++sstep) {
-                const double *r4 = rec + sstep * 32;
-                const double x = r4[(sstep & 1) ? x_o : x_e], w = r4[(sstep & 1) ? w_o : w_e];
-                dmma884(ef0, ef1, w * x, x);
-            }
-            __syncwarp();
-            // the (s, d) records of the same 32 pairs reuse the first half of the buffer
-            if (have) store_record(rec, lane, sx, sy, sz, 1.0, dx, dy, dz, 1.0);
-            else store_record(rec, lane, 0, 0, 0, 0, 0, 0, 0, 0);
-            __syncwarp();
-#pragma unroll 2
-            for (int sstep = 0; sstep < 8; ++sstep) {
-                const double *r4 = rec + sstep * 32;
-                const double x = r4[(sstep & 1) ? x_o : x_e], w = r4[(sstep & 1) ? w_o : w_e];
-                dmma884(sd0, sd1, w * x, x);
-            }
-            __syncwarp();
-            if (nk == 2) { ORPCD_SWAP(int, tja, tjb) ORPCD_SWAP(double, fda, fdb) }
-        }
-#else
 #pragma unroll 1
         for (int k = 0; k < nk; ++k) {
             const int i = wbase + k * 32 + lane;
@@ -2094,7 +1893,6 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
             __syncwarp();
             if (nk == 2) { ORPCD_SWAP(int, tja, tjb) ORPCD_SWAP(double, fda, fdb) }
         }
-#endif
         d2sum = warp_sum(d2sum);
         if (lane == 31) ef1 = d2sum;      // EF(7,7) is not a needed sum: its slot carries sum d2
         double *part = c.red_partial + ((size_t)u * c.red_blocks + wi) * RED_STRIDE_MMA;
