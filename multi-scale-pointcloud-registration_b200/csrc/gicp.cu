@@ -108,6 +108,7 @@ struct Ctx {
     int *tperm;          // [tgt_sets][nt_pad] spatially sorted position -> original target index (-1 = padding)
     float4 *chunk_sph;   // [tgt_sets][n_chunks] bounding sphere (centre, radius) of each 32-target chunk, centred coords
     float4 *super_sph;   // [tgt_sets][n_super] bounding sphere of each group of 32 chunks (1024 targets)
+    float4 *chunk_half;  // [tgt_sets][n_chunks] half extents (hx, hy, hz, 0) of each chunk's bounding box about the sphere's centre
     int n_super;
     unsigned long long *sortbuf;  // Morton keys being sorted
     double *bbox;        // [max(src_sets, tgt_sets)][6]
@@ -175,6 +176,32 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
     uint64_t d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
+}
+// min / max over the 32 lanes of a (converged) warp; the same value in every lane.  No NaN inputs on these paths.
+#ifndef ORPCD_CREDUX
+#define ORPCD_CREDUX 1
+#endif
+__device__ __forceinline__ float warp_min_f32(float v)
+{
+#if ORPCD_CREDUX
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+#else
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+#endif
+}
+__device__ __forceinline__ float warp_max_f32(float v)
+{
+#if ORPCD_CREDUX
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+#else
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+#endif
 }
 __device__ __forceinline__ float min3f(float a, float b, float c)
 {
@@ -346,7 +373,13 @@ __global__ void __launch_bounds__(1024) prep_targets_kernel(Ctx c)
         const float mx = 0.5f * (lo[0] + hi[0]), my = 0.5f * (lo[1] + hi[1]), mz = 0.5f * (lo[2] + hi[2]);
         float r = valid ? sqrtf((x - mx) * (x - mx) + (y - my) * (y - my) + (z - mz) * (z - mz)) : 0.f;
         for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
-        if (lane == 0) sph[ch] = make_float4(mx, my, mz, r * (1.f + 1e-5f) + 1e-30f);
+        if (lane == 0) {
+            sph[ch] = make_float4(mx, my, mz, r * (1.f + 1e-5f) + 1e-30f);
+            // the chunk's bounding box as half extents about the same centre, rounded up
+            c.chunk_half[(size_t)s * c.n_chunks + ch] =
+                make_float4(fmaxf(hi[0] - mx, mx - lo[0]) * (1.f + 1e-6f) + 1e-30f, fmaxf(hi[1] - my, my - lo[1]) * (1.f + 1e-6f) + 1e-30f,
+                            fmaxf(hi[2] - mz, mz - lo[2]) * (1.f + 1e-6f) + 1e-30f, 0.f);
+        }
     }
     __syncthreads();
     // second level: one sphere around each group of 32 chunk spheres
@@ -571,6 +604,9 @@ __global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c, int round)
 // best) certificate over the visited chunks is still a certificate over all targets.
 // ----------------------------------------------------------------------------
 // warps per block (template parameter W): warps are independent workers, 2 by default
+#ifndef ORPCD_CULL_AABB
+#define ORPCD_CULL_AABB 1      // chunk bounding boxes (0: bounding spheres) in the visit-list tests of the culled sweep
+#endif
 constexpr int CULL_RING = 4;       // chunk buffers per warp (512 B each), filled by cp.async
 constexpr int CULL_LIST = 1024;    // visit-list capacity per pass (chunk ids)
 constexpr int RED_STRIDE_MMA = 128;   // doubles per patch partial of the tensor-core Jacobian sums (two 8x8 tiles)
@@ -627,20 +663,18 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
             qy[h] = pack_f2(qv[2 * h].y, qv[2 * h + 1].y);
             qz[h] = pack_f2(qv[2 * h].z, qv[2 * h + 1].z);
         }
+        // warp-wide min / max in ONE instruction each (redux.sync.f32, sm_100a: SASS CREDUX) instead of five
+        // shuffle + min steps: the patch's bounding box, largest reach and radius are eight reductions per item
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            for (int o = 16; o > 0; o >>= 1) {
-                lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
-                hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
-            }
-        for (int o = 16; o > 0; o >>= 1) D = fmaxf(D, __shfl_xor_sync(0xffffffffu, D, o));
+        for (int k = 0; k < 3; ++k) { lo[k] = warp_min_f32(lo[k]); hi[k] = warp_max_f32(hi[k]); }
+        D = warp_max_f32(D);
         pcx = 0.5f * (lo[0] + hi[0]); pcy = 0.5f * (lo[1] + hi[1]); pcz = 0.5f * (lo[2] + hi[2]);
 #pragma unroll
         for (int k = 0; k < Q; ++k) {
             const float dx = qv[k].x - pcx, dy = qv[k].y - pcy, dz = qv[k].z - pcz;
             rw = fmaxf(rw, sqrtf(dx * dx + dy * dy + dz * dz));
         }
-        for (int o = 16; o > 0; o >>= 1) rw = fmaxf(rw, __shfl_xor_sync(0xffffffffu, rw, o));
+        rw = warp_max_f32(rw);
     }
     // FP32 slack: every quantity below carries a few ulps of the coordinate magnitude
     const float mag = fabsf(pcx) + fabsf(pcy) + fabsf(pcz) + rw + rmax_tgt;
@@ -650,6 +684,12 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
     uint64_t dq2[Q / 2];
 #pragma unroll
     for (int h = 0; h < Q / 2; ++h) dq2[h] = pack_f2(dq[2 * h], dq[2 * h + 1]);
+#if ORPCD_CULL_AABB
+    const float4 *__restrict__ half = c.chunk_half + (sph - c.chunk_sph);   // same (target set, chunk) indexing as `sph`
+    uint64_t dlim2[Q / 2];     // squared reach of each query, with the slack of the squared comparison
+#pragma unroll
+    for (int h = 0; h < Q / 2; ++h) dlim2[h] = mul2(mul2(dq2[h], dq2[h]), pack_f2(1.f + 1e-6f, 1.f + 1e-6f));
+#endif
 
 #pragma unroll
     for (int k = 0; k < Q; ++k) { m1[k] = CUDART_INF_F; m2[k] = CUDART_INF_F; c1[k] = 0; }
@@ -680,6 +720,18 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
             const int chunk = base + lane;
             bool need = false;
             float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+#if ORPCD_CULL_AABB
+            float4 hf = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (chunk < pe) {
+                sp = __ldg(sph + chunk);
+                hf = __ldg(half + chunk);
+                // distance between the chunk's bounding box and the patch's
+                const float bx = fmaxf(fmaxf(lo[0] - (sp.x + hf.x), (sp.x - hf.x) - hi[0]), 0.f);
+                const float by = fmaxf(fmaxf(lo[1] - (sp.y + hf.y), (sp.y - hf.y) - hi[1]), 0.f);
+                const float bz = fmaxf(fmaxf(lo[2] - (sp.z + hf.z), (sp.z - hf.z) - hi[2]), 0.f);
+                need = !(sqrtf(__fmaf_rn(bx, bx, __fmaf_rn(by, by, bz * bz))) > reach_box);
+            }
+#else
             if (chunk < pe) {
                 sp = __ldg(sph + chunk);
                 // distance from the chunk centre to the patch's bounding box (tighter than its bounding sphere)
@@ -687,6 +739,7 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                 const float bz = fmaxf(fmaxf(lo[2] - sp.z, sp.z - hi[2]), 0.f);
                 need = !(sqrtf(__fmaf_rn(bx, bx, __fmaf_rn(by, by, bz * bz))) - sp.w > reach_box);
             }
+#endif
             const unsigned bal = __ballot_sync(0xffffffffu, need);
             if (bal) {
                 // The exact test of the box survivors.  Their spheres are staged in the (still idle) first ring slot
@@ -694,6 +747,52 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                 // two candidates per step (independent chains) and keeps a private bit mask; ONE warp-wide OR per
                 // group of 32 chunks then replaces the vote + branch + lane-0 store per candidate of the first
                 // version (which was 13 % of the persistent kernel's stall samples).  List order: ascending chunk id.
+#if ORPCD_CULL_AABB
+                // exact test against the chunk's BOUNDING BOX: some query q of the patch has dist(q, box) <= d_ub(q).
+                // (Hilbert-consecutive targets of a surface scan form flat pieces: their boxes hold a third less empty
+                // space than their spheres, 17.7 -> 12.2 listed chunks per patch on the bench clouds.)
+                ring[0][lane] = sp;
+                ring[1][lane] = hf;
+                __syncwarp();
+                unsigned mymask = 0u, b = bal;
+                while (b) {
+                    const int l0 = __ffs(b) - 1;
+                    b &= b - 1;
+                    const int l1 = b ? __ffs(b) - 1 : l0;   // (a repeat of the first candidate when it was the last)
+                    b &= b - 1;
+                    const float4 s0 = ring[0][l0], s1 = ring[0][l1], h0 = ring[1][l0], h1 = ring[1][l1];
+                    bool mine0 = false, mine1 = false;
+#pragma unroll
+                    for (int h = 0; h < Q / 2; ++h) {
+                        // both queries of the pair: sum_k max(|q_k - m_k| - h_k, 0)^2 <= d_ub(q)^2 (1 + 1e-6)
+                        float ex[2][2], ey[2][2], ez[2][2];
+                        unpack_f2(add2_s(qx[h], -s0.x), ex[0][0], ex[0][1]);
+                        unpack_f2(add2_s(qy[h], -s0.y), ey[0][0], ey[0][1]);
+                        unpack_f2(add2_s(qz[h], -s0.z), ez[0][0], ez[0][1]);
+                        unpack_f2(add2_s(qx[h], -s1.x), ex[1][0], ex[1][1]);
+                        unpack_f2(add2_s(qy[h], -s1.y), ey[1][0], ey[1][1]);
+                        unpack_f2(add2_s(qz[h], -s1.z), ez[1][0], ez[1][1]);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            ex[0][e] = fmaxf(fabsf(ex[0][e]) - h0.x, 0.f); ey[0][e] = fmaxf(fabsf(ey[0][e]) - h0.y, 0.f);
+                            ez[0][e] = fmaxf(fabsf(ez[0][e]) - h0.z, 0.f);
+                            ex[1][e] = fmaxf(fabsf(ex[1][e]) - h1.x, 0.f); ey[1][e] = fmaxf(fabsf(ey[1][e]) - h1.y, 0.f);
+                            ez[1][e] = fmaxf(fabsf(ez[1][e]) - h1.z, 0.f);
+                        }
+                        const uint64_t X0 = pack_f2(ex[0][0], ex[0][1]), Y0 = pack_f2(ey[0][0], ey[0][1]), Z0 = pack_f2(ez[0][0], ez[0][1]);
+                        const uint64_t X1 = pack_f2(ex[1][0], ex[1][1]), Y1 = pack_f2(ey[1][0], ey[1][1]), Z1 = pack_f2(ez[1][0], ez[1][1]);
+                        const uint64_t d20 = fma2(X0, X0, fma2(Y0, Y0, mul2(Z0, Z0)));
+                        const uint64_t d21 = fma2(X1, X1, fma2(Y1, Y1, mul2(Z1, Z1)));
+                        float da, db, la, lb;
+                        unpack_f2(dlim2[h], la, lb);
+                        unpack_f2(d20, da, db);
+                        mine0 |= (da <= la) | (db <= lb);
+                        unpack_f2(d21, da, db);
+                        mine1 |= (da <= la) | (db <= lb);
+                    }
+                    mymask |= (mine0 ? 1u << l0 : 0u) | (mine1 ? 1u << l1 : 0u);
+                }
+#else
                 ring[0][lane] = sp;
                 __syncwarp();
                 unsigned mymask = 0u, b = bal;
@@ -724,9 +823,13 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                     }
                     mymask |= (mine0 ? 1u << l0 : 0u) | (mine1 ? 1u << l1 : 0u);
                 }
+#endif
                 const unsigned keep = __reduce_or_sync(0xffffffffu, mymask);
                 if ((keep >> lane) & 1u) vl[nv + __popc(keep & ((1u << lane) - 1u))] = (unsigned short)(base + lane - pass);
                 nv += __popc(keep);
+#ifdef ORPCD_QUEUE_STATS
+                if (lane == 0) { atomicAdd(c.q_stats + 632, (unsigned long long)__popc(bal)); atomicAdd(c.q_stats + 633, (unsigned long long)__popc(keep)); }
+#endif
             }
         }
         __syncwarp();
@@ -747,6 +850,10 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
             float mc[Q];
 #pragma unroll
             for (int q = 0; q < Q; ++q) mc[q] = CUDART_INF_F;
+#ifdef ORPCD_QUEUE_STATS
+            float mall[Q];
+            for (int q = 0; q < Q; ++q) mall[q] = CUDART_INF_F;
+#endif
 #pragma unroll
             for (int j = 0; j < (HALF ? NN_CH / 2 : NN_CH); j += TJ) {
                 float4 t[TJ];
@@ -774,6 +881,9 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                     const int id = HALF ? chunk * 4 + par * 2 + (j >> 3) : chunk * 4 + (j >> 3);
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
+#ifdef ORPCD_QUEUE_STATS
+                        mall[q] = fminf(mall[q], mc[q]);
+#endif
                         m2[q] = fminf(m2[q], fmaxf(m1[q], mc[q]));
                         c1[q] = mc[q] < m1[q] ? id : c1[q];
                         m1[q] = fminf(m1[q], mc[q]);
@@ -781,6 +891,16 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
                     }
                 }
             }
+#ifdef ORPCD_QUEUE_STATS
+            {
+                bool useful = false;
+                for (int q = 0; q < Q; ++q) {
+                    const float qn = qv[q].x * qv[q].x + qv[q].y * qv[q].y + qv[q].z * qv[q].z;
+                    useful |= mall[q] + qn <= qv[q].w * qv[q].w * 1.001f;
+                }
+                if (__any_sync(0xffffffffu, useful) && lane == 0) atomicAdd(c.q_stats + 634, 1ull);
+            }
+#endif
             if (!SUB) {
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
@@ -2207,7 +2327,7 @@ __global__ void __launch_bounds__(256) unpermute_corr_kernel(Ctx c, int *__restr
 struct Layout {
     size_t off_state, off_pts, off_cov, off_qf, off_corr, off_d2, off_m1, off_c1, off_m2, off_tgt4, off_meta,
         off_partial, off_counter, off_worklist, off_wcount, off_ract, off_done, off_visit, off_sperm, off_tperm,
-        off_sph, off_ssph, off_sort, off_bbox, off_qslots, off_qctrl, off_qstats, total;
+        off_sph, off_half, off_ssph, off_sort, off_bbox, off_qslots, off_qctrl, off_qstats, total;
     int nt_pad, n_chunks, splits, chunks_per_split, red_blocks, q_tiles, nn_q, nn_tj, cov_stride, smem_pad, nn_mode;
     int cull;
     int fused;       // one gicp_round_kernel launch per round instead of update / sweep / resolve / fix / reduce
@@ -2297,6 +2417,7 @@ bool make_layout(const orpcd_gicp_params *p, Layout &L)
     L.off_sperm = take((size_t)p->n_src_sets * ns * sizeof(int));
     L.off_tperm = take((size_t)p->n_tgt_sets * L.nt_pad * sizeof(int));
     L.off_sph = take((size_t)p->n_tgt_sets * L.n_chunks * sizeof(float4));
+    L.off_half = take((size_t)p->n_tgt_sets * L.n_chunks * sizeof(float4));
     L.off_ssph = take((size_t)p->n_tgt_sets * ((L.n_chunks + 31) / 32) * sizeof(float4));
     const size_t sort_s = (size_t)p->n_src_sets * sort_pad(p->n_src), sort_t = (size_t)p->n_tgt_sets * sort_pad(p->n_tgt);
     L.off_sort = take((sort_s > sort_t ? sort_s : sort_t) * sizeof(unsigned long long));
@@ -2339,6 +2460,7 @@ void fill_ctx(const orpcd_gicp_params *p, const Layout &L, void *ws, Ctx &c)
     c.sperm = (int *)(w + L.off_sperm);
     c.tperm = (int *)(w + L.off_tperm);
     c.chunk_sph = (float4 *)(w + L.off_sph);
+    c.chunk_half = (float4 *)(w + L.off_half);
     c.super_sph = (float4 *)(w + L.off_ssph);
     c.n_super = (L.n_chunks + 31) / 32;
     c.sortbuf = (unsigned long long *)(w + L.off_sort);
@@ -2639,6 +2761,7 @@ int run_registration(const orpcd_gicp_params *p, int est_mode, const double *d_s
         {
             unsigned long long hq[640];
             cudaMemcpy(hq, c.q_stats, sizeof(hq), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "visit lists: %llu box survivors, %llu listed, %llu chunks with a target within some query's reach\n", hq[632], hq[633], hq[634]);
             for (int b = 0; b < 64; ++b)
                 if (hq[128 + b] || hq[64 + b])
                     fprintf(stderr, "t %5.2f ms  items %7llu  idle %5.1f %%  item mean %6.1f us max %6.1f us  closings %5llu mean %5.1f us\n",
