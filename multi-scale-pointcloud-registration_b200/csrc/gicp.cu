@@ -31,6 +31,8 @@
 //   reduce_kernel     residual / Jacobian sums per correspondence, block partials, the
 //                     last block of a unit sums them in index order, tests convergence,
 //                     solves the 6x6 system and composes the transform.
+#include <vector>
+#include <algorithm>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -604,6 +606,12 @@ __global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c, int round)
 // best) certificate over the visited chunks is still a certificate over all targets.
 // ----------------------------------------------------------------------------
 // warps per block (template parameter W): warps are independent workers, 2 by default
+#ifndef ORPCD_PH1_HOIST
+#define ORPCD_PH1_HOIST 1
+#endif
+#ifndef ORPCD_PH5_HOIST
+#define ORPCD_PH5_HOIST 1
+#endif
 #ifndef ORPCD_CULL_AABB
 #define ORPCD_CULL_AABB 1      // chunk bounding boxes (0: bounding spheres) in the visit-list tests of the culled sweep
 #endif
@@ -633,15 +641,100 @@ static_assert(sizeof(WarpSmem) == 4096, "WarpSmem holds 64 records of 8 doubles"
 // split the 32 targets of a chunk by parity -- lane l takes targets 2 i + (l >> 4) -- so a warp spends half the FMA
 // work per chunk on half the queries; each half folds the 8-target sub-chunks it sees, id = chunk * 4 + parity * 2 +
 // (first | second 16 targets), and the caller merges the two halves' (m1, c1, m2).
-template <int Q, bool SUB, bool HALF = false>
+// (`half` is a run-time argument: the set-up and the visit list are the same code for both patch sizes and exist once
+// in the kernel -- the persistent kernel is bound by instruction fetch, see DESIGN 4.1 -- and only the per-chunk
+// arithmetic, sweep_chunk<>, is instantiated per layout.)
+template <int Q, bool SUB, bool HALF>
+__device__ __forceinline__ void sweep_chunk(const float4 *__restrict__ tc, int chunk, int par, const uint64_t (&qx)[Q / 2],
+                                            const uint64_t (&qy)[Q / 2], const uint64_t (&qz)[Q / 2], float (&m1)[Q],
+                                            int (&c1)[Q], float (&m2)[Q])
+{
+    constexpr int TJ = 4;
+    static_assert(!HALF || (Q == 2 && SUB), "the half-warp split is written for one query pair per lane and sub-chunk folds");
+    float mc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) mc[q] = CUDART_INF_F;
+    if constexpr (SUB) {
+        // one 8-target sub-chunk per trip of a ROLLED loop (4 trips, 2 for the half-warp split): the unrolled form was
+        // 150 instructions per instantiation of straight-line code in the hottest loop of an instruction-fetch-bound kernel
+        constexpr int STRIDE = HALF ? 2 : 1;
+        const float4 *ts = tc + par;
+        int id = chunk * 4 + par * 2;
+#pragma unroll 1
+        for (int sc = 0; sc < (HALF ? 2 : 4); ++sc, ts += 8 * STRIDE, ++id) {
+#pragma unroll
+            for (int j = 0; j < 8; j += TJ) {
+                float4 t[TJ];
+#pragma unroll
+                for (int r = 0; r < TJ; ++r) t[r] = ts[(j + r) * STRIDE];
+#pragma unroll
+                for (int h = 0; h < Q / 2; ++h) {
+                    uint64_t a[TJ];
+#pragma unroll
+                    for (int r = 0; r < TJ; ++r) a[r] = fma2_ss(qz[h], t[r].z, t[r].w);
+#pragma unroll
+                    for (int r = 0; r < TJ; ++r) a[r] = fma2_sv(qy[h], t[r].y, a[r]);
+#pragma unroll
+                    for (int r = 0; r < TJ; ++r) a[r] = fma2_sv(qx[h], t[r].x, a[r]);
+#pragma unroll
+                    for (int r = 0; r < TJ; r += 2) {
+                        float l0, h0, l1, h1;
+                        unpack_f2(a[r], l0, h0);
+                        unpack_f2(a[r + 1], l1, h1);
+                        mc[2 * h] = min3f(mc[2 * h], l0, l1);
+                        mc[2 * h + 1] = min3f(mc[2 * h + 1], h0, h1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                m2[q] = fminf(m2[q], fmaxf(m1[q], mc[q]));
+                c1[q] = mc[q] < m1[q] ? id : c1[q];
+                m1[q] = fminf(m1[q], mc[q]);
+                mc[q] = CUDART_INF_F;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NN_CH; j += TJ) {
+            float4 t[TJ];
+#pragma unroll
+            for (int r = 0; r < TJ; ++r) t[r] = tc[j + r];
+#pragma unroll
+            for (int h = 0; h < Q / 2; ++h) {
+                uint64_t a[TJ];
+#pragma unroll
+                for (int r = 0; r < TJ; ++r) a[r] = fma2_ss(qz[h], t[r].z, t[r].w);
+#pragma unroll
+                for (int r = 0; r < TJ; ++r) a[r] = fma2_sv(qy[h], t[r].y, a[r]);
+#pragma unroll
+                for (int r = 0; r < TJ; ++r) a[r] = fma2_sv(qx[h], t[r].x, a[r]);
+#pragma unroll
+                for (int r = 0; r < TJ; r += 2) {
+                    float l0, h0, l1, h1;
+                    unpack_f2(a[r], l0, h0);
+                    unpack_f2(a[r + 1], l1, h1);
+                    mc[2 * h] = min3f(mc[2 * h], l0, l1);
+                    mc[2 * h + 1] = min3f(mc[2 * h + 1], h0, h1);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            m2[q] = fminf(m2[q], fmaxf(m1[q], mc[q]));
+            c1[q] = mc[q] < m1[q] ? chunk : c1[q];
+            m1[q] = fminf(m1[q], mc[q]);
+        }
+    }
+}
+
+template <int Q, bool SUB>
 __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__restrict__ tg, const float4 *__restrict__ sph,
                                                const float4 *__restrict__ ssph, int n_super, float rmax_tgt, int cb,
                                                int ce, const float4 (&qv)[Q],
                                                float4 (*ring)[NN_CH], unsigned short *vl, float (&m1)[Q], int (&c1)[Q],
-                                               float (&m2)[Q])
+                                               float (&m2)[Q], bool HALF = false)
 {
-    constexpr int TJ = 4;
-    static_assert(!HALF || (Q == 2 && SUB), "the half-warp split is written for one query pair per lane and sub-chunk folds");
     const int lane = threadIdx.x & 31;
     const int par = HALF ? (lane >> 4) : 0;      // which targets of a chunk this half-warp takes
     uint64_t qx[Q / 2], qy[Q / 2], qz[Q / 2];
@@ -847,67 +940,11 @@ __device__ __forceinline__ int cull_sweep_core(const Ctx &c, const float4 *__res
             __syncwarp();
             const float4 *tc = ring[k % CULL_RING];
             const int chunk = pass + vl[k];
-            float mc[Q];
-#pragma unroll
-            for (int q = 0; q < Q; ++q) mc[q] = CUDART_INF_F;
-#ifdef ORPCD_QUEUE_STATS
-            float mall[Q];
-            for (int q = 0; q < Q; ++q) mall[q] = CUDART_INF_F;
-#endif
-#pragma unroll
-            for (int j = 0; j < (HALF ? NN_CH / 2 : NN_CH); j += TJ) {
-                float4 t[TJ];
-#pragma unroll
-                for (int r = 0; r < TJ; ++r) t[r] = HALF ? tc[(j + r) * 2 + par] : tc[j + r];
-#pragma unroll
-                for (int h = 0; h < Q / 2; ++h) {
-                    uint64_t a[TJ];
-#pragma unroll
-                    for (int r = 0; r < TJ; ++r) a[r] = fma2_ss(qz[h], t[r].z, t[r].w);
-#pragma unroll
-                    for (int r = 0; r < TJ; ++r) a[r] = fma2_sv(qy[h], t[r].y, a[r]);
-#pragma unroll
-                    for (int r = 0; r < TJ; ++r) a[r] = fma2_sv(qx[h], t[r].x, a[r]);
-#pragma unroll
-                    for (int r = 0; r < TJ; r += 2) {
-                        float l0, h0, l1, h1;
-                        unpack_f2(a[r], l0, h0);
-                        unpack_f2(a[r + 1], l1, h1);
-                        mc[2 * h] = min3f(mc[2 * h], l0, l1);
-                        mc[2 * h + 1] = min3f(mc[2 * h + 1], h0, h1);
-                    }
-                }
-                if (SUB && ((j + TJ) & 7) == 0) {   // end of an 8-target sub-chunk
-                    const int id = HALF ? chunk * 4 + par * 2 + (j >> 3) : chunk * 4 + (j >> 3);
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) {
-#ifdef ORPCD_QUEUE_STATS
-                        mall[q] = fminf(mall[q], mc[q]);
-#endif
-                        m2[q] = fminf(m2[q], fmaxf(m1[q], mc[q]));
-                        c1[q] = mc[q] < m1[q] ? id : c1[q];
-                        m1[q] = fminf(m1[q], mc[q]);
-                        mc[q] = CUDART_INF_F;
-                    }
-                }
-            }
-#ifdef ORPCD_QUEUE_STATS
-            {
-                bool useful = false;
-                for (int q = 0; q < Q; ++q) {
-                    const float qn = qv[q].x * qv[q].x + qv[q].y * qv[q].y + qv[q].z * qv[q].z;
-                    useful |= mall[q] + qn <= qv[q].w * qv[q].w * 1.001f;
-                }
-                if (__any_sync(0xffffffffu, useful) && lane == 0) atomicAdd(c.q_stats + 634, 1ull);
-            }
-#endif
-            if (!SUB) {
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    m2[q] = fminf(m2[q], fmaxf(m1[q], mc[q]));
-                    c1[q] = mc[q] < m1[q] ? chunk : c1[q];
-                    m1[q] = fminf(m1[q], mc[q]);
-                }
+            if constexpr (Q == 2 && SUB) {
+                if (HALF) sweep_chunk<Q, SUB, true>(tc, chunk, par, qx, qy, qz, m1, c1, m2);
+                else sweep_chunk<Q, SUB, false>(tc, chunk, 0, qx, qy, qz, m1, c1, m2);
+            } else {
+                sweep_chunk<Q, SUB, false>(tc, chunk, 0, qx, qy, qz, m1, c1, m2);
             }
             __syncwarp();   // everyone is done with this slot before it is refilled
         }
@@ -1053,6 +1090,7 @@ __device__ __forceinline__ void exact_search_warp(const Ctx &c, int tgt_set, dou
     const double *tp = c.tgt_pts + (size_t)tgt_set * c.n_tgt * 3;
     const int *perm = c.tperm + (size_t)tgt_set * c.nt_pad;
     const float4 *sph = c.chunk_sph + (size_t)tgt_set * c.n_chunks;
+    const float4 *half = c.chunk_half + (size_t)tgt_set * c.n_chunks;
     best = CUDART_INF;
     bj = 0x7fffffff;
     auto score = [&](int chunk) {
@@ -1084,15 +1122,34 @@ __device__ __forceinline__ void exact_search_warp(const Ctx &c, int tgt_set, dou
             const int chunk = base + lane;
             bool need = false;
             if (chunk < c.n_chunks && chunk != c1) {
-                const float4 sp = sph[chunk];
-                const float sx = sp.x - qfx, sy = sp.y - qfy, sz = sp.z - qfz;
-                need = !(sqrtf(sx * sx + sy * sy + sz * sz) - sp.w > thr);
+                // the chunk's bounding BOX (centre + half extents) against the query: a third fewer chunks to score
+                // than with the bounding sphere
+                const float4 sp = sph[chunk], hf = half[chunk];
+                const float ex = fmaxf(fabsf(sp.x - qfx) - hf.x, 0.f), ey = fmaxf(fabsf(sp.y - qfy) - hf.y, 0.f);
+                const float ez = fmaxf(fabsf(sp.z - qfz) - hf.z, 0.f);
+                need = !(sqrtf(ex * ex + ey * ey + ez * ez) > thr);
             }
             unsigned bal = __ballot_sync(0xffffffffu, need);
             while (bal) {
-                const int l = __ffs(bal) - 1;
+                // two chunks per step: their index and coordinate gathers are in flight together (each is two
+                // dependent L2 round trips, and this search sits on the critical path of a unit's round)
+                const int l0 = __ffs(bal) - 1;
                 bal &= bal - 1;
-                score(base + l);
+                const int l1 = bal ? __ffs(bal) - 1 : -1;
+                bal &= bal - 1;
+                const int j0 = perm[(size_t)(base + l0) * NN_CH + lane];
+                const int j1 = l1 >= 0 ? perm[(size_t)(base + l1) * NN_CH + lane] : -1;
+                double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+                if (j0 >= 0) { a0 = tp[(size_t)j0 * 3]; a1 = tp[(size_t)j0 * 3 + 1]; a2 = tp[(size_t)j0 * 3 + 2]; }
+                if (j1 >= 0) { b0 = tp[(size_t)j1 * 3]; b1 = tp[(size_t)j1 * 3 + 1]; b2 = tp[(size_t)j1 * 3 + 2]; }
+                if (j0 >= 0) {
+                    const double d = sqdist3_rn(x, y, z, a0, a1, a2);
+                    if (d < best || (d == best && j0 < bj)) { best = d; bj = j0; }
+                }
+                if (j1 >= 0) {
+                    const double d = sqdist3_rn(x, y, z, b0, b1, b2);
+                    if (d < best || (d == best && j1 < bj)) { best = d; bj = j1; }
+                }
             }
         }
     }
@@ -1768,6 +1825,56 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
         double U[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) U[k] = __ldcg(&st.U[k]);
+#if ORPCD_PH1_HOIST
+#pragma unroll 1
+        for (int k = 0; k < nk; ++k) {
+            const int i = wbase + k * 32 + lane;
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < c.n_src) {
+                const size_t oi = (size_t)u * c.n_src + i;
+                double *p = c.cur_pts + oi * 3;
+                // every load of the pass is issued before its first store (the compiler cannot move a load above a
+                // store that might alias it): point, axis and previous match together, then the matched target's point --
+                // two L2 round trips per pass instead of four (point | axis | match | target point, each behind stores)
+                const int j = round >= 1 ? __ldcg(c.corr + oi) : -1;
+                double x = __ldcg(p), y = __ldcg(p + 1), z = __ldcg(p + 2);
+                double ax = 0.0, ay = 0.0, az = 0.0;
+                if (EST == 1) {
+                    const double *ap = c.cur_cov + oi * 3;
+                    ax = __ldcg(ap); ay = __ldcg(ap + 1); az = __ldcg(ap + 2);
+                }
+                double tx = 0.0, ty = 0.0, tz = 0.0;
+                if (j >= 0) {
+                    const double *tp = tpts + (size_t)j * 3;
+                    tx = tp[0]; ty = tp[1]; tz = tp[2];
+                }
+                if (has_update) {
+                    transform_point(U, x, y, z);
+                    p[0] = x; p[1] = y; p[2] = z;
+                    if (EST == 0) {
+                        double *cp = c.cur_cov + oi * 6;
+                        Sym3 C;
+                        C.xx = __ldcg(cp); C.xy = __ldcg(cp + 1); C.xz = __ldcg(cp + 2);
+                        C.yy = __ldcg(cp + 3); C.yz = __ldcg(cp + 4); C.zz = __ldcg(cp + 5);
+                        store_sym3(cp, rotate_sym3(U, C));
+                    } else if (EST == 1) {
+                        double *ap = c.cur_cov + oi * 3;
+                        ap[0] = U[0] * ax + U[1] * ay + U[2] * az;
+                        ap[1] = U[4] * ax + U[5] * ay + U[6] * az;
+                        ap[2] = U[8] * ax + U[9] * ay + U[10] * az;
+                    }
+                }
+                float dub = c.dcap;
+                if (j >= 0) {
+                    const double dx = x - tx, dy = y - ty, dz = z - tz;
+                    dub = fminf(dub, __double2float_ru(sqrt(dx * dx + dy * dy + dz * dz)) * (1.f + 1e-6f));
+                }
+                r = make_float4((float)(x - tm.cx), (float)(y - tm.cy), (float)(z - tm.cz), dub);
+            }
+            if (k == 0) qa = r;
+            else qb = r;
+        }
+#else
 #pragma unroll 1
         for (int k = 0; k < nk; ++k) {
             const int i = wbase + k * 32 + lane;
@@ -1807,6 +1914,7 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
             if (k == 0) qa = r;
             else qb = r;
         }
+#endif
         // lanes past the end of the cloud carry the patch's first query (always a real one)
         const float fx = __shfl_sync(0xffffffffu, qa.x, 0), fy = __shfl_sync(0xffffffffu, qa.y, 0);
         const float fz = __shfl_sync(0xffffffffu, qa.z, 0), fw = __shfl_sync(0xffffffffu, qa.w, 0);
@@ -1814,50 +1922,46 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
         if (half || wbase + 32 + lane >= c.n_src) qb = make_float4(fx, fy, fz, fw);
     }
 
-    // ---- 2. sweep
+    // ---- 2. sweep (ONE call site: the set-up and the visit list of cull_sweep_core exist once in the kernel)
     float m1a, m1b, m2a, m2b;
     int c1a, c1b;
-    if (!half) {
-        const float4 qv[Q] = {qa, qb};
+    {
+        float4 qv[Q] = {qa, qb};
+        if (half) {
+            // both half-warps take the pair (query l & 15, query (l & 15) + 16) and one parity of every chunk's targets
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int from = (lane & 15) + 16 * e;
+                qv[e].x = __shfl_sync(0xffffffffu, qa.x, from); qv[e].y = __shfl_sync(0xffffffffu, qa.y, from);
+                qv[e].z = __shfl_sync(0xffffffffu, qa.z, from); qv[e].w = __shfl_sync(0xffffffffu, qa.w, from);
+            }
+        }
         float m1[Q], m2[Q];
         int c1[Q];
         const int visited = cull_sweep_core<Q, true>(c, tg, c.chunk_sph + (size_t)tgt_set * c.n_chunks,
                                                      c.super_sph + (size_t)tgt_set * c.n_super, c.n_super, (float)tm.rmax, 0,
-                                                     c.n_chunks, qv, ring, vl, m1, c1, m2);
+                                                     c.n_chunks, qv, ring, vl, m1, c1, m2, half);
         if (lane == 0)
-            atomicAdd(c.visit_count + round, (unsigned long long)visited * NN_CH * min(64, c.n_src - wbase));
-        m1a = m1[0]; m1b = m1[1]; m2a = m2[0]; m2b = m2[1]; c1a = c1[0]; c1b = c1[1];
-    } else {
-        // both half-warps take the pair (query l & 15, query (l & 15) + 16) and one parity of every chunk's targets
-        float4 qv[Q];
+            atomicAdd(c.visit_count + round, (unsigned long long)visited * NN_CH * min(half ? 32 : 64, c.n_src - wbase));
+        if (!half) {
+            m1a = m1[0]; m1b = m1[1]; m2a = m2[0]; m2b = m2[1]; c1a = c1[0]; c1b = c1[1];
+        } else {
+            // merge the two halves (each saw the targets of one parity); on an exact tie both keep parity 0's sub-chunk --
+            // the certificate then sees m2 == m1 and sends the query to the exact search
+            const int par = lane >> 4;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int from = (lane & 15) + 16 * e;
-            qv[e].x = __shfl_sync(0xffffffffu, qa.x, from); qv[e].y = __shfl_sync(0xffffffffu, qa.y, from);
-            qv[e].z = __shfl_sync(0xffffffffu, qa.z, from); qv[e].w = __shfl_sync(0xffffffffu, qa.w, from);
+            for (int e = 0; e < 2; ++e) {
+                const float om1 = __shfl_xor_sync(0xffffffffu, m1[e], 16), om2 = __shfl_xor_sync(0xffffffffu, m2[e], 16);
+                const int oc1 = __shfl_xor_sync(0xffffffffu, c1[e], 16);
+                const bool take = om1 < m1[e] || (om1 == m1[e] && par == 1);
+                m2[e] = fminf(fminf(m2[e], om2), fmaxf(m1[e], om1));
+                c1[e] = take ? oc1 : c1[e];
+                m1[e] = fminf(m1[e], om1);
+            }
+            // lane l's own query is element l >> 4 of its pair
+            m1a = par ? m1[1] : m1[0]; m2a = par ? m2[1] : m2[0]; c1a = par ? c1[1] : c1[0];
+            m1b = CUDART_INF_F; m2b = CUDART_INF_F; c1b = 0;
         }
-        float m1[Q], m2[Q];
-        int c1[Q];
-        const int visited = cull_sweep_core<Q, true, true>(c, tg, c.chunk_sph + (size_t)tgt_set * c.n_chunks,
-                                                           c.super_sph + (size_t)tgt_set * c.n_super, c.n_super,
-                                                           (float)tm.rmax, 0, c.n_chunks, qv, ring, vl, m1, c1, m2);
-        if (lane == 0)
-            atomicAdd(c.visit_count + round, (unsigned long long)visited * NN_CH * min(32, c.n_src - wbase));
-        // merge the two halves (each saw the targets of one parity); on an exact tie both keep parity 0's sub-chunk --
-        // the certificate then sees m2 == m1 and sends the query to the exact search
-        const int par = lane >> 4;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const float om1 = __shfl_xor_sync(0xffffffffu, m1[e], 16), om2 = __shfl_xor_sync(0xffffffffu, m2[e], 16);
-            const int oc1 = __shfl_xor_sync(0xffffffffu, c1[e], 16);
-            const bool take = om1 < m1[e] || (om1 == m1[e] && par == 1);
-            m2[e] = fminf(fminf(m2[e], om2), fmaxf(m1[e], om1));
-            c1[e] = take ? oc1 : c1[e];
-            m1[e] = fminf(m1[e], om1);
-        }
-        // lane l's own query is element l >> 4 of its pair
-        m1a = par ? m1[1] : m1[0]; m2a = par ? m2[1] : m2[0]; c1a = par ? c1[1] : c1[0];
-        m1b = CUDART_INF_F; m2b = CUDART_INF_F; c1b = 0;
     }
 
     // ---- 3. certificate (nn_resolve_kernel's bound), then each lane scans the best 8-target sub-chunk of its own queries:
@@ -1869,10 +1973,12 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     for (int k = 0; k < nk; ++k) {
         const float fx = qa.x, fy = qa.y, fz = qa.z;
         const double qn = (double)fx * fx + (double)fy * fy + (double)fz * fz;
-        const double qnorm = sqrt(qn);
+        // |q| and d_ub only enter the error BOUND below: any upper bound serves, so the two square roots are single
+        // FP32 instructions rounded up (of arguments rounded up) instead of two float64 sqrt sequences per query
+        const double qnorm = (double)__fsqrt_ru(__double2float_ru(qn));
         const double rho_max = qnorm + tm.rmax;
         const double e_glob = (double)F32_EPS * 6.0 * rho_max * rho_max * 1.001;
-        const double d_ub = sqrt(fmax((double)m1a + qn, 0.0) + e_glob) * (1.0 + 1e-6);
+        const double d_ub = (double)__fsqrt_ru(__double2float_ru(fmax((double)m1a + qn, 0.0) + e_glob)) * (1.0 + 1e-6);
         const double rho = 2.0 * qnorm + d_ub + 4.0 * (double)F32_EPS * rho_max;
         const double margin = 2.02 * (double)F32_EPS * (4.0 * rho * rho + 2.0 * d_ub * rho) * 1.001 + 1e-300;
         const double lim = (double)m1a + margin;
@@ -1957,15 +2063,24 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
                     const double *pt = tpts + (size_t)j * 3;
                     sx = __ldcg(ps); sy = __ldcg(ps + 1); sz = __ldcg(ps + 2);
                     const double tx = pt[0], ty = pt[1], tz = pt[2];
+#if ORPCD_PH5_HOIST
+                    // both axes are requested with the points (a match beyond the cut-off is the rare case)
+                    const double *as = c.cur_cov + oi * 3;   // moving source axis: written this round, read through L2
+                    const double *bt = c.tgt_cov + ((size_t)tgt_set * c.n_tgt + j) * 3;
+                    const double ax = __ldcg(as), ay = __ldcg(as + 1), az = __ldcg(as + 2);
+                    const double bx = bt[0], by = bt[1], bz = bt[2];
+#endif
                     const double d2 = fda >= 0.0 ? fda : sqdist3_rn(sx, sy, sz, tx, ty, tz);
                     if (d2 < c.r2) {
                         have = true;
                         d2sum += d2;
                         dx = sx - tx; dy = sy - ty; dz = sz - tz;
+#if !ORPCD_PH5_HOIST
                         const double *as = c.cur_cov + oi * 3;   // moving source axis: written this round, read through L2
                         const double *bt = c.tgt_cov + ((size_t)tgt_set * c.n_tgt + j) * 3;
                         const double ax = __ldcg(as), ay = __ldcg(as + 1), az = __ldcg(as + 2);
                         const double bx = bt[0], by = bt[1], bz = bt[2];
+#endif
                         const double dot = fma(ax, bx, fma(ay, by, az * bz));
                         const double sg = dot >= 0 ? 1.0 : -1.0;
                         const double ac = fmin(fabs(dot), 1.0);
@@ -2155,6 +2270,14 @@ __device__ __forceinline__ void round_body(const Ctx &c, UnitState &st, int u, i
     fence_release_side();  // the unit's new state is visible before its next round is published
     __syncwarp();
     if (!PERSIST) return;
+#ifdef ORPCD_QUEUE_STATS
+    if (!go_on && lane == 0) {   // finish stamp of the unit (ns since the first worker started), tagged with bit 63
+        unsigned long long tf;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tf));
+        reinterpret_cast<unsigned long long *>(c.worklist)[u] =
+            (tf - *reinterpret_cast<volatile unsigned long long *>(c.q_stats)) | (1ull << 63);
+    }
+#endif
     if (!go_on) return;
     // publish the work items of the unit's next round: consecutive tickets of the ring.  The ticket atomic is the
     // release: the slot writes below depend on its result.
@@ -2761,7 +2884,21 @@ int run_registration(const orpcd_gicp_params *p, int est_mode, const double *d_s
         {
             unsigned long long hq[640];
             cudaMemcpy(hq, c.q_stats, sizeof(hq), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "visit lists: %llu box survivors, %llu listed, %llu chunks with a target within some query's reach\n", hq[632], hq[633], hq[634]);
+            {
+                std::vector<unsigned long long> fin(p->n_units);
+                std::vector<int> it(p->n_units);
+                cudaMemcpy(fin.data(), c.worklist, sizeof(unsigned long long) * p->n_units, cudaMemcpyDeviceToHost);
+                std::vector<UnitState> hs(p->n_units);
+                cudaMemcpy(hs.data(), c.state, sizeof(UnitState) * p->n_units, cudaMemcpyDeviceToHost);
+                std::vector<int> ord(p->n_units);
+                for (int i = 0; i < p->n_units; ++i) ord[i] = i;
+                std::sort(ord.begin(), ord.end(), [&](int a, int b) { return (fin[a] & ~(1ull << 63)) > (fin[b] & ~(1ull << 63)); });
+                fprintf(stderr, "last units to finish (unit: ms, iterations):");
+                for (int i = 0; i < std::min(p->n_units, 24); ++i)
+                    fprintf(stderr, " %d: %.2f, %d;", ord[i], (fin[ord[i]] & ~(1ull << 63)) * 1e-6, hs[ord[i]].iters);
+                fprintf(stderr, "\n");
+            }
+            fprintf(stderr, "visit lists: %llu box survivors, %llu listed\n", hq[632], hq[633]);
             for (int b = 0; b < 64; ++b)
                 if (hq[128 + b] || hq[64 + b])
                     fprintf(stderr, "t %5.2f ms  items %7llu  idle %5.1f %%  item mean %6.1f us max %6.1f us  closings %5llu mean %5.1f us\n",
