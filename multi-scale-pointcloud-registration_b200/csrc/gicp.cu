@@ -612,6 +612,9 @@ __global__ void __launch_bounds__(NN_THREADS) nn_sweep_kernel(Ctx c, int round)
 #ifndef ORPCD_PH5_HOIST
 #define ORPCD_PH5_HOIST 1
 #endif
+#ifndef ORPCD_SWEEP_ROLLED
+#define ORPCD_SWEEP_ROLLED 1   // per-chunk arithmetic of the culled sweep rolled over its 8-target sub-chunks (code size)
+#endif
 #ifndef ORPCD_CULL_AABB
 #define ORPCD_CULL_AABB 1      // chunk bounding boxes (0: bounding spheres) in the visit-list tests of the culled sweep
 #endif
@@ -660,7 +663,11 @@ __device__ __forceinline__ void sweep_chunk(const float4 *__restrict__ tc, int c
         constexpr int STRIDE = HALF ? 2 : 1;
         const float4 *ts = tc + par;
         int id = chunk * 4 + par * 2;
+#if ORPCD_SWEEP_ROLLED
 #pragma unroll 1
+#else
+#pragma unroll
+#endif
         for (int sc = 0; sc < (HALF ? 2 : 4); ++sc, ts += 8 * STRIDE, ++id) {
 #pragma unroll
             for (int j = 0; j < 8; j += TJ) {
