@@ -27,6 +27,7 @@ the device, one small NCCL all-gather, every rank ends with every result.
 port (kind "port": Open3D is an un-vendored wheel that cannot be installed offline).
 """
 import argparse
+import contextlib
 import csv
 import glob
 import json
@@ -289,15 +290,20 @@ def run_b200(args):
         inner._base_key = None   # no neighbour lists carried over from the previous step: every step does all its work
         return opt.optimize_batch(s, t, unit_src, unit_tgt, rigid_base=src)
 
+    # The clock sampler (`nvidia-smi -lms 100`) is started BEFORE the warm-up so that its start-up -- NVML initialisation
+    # takes driver locks on every GPU of the box; eight of them starting inside the timed region cost one rank a 70 ms
+    # stall in one step of an 8-GPU run -- happens outside the timed region, and only rank 0 samples (its own GPU): the
+    # samples cover the warm-up and the timed steps, all under load.
     warmup = max(args.warmup, 3)
-    for _ in range(warmup):
-        step(d_src, d_tgt)
-    barrier()
+    with (ClockSampler(local) if rank == 0 else contextlib.nullcontext()) as clk:
+        time.sleep(0.5 if rank == 0 else 0.0)
+        for _ in range(warmup):
+            step(d_src, d_tgt)
+        barrier()
 
-    # ---- timed: K steps, inputs resident in HBM, L2 flushed between them, no profiling
-    k0 = ops.launch_counter["kernels"]
-    dev_ms = gather_ms = compute_ms = 0.0
-    with ClockSampler(local) as clk:
+        # ---- timed: K steps, inputs resident in HBM, L2 flushed between them, no profiling
+        k0 = ops.launch_counter["kernels"]
+        dev_ms = gather_ms = compute_ms = 0.0
         for _ in range(args.steps):
             flush.fill_(1)
             barrier()
@@ -310,7 +316,7 @@ def run_b200(args):
             gather_ms += opt.last_timing.get("gather_ms", 0.0)
             compute_ms += opt.last_timing.get("compute_ms", 0.0)
     launches = ops.launch_counter["kernels"] - k0
-    clocks = clk.summary()
+    clocks = clk.summary() if clk is not None else None
     mean_iters = float(np.mean(res.iterations))
 
     # ---- e2e: host buffers in, host results out, through the same public call
@@ -411,10 +417,11 @@ def strong_scaling(opt, world, barrier):
     inner = opt._inner
     best, weights, walls = None, None, []
     opt.time_feedback = True       # 200k-point units: correct the iteration proxy by the measured rank times
-    for rep in range(3 if world > 1 else 2):
+    for rep in range(6 if world > 1 else 2):
         # rep 0 cuts blocks of equal unit counts; rep 1 cuts blocks of equal expected work: ShardedOptimizer weighs every
         # unit by the mean iteration count of its target set (scale candidate) in the previous call of the same layout
-        # -- what the Aligner has from the previous poll sweep; rep 2 corrects that proxy by the measured rank times
+        # -- what the Aligner has from the previous poll sweep; reps 2.. correct that proxy by the measured rank times of
+        # the call before (damped: a square-root step per call, so the partition settles over a few calls of the layout)
         inner._base_key = None
         barrier()
         t0 = time.perf_counter()
@@ -446,7 +453,7 @@ def strong_scaling(opt, world, barrier):
             "failed_units": int((res.status != 0).sum()), "local_units": opt.last_local_units,
             "local_target_sets": opt.last_local_target_sets, "mean_iterations": float(np.mean(res.iterations)),
             "wall_s_per_repetition": walls, "per_rank_compute_s_weighted": per_rank_compute,
-            "sharding": "contiguous target-set blocks; repetition 0 equal counts, 1 weighted by per-target-set mean iterations of the previous call, 2 corrected by measured rank times"}
+            "sharding": "contiguous target-set blocks; repetition 0 equal counts, 1 weighted by per-target-set mean iterations of the previous call, 2..5 corrected (damped) by the measured rank times of the call before; wall_s is the best repetition"}
 
 
 def single_gpu_extras(inner, src, sources, targets, unit_src, unit_tgt, d_src, d_tgt, ms_per_step):
