@@ -102,23 +102,62 @@ def make_workload(world=1, pinned=None):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """`nvidia-smi -lms 100` streamed for the duration of the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons sampled every 50 ms for the duration of the timed region (B200_PROFILING.md clocks
+    line).  Read in-process through NVML (pynvml: two light queries per sample from a background thread); a streamed
+    `nvidia-smi -lms 100` is the fallback.  (The nvidia-smi process measurably disturbed what it watched: its NVML
+    start-up and its polls take driver locks, and 8-GPU runs lost steps of 12.9 instead of 10.8 ms to it.)"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.samples = index, None, []
+        self.thread, self.stop, self.source = None, None, None
+
+    def _nvml_loop(self, nv, handle, max_mhz):
+        bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                r = int(get_reasons(handle))
+                self.samples.append([str(mhz), str(max_mhz)] + ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            self.stop.wait(0.05)
 
     def __enter__(self):
+        try:
+            import threading
+
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            max_mhz = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+            self.stop = threading.Event()
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle, max_mhz), daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return self
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
         except Exception:
             self.proc = None
         return self
 
     def __exit__(self, *a):
+        if self.thread is not None:
+            self.stop.set()
+            self.thread.join(timeout=2)
+            return
         if self.proc is None:
             return
         time.sleep(0.15)
@@ -140,7 +179,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(mhz)}
+                "samples": len(mhz), "source": self.source}
 
 
 # ----------------------------------------------------------------------------- CPU paths
@@ -290,13 +329,13 @@ def run_b200(args):
         inner._base_key = None   # no neighbour lists carried over from the previous step: every step does all its work
         return opt.optimize_batch(s, t, unit_src, unit_tgt, rigid_base=src)
 
-    # The clock sampler (`nvidia-smi -lms 100`) is started BEFORE the warm-up so that its start-up -- NVML initialisation
-    # takes driver locks on every GPU of the box; eight of them starting inside the timed region cost one rank a 70 ms
-    # stall in one step of an 8-GPU run -- happens outside the timed region, and only rank 0 samples (its own GPU): the
-    # samples cover the warm-up and the timed steps, all under load.
+    # The clock sampler is started BEFORE the warm-up so that its start-up -- NVML initialisation takes driver locks on
+    # every GPU of the box; eight `nvidia-smi` processes starting inside the timed region cost one rank a 70 ms stall
+    # in one step of an 8-GPU run -- happens outside the timed region, and only rank 0 samples (its own GPU): the samples
+    # cover the warm-up and the timed steps, all under load.
     warmup = max(args.warmup, 3)
     with (ClockSampler(local) if rank == 0 else contextlib.nullcontext()) as clk:
-        time.sleep(0.5 if rank == 0 else 0.0)
+        time.sleep(0.3 if rank == 0 else 0.0)
         for _ in range(warmup):
             step(d_src, d_tgt)
         barrier()
