@@ -302,3 +302,34 @@ def test_fused_round_kernel_agrees_with_the_unfused_and_dense_paths(oracle, arma
         assert np.array_equal(res[0].iterations, other.iterations)
         assert np.allclose(res[0].rmse, other.rmse, rtol=1e-9, atol=0)
         assert np.allclose(res[0].transforms, other.transforms, rtol=0, atol=1e-9)
+
+
+def test_correspondence_search_degenerate_boxes_and_exact_ties():
+    """The culled 1-NN sweep on geometry that degenerates its culling data: an axis-aligned planar lattice (every chunk's
+    bounding box has zero extent in z, rows of the lattice give boxes of zero extent in two axes) queried from points
+    exactly half-way between lattice nodes (two or four targets at EXACTLY the same float64 distance: the FP32 filter
+    cannot decide, the box-based exact search must, and ties go to the lowest index).  Coordinates are multiples of
+    2^-5, so every squared distance is exact in float64 and the reference answer is a plain numpy arg-min."""
+    import torch
+
+    from or_pcd_b200 import ops
+
+    g = np.arange(48, dtype=np.float64) / 32.0
+    tgt = np.stack([a.ravel() for a in np.meshgrid(g, g, [0.25], indexing="ij")], axis=1)          # 2304 targets, z = 0.25
+    rng = np.random.default_rng(5)
+    tgt = tgt[rng.permutation(len(tgt))]                     # index order unrelated to position
+    base = np.stack([a.ravel() for a in np.meshgrid(g[:-1], g[:-1], [0.25], indexing="ij")], axis=1)
+    sources = np.stack([base + np.array([1 / 64.0, 0.0, 0.0]),            # between two nodes along x: 2-way ties
+                        base + np.array([1 / 64.0, 1 / 64.0, 1 / 32.0]),  # cell centres, off the plane: 4-way ties
+                        base + np.array([0.0, 0.0, 1 / 16.0])])           # straight above a node: unique
+    T = np.tile(np.eye(4), (3, 1, 1))
+    stats, status, corr, _ = ops.evaluate_batch(_dev(sources), _dev(tgt[None]), torch.tensor([0, 1, 2], dtype=torch.int32, device="cuda"),
+                                                torch.zeros(3, dtype=torch.int32, device="cuda"), _dev(T), 0.5, want_corr=True)
+    corr = corr.cpu().numpy()
+    for u in range(3):
+        d2 = ((sources[u][:, None, 0] - tgt[None, :, 0]) ** 2 + (sources[u][:, None, 1] - tgt[None, :, 1]) ** 2) + \
+             (sources[u][:, None, 2] - tgt[None, :, 2]) ** 2
+        ref = d2.argmin(axis=1)                              # first minimum = lowest index
+        assert np.array_equal(corr[u], ref), (u, int((corr[u] != ref).sum()))
+        rmse = np.sqrt(d2.min(axis=1).mean())
+        assert abs(float(stats[u, 1]) - rmse) <= 1e-12 * rmse
