@@ -28,3 +28,37 @@ def test_bench_line_of_the_round_has_the_contract_keys():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
     assert d["gpu_launches"] > 0 and d["config"]["workload"]
+
+
+def test_round2_bench_lines_and_traffic_lookup():
+    """The committed bench lines of the round's final state (1, 2 and 8 GPUs) carry the contract keys, and bench.py
+    finds the dominant kernel's DRAM traffic in the newest committed ncu raw page."""
+    import json
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    for name, n in (("r2_02_bench_line.json", 1), ("r2_02_bench_line_2gpu.json", 2), ("r2_02_bench_line_8gpu.json", 8)):
+        d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+        assert d["n_gpus"] == n and d["value"] > 0 and d["gpu_launches"] > 0
+        assert d["clocks"]["reasons"] == [] and d["clocks"]["sm_mhz"] > 0
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        if n == 1:
+            assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+            assert d["e2e"]["align"]["matches_oracle_run"] is True
+        else:
+            assert len(d["e2e"]["multi_gpu"]["per_rank_compute_ms_per_step"]) == n
+            assert d["e2e"]["strong_scaling"]["failed_units"] == 0
+    traffic, source = bench.ncu_traffic()
+    assert source.endswith("r2_02_gicp_persistent_ncu_raw.csv") and 1e8 < traffic < 2e9
+
+
+def test_clock_sampler_degrades_without_a_gpu():
+    """No NVML device and no nvidia-smi (this container): the sampler reports "unsampled" instead of raising."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    with bench.ClockSampler(0) as s:
+        pass
+    out = s.summary()
+    assert out["reasons"] == ["unsampled"] or out["sm_mhz"] is not None
