@@ -31,14 +31,15 @@ def test_bench_line_of_the_round_has_the_contract_keys():
 
 
 def test_round2_bench_lines_and_traffic_lookup():
-    """The committed bench lines of the round's final state (1, 2 and 8 GPUs) carry the contract keys, and bench.py
+    """The committed bench lines of the round's final state (1, 2, 4 and 8 GPUs) carry the contract keys, and bench.py
     finds the dominant kernel's DRAM traffic in the newest committed ncu raw page."""
     import json
 
     sys.path.insert(0, ROOT)
     import bench
 
-    for name, n in (("r2_02_bench_line.json", 1), ("r2_02_bench_line_2gpu.json", 2), ("r2_02_bench_line_8gpu.json", 8)):
+    for name, n in (("r2_02_bench_line.json", 1), ("r2_02_bench_line_2gpu.json", 2), ("r2_02_bench_line_4gpu.json", 4),
+                    ("r2_02_bench_line_8gpu.json", 8)):
         d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
         assert d["n_gpus"] == n and d["value"] > 0 and d["gpu_launches"] > 0
         assert d["clocks"]["reasons"] == [] and d["clocks"]["sm_mhz"] > 0
