@@ -194,3 +194,67 @@ def test_cloud_io_ply_and_npz(tmp_path):
     np.savez(tmp_path / "nopoints.npz", other=v)
     with pytest.raises(ValueError):
         load_cloud(str(tmp_path / "nopoints.npz"))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Against the REFERENCE'S OWN Aligner class (tests/golden/make_golden_aligner_ref.py ran the unmodified
+# /root/reference/src/or_pcd/Aligner/Aligner.py with open3d stubbed out and the fake optimizer of tests/fakes.py)
+# ---------------------------------------------------------------------------------------------------------------------
+_REF_CASES = ["plain", "more_starts", "fails_late", "fails_at_once"]
+
+
+def _run_against_reference_golden(g, name, make_aligner, optimizer):
+    seed, attempts, size = int(g[f"{name}_seed"]), int(g[f"{name}_attempts"]), int(g[f"{name}_size"])
+    np.random.seed(seed)
+    al = make_aligner(size, optimizer, attempts)
+    raised, res = 0, None
+    try:
+        res = al.align(g["source"], g["target"], refine_registration=False)
+    except ValueError:
+        raised = 1
+    st = np.random.get_state()
+    assert raised == int(g[f"{name}_raised"]), name
+    if not raised:
+        T, metric, scale, errors = res
+        assert np.array_equal(np.asarray(T), g[f"{name}_T"]), name
+        assert metric == float(g[f"{name}_metric"]), name
+        assert np.array_equal(np.asarray(scale), g[f"{name}_scale"]) and np.asarray(scale).shape == (1, 3), name
+        assert np.array_equal(np.asarray(errors), g[f"{name}_errors"]), name
+        # the global numpy stream is left exactly where the reference leaves it
+        assert np.array_equal(st[1], g[f"{name}_rng_keys"]) and st[2] == int(g[f"{name}_rng_pos"]), name
+    return al
+
+
+@pytest.mark.parametrize("name", _REF_CASES)
+def test_oracle_aligner_equals_the_references_own_class(oracle, name):
+    """oracle.Aligner (the restatement every GPU test is judged against) takes the decisions of the reference's class:
+    transformation, metric, scale factors, error list bit for bit, the same number of optimizer calls, the same
+    exception behaviour and the same position of the global numpy stream."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_aligner_ref.npz"))
+    opt = FakeSequential(float(g[f"{name}_fail_above"]))
+    _run_against_reference_golden(
+        g, name, lambda size, o, attempts: oracle.Aligner(oracle.Preprocessor([oracle.RandomDownsampler(size)]),
+                                                          oracle.Preprocessor([oracle.RandomDownsampler(size)]), o,
+                                                          attempts=attempts), opt)
+    assert opt.calls == int(g[f"{name}_calls"])
+
+
+@pytest.mark.parametrize("name", _REF_CASES)
+@pytest.mark.parametrize("batched", [False, True])
+def test_b200_aligner_equals_the_references_own_class(name, batched):
+    """The B200 Aligner -- driven one call at a time by a reference-style optimizer, or speculatively in batches -- against
+    the same golden vectors of the reference's class.  The batched path evaluates more units than the sequential code
+    reaches; the calls the sequential code WOULD have made are what is compared."""
+    from or_pcd_b200.Aligner.Aligner import Aligner
+    from or_pcd_b200.Preprocessor import Preprocessor, RandomDownsampler
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_aligner_ref.npz"))
+    opt = (FakeBatched if batched else FakeSequential)(float(g[f"{name}_fail_above"]))
+    al = _run_against_reference_golden(
+        g, name, lambda size, o, attempts: Aligner(Preprocessor([RandomDownsampler(size)]),
+                                                   Preprocessor([RandomDownsampler(size)]), o, attempts=attempts), opt)
+    if batched:
+        if not int(g[f"{name}_raised"]):      # (after a failure the sequential-equivalent count is the failing call's)
+            assert al.n_optimize_calls == int(g[f"{name}_calls"])
+    else:
+        assert opt.calls == int(g[f"{name}_calls"])
