@@ -186,3 +186,31 @@ def test_device_start_clouds_equal_numpy_bit_for_bit(armadillo_pair):
     dev = ops.apply_rigid_batch(_lib.to_device(s), _lib.to_device(np.stack(rots)), _lib.to_device(np.stack(trans)))
     host = np.stack([np.dot(s, r) + t for r, t in zip(rots, trans)])
     assert np.array_equal(dev.cpu().numpy(), host)
+
+
+def test_single_calls_equal_the_references_own_wrapper_classes():
+    """GeneralizedICP.optimize / FastGlobalOptimizer.optimize through the C ABI against the golden vectors of the
+    reference's OWN wrapper classes (tests/golden/make_golden_wrappers_ref.py: generalizedICP.py / fastGlobalOptimizer.py
+    run unmodified over an oracle-backed open3d stub): the rotation block comes out transposed like the reference's, the
+    constructor arguments mean the same, and the failure rules raise the same exceptions.  north_star tolerances."""
+    from or_pcd_b200.Optimizer import FastGlobalOptimizer, GeneralizedICP
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_wrappers_ref.npz"))
+    s, t = g["source"], g["target"]
+    diag = np.linalg.norm(t.max(0) - t.min(0))
+    for name, kw in (("gicp_default", {}), ("gicp_params", dict(max_correspondence_distance=0.3, max_iterations=7)),
+                     ("gicp_nonpositive", dict(max_correspondence_distance=-1.0, max_iterations=0))):
+        T, rmse = GeneralizedICP(**kw).optimize(s, t)
+        assert abs(rmse - float(g[f"{name}_rmse"])) <= 1e-5 * rmse, name
+        assert _rot_angle(T[:3, :3], g[f"{name}_T"][:3, :3]) < 1e-4, name
+        assert np.linalg.norm(T[:3, 3] - g[f"{name}_T"][:3, 3]) < 1e-5 * diag, name
+    with pytest.raises(ValueError):
+        GeneralizedICP(max_correspondence_distance=1e-3).optimize(s[:200] + 50.0, t[:300])
+    for name, kw in (("fgr_default", {}), ("fgr_params", dict(tuple_scale=0.8, iteration_number=40, decrease_mu=False,
+                                                              maximum_correspondence_distance=0.3))):
+        T, rmse = FastGlobalOptimizer(**kw).optimize(s, t)
+        assert abs(rmse - float(g[f"{name}_rmse"])) <= 1e-5 * rmse, name
+        assert _rot_angle(T[:3, :3], g[f"{name}_T"][:3, :3]) < 1e-4, name
+        assert np.linalg.norm(T[:3, 3] - g[f"{name}_T"][:3, 3]) < 1e-5 * diag, name
+    with pytest.raises(Warning):
+        FastGlobalOptimizer(maximum_correspondence_distance=1e-4).optimize(s, t + 30.0)

@@ -258,3 +258,27 @@ def test_b200_aligner_equals_the_references_own_class(name, batched):
             assert al.n_optimize_calls == int(g[f"{name}_calls"])
     else:
         assert opt.calls == int(g[f"{name}_calls"])
+
+
+def test_b200_optimizer_constructors_equal_the_references_own_classes():
+    """Constructor semantics of the plugin classes against what the reference's own classes handed to Open3D
+    (golden_wrappers_ref.npz): defaults, explicit values, and non-positive values replaced by the defaults."""
+    from or_pcd_b200.Optimizer import FastGlobalOptimizer, GeneralizedICP
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_wrappers_ref.npz"))
+    for name, kw in (("gicp_default", {}), ("gicp_params", dict(max_correspondence_distance=0.3, max_iterations=7)),
+                     ("gicp_nonpositive", dict(max_correspondence_distance=-1.0, max_iterations=0))):
+        opt = GeneralizedICP(**kw)
+        assert opt._max_correspondence_distance == float(g[f"{name}_max_dist"]), name
+        assert opt._max_iterations == int(g[f"{name}_max_iteration"]), name
+    for name, kw in (("fgr_default", {}), ("fgr_params", dict(tuple_scale=0.8, iteration_number=40, decrease_mu=False,
+                                                              maximum_correspondence_distance=0.3))):
+        opt = FastGlobalOptimizer(**kw)
+        o = g[f"{name}_option"]
+        assert (opt._division_factor, opt._tuple_scale, opt._maximum_correspondence_distance, opt._iteration_number,
+                float(opt._decrease_mu)) == (o[0], o[1], o[2], int(o[3]), o[4]), name
+        assert (opt._normal_estimate_radius, opt._normal_estimate_knn) == (float(g[f"{name}_normal_radius"]),
+                                                                           int(g[f"{name}_normal_knn"]))
+        assert (opt._fpfh_radius, opt._fpfh_knn) == (float(g[f"{name}_fpfh_radius"]), int(g[f"{name}_fpfh_knn"]))
+        assert opt.feature_mode == "reference_compat"     # the default reproduces the reference: both FPFH sets from the source
+        assert list(g[f"{name}_fpfh_clouds"]) == ["source", "source"]

@@ -322,3 +322,56 @@ def test_downsampler_fixtures(oracle):
     v = oracle.VoxelDownsampler(2000)
     out = v.process(cloud)
     assert np.array_equal(np.array(v.probes), g["voxel_ArmadilloBack_30_probes"]) and out.shape[0] == int(g["voxel_ArmadilloBack_30_count"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The restated optimizer WRAPPERS against the reference's own classes (tests/golden/make_golden_wrappers_ref.py ran the
+# unmodified generalizedICP.py / fastGlobalOptimizer.py over an open3d stub whose numerical entry points are this oracle)
+# ---------------------------------------------------------------------------------------------------------------------
+def _wrappers_golden():
+    import os
+
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_wrappers_ref.npz"))
+
+
+def test_gicp_wrapper_equals_the_references_own_class(oracle):
+    """Arguments that reach registration_generalized_icp, the transposed rotation block on the way out, the fallback of
+    non-positive constructor arguments and the ValueError rule: oracle.GeneralizedICP == the reference's class."""
+    g = _wrappers_golden()
+    s, t = g["source"], g["target"]
+    for name, kw in (("gicp_default", {}), ("gicp_params", dict(max_correspondence_distance=0.3, max_iterations=7)),
+                     ("gicp_nonpositive", dict(max_correspondence_distance=-1.0, max_iterations=0))):
+        opt = oracle.GeneralizedICP(**kw)
+        assert opt._max_correspondence_distance == float(g[f"{name}_max_dist"])
+        assert opt._max_iterations == int(g[f"{name}_max_iteration"])
+        T, rmse = opt.optimize(s, t)
+        assert np.array_equal(T, g[f"{name}_T"]) and rmse == float(g[f"{name}_rmse"]), name
+    assert int(g["gicp_far_apart_raises_valueerror"]) == 1
+    with pytest.raises(ValueError):
+        oracle.GeneralizedICP(max_correspondence_distance=1e-3).optimize(s[:200] + 50.0, t[:300])
+
+
+def test_fgr_wrapper_equals_the_references_own_class(oracle):
+    """The reference's class computes BOTH FPFH sets on the source cloud (its own code, recorded by the stub), estimates
+    normals on both, uses Hybrid(0.1, 20) for either search, hands FastGlobalRegistrationOption its five arguments and
+    leaves the other three at Open3D's defaults, transposes the rotation block and raises Warning on an empty
+    correspondence set: oracle.FastGlobalOptimizer(feature_mode="reference_compat") == the reference's class."""
+    g = _wrappers_golden()
+    s, t = g["source"], g["target"]
+    for name, kw in (("fgr_default", {}), ("fgr_params", dict(tuple_scale=0.8, iteration_number=40, decrease_mu=False,
+                                                              maximum_correspondence_distance=0.3))):
+        assert list(g[f"{name}_fpfh_clouds"]) == ["source", "source"]              # SURVEY B.4, by the reference's code
+        assert list(g[f"{name}_normal_clouds"]) == ["source", "target"]
+        opt = oracle.FastGlobalOptimizer(feature_mode="reference_compat", **kw)
+        assert (opt._normal_estimate_radius, opt._normal_estimate_knn) == (float(g[f"{name}_normal_radius"]),
+                                                                           int(g[f"{name}_normal_knn"]))
+        assert (opt._fpfh_radius, opt._fpfh_knn) == (float(g[f"{name}_fpfh_radius"]), int(g[f"{name}_fpfh_knn"]))
+        o = g[f"{name}_option"]       # division_factor, tuple_scale, max distance, iterations, decrease_mu, max tuples, tuple_test, absolute scale
+        assert (opt._division_factor, opt._tuple_scale, opt._maximum_correspondence_distance, opt._iteration_number,
+                float(opt._decrease_mu)) == (o[0], o[1], o[2], int(o[3]), o[4])
+        assert (o[5], o[6], o[7]) == (1000.0, 1.0, 0.0)      # maximum_tuple_count, tuple_test, use_absolute_scale: defaults
+        T, rmse = opt.optimize(s, t)
+        assert np.array_equal(T, g[f"{name}_T"]) and rmse == float(g[f"{name}_rmse"]), name
+    assert int(g["fgr_far_apart_raises_warning"]) == 1
+    with pytest.raises(Warning):
+        oracle.FastGlobalOptimizer(maximum_correspondence_distance=1e-4).optimize(s, t + 30.0)
