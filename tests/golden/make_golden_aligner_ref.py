@@ -25,12 +25,54 @@ from fakes import FakeSequential  # noqa: E402
 REF = "/root/reference/src/or_pcd"
 
 
+ICP_CALLS = []      # what the reference's refine_registration handed to registration_icp
+
+
+def make_open3d_stub():
+    """`align(refine_registration=False)` and `transfrom` never touch Open3D; `refine_registration` calls
+    registration_icp, which the stub answers with the oracle's restatement (oracle.icp) and records."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle"))
+    import oracle as O
+
+    o3d = types.ModuleType("open3d")
+    pipelines, registration = types.ModuleType("open3d.pipelines"), types.ModuleType("open3d.pipelines.registration")
+
+    class TransformationEstimationPointToPoint:
+        mode = "PointToPoint"
+
+    class TransformationEstimationPointToPlane:
+        mode = "PointToPlane"
+
+    class ICPConvergenceCriteria:
+        def __init__(self, relative_fitness=1e-6, relative_rmse=1e-6, max_iteration=30):
+            self.relative_fitness, self.relative_rmse, self.max_iteration = relative_fitness, relative_rmse, max_iteration
+
+    class Result:
+        pass
+
+    def registration_icp(source, target, max_correspondence_distance, init, estimation_method, criteria):
+        ICP_CALLS.append(dict(max_dist=max_correspondence_distance, init=np.array(init), mode=estimation_method.mode,
+                              max_iteration=criteria.max_iteration))
+        r = O.icp(source, target, max_correspondence_distance, criteria.max_iteration, init, estimation_method.mode)
+        out = Result()
+        out.transformation, out.inlier_rmse, out.fitness = r["T"], r["rmse"], r["fitness"]
+        return out
+
+    registration.TransformationEstimationPointToPoint = TransformationEstimationPointToPoint
+    registration.TransformationEstimationPointToPlane = TransformationEstimationPointToPlane
+    registration.ICPConvergenceCriteria = ICPConvergenceCriteria
+    registration.registration_icp = registration_icp
+    pipelines.registration = registration
+    o3d.pipelines = pipelines
+    return o3d
+
+
 def load_reference_aligner():
     """The reference's Aligner, Preprocessor, RadiusScaler and RandomDownsampler classes (unmodified source files)."""
     for name in ["or_pcd", "or_pcd.utils", "or_pcd.Preprocessor", "or_pcd.Preprocessor.Scalers",
                  "or_pcd.Preprocessor.Downsamplers", "or_pcd.Optimizer", "or_pcd.Aligner", "or_pcd.Visualizer"]:
         sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules.setdefault("open3d", types.ModuleType("open3d"))          # never called on this path
+    sys.modules["open3d"] = make_open3d_stub()          # only refine_registration reaches it (oracle-backed ICP)
     lf = types.ModuleType("or_pcd.utils.logger_factory")
 
     class LoggerFactory:
@@ -46,7 +88,7 @@ def load_reference_aligner():
     vis.visualize_point_clouds = vis.draw_registration_result = lambda *a, **k: None
     sys.modules["or_pcd.Visualizer.Visualizer"] = vis
     cc = types.ModuleType("or_pcd.utils.create_cloud")
-    cc.create_cloud = lambda pts: pts
+    cc.create_cloud = lambda points: points
     sys.modules["or_pcd.utils.create_cloud"] = cc
 
     def load(mod, rel):
@@ -111,6 +153,29 @@ def main():
                     f"{name}_calls": opt.calls, f"{name}_rng_keys": st[1].copy(), f"{name}_rng_pos": st[2]})
         print(name, "raised" if raised else f"metric {metric:.6g} scale {np.asarray(scale).ravel()} "
               f"errors {len(errors)}", "optimizer calls", opt.calls)
+        if name == "plain":
+            # Aligner.transfrom (Aligner.py:367-394) of the raw source with the result of this run, and
+            # Aligner.refine_registration (Aligner.py:319-364) called directly: what reaches registration_icp and what comes back
+            out["plain_transformed_source"] = al.transfrom(src)
+            s2 = RadiusScaler().process(cloud(4, 500))
+            t2 = RadiusScaler().process(cloud(4, 520)[::-1].copy() * np.array([1.0, 1.05, 1.0]))
+            a = 0.2
+            init = np.eye(4)
+            init[:3, :3] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+            init[:3, 3] = [0.02, -0.01, 0.03]
+            T2, rmse2 = al.refine_registration(s2, t2, init, icp_type="PointToPoint")
+            call = ICP_CALLS[-1]
+            out.update({"refine_source": s2, "refine_target": t2, "refine_init": init, "refine_T": np.asarray(T2),
+                        "refine_rmse": rmse2, "refine_init_passed_unchanged": int(np.array_equal(call["init"], init)),
+                        "refine_max_dist": call["max_dist"], "refine_max_iteration": call["max_iteration"]})
+            raised_plane = 0
+            try:      # the default icp_type of align(refine_registration=True): no target normals -> Open3D raises
+                al.refine_registration(s2, t2, init, icp_type="PointToPlane")
+            except RuntimeError:
+                raised_plane = 1
+            out["refine_point_to_plane_without_normals_raises"] = raised_plane
+            print("refine: rmse", rmse2, "max_dist", call["max_dist"], "max_iteration", call["max_iteration"],
+                  "init unchanged", out["refine_init_passed_unchanged"], "PointToPlane raises", raised_plane)
     np.savez_compressed(os.path.join(HERE, "golden_aligner_ref.npz"), **out)
 
 

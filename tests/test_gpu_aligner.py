@@ -214,3 +214,30 @@ def test_single_calls_equal_the_references_own_wrapper_classes():
         assert np.linalg.norm(T[:3, 3] - g[f"{name}_T"][:3, 3]) < 1e-5 * diag, name
     with pytest.raises(Warning):
         FastGlobalOptimizer(maximum_correspondence_distance=1e-4).optimize(s, t + 30.0)
+
+
+def test_refine_registration_equals_the_references_own_method():
+    """Aligner.refine_registration against the reference's OWN method (golden_aligner_ref.npz: Aligner.py:319-364 run
+    unmodified over an open3d stub whose registration_icp is the oracle's): the initial transform is handed over
+    unchanged, the defaults are distance 0.5 / 200 iterations, the result comes back untransposed, and the default
+    "PointToPlane" without target normals raises."""
+    import inspect
+
+    from or_pcd_b200.Aligner.Aligner import Aligner
+    from or_pcd_b200.Optimizer import GeneralizedICP
+    from or_pcd_b200.Preprocessor import Preprocessor, RadiusScaler
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_aligner_ref.npz"))
+    assert int(g["refine_init_passed_unchanged"]) == 1 and int(g["refine_point_to_plane_without_normals_raises"]) == 1
+    al = Aligner(Preprocessor([RadiusScaler()]), Preprocessor([RadiusScaler()]), GeneralizedICP())
+    sig = inspect.signature(al.refine_registration).parameters
+    assert sig["max_iteration"].default == int(g["refine_max_iteration"])
+    assert sig["distance_threshold"].default == float(g["refine_max_dist"])
+    s, t, init = g["refine_source"], g["refine_target"], g["refine_init"]
+    T, rmse = al.refine_registration(s, t, init, icp_type="PointToPoint")
+    diag = np.linalg.norm(t.max(0) - t.min(0))
+    assert abs(rmse - float(g["refine_rmse"])) <= 1e-5 * rmse
+    assert _rot_angle(T[:3, :3], g["refine_T"][:3, :3]) < 1e-4
+    assert np.linalg.norm(T[:3, 3] - g["refine_T"][:3, 3]) < 1e-5 * diag
+    with pytest.raises(RuntimeError):
+        al.refine_registration(s, t, init, icp_type="PointToPlane")

@@ -258,6 +258,8 @@ def test_b200_aligner_equals_the_references_own_class(name, batched):
             assert al.n_optimize_calls == int(g[f"{name}_calls"])
     else:
         assert opt.calls == int(g[f"{name}_calls"])
+    if name == "plain":     # Aligner.transfrom (Aligner.py:367-394) with this run's result, against the reference's class
+        assert np.array_equal(al.transfrom(g["source"]), g["plain_transformed_source"])
 
 
 def test_b200_optimizer_constructors_equal_the_references_own_classes():
