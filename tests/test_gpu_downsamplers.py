@@ -81,3 +81,24 @@ def test_voxel_grid_limits_are_told_apart():
     out, first, _ = ops.voxel_downsample(_lib.to_device(cloud), 5.0)
     assert 0 < out.shape[0] <= 4000
 
+
+
+def test_blocks_equal_the_references_own_classes():
+    """The B200 SOR and VoxelDownsampler blocks through the C ABI against golden vectors of the reference's OWN classes
+    (tests/golden/make_golden_blocks_ref.py): inlier points bit for bit; the voxel-size search probe for probe and the
+    returned voxel averages bit for bit."""
+    import os
+
+    from or_pcd_b200.Preprocessor import SOR, VoxelDownsampler
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_blocks_ref.npz"))
+    for name in ("ArmadilloBack_30", "ArmadilloOnface_270"):
+        cloud = g[f"{name}_cloud"]
+        for tag, kw in (("default", {}), ("k16", dict(nb_neighbours=16, std_ratio=1.0))):
+            assert np.array_equal(SOR(**kw).process(cloud), g[f"sor_{name}_{tag}_kept"]), (name, tag)
+        for tag, target, kw in (("t800", 800, {}), ("t300_coarse", 300, dict(base_voxel_size=0.05, delta=0.02, eps=0.001)),
+                                ("t2900_clamped", 2900, dict(base_voxel_size=0.002, min_voxel_size=0.0015, delta=0.004))):
+            blk = VoxelDownsampler(target, **kw)
+            pts = blk.process(cloud)
+            assert np.array_equal(np.array(blk.probes, dtype=np.float64), g[f"voxel_{name}_{tag}_probes"]), (name, tag)
+            assert np.array_equal(pts, g[f"voxel_{name}_{tag}_points"]), (name, tag)

@@ -375,3 +375,28 @@ def test_fgr_wrapper_equals_the_references_own_class(oracle):
     assert int(g["fgr_far_apart_raises_warning"]) == 1
     with pytest.raises(Warning):
         oracle.FastGlobalOptimizer(maximum_correspondence_distance=1e-4).optimize(s, t + 30.0)
+
+
+_BLOCK_SCANS = ["ArmadilloBack_30", "ArmadilloOnface_270"]
+_SOR_CASES = (("default", {}), ("k16", dict(nb_neighbours=16, std_ratio=1.0)))
+_VOXEL_CASES = (("t800", 800, {}), ("t300_coarse", 300, dict(base_voxel_size=0.05, delta=0.02, eps=0.001)),
+                ("t2900_clamped", 2900, dict(base_voxel_size=0.002, min_voxel_size=0.0015, delta=0.004)))
+
+
+def test_preprocessing_blocks_equal_the_references_own_classes(oracle):
+    """oracle.SOR / oracle.VoxelDownsampler against golden vectors of the reference's OWN SOR.process and
+    VoxelDownsampler.process (tests/golden/make_golden_blocks_ref.py: sor.py / voxelDownsampler.py run unmodified over an
+    open3d stub backed by this oracle): arguments reaching Open3D, inlier points in original order, and every probe of the
+    voxel-size search -- sizes, counts, order, the clamp at min_voxel_size -- with the cloud finally returned."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_blocks_ref.npz"))
+    for name in _BLOCK_SCANS:
+        cloud = g[f"{name}_cloud"]
+        for tag, kw in _SOR_CASES:
+            blk = oracle.SOR(**kw)
+            assert (blk._nb_neighbours, float(blk._std_ratio)) == tuple(g[f"sor_{name}_{tag}_args"])
+            assert np.array_equal(blk.process(cloud), g[f"sor_{name}_{tag}_kept"]), (name, tag)
+        for tag, target, kw in _VOXEL_CASES:
+            blk = oracle.VoxelDownsampler(target, **kw)
+            pts = blk.process(cloud)
+            assert np.array_equal(np.array(blk.probes, dtype=np.float64), g[f"voxel_{name}_{tag}_probes"]), (name, tag)
+            assert np.array_equal(pts, g[f"voxel_{name}_{tag}_points"]), (name, tag)
