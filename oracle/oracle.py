@@ -2,9 +2,13 @@
 
 ctypes face of ``oracle/orpcd_oracle.c`` (the float64 restatement of the Open3D
 0.18.0 algorithms the reference calls) plus a restatement of the reference's
-pure-Python control flow on top of it.  PARITY UNPINNED: the reference has no
-tests/golden vectors for this path and Open3D cannot be installed here; see the
-header of ``orpcd_oracle.c`` and DESIGN.md.
+pure-Python control flow on top of it.  PARITY UNPINNED for the arithmetic of the
+Open3D entry points (the reference has no tests/golden vectors for this path and
+Open3D cannot be installed here); the classes of THIS module are pinned bit for bit
+to golden vectors of the reference's own classes (``tests/golden/make_golden*_ref.py``:
+Aligner, GeneralizedICP, FastGlobalOptimizer, SOR, VoxelDownsampler run unmodified,
+the Open3D-backed ones over a stub whose numerical entry points are this oracle's).
+See the header of ``orpcd_oracle.c`` and DESIGN.md section 5.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs
 may import this module.  Each function cites the reference file:line it follows

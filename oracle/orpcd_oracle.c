@@ -8,11 +8,17 @@
  * installable here, so this file restates its PUBLISHED algorithms; SURVEY.md
  * Appendix A is the specification it follows.
  *
- *   PARITY UNPINNED: the reference ships no tests and no golden vectors for
- *   this path, and Open3D itself cannot be run here.  This oracle is pinned
- *   only against independent libraries (scipy cKDTree, numpy eigh/inv/sqrtm)
- *   and against the reference's own importable numpy blocks
- *   (tests/golden/make_golden.py).
+ *   PARITY UNPINNED (the arithmetic of the five Open3D entry points below):
+ *   the reference ships no tests and no golden vectors for this path, and
+ *   Open3D itself cannot be run here.  This file is pinned only against
+ *   independent libraries (scipy cKDTree, numpy eigh/inv/sqrtm) and known
+ *   answers.  What IS pinned to the reference itself is everything around
+ *   these entry points (oracle.py): golden vectors of the reference's own
+ *   classes -- RadiusScaler, RandomDownsampler, FarthestDownsampler, the
+ *   Aligner (control flow, RNG consumption, transfrom, refine_registration),
+ *   GeneralizedICP, FastGlobalOptimizer, SOR and VoxelDownsampler, the last
+ *   five run unmodified over an open3d stub backed by this oracle
+ *   (tests/golden/make_golden*.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.  The product path
