@@ -400,3 +400,18 @@ def test_preprocessing_blocks_equal_the_references_own_classes(oracle):
             pts = blk.process(cloud)
             assert np.array_equal(np.array(blk.probes, dtype=np.float64), g[f"voxel_{name}_{tag}_probes"]), (name, tag)
             assert np.array_equal(pts, g[f"voxel_{name}_{tag}_points"]), (name, tag)
+
+
+def test_config1_end_to_end_with_the_references_own_classes_equals_the_oracle_run(golden):
+    """BASELINE config 1 run END TO END by the reference's unmodified Aligner / Preprocessor / RandomDownsampler / SOR /
+    RadiusScaler / GeneralizedICP classes over an open3d stub that only answers remove_statistical_outlier and
+    registration_generalized_icp with the oracle (tests/golden/make_golden_config1_ref.py, 870 registrations) gives, bit
+    for bit, what oracle.Aligner gave (golden_v1.npz) -- the run every GPU test of Aligner.align() is held to: the
+    Python restatement of the whole pipeline IS the reference's pipeline."""
+    r = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_config1_ref.npz"))
+    assert np.array_equal(r["T"], golden["align_back_T"])
+    assert float(r["rmse"]) == float(golden["align_back_metric"])
+    assert np.array_equal(r["scale"], golden["align_back_scale"]) and r["scale"].shape == (1, 3)
+    assert np.array_equal(r["errors"], golden["align_back_errors"])
+    assert int(r["calls"]) == int(golden["align_back_calls"]) == 870 and int(r["sor_calls"]) == 2
+    assert np.array_equal(r["rng_after"], golden["align_back_rng_after"])
