@@ -133,9 +133,21 @@ class ClockSampler:
             import pynvml as nv
 
             nv.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
-            handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            handle = None
+            try:      # the device THIS process computes on, whatever CUDA_VISIBLE_DEVICES says: by UUID
+                import torch
+
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                handle = nv.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:
+                handle = None
+            if handle is None:
+                vis = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+                if self.index < len(vis) and vis[self.index].startswith(("GPU-", "MIG-")):
+                    handle = nv.nvmlDeviceGetHandleByUUID(vis[self.index])
+                else:
+                    phys = int(vis[self.index]) if self.index < len(vis) and vis[self.index].isdigit() else self.index
+                    handle = nv.nvmlDeviceGetHandleByIndex(phys)
             max_mhz = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
             self.stop = threading.Event()
             self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle, max_mhz), daemon=True)
